@@ -1,0 +1,55 @@
+"""Case tables and deterministic inputs shared by make_golden.py (reference side) and the tests."""
+import numpy as np
+
+from oracle.detrand import det_uniform, det_normal
+
+WG_STRIDE = 17
+
+# ----------------------------------------------------------------------------- case tables
+TABLEAU_CASES = [
+    # method, parameterization, u0, v0
+    ("euler", None, -1, -1),
+    ("rk2", "u", 0.5, -1), ("rk2", "u", 1.0, -1), ("rk2", "u", 0.3, -1), ("rk2", "u", 2 / 3., -1),
+    ("rk2", "u", 0.05, -1), ("rk2", "u", 1.5, -1), ("rk2", "u", 1e-5, -1), ("rk2", "u", 0.5125, -1),
+    ("rk3", "uv", 1 / 3., 2 / 3.), ("rk3", "uv", 0.5, 1.0), ("rk3", "uv", 0.4, 0.4), ("rk3", "uv", 1.0, 1.0),
+    ("rk3", "uv", 0.25, 0.8),
+    ("rk4", "u1", 0.2, -1), ("rk4", "u2", 1 / 3., -1), ("rk4", "u3", 0.1, -1), ("rk4", "u2", 0.45, -1),
+    ("rk4", "uv", 1 / 3., 2 / 3.), ("rk4", "uv", 0.5, 0.7), ("rk4", "uv", 0.3, 0.3), ("rk4", "uv", 0.6, 0.9),
+    ("rk4", "u1", 1.2, -1),
+]
+
+# name, C, H, W, B, rhs kind, solver tuple (method, param, n_steps, step_size, u0, v0)
+ODE_CASES = [
+    ("c64_rk2_u05_n8", 64, 8, 32, 2, "preact", ("rk2", "u", 8, -1, 0.5, -1)),
+    ("c64_rk2_u03_n3", 64, 8, 32, 2, "preact", ("rk2", "u", 3, -1, 0.3, -1)),
+    ("c64_rk2_u1_n10", 64, 4, 32, 1, "preact", ("rk2", "u", 10, -1, 1.0, -1)),
+    ("c64_euler_n2", 64, 8, 32, 2, "preact", ("euler", None, 2, -1, -1, -1)),
+    ("c64_rk3_n2", 64, 8, 32, 2, "preact", ("rk3", "uv", 2, -1, 1 / 3., 2 / 3.)),
+    ("c64_rk4u2_n2", 64, 8, 32, 2, "preact", ("rk4", "u2", 2, -1, 1 / 3., -1)),
+    ("c64_rk4uv_n1", 64, 8, 32, 2, "preact", ("rk4", "uv", 1, -1, 1 / 3., 2 / 3.)),
+    ("c64_rk4u1_n1", 64, 4, 32, 1, "preact", ("rk4", "u1", 1, -1, 0.2, -1)),
+    ("c64_rk4u3_n1", 64, 4, 32, 1, "preact", ("rk4", "u3", 1, -1, 0.1, -1)),
+    ("c64_rk2_step03", 64, 4, 32, 1, "preact", ("rk2", "u", -1, 0.3, 0.5, -1)),
+    ("c128_rk2_u05_n8", 128, 8, 16, 2, "preact", ("rk2", "u", 8, -1, 0.5, -1)),
+    ("c128_rk4u2_n1", 128, 16, 16, 1, "preact", ("rk4", "u2", 1, -1, 1 / 3., -1)),
+    ("c16_rk2_u05_n2_odd", 16, 5, 7, 3, "preact", ("rk2", "u", 2, -1, 0.5, -1)),
+    ("c64_post_rk2_n2", 64, 8, 32, 2, "postact", ("rk2", "u", 2, -1, 0.5, -1)),
+]
+
+
+def conv_w(c_out, c_in, seed, k=3):
+    bound = 1.0 / np.sqrt(c_in * k * k)          # nn.Conv2d default init range
+    return det_uniform((c_out, c_in, k, k), seed, -bound, bound)
+
+
+def ode_case_inputs(C, H, W, B, seed=0):
+    x = det_normal((B, C, H, W), 11 + seed)
+    w1 = conv_w(C, C, 21 + seed)
+    w2 = conv_w(C, C, 31 + seed)
+    r = det_normal((B, C, H, W), 41 + seed)
+    return x, w1, w2, r
+
+
+
+REGIME_SOLVERS = [("rk2", "u", 4, -1, 0.3, -1), ("rk2", "u", 4, -1, 0.5, -1), ("rk2", "u", 2, -1, 2 / 3., -1),
+                  ("rk4", "u2", 2, -1, 1 / 3., -1)]
