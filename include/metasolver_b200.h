@@ -1,0 +1,134 @@
+/*
+ * metasolver_b200 -- C ABI of the B200-native meta-solver ODE-block hot path.
+ *
+ * The reference (juliagusak/neural-ode-metasolver) is pure Python/PyTorch and has no FFI layer;
+ * the seam it offers is the `sopa` Python API.  This header is the C boundary that API binds to
+ * (ctypes stub: neural-ode-metasolver_b200/_cabi.py).  Plain pointers and
+ * sizes only -- no torch types.  Every entry point:
+ *   - borrows all device buffers for the duration of the call (caller allocates / frees),
+ *   - enqueues its kernels on the caller's CUDA stream and never synchronises the host,
+ *   - returns 0 on success, non-zero on error (text via msb_last_error(), thread-local),
+ *   - refuses unsupported (rhs kind, activation, shape) combinations: there is no cuDNN / CPU
+ *     fallback behind this ABI.
+ *
+ * Device layouts
+ *   state tensors : fp32  NHWC            [B][H][W][C]              ("channels-last")
+ *   split tensors : bf16  [B][H][2][W][C] plane 0 = hi = bf16(x), plane 1 = lo = bf16(x - hi)
+ *                   (the form in which every convolution operand lives in HBM; hi+lo carries
+ *                    ~16 significand bits, the tensor cores multiply all four hi/lo products
+ *                    and accumulate in fp32)
+ *   conv weights  : fp32  OIHW            [C_out][C_in][3][3]       (PyTorch's own layout)
+ *
+ * What each function replaces in the reference (paths relative to the reference root):
+ *   msb_odeblock_forward   RKParametricSolver.integrate            sopa/src/solvers/rk_parametric.py:89-113
+ *                          + RK*._make_step                        sopa/src/solvers/rk_parametric_order2stage2.py:87-93,
+ *                                                                  ..order3stage3.py:96-103, ..order4stage4.py:184-192, euler.py:63-68
+ *                          + PreBasicBlock2 / BasicBlock2.forward  sopa/src/models/odenet_cifar10/layers.py:148-161, 108-121
+ *                          + ODEfunc / ConcatConv2d.forward        sopa/src/models/odenet_mnist/layers.py:158-171, 250-253
+ *   msb_odeblock_backward  torch.autograd through all of the above (discretize-then-optimize;
+ *                          consumers: examples/cifar10/train_and_attack.py:310-311,
+ *                          MegaAdversarial/src/attacks/fgsm.py:34-36,98, pgd.py:44-46)
+ */
+#ifndef METASOLVER_B200_H_
+#define METASOLVER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSB_ABI_VERSION 1
+#define MSB_MAX_STAGES 4
+
+/* right-hand-side families */
+enum { MSB_RHS_PREACT_NF = 0,   /* conv2(act(conv1(act(x))))          cifar10/layers.py:148-161 */
+       MSB_RHS_POSTACT_NF = 1,  /* act(conv2(act(conv1(x))))          cifar10/layers.py:108-121 */
+       MSB_RHS_MNIST_GN_T = 2   /* GN-ReLU-cconv(t)-GN-ReLU-cconv(t)-GN  mnist/layers.py:158-171 */ };
+/* activations */
+enum { MSB_ACT_NONE = 0, MSB_ACT_GELU_ERF = 1, MSB_ACT_RELU = 2 };
+/* GEMM engines */
+enum { MSB_ENGINE_AUTO = 0,     /* tcgen05 when the shape is supported, else error unless allow_simt */
+       MSB_ENGINE_TCGEN05 = 1,  /* implicit-GEMM on tcgen05/TMEM fed by TMA (sm_100a) */
+       MSB_ENGINE_SIMT = 2      /* plain fp32 FFMA CUDA kernels (any shape; validation / small shapes) */ };
+
+/* One ODE-block integration problem.  All scalar arrays are HOST values, read during the call. */
+typedef struct MsbOdeDesc {
+    int32_t rhs_kind;                 /* MSB_RHS_* */
+    int32_t act;                      /* MSB_ACT_* used inside the RHS */
+    int32_t engine;                   /* MSB_ENGINE_* */
+    int32_t batch, height, width, channels;
+    int32_t n_steps;                  /* number of RK steps = len(grid) - 1 */
+    int32_t stages;                   /* 1..4 */
+    float c[MSB_MAX_STAGES];          /* Butcher nodes   (rk_parametric.py:68-75) */
+    float b[MSB_MAX_STAGES];          /* Butcher weights */
+    float w[MSB_MAX_STAGES * MSB_MAX_STAGES]; /* row-major lower-triangular stage matrix w[i][j] */
+    const float* time_grid;           /* HOST pointer, n_steps+1 grid points (rk_parametric.py:93-96) */
+    int32_t save_tape;                /* 1: record what backward needs into `tape` */
+    int32_t reserved;
+} MsbOdeDesc;
+
+/* Extra parameters of the MNIST RHS (device pointers, fp32). */
+typedef struct MsbMnistParams {
+    const float* norm_w[3];           /* GroupNorm gamma [C]            mnist/layers.py:152-157 */
+    const float* norm_b[3];           /* GroupNorm beta  [C] */
+    const float* conv_w[2];           /* [C][C+1][3][3] (input channel 0 is the time channel) */
+    const float* conv_b[2];           /* [C] */
+    int32_t groups;                   /* min(32, C)                      mnist/layers.py:208-209 */
+    float eps;                        /* 1e-5 */
+} MsbMnistParams;
+
+int         msb_abi_version(void);
+const char* msb_last_error(void);
+/* 1 if `device` can run the tcgen05 engine (compute capability 10.x), 0 if not, <0 on error. */
+int         msb_device_supports_tcgen05(int device);
+/* 1 if (C,H,W) is covered by the tcgen05 engine. */
+int         msb_shape_supports_tcgen05(int channels, int height, int width);
+
+/* Scratch (not preserved between calls) and tape (forward -> backward) sizes in bytes. */
+size_t msb_odeblock_workspace_bytes(const MsbOdeDesc* d);
+size_t msb_odeblock_tape_bytes(const MsbOdeDesc* d);
+size_t msb_odeblock_bwd_workspace_bytes(const MsbOdeDesc* d);
+
+/* y_out = state at time_grid[n_steps] starting from x at time_grid[0].  x, y_out: fp32 NHWC.
+ * w1, w2: fp32 OIHW conv weights of the RHS (CIFAR families).  `mnist` non-NULL only for
+ * MSB_RHS_MNIST_GN_T (then w1/w2 are ignored).  `tape` may be NULL when save_tape == 0. */
+int msb_odeblock_forward(const MsbOdeDesc* d, const float* x, const float* w1, const float* w2,
+                         const MsbMnistParams* mnist, float* y_out,
+                         void* workspace, size_t workspace_bytes, void* tape, size_t tape_bytes,
+                         void* cuda_stream);
+
+/* Discretize-then-optimize gradient of the same integration.  grad_y, grad_x: fp32 NHWC.
+ * grad_w1/grad_w2 (fp32 OIHW) are OVERWRITTEN when non-NULL; pass NULL for the input-gradient
+ * only mode used by FGSM/PGD (pgd.py:44-46). */
+int msb_odeblock_backward(const MsbOdeDesc* d, const float* grad_y, const float* w1, const float* w2,
+                          const void* tape, size_t tape_bytes, float* grad_x, float* grad_w1, float* grad_w2,
+                          void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* ---- building blocks, exported so the parity tests can exercise each kernel through the C ABI ---- */
+
+/* split[B][H][2][W][C] = hi/lo(act(x)) ; dact (optional, fp32 NHWC) = act'(x). */
+int msb_act_split(const float* x, int act, void* split_out, float* dact_out,
+                  int batch, int height, int width, int channels, void* cuda_stream);
+
+/* out = conv3x3(split_in, w) (stride 1, pad 1, no bias), fp32 NHWC.  transpose != 0 computes the
+ * input-gradient convolution (weights transposed and rotated by 180 degrees). */
+int msb_conv3x3(const void* split_in, const float* w_oihw, float* out, int transpose, int engine,
+                int batch, int height, int width, int channels,
+                void* workspace, size_t workspace_bytes, void* cuda_stream);
+size_t msb_conv3x3_workspace_bytes(int channels);
+
+/* grad_w[O][I][3][3] = sum over pixels of grad_out (x) shifted input; both operands split tensors. */
+int msb_wgrad3x3(const void* split_grad_out, const void* split_in, float* grad_w_oihw, int engine,
+                 int batch, int height, int width, int channels,
+                 void* workspace, size_t workspace_bytes, void* cuda_stream);
+size_t msb_wgrad3x3_workspace_bytes(int channels, int engine);
+
+/* Number of kernels this library has launched since load (bench.py's `gpu_launches`). */
+uint64_t msb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* METASOLVER_B200_H_ */

@@ -1,0 +1,92 @@
+"""ctypes binding of libmetasolver_b200.so (C ABI: include/metasolver_b200.h).
+
+The library is built in-tree (build.py).  Loading fails loudly: the product has no other path.
+"""
+import ctypes
+import os
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmetasolver_b200.so")
+
+MSB_MAX_STAGES = 4
+RHS_PREACT_NF, RHS_POSTACT_NF, RHS_MNIST_GN_T = 0, 1, 2
+ACT_NONE, ACT_GELU_ERF, ACT_RELU = 0, 1, 2
+ENGINE_AUTO, ENGINE_TCGEN05, ENGINE_SIMT = 0, 1, 2
+ENGINES = {"auto": ENGINE_AUTO, "tcgen05": ENGINE_TCGEN05, "simt": ENGINE_SIMT}
+
+EXPORTS = [
+    "msb_abi_version", "msb_last_error", "msb_device_supports_tcgen05", "msb_shape_supports_tcgen05",
+    "msb_odeblock_workspace_bytes", "msb_odeblock_tape_bytes", "msb_odeblock_bwd_workspace_bytes",
+    "msb_odeblock_forward", "msb_odeblock_backward", "msb_act_split", "msb_conv3x3",
+    "msb_conv3x3_workspace_bytes", "msb_wgrad3x3", "msb_wgrad3x3_workspace_bytes", "msb_launch_count",
+]
+
+
+class MsbOdeDesc(ctypes.Structure):
+    _fields_ = [
+        ("rhs_kind", ctypes.c_int32), ("act", ctypes.c_int32), ("engine", ctypes.c_int32),
+        ("batch", ctypes.c_int32), ("height", ctypes.c_int32), ("width", ctypes.c_int32),
+        ("channels", ctypes.c_int32), ("n_steps", ctypes.c_int32), ("stages", ctypes.c_int32),
+        ("c", ctypes.c_float * MSB_MAX_STAGES), ("b", ctypes.c_float * MSB_MAX_STAGES),
+        ("w", ctypes.c_float * (MSB_MAX_STAGES * MSB_MAX_STAGES)),
+        ("time_grid", ctypes.POINTER(ctypes.c_float)),
+        ("save_tape", ctypes.c_int32), ("reserved", ctypes.c_int32),
+    ]
+
+
+class MsbMnistParams(ctypes.Structure):
+    _fields_ = [
+        ("norm_w", ctypes.c_void_p * 3), ("norm_b", ctypes.c_void_p * 3),
+        ("conv_w", ctypes.c_void_p * 2), ("conv_b", ctypes.c_void_p * 2),
+        ("groups", ctypes.c_int32), ("eps", ctypes.c_float),
+    ]
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def _declare(lib):
+    vp, sz, i32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+    dp = ctypes.POINTER(MsbOdeDesc)
+    lib.msb_abi_version.restype = i32
+    lib.msb_last_error.restype = ctypes.c_char_p
+    lib.msb_launch_count.restype = ctypes.c_uint64
+    lib.msb_device_supports_tcgen05.argtypes = [i32]
+    lib.msb_shape_supports_tcgen05.argtypes = [i32, i32, i32]
+    for f in (lib.msb_odeblock_workspace_bytes, lib.msb_odeblock_tape_bytes, lib.msb_odeblock_bwd_workspace_bytes):
+        f.argtypes = [dp]
+        f.restype = sz
+    lib.msb_odeblock_forward.argtypes = [dp, vp, vp, vp, ctypes.POINTER(MsbMnistParams), vp, vp, sz, vp, sz, vp]
+    lib.msb_odeblock_backward.argtypes = [dp, vp, vp, vp, vp, sz, vp, vp, vp, vp, sz, vp]
+    lib.msb_act_split.argtypes = [vp, i32, vp, vp, i32, i32, i32, i32, vp]
+    lib.msb_conv3x3.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, sz, vp]
+    lib.msb_conv3x3_workspace_bytes.argtypes = [i32]
+    lib.msb_conv3x3_workspace_bytes.restype = sz
+    lib.msb_wgrad3x3.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, sz, vp]
+    lib.msb_wgrad3x3_workspace_bytes.argtypes = [i32, i32]
+    lib.msb_wgrad3x3_workspace_bytes.restype = sz
+
+
+def lib():
+    """Load (once) and return the shared library; raise RuntimeError if it is not built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        "metasolver_b200: %s is missing. Build it with `python neural-ode-metasolver_b200/build.py` "
+                        "(or __graft_entry__.build()). There is no CPU / cuDNN path to fall back to." % LIB_PATH)
+                l = ctypes.CDLL(LIB_PATH)
+                _declare(l)
+                if l.msb_abi_version() != 1:
+                    raise RuntimeError("metasolver_b200: ABI version mismatch")
+                _lib = l
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError("metasolver_b200 %s failed: %s" % (what, lib().msb_last_error().decode()))

@@ -1,0 +1,154 @@
+// Shared device-side definitions: the fused epilogue contract, activation math, bf16 hi/lo split.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace msb {
+
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
+
+// ---------------------------------------------------------------------------------------------
+// Fused epilogue applied to every accumulator element of a convolution.  One struct covers the
+// forward RK stage combinations, the activation that feeds the next convolution, and the
+// backward (adjoint) stage combinations -- see odeblock.cu for how each stage fills it in.
+//
+//   v   = acc (+ chan_bias[c] + pix_bias_scale * pix_bias[h,w,c])       bias terms: MNIST ConcatConv2d only
+//   v   = act_v ? act(v) : v               (dact_v_out <- act'(pre-activation))
+//   v   = mul ? v * mul[idx] : v           (backward: multiply by a saved activation derivative)
+//   v_out[idx]  <- v                       (k_i in forward, xbar_i in backward)
+//   s   = src0*coef0 + src1*coef1 + src2*coef2 + v*coef_v      summed left to right, no FMA,
+//   out = base*base_coef + s*dt                                exactly the reference's order
+//         (rk_parametric_order2stage2.py:91-93: x + k1*w21*dt ; (k1*b1 + k2*b2)*dt ; rk_parametric.py:106)
+//   out_f32[idx]   <- out
+//   out_split      <- hi/lo( (act ? act(out) : out) * split_scale )     operand of the next conv
+//   dact_out[idx]  <- act'(out)
+// ---------------------------------------------------------------------------------------------
+struct EpiParams {
+    const float* mul;
+    float* v_out;
+    const float* base;
+    const float* src[3];
+    float* out_f32;
+    __nv_bfloat16* out_split;
+    float* dact_out;
+    float* dact_v_out;
+    const float* chan_bias;
+    const float* pix_bias;
+    float coef[3];
+    float base_coef;
+    float coef_v;
+    float dt;
+    float split_scale;
+    float pix_bias_scale;
+    int nsrc;
+    int act;
+    int act_v;
+    int base_is_one;   // base_coef == 1 -> skip the multiply (keeps forward bit-order exact)
+};
+
+__host__ inline EpiParams epi_default() {
+    EpiParams e;
+    e.mul = nullptr; e.v_out = nullptr; e.base = nullptr;
+    e.src[0] = e.src[1] = e.src[2] = nullptr;
+    e.out_f32 = nullptr; e.out_split = nullptr; e.dact_out = nullptr; e.dact_v_out = nullptr;
+    e.chan_bias = nullptr; e.pix_bias = nullptr;
+    e.coef[0] = e.coef[1] = e.coef[2] = 0.f;
+    e.base_coef = 1.f; e.coef_v = 1.f; e.dt = 1.f; e.split_scale = 1.f; e.pix_bias_scale = 0.f;
+    e.nsrc = 0; e.act = ACT_NONE; e.act_v = ACT_NONE; e.base_is_one = 1;
+    return e;
+}
+
+// ---- activations -----------------------------------------------------------------------------
+// Exact-erf GeLU as torch.nn.functional.gelu (cifar10/utils.py:67-68): x * 0.5 * (1 + erf(x / sqrt 2)).
+__device__ __forceinline__ float gelu_f(float x) {
+    return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+}
+// d/dx gelu = Phi(x) + x * phi(x)
+__device__ __forceinline__ float dgelu_f(float x) {
+    float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+    return cdf + x * pdf;
+}
+__device__ __forceinline__ float act_f(int act, float x) {
+    if (act == ACT_GELU) return gelu_f(x);
+    if (act == ACT_RELU) return x > 0.f ? x : 0.f;
+    return x;
+}
+__device__ __forceinline__ float dact_f(int act, float x) {
+    if (act == ACT_GELU) return dgelu_f(x);
+    if (act == ACT_RELU) return x > 0.f ? 1.f : 0.f;
+    return 1.f;
+}
+// value and derivative together (shares the erf)
+__device__ __forceinline__ void act_both(int act, float x, float& a, float& d) {
+    if (act == ACT_GELU) {
+        float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+        float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+        a = x * cdf;
+        d = cdf + x * pdf;
+    } else if (act == ACT_RELU) {
+        a = x > 0.f ? x : 0.f;
+        d = x > 0.f ? 1.f : 0.f;
+    } else {
+        a = x; d = 1.f;
+    }
+}
+
+// ---- bf16 hi/lo split --------------------------------------------------------------------------
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(x);
+    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// split tensor index: [B][H][2][W][C]
+__device__ __forceinline__ size_t split_index(int n, int h, int plane, int w, int c, int H, int W, int C) {
+    return ((((size_t)n * H + h) * 2 + plane) * W + w) * (size_t)C + c;
+}
+
+// ---- the epilogue itself (scalar form; engines may vectorise around it) ------------------------
+// idx = NHWC linear index of the element, (n,h,w,c) its coordinates.
+__device__ __forceinline__ void epilogue_apply(const EpiParams& e, float acc, size_t idx,
+                                               int n, int h, int w, int c, int H, int W, int C) {
+    float v = acc;
+    if (e.chan_bias) v = __fadd_rn(v, e.chan_bias[c]);
+    if (e.pix_bias) v = __fadd_rn(v, __fmul_rn(e.pix_bias_scale, e.pix_bias[((size_t)h * W + w) * C + c]));
+    if (e.act_v != ACT_NONE) {
+        float a, d;
+        act_both(e.act_v, v, a, d);
+        if (e.dact_v_out) e.dact_v_out[idx] = d;
+        v = a;
+    }
+    if (e.mul) v = __fmul_rn(v, e.mul[idx]);
+    if (e.v_out) e.v_out[idx] = v;
+    float s;
+    if (e.nsrc == 0) {
+        s = __fmul_rn(v, e.coef_v);
+    } else {
+        s = __fmul_rn(e.src[0][idx], e.coef[0]);
+        if (e.nsrc > 1) s = __fadd_rn(s, __fmul_rn(e.src[1][idx], e.coef[1]));
+        if (e.nsrc > 2) s = __fadd_rn(s, __fmul_rn(e.src[2][idx], e.coef[2]));
+        s = __fadd_rn(s, __fmul_rn(v, e.coef_v));
+    }
+    float out = __fmul_rn(s, e.dt);
+    if (e.base) {
+        float bv = e.base[idx];
+        if (!e.base_is_one) bv = __fmul_rn(bv, e.base_coef);
+        out = __fadd_rn(bv, out);
+    }
+    if (e.out_f32) e.out_f32[idx] = out;
+    if (e.out_split || e.dact_out) {
+        float a, d;
+        act_both(e.act, out, a, d);
+        if (e.dact_out) e.dact_out[idx] = d;
+        if (e.out_split) {
+            a = __fmul_rn(a, e.split_scale);
+            __nv_bfloat16 hi, lo;
+            split_bf16(a, hi, lo);
+            e.out_split[split_index(n, h, 0, w, c, H, W, C)] = hi;
+            e.out_split[split_index(n, h, 1, w, c, H, W, C)] = lo;
+        }
+    }
+}
+
+}  // namespace msb

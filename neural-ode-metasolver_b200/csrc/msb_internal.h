@@ -1,0 +1,47 @@
+// Internal (non-ABI) declarations shared by the .cu files of libmetasolver_b200.so
+#pragma once
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "msb_common.cuh"
+
+namespace msb {
+
+// ---- runtime helpers (api.cu) ----
+int num_sms();
+void count_launch(int n = 1);
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);   // 0 if ok, else sets error and returns -1
+
+struct ConvShape { int B, H, W, C; };
+
+// ---- elementwise.cu ----
+void launch_act_split(const float* x, int act, float scale, __nv_bfloat16* split, float* dact,
+                      int B, int H, int W, int C, cudaStream_t st);
+void launch_pack_w_simt(const float* w, float* out, int C, int Cin_total, int skip_in, int transpose, cudaStream_t st);
+void launch_pack_w_tc(const float* w, __nv_bfloat16* out, int C, int transpose, cudaStream_t st);
+void launch_wgrad_reduce(const float* partial, int nparts, float* grad_w, int C, int accumulate, cudaStream_t st);
+
+// ---- conv_simt.cu : plain fp32 FFMA engine (any C multiple of 4, any H, W) ----
+//   out-epilogue(conv3x3(split_in, w_packed[tap][ci][co]))
+int launch_conv3x3_simt(const __nv_bfloat16* split_in, const float* w_packed, const EpiParams& epi,
+                        ConvShape s, cudaStream_t st);
+//   partial[nparts][tap][ci][co] = per-slice sums of in(shifted)[ci] * gout[co]; returns nparts via *nparts_out
+int launch_wgrad3x3_simt(const __nv_bfloat16* split_gout, const __nv_bfloat16* split_in, float* partial,
+                         int* nparts_out, ConvShape s, cudaStream_t st);
+int wgrad_simt_nparts(ConvShape s);
+
+// ---- conv_tc.cu : tcgen05 / TMEM / TMA implicit-GEMM engine ----
+bool tc_shape_supported(int C, int H, int W);
+size_t tc_packed_weight_bytes(int C);
+int launch_conv3x3_tc(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, const EpiParams& epi,
+                      ConvShape s, cudaStream_t st);
+
+// ---- wgrad_tc.cu ----
+int wgrad_tc_nparts(ConvShape s);
+int launch_wgrad3x3_tc(const __nv_bfloat16* split_gout, const __nv_bfloat16* split_in, float* partial,
+                       int* nparts_out, ConvShape s, cudaStream_t st);
+
+}  // namespace msb

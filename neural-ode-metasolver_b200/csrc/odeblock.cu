@@ -1,0 +1,390 @@
+// Host side of libmetasolver_b200.so: the C ABI (include/metasolver_b200.h) and the orchestration
+// of one ODE-block integration (forward) and its discretize-then-optimize gradient (backward).
+//
+// The step x stage loop of the reference (`RKParametricSolver.integrate`, rk_parametric.py:104-112
+// and `_make_step`, rk_parametric_order{2stage2,3stage3,4stage4}.py / euler.py) becomes a fixed
+// sequence of 2*stages*n_steps convolution launches on the caller's stream; every elementwise
+// operation of the reference (activations, k*w*dt, y + dt*sum b_i k_i, the adjoint combinations)
+// is folded into the epilogue of the convolution that produces its operand.  No host sync.
+#include <cstdarg>
+#include <atomic>
+#include <vector>
+
+#include "metasolver_b200.h"
+#include "msb_internal.h"
+
+namespace msb {
+
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return 0;
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return -1;
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+int num_sms() {
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!cached[dev]) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        cached[dev] = n > 0 ? n : 148;
+    }
+    return cached[dev];
+}
+
+namespace {
+
+inline size_t align_up(size_t x, size_t a = 1024) { return (x + a - 1) / a * a; }
+
+struct Carver {
+    char* base; size_t off, cap;
+    Carver(void* p, size_t c) : base((char*)p), off(0), cap(c) {}
+    template <typename T> T* take(size_t bytes) {
+        size_t o = align_up(off);
+        off = o + bytes;
+        return (T*)(base + o);
+    }
+    bool ok() const { return off <= cap; }
+};
+
+int validate(const MsbOdeDesc* d) {
+    if (!d) { set_error("null descriptor"); return -1; }
+    if (d->rhs_kind != MSB_RHS_PREACT_NF) {
+        set_error("rhs_kind %d is not implemented by this entry point (supported: MSB_RHS_PREACT_NF)", d->rhs_kind);
+        return -1;
+    }
+    if (d->act != MSB_ACT_GELU_ERF && d->act != MSB_ACT_RELU && d->act != MSB_ACT_NONE) {
+        set_error("unsupported activation %d", d->act); return -1;
+    }
+    if (d->stages < 1 || d->stages > MSB_MAX_STAGES) { set_error("stages must be 1..4 (got %d)", d->stages); return -1; }
+    if (d->n_steps < 1) { set_error("n_steps must be >= 1 (got %d)", d->n_steps); return -1; }
+    if (d->batch < 1 || d->height < 1 || d->width < 1 || d->channels < 4 || d->channels % 4) {
+        set_error("bad shape B=%d H=%d W=%d C=%d (C must be a positive multiple of 4)", d->batch, d->height, d->width, d->channels);
+        return -1;
+    }
+    if (!d->time_grid) { set_error("time_grid is NULL"); return -1; }
+    return 0;
+}
+
+// Resolve MSB_ENGINE_AUTO.  Both engines are this library's own CUDA kernels; there is no
+// library (cuDNN) or CPU path to fall back to.
+int resolve_engine(const MsbOdeDesc* d) {
+    bool tc_ok = tc_shape_supported(d->channels, d->height, d->width);
+    if (d->engine == MSB_ENGINE_SIMT) return MSB_ENGINE_SIMT;
+    if (d->engine == MSB_ENGINE_TCGEN05) {
+        if (!tc_ok) { set_error("tcgen05 engine does not cover C=%d H=%d W=%d", d->channels, d->height, d->width); return -1; }
+        return MSB_ENGINE_TCGEN05;
+    }
+    if (d->engine == MSB_ENGINE_AUTO) return tc_ok ? MSB_ENGINE_TCGEN05 : MSB_ENGINE_SIMT;
+    set_error("unknown engine %d", d->engine);
+    return -1;
+}
+
+size_t packed_w_bytes(int engine, int C) {
+    return engine == MSB_ENGINE_TCGEN05 ? tc_packed_weight_bytes(C) : (size_t)9 * C * C * sizeof(float);
+}
+size_t state_elems(const MsbOdeDesc* d) { return (size_t)d->batch * d->height * d->width * d->channels; }
+
+struct TapeSlot { __nv_bfloat16* A; float* G0; __nv_bfloat16* Hs; float* G1; };
+TapeSlot tape_slot(void* tape, size_t E, int slot) {
+    char* p = (char*)tape + (size_t)slot * 4 * align_up(E * 4);
+    size_t q = align_up(E * 4);
+    return TapeSlot{(__nv_bfloat16*)p, (float*)(p + q), (__nv_bfloat16*)(p + 2 * q), (float*)(p + 3 * q)};
+}
+
+int run_conv(int engine, const __nv_bfloat16* in, const void* wpacked, const EpiParams& e, ConvShape s, cudaStream_t st) {
+    if (engine == MSB_ENGINE_TCGEN05) return launch_conv3x3_tc(in, (const __nv_bfloat16*)wpacked, e, s, st);
+    return launch_conv3x3_simt(in, (const float*)wpacked, e, s, st);
+}
+void pack_w(int engine, const float* w, void* out, int C, int transpose, cudaStream_t st) {
+    if (engine == MSB_ENGINE_TCGEN05) launch_pack_w_tc(w, (__nv_bfloat16*)out, C, transpose, st);
+    else launch_pack_w_simt(w, (float*)out, C, C, 0, transpose, st);
+}
+int wgrad_nparts(int engine, ConvShape s) {
+    return engine == MSB_ENGINE_TCGEN05 ? wgrad_tc_nparts(s) : wgrad_simt_nparts(s);
+}
+int run_wgrad(int engine, const __nv_bfloat16* gout, const __nv_bfloat16* in, float* partial, float* grad_w,
+              int accumulate, ConvShape s, cudaStream_t st) {
+    int nparts = 0, rc;
+    if (engine == MSB_ENGINE_TCGEN05) rc = launch_wgrad3x3_tc(gout, in, partial, &nparts, s, st);
+    else rc = launch_wgrad3x3_simt(gout, in, partial, &nparts, s, st);
+    if (rc) return rc;
+    launch_wgrad_reduce(partial, nparts, grad_w, s.C, accumulate, st);
+    return check_cuda(cudaGetLastError(), "wgrad reduce launch");
+}
+
+}  // namespace
+}  // namespace msb
+
+using namespace msb;
+
+extern "C" {
+
+int msb_abi_version(void) { return MSB_ABI_VERSION; }
+const char* msb_last_error(void) { return g_err.c_str(); }
+uint64_t msb_launch_count(void) { return g_launches.load(); }
+
+int msb_device_supports_tcgen05(int device) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess) {
+        set_error("cannot query device %d", device);
+        return -1;
+    }
+    return major == 10 ? 1 : 0;
+}
+int msb_shape_supports_tcgen05(int channels, int height, int width) {
+    return tc_shape_supported(channels, height, width) ? 1 : 0;
+}
+
+size_t msb_odeblock_workspace_bytes(const MsbOdeDesc* d) {
+    if (validate(d)) return 0;
+    int engine = resolve_engine(d);
+    if (engine < 0) return 0;
+    size_t E = state_elems(d);
+    size_t n = 0;
+    n += 2 * align_up(packed_w_bytes(engine, d->channels));
+    n += 2 * align_up(E * 4);                                  // y ping-pong
+    n += (size_t)(d->stages - 1) * align_up(E * 4);            // k_1 .. k_{s-1}
+    n += 2 * align_up(E * 4);                                  // A / Hs split (inference)
+    return n + 4096;
+}
+size_t msb_odeblock_tape_bytes(const MsbOdeDesc* d) {
+    if (validate(d)) return 0;
+    return (size_t)d->n_steps * d->stages * 4 * align_up(state_elems(d) * 4);
+}
+size_t msb_odeblock_bwd_workspace_bytes(const MsbOdeDesc* d) {
+    if (validate(d)) return 0;
+    int engine = resolve_engine(d);
+    if (engine < 0) return 0;
+    size_t E = state_elems(d);
+    ConvShape s{d->batch, d->height, d->width, d->channels};
+    size_t n = 0;
+    n += 2 * align_up(packed_w_bytes(engine, d->channels));
+    n += 2 * align_up(E * 4);                                  // gbar ping-pong
+    n += (size_t)(d->stages - 1) * align_up(E * 4);            // xbar_1 .. xbar_{s-1}
+    n += 2 * align_up(E * 4);                                  // Kbar / DP split
+    n += align_up((size_t)wgrad_nparts(engine, s) * 9 * d->channels * d->channels * 4);
+    return n + 4096;
+}
+
+int msb_odeblock_forward(const MsbOdeDesc* d, const float* x, const float* w1, const float* w2,
+                         const MsbMnistParams* mnist, float* y_out, void* workspace, size_t workspace_bytes,
+                         void* tape, size_t tape_bytes, void* cuda_stream) {
+    if (validate(d)) return -1;
+    (void)mnist;
+    int engine = resolve_engine(d);
+    if (engine < 0) return -1;
+    if (!x || !w1 || !w2 || !y_out || !workspace) { set_error("null pointer argument"); return -1; }
+    if (workspace_bytes < msb_odeblock_workspace_bytes(d)) { set_error("workspace too small"); return -1; }
+    const bool save = d->save_tape != 0;
+    if (save && (!tape || tape_bytes < msb_odeblock_tape_bytes(d))) { set_error("tape missing or too small"); return -1; }
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int S = d->stages, N = d->n_steps, C = d->channels;
+    const size_t E = state_elems(d);
+    ConvShape shp{d->batch, d->height, d->width, C};
+
+    Carver cv(workspace, workspace_bytes);
+    void* wp1 = cv.take<char>(packed_w_bytes(engine, C));
+    void* wp2 = cv.take<char>(packed_w_bytes(engine, C));
+    float* ybuf[2] = {cv.take<float>(E * 4), cv.take<float>(E * 4)};
+    float* kbuf[MSB_MAX_STAGES] = {nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < S - 1; ++i) kbuf[i] = cv.take<float>(E * 4);
+    __nv_bfloat16* A_inf = cv.take<__nv_bfloat16>(E * 4);
+    __nv_bfloat16* Hs_inf = cv.take<__nv_bfloat16>(E * 4);
+    if (!cv.ok()) { set_error("internal: workspace carve overflow"); return -1; }
+
+    pack_w(engine, w1, wp1, C, 0, st);
+    pack_w(engine, w2, wp2, C, 0, st);
+
+    auto slot = [&](int n, int i) {
+        if (save) return tape_slot(tape, E, n * S + i);
+        return TapeSlot{A_inf, nullptr, Hs_inf, nullptr};
+    };
+    // prologue: operand of the very first conv1 = act(x)
+    {
+        TapeSlot s0 = slot(0, 0);
+        launch_act_split(x, d->act, 1.f, s0.A, s0.G0, d->batch, d->height, d->width, C, st);
+    }
+    const float* y_cur = x;
+    for (int n = 0; n < N; ++n) {
+        const float dt = d->time_grid[n + 1] - d->time_grid[n];      // fp32, as `t1 - t0` (rk_parametric.py:105)
+        float* y_next = (n == N - 1) ? y_out : ybuf[n & 1];
+        for (int i = 0; i < S; ++i) {
+            TapeSlot cur = slot(n, i);
+            // conv1: P = conv(A_i, W1);  Hs_i = split(act(P)),  G1_i = act'(P)
+            EpiParams e1 = epi_default();
+            e1.out_split = cur.Hs; e1.act = d->act; e1.dact_out = cur.G1;
+            if (run_conv(engine, cur.A, wp1, e1, shp, st)) return -1;
+            // conv2: k_i = conv(Hs_i, W2) and the Runge-Kutta combination that follows it
+            EpiParams e2 = epi_default();
+            e2.base = y_cur; e2.dt = dt; e2.act = d->act;
+            if (i < S - 1) {
+                // x_{i+1} = y + (sum_j k_j w[i+1][j]) dt          (order2stage2.py:91, order3stage3.py:100-101 ...)
+                e2.v_out = kbuf[i];
+                e2.nsrc = i;
+                for (int j = 0; j < i; ++j) { e2.src[j] = kbuf[j]; e2.coef[j] = d->w[(i + 1) * MSB_MAX_STAGES + j]; }
+                e2.coef_v = d->w[(i + 1) * MSB_MAX_STAGES + i];
+                TapeSlot nx = slot(n, i + 1);
+                e2.out_split = nx.A; e2.dact_out = nx.G0;
+            } else {
+                // y1 = y0 + (sum_j k_j b_j) dt                     (order2stage2.py:93, rk_parametric.py:106)
+                e2.nsrc = S - 1;
+                for (int j = 0; j < S - 1; ++j) { e2.src[j] = kbuf[j]; e2.coef[j] = d->b[j]; }
+                e2.coef_v = d->b[S - 1];
+                e2.out_f32 = y_next;
+                if (n < N - 1) { TapeSlot nx = slot(n + 1, 0); e2.out_split = nx.A; e2.dact_out = nx.G0; }
+            }
+            if (run_conv(engine, cur.Hs, wp2, e2, shp, st)) return -1;
+        }
+        y_cur = y_next;
+    }
+    return check_cuda(cudaGetLastError(), "odeblock forward");
+}
+
+int msb_odeblock_backward(const MsbOdeDesc* d, const float* grad_y, const float* w1, const float* w2,
+                          const void* tape, size_t tape_bytes, float* grad_x, float* grad_w1, float* grad_w2,
+                          void* workspace, size_t workspace_bytes, void* cuda_stream) {
+    if (validate(d)) return -1;
+    int engine = resolve_engine(d);
+    if (engine < 0) return -1;
+    if (!grad_y || !w1 || !w2 || !tape || !grad_x || !workspace) { set_error("null pointer argument"); return -1; }
+    if (tape_bytes < msb_odeblock_tape_bytes(d)) { set_error("tape too small"); return -1; }
+    if (workspace_bytes < msb_odeblock_bwd_workspace_bytes(d)) { set_error("workspace too small"); return -1; }
+    if ((grad_w1 == nullptr) != (grad_w2 == nullptr)) { set_error("grad_w1 and grad_w2 must both be given or both be NULL"); return -1; }
+    const bool need_w = grad_w1 != nullptr;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int S = d->stages, N = d->n_steps, C = d->channels;
+    const size_t E = state_elems(d);
+    ConvShape shp{d->batch, d->height, d->width, C};
+
+    Carver cv(workspace, workspace_bytes);
+    void* wt1 = cv.take<char>(packed_w_bytes(engine, C));
+    void* wt2 = cv.take<char>(packed_w_bytes(engine, C));
+    float* gbuf[2] = {cv.take<float>(E * 4), cv.take<float>(E * 4)};
+    float* xbar[MSB_MAX_STAGES] = {nullptr, nullptr, nullptr, nullptr};   // xbar[i], i = 1..S-1
+    for (int i = 1; i < S; ++i) xbar[i] = cv.take<float>(E * 4);
+    __nv_bfloat16* Kbar = cv.take<__nv_bfloat16>(E * 4);
+    __nv_bfloat16* DP = cv.take<__nv_bfloat16>(E * 4);
+    float* partial = cv.take<float>((size_t)wgrad_nparts(engine, shp) * 9 * C * C * 4);
+    if (!cv.ok()) { set_error("internal: workspace carve overflow"); return -1; }
+
+    pack_w(engine, w1, wt1, C, 1, st);
+    pack_w(engine, w2, wt2, C, 1, st);
+
+    auto dt_of = [&](int n) { return d->time_grid[n + 1] - d->time_grid[n]; };
+    // kbar_S of the last step = dt * b_S * gbar
+    launch_act_split(grad_y, ACT_NONE, dt_of(N - 1) * d->b[S - 1], Kbar, nullptr, d->batch, d->height, d->width, C, st);
+    const float* g_cur = grad_y;
+    int first_w = 1;
+    for (int n = N - 1; n >= 0; --n) {
+        const float dt = dt_of(n);
+        float* g_next = (n == 0) ? grad_x : gbuf[n & 1];
+        for (int i = S - 1; i >= 0; --i) {
+            TapeSlot cur = tape_slot(const_cast<void*>(tape), E, n * S + i);
+            // Kbar = split(kbar_i).   dW2 += kbar_i (x) Hs_i
+            if (need_w && run_wgrad(engine, Kbar, cur.Hs, partial, grad_w2, !first_w, shp, st)) return -1;
+            // dP = dgrad_W2(kbar_i) * act'(P_i)
+            EpiParams e3 = epi_default();
+            e3.mul = cur.G1; e3.out_split = DP;
+            if (run_conv(engine, Kbar, wt2, e3, shp, st)) return -1;
+            // dW1 += dP (x) A_i
+            if (need_w && run_wgrad(engine, DP, cur.A, partial, grad_w1, !first_w, shp, st)) return -1;
+            first_w = 0;
+            // xbar_i = dgrad_W1(dP) * act'(x_i), then the adjoint stage combination
+            EpiParams e4 = epi_default();
+            e4.mul = cur.G0; e4.base = g_cur;
+            if (i > 0) {
+                // kbar_{i-1} = dt b_{i-1} gbar + dt sum_{j >= i} w[j][i-1] xbar_j
+                e4.v_out = xbar[i];
+                e4.base_coef = dt * d->b[i - 1]; e4.base_is_one = 0;
+                int ns = 0;
+                for (int j = S - 1; j > i; --j) { e4.src[ns] = xbar[j]; e4.coef[ns] = d->w[j * MSB_MAX_STAGES + (i - 1)]; ++ns; }
+                e4.nsrc = ns;
+                e4.coef_v = d->w[i * MSB_MAX_STAGES + (i - 1)];
+                e4.dt = dt;
+                e4.out_split = Kbar;
+            } else {
+                // ybar = gbar + sum_i xbar_i ; and kbar_S of the previous step
+                int ns = 0;
+                for (int j = S - 1; j > 0; --j) { e4.src[ns] = xbar[j]; e4.coef[ns] = 1.f; ++ns; }
+                e4.nsrc = ns;
+                e4.out_f32 = g_next;
+                if (n > 0) { e4.out_split = Kbar; e4.split_scale = dt_of(n - 1) * d->b[S - 1]; }
+            }
+            if (run_conv(engine, DP, wt1, e4, shp, st)) return -1;
+        }
+        g_cur = g_next;
+    }
+    return check_cuda(cudaGetLastError(), "odeblock backward");
+}
+
+int msb_act_split(const float* x, int act, void* split_out, float* dact_out, int batch, int height, int width,
+                  int channels, void* cuda_stream) {
+    if (!x || !split_out || channels % 4) { set_error("msb_act_split: bad arguments"); return -1; }
+    launch_act_split(x, act, 1.f, (__nv_bfloat16*)split_out, dact_out, batch, height, width, channels, (cudaStream_t)cuda_stream);
+    return check_cuda(cudaGetLastError(), "act_split");
+}
+
+size_t msb_conv3x3_workspace_bytes(int channels) {
+    size_t a = tc_packed_weight_bytes(channels), b = (size_t)9 * channels * channels * 4;
+    return align_up(a > b ? a : b) + 1024;
+}
+
+int msb_conv3x3(const void* split_in, const float* w_oihw, float* out, int transpose, int engine, int batch, int height,
+                int width, int channels, void* workspace, size_t workspace_bytes, void* cuda_stream) {
+    MsbOdeDesc d;
+    memset(&d, 0, sizeof(d));
+    d.engine = engine; d.batch = batch; d.height = height; d.width = width; d.channels = channels;
+    d.stages = 1; d.n_steps = 1; d.act = MSB_ACT_NONE; d.rhs_kind = MSB_RHS_PREACT_NF;
+    float tg[2] = {0.f, 1.f}; d.time_grid = tg;
+    if (validate(&d)) return -1;
+    int eng = resolve_engine(&d);
+    if (eng < 0) return -1;
+    if (!split_in || !w_oihw || !out || !workspace || workspace_bytes < msb_conv3x3_workspace_bytes(channels)) {
+        set_error("msb_conv3x3: bad arguments / workspace too small"); return -1;
+    }
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    pack_w(eng, w_oihw, workspace, channels, transpose, st);
+    EpiParams e = epi_default();
+    e.out_f32 = out;
+    return run_conv(eng, (const __nv_bfloat16*)split_in, workspace, e, ConvShape{batch, height, width, channels}, st);
+}
+
+size_t msb_wgrad3x3_workspace_bytes(int channels, int engine) {
+    (void)engine;
+    return (size_t)160 * 9 * channels * channels * 4 + 1024;   // >= max nparts of either engine
+}
+
+int msb_wgrad3x3(const void* split_grad_out, const void* split_in, float* grad_w_oihw, int engine, int batch, int height,
+                 int width, int channels, void* workspace, size_t workspace_bytes, void* cuda_stream) {
+    MsbOdeDesc d;
+    memset(&d, 0, sizeof(d));
+    d.engine = engine; d.batch = batch; d.height = height; d.width = width; d.channels = channels;
+    d.stages = 1; d.n_steps = 1; d.act = MSB_ACT_NONE; d.rhs_kind = MSB_RHS_PREACT_NF;
+    float tg[2] = {0.f, 1.f}; d.time_grid = tg;
+    if (validate(&d)) return -1;
+    int eng = resolve_engine(&d);
+    if (eng < 0) return -1;
+    ConvShape s{batch, height, width, channels};
+    if (!split_grad_out || !split_in || !grad_w_oihw || !workspace ||
+        workspace_bytes < (size_t)wgrad_nparts(eng, s) * 9 * channels * channels * 4) {
+        set_error("msb_wgrad3x3: bad arguments / workspace too small"); return -1;
+    }
+    return run_wgrad(eng, (const __nv_bfloat16*)split_grad_out, (const __nv_bfloat16*)split_in, (float*)workspace,
+                     grad_w_oihw, 0, s, (cudaStream_t)cuda_stream);
+}
+
+}  // extern "C"

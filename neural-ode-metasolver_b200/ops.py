@@ -1,0 +1,202 @@
+"""torch.autograd binding of the fused ODE-block kernels (C ABI: include/metasolver_b200.h).
+
+`ode_block_integrate` is what `RKParametricSolver.integrate` (sopa/src/solvers/rk_parametric.py)
+calls for a recognised right-hand side: one C call enqueues the whole steps x stages loop on the
+current CUDA stream; the backward is the matching fused discretize-then-optimize pass.
+
+Tensors cross the boundary as raw device pointers.  Activations are channels-last (NHWC) inside;
+the returned tensor keeps the logical NCHW shape with channels_last strides, so callers written
+against the reference keep working unchanged.
+"""
+import contextlib
+import ctypes
+import threading
+
+import torch
+
+from . import _cabi
+
+_state = threading.local()
+_default_engine = ["auto"]
+
+
+def set_default_engine(name):
+    """'auto' (tcgen05 where the shape is covered, SIMT otherwise), 'tcgen05' or 'simt'."""
+    if name not in _cabi.ENGINES:
+        raise ValueError("unknown engine %r" % (name,))
+    _default_engine[0] = name
+
+
+def launch_count():
+    """Kernels launched by libmetasolver_b200.so since it was loaded."""
+    return int(_cabi.lib().msb_launch_count())
+
+
+@contextlib.contextmanager
+def input_grad_only():
+    """Inside this context backward passes skip the weight gradients (FGSM / PGD input-gradient
+    mode, MegaAdversarial/src/attacks/pgd.py:44-46 uses autograd.grad w.r.t. the input only)."""
+    prev = getattr(_state, "input_only", False)
+    _state.input_only = True
+    try:
+        yield
+    finally:
+        _state.input_only = prev
+
+
+class OdeProblem:
+    """Host-side description of one integration: tableau, time grid, RHS family."""
+
+    def __init__(self, rhs_kind, act, tableau, time_grid, engine=None):
+        self.rhs_kind = rhs_kind
+        self.act = act
+        self.tableau = tableau              # dict(stages, c, b, w) of python floats
+        self.time_grid = [float(v) for v in time_grid]
+        self.engine = _cabi.ENGINES[engine or _default_engine[0]]
+        if len(self.time_grid) < 2:
+            raise ValueError("time grid needs at least two points")
+
+    def desc(self, x_shape, save_tape):
+        B, C, H, W = x_shape
+        d = _cabi.MsbOdeDesc()
+        d.rhs_kind, d.act, d.engine = self.rhs_kind, self.act, self.engine
+        d.batch, d.height, d.width, d.channels = B, H, W, C
+        d.n_steps = len(self.time_grid) - 1
+        s = self.tableau["stages"]
+        d.stages = s
+        for i in range(s):
+            d.c[i] = self.tableau["c"][i]
+            d.b[i] = self.tableau["b"][i]
+            for j in range(s):
+                d.w[i * _cabi.MSB_MAX_STAGES + j] = self.tableau["w"][i][j]
+        grid = (ctypes.c_float * len(self.time_grid))(*self.time_grid)
+        d.time_grid = ctypes.cast(grid, ctypes.POINTER(ctypes.c_float))
+        d.save_tape = 1 if save_tape else 0
+        d._keepalive = grid
+        return d
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _check_inputs(x, w1, w2):
+    if not x.is_cuda:
+        raise RuntimeError("metasolver_b200: the ODE-block path runs on CUDA only (got a %s tensor); "
+                           "there is no CPU fallback" % x.device)
+    if x.dtype != torch.float32 or w1.dtype != torch.float32 or w2.dtype != torch.float32:
+        raise RuntimeError("metasolver_b200: float32 tensors required")
+    if x.dim() != 4:
+        raise RuntimeError("metasolver_b200: expected a (B, C, H, W) state")
+    C = x.shape[1]
+    for w in (w1, w2):
+        if tuple(w.shape) != (C, C, 3, 3):
+            raise RuntimeError("metasolver_b200: conv weight must be (%d, %d, 3, 3), got %s" % (C, C, tuple(w.shape)))
+
+
+class _OdeBlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w1, w2, prob):
+        _check_inputs(x, w1, w2)
+        lib = _cabi.lib()
+        dev = x.device
+        need_grad = torch.is_grad_enabled() and (x.requires_grad or w1.requires_grad or w2.requires_grad)
+        with torch.cuda.device(dev):
+            xc = x.detach().contiguous(memory_format=torch.channels_last)
+            w1c, w2c = w1.detach().contiguous(), w2.detach().contiguous()
+            d = prob.desc(tuple(x.shape), need_grad)
+            ws_bytes = lib.msb_odeblock_workspace_bytes(ctypes.byref(d))
+            if ws_bytes == 0:
+                _cabi.check(-1, "odeblock workspace query")
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            tape = None
+            tape_bytes = 0
+            if need_grad:
+                tape_bytes = lib.msb_odeblock_tape_bytes(ctypes.byref(d))
+                tape = torch.empty(tape_bytes, dtype=torch.uint8, device=dev)
+            y = torch.empty_like(xc)          # channels_last strides, logical NCHW
+            rc = lib.msb_odeblock_forward(ctypes.byref(d), _ptr(xc), _ptr(w1c), _ptr(w2c), None, _ptr(y),
+                                          _ptr(ws), ws_bytes, _ptr(tape), tape_bytes, _stream(dev))
+            _cabi.check(rc, "odeblock forward")
+        ctx.prob = prob
+        ctx.tape = tape
+        ctx.tape_bytes = tape_bytes
+        ctx.shape = tuple(x.shape)
+        ctx.save_for_backward(w1c, w2c)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _cabi.lib()
+        w1c, w2c = ctx.saved_tensors
+        if ctx.tape is None:
+            raise RuntimeError("metasolver_b200: backward called but no tape was recorded")
+        dev = gy.device
+        need_w = (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]) and not getattr(_state, "input_only", False)
+        with torch.cuda.device(dev):
+            gyc = gy.contiguous(memory_format=torch.channels_last)
+            d = ctx.prob.desc(ctx.shape, True)
+            ws_bytes = lib.msb_odeblock_bwd_workspace_bytes(ctypes.byref(d))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            gx = torch.empty_like(gyc)
+            gw1 = torch.empty_like(w1c) if need_w else None
+            gw2 = torch.empty_like(w2c) if need_w else None
+            rc = lib.msb_odeblock_backward(ctypes.byref(d), _ptr(gyc), _ptr(w1c), _ptr(w2c), _ptr(ctx.tape),
+                                           ctx.tape_bytes, _ptr(gx), _ptr(gw1), _ptr(gw2), _ptr(ws), ws_bytes,
+                                           _stream(dev))
+            _cabi.check(rc, "odeblock backward")
+        ctx.tape = None       # the tape is large; release it as soon as it has been consumed
+        return gx, gw1, gw2, None
+
+
+def ode_block_integrate(x, w1, w2, tableau, time_grid, rhs_kind=_cabi.RHS_PREACT_NF, act=_cabi.ACT_GELU_ERF,
+                        engine=None):
+    """y(t_end) of dy/dt = f(y) with f = conv2(act(conv1(act(y)))) integrated on `time_grid`
+    by the explicit RK method `tableau`; differentiable w.r.t. x, w1, w2."""
+    prob = OdeProblem(rhs_kind, act, tableau, time_grid, engine)
+    return _OdeBlockFn.apply(x, w1, w2, prob)
+
+
+# --------------------------------------------------------------------------- single-kernel entry points
+def act_split(x_cl, act=_cabi.ACT_NONE, want_dact=False):
+    """x_cl: (B,C,H,W) channels_last fp32 -> (split uint16-view tensor [B,H,2,W,C], dact or None)."""
+    lib = _cabi.lib()
+    B, C, H, W = x_cl.shape
+    assert x_cl.is_contiguous(memory_format=torch.channels_last)
+    split = torch.empty((B, H, 2, W, C), dtype=torch.bfloat16, device=x_cl.device)
+    dact = torch.empty_like(x_cl) if want_dact else None
+    with torch.cuda.device(x_cl.device):
+        _cabi.check(lib.msb_act_split(_ptr(x_cl), act, _ptr(split), _ptr(dact), B, H, W, C, _stream(x_cl.device)),
+                    "act_split")
+    return split, dact
+
+
+def conv3x3(split, w, transpose=False, engine="auto"):
+    """split: [B,H,2,W,C] bf16 hi/lo operand, w: (C,C,3,3) fp32 -> (B,C,H,W) channels_last fp32."""
+    lib = _cabi.lib()
+    B, H, _, W, C = split.shape
+    dev = split.device
+    out = torch.empty((B, C, H, W), dtype=torch.float32, device=dev).contiguous(memory_format=torch.channels_last)
+    ws_bytes = lib.msb_conv3x3_workspace_bytes(C)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _cabi.check(lib.msb_conv3x3(_ptr(split), _ptr(w.contiguous()), _ptr(out), 1 if transpose else 0,
+                                    _cabi.ENGINES[engine], B, H, W, C, _ptr(ws), ws_bytes, _stream(dev)), "conv3x3")
+    return out
+
+
+def wgrad3x3(split_gout, split_in, engine="auto"):
+    lib = _cabi.lib()
+    B, H, _, W, C = split_in.shape
+    dev = split_in.device
+    gw = torch.empty((C, C, 3, 3), dtype=torch.float32, device=dev)
+    ws_bytes = lib.msb_wgrad3x3_workspace_bytes(C, _cabi.ENGINES[engine])
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _cabi.check(lib.msb_wgrad3x3(_ptr(split_gout), _ptr(split_in), _ptr(gw), _cabi.ENGINES[engine], B, H, W, C,
+                                     _ptr(ws), ws_bytes, _stream(dev)), "wgrad3x3")
+    return gw

@@ -1,0 +1,324 @@
+"""Solver objects of the `sopa` API (same names, attributes and error behaviour as the reference's
+sopa/src/solvers/{rk_parametric,rk_parametric_order2stage2,..order3stage3,..order4stage4,euler}.py).
+
+Design difference: a solver here is a HOST-side object.  u, v and the derived Butcher scalars are
+1-element CPU tensors / numpy scalars computed with exactly the reference's fp32 (or fp64)
+operation order, so no device kernels and no device->host syncs are spent on them
+(the reference keeps them on `device`: rk_parametric_order2stage2.py:37-49 and syncs in
+rk_parametric.py:95,109,117-119).  `integrate` hands the whole steps x stages loop to the fused
+CUDA path (ops.ode_block_integrate); it does not evaluate `rhs_func` from Python.
+"""
+import abc
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ....ops import ode_block_integrate
+from .... import _cabi
+
+
+def _np_dtype(dtype):
+    if dtype == torch.float64:
+        return np.float64
+    if dtype == torch.float32:
+        return np.float32
+    raise ValueError("solver dtype must be torch.float32 or torch.float64")
+
+
+def _clamp_eps(dtype):
+    # fp64 parameters are clamped with the fp32 machine epsilon, fp32 ones with the fp16 epsilon
+    # (rk_parametric_order2stage2.py:56-60)
+    return float(torch.finfo(torch.float32).eps if dtype == torch.float64 else torch.finfo(torch.float16).eps)
+
+
+class RKParametricSolver(object, metaclass=abc.ABCMeta):
+    """Fixed-grid explicit RK integrator with a u/v-parametrized tableau (rk_parametric.py:5-113)."""
+
+    n_stages = None
+    method = None
+
+    def __init__(self, n_steps=None, step_size=None, grid_constructor=None):
+        given = [a for a in (n_steps, step_size, grid_constructor) if a is not None]
+        if len(given) >= 2:
+            raise ValueError("n_steps, step_size and grid_constructor are pairwise exclusive arguments.")
+        if n_steps is not None:
+            self.grid_constructor = self._grid_constructor_from_n_steps(n_steps)
+        elif step_size is not None:
+            self.grid_constructor = self._grid_constructor_from_step_size(step_size)
+        elif grid_constructor is not None:
+            self.grid_constructor = grid_constructor
+        else:
+            self.grid_constructor = lambda t: t
+
+    # ---- time grids (rk_parametric.py:23-47); always evaluated on the host ----
+    def _grid_constructor_from_step_size(self, step_size):
+        step = float(step_size)
+
+        def make(t):
+            count = torch.ceil((t[-1] - t[0]) / step + 1).item()
+            grid = torch.arange(0, count).to(t) * step + t[0]
+            if grid[-1] > t[-1]:
+                grid[-1] = t[-1]
+            return grid
+        return make
+
+    def _grid_constructor_from_n_steps(self, n_steps):
+        def make(t):
+            # default-dtype CPU linspace, then cast -- the reference's exact recipe (rk_parametric.py:43)
+            return torch.linspace(float(t[0]), float(t[-1]), int(n_steps) + 1).to(t)
+        return make
+
+    # ---- parameters -> tableau ----
+    def _param_np(self, p):
+        """current value of u / v as a numpy scalar of the solver dtype"""
+        return _np_dtype(self.dtype)(p.detach().cpu().reshape(-1)[0].item())
+
+    @abc.abstractmethod
+    def _tableau_np(self):
+        """-> (c list, b list, w lower-triangular rows, valid (u_, v_)) as numpy scalars"""
+
+    def build_ButcherTableau(self, return_tableau=False):
+        c, b, w, (u_, v_) = self._tableau_np()
+        mk = lambda val: torch.tensor((float(val),), dtype=self.dtype)
+        self.u_ = None if u_ is None else mk(u_)
+        self.v_ = None if v_ is None else mk(v_)
+        s = len(c)
+        for i in range(s):
+            setattr(self, "c%d" % (i + 1), mk(c[i]))
+            setattr(self, "b%d" % (i + 1), mk(b[i]))
+            for j in range(i + 1):
+                setattr(self, "w%d%d" % (i + 1, j + 1), mk(w[i][j]))
+        self._host_tableau = dict(stages=s, c=[float(x) for x in c], b=[float(x) for x in b],
+                                  w=[[float(w[i][j]) if j < i else 0.0 for j in range(s)] for i in range(s)])
+        if return_tableau:
+            return self._collect_ButcherTableau()
+
+    def _collect_ButcherTableau(self):
+        t = self._host_tableau
+        s = t["stages"]
+        c = torch.tensor(t["c"])
+        w = [torch.tensor(t["w"][i][:i + 1]) for i in range(s)]
+        b = torch.tensor(t["b"])
+        return c, w, b
+
+    def host_tableau(self):
+        return self._host_tableau
+
+    # ---- requires_grad plumbing (API surface; every shipped script freezes: train_and_attack.py:413-414) ----
+    def freeze_params(self):
+        for p in (self.u, self.v):
+            if p is not None:
+                p.requires_grad = False
+        self.build_ButcherTableau()
+
+    def unfreeze_params(self):
+        for p in (self.u, self.v):
+            if p is not None:
+                p.requires_grad = True
+        self.build_ButcherTableau()
+
+    def _params_need_grad(self):
+        return any(p is not None and torch.is_tensor(p) and p.requires_grad for p in (self.u, self.v))
+
+    @property
+    @abc.abstractmethod
+    def order(self):
+        pass
+
+    # ---- integration ----
+    def host_time_grid(self, t):
+        t_host = t.detach().to("cpu", torch.float32)
+        grid = self.grid_constructor(t_host)
+        assert grid[0] == t_host[0] and grid[-1] == t_host[-1]        # rk_parametric.py:95
+        return grid.to(torch.float32)
+
+    def integrate(self, rhs_func, x, t):
+        """-> Tensor[len(t), B, C, H, W]; differentiable w.r.t. x and rhs_func's conv weights."""
+        if len(t) != 2:
+            raise NotImplementedError("metasolver_b200: integrate() returns the solution at t[0] and t[-1] only "
+                                      "(MetaODEBlock uses t=[0,1]); intermediate output times are not supported")
+        if self._params_need_grad() and torch.is_grad_enabled():
+            raise NotImplementedError("metasolver_b200: gradients w.r.t. the solver parameters u/v are not "
+                                      "implemented; call freeze_params() (as every reference script does)")
+        spec = getattr(rhs_func, "fused_rhs_spec", None)
+        if spec is None:
+            raise NotImplementedError("metasolver_b200: %s is not a right-hand side the fused CUDA path knows; "
+                                      "there is no unfused fallback" % type(rhs_func).__name__)
+        spec = spec()
+        grid = self.host_time_grid(t)
+        y = ode_block_integrate(x, spec["w1"], spec["w2"], self._host_tableau, grid.tolist(),
+                                rhs_kind=spec["rhs_kind"], act=spec["act"], engine=spec.get("engine"))
+        rhs_func.nfe += self.n_stages * (len(grid) - 1)               # cifar10/layers.py:149
+        return torch.stack((x, y))
+
+    def print_is_requires_grad(self):
+        print('\nIs requires grad? (RK solver)')
+        for name, p in self.__dict__.items():
+            if hasattr(p, 'requires_grad'):
+                print(name, p.requires_grad)
+
+
+def _init_params(self, parameterization, u0, v0, dtype, device, with_v):
+    self.dtype = dtype
+    self.device = device          # kept for API compatibility; solver scalars live on the host
+    self.parameterization = parameterization
+    self.u = nn.Parameter(torch.tensor((u0,), dtype=dtype))
+    self.u0 = torch.tensor((u0,), dtype=dtype)
+    if with_v:
+        self.v = nn.Parameter(torch.tensor((v0,), dtype=dtype))
+        self.v0 = torch.tensor((v0,), dtype=dtype)
+    else:
+        self.v = None
+        self.v0 = None
+
+
+def _separate(u_, v_, eps, T):
+    # keep the two nodes distinct (rk_parametric_order3stage3.py:64-68, order4stage4.py:150-156)
+    if u_ == v_:
+        if u_ < T(1.0 - eps):
+            v_ = u_ + T(eps)
+        else:
+            u_ = v_ - T(eps)
+    return u_, v_
+
+
+class Euler(RKParametricSolver):
+    n_stages, method = 1, "euler"
+
+    def __init__(self, parameterization=None, u0=None, v0=None, dtype=None, device=None, **kwargs):
+        super().__init__(**kwargs)
+        self.dtype, self.device, self.parameterization = dtype, device, None
+        self.u = self.u0 = self.v = self.v0 = None
+        self.build_ButcherTableau()
+
+    def _tableau_np(self):
+        T = _np_dtype(self.dtype)
+        return [T(0)], [T(1)], [[T(0)]], (None, None)
+
+    def freeze_params(self):
+        pass
+
+    def unfreeze_params(self):
+        pass
+
+    @property
+    def order(self):
+        return 1
+
+
+class RKOrder2Stage2(RKParametricSolver):
+    """c2 = u, b2 = 1/(2u), b1 = 1 - b2, w21 = u  (rk_parametric_order2stage2.py:37-49)."""
+    n_stages, method = 2, "rk2"
+
+    def __init__(self, parameterization='u', u0=None, v0=None, dtype=None, device=None, **kwargs):
+        super().__init__(**kwargs)
+        if parameterization != 'u':
+            raise ValueError('Unknown parameterization for RKOrder2Stage2 solver')
+        _init_params(self, parameterization, u0, v0, dtype, device, with_v=False)
+        self.build_ButcherTableau()
+
+    def _tableau_np(self):
+        T = _np_dtype(self.dtype)
+        eps = _clamp_eps(self.dtype)
+        u_ = min(max(self._param_np(self.u), T(eps)), T(1.0))
+        b2 = T(1.0) / (T(2) * u_)
+        b1 = T(1.0) - b2
+        return [T(0), u_], [b1, b2], [[T(0)], [u_, T(0)]], (u_, None)
+
+    @property
+    def order(self):
+        return 2
+
+
+class RKOrder3Stage3(RKParametricSolver):
+    """Two-parameter 3-stage family (rk_parametric_order3stage3.py:25-44)."""
+    n_stages, method = 3, "rk3"
+
+    def __init__(self, parameterization='uv', u0=1 / 3., v0=2 / 3., dtype=None, device=None, **kwargs):
+        super().__init__(**kwargs)
+        if parameterization != 'uv':
+            raise ValueError('Unknown parameterization for RKOrder3Stage3 solver')
+        _init_params(self, parameterization, u0, v0, dtype, device, with_v=True)
+        self.build_ButcherTableau()
+
+    def _tableau_np(self):
+        T = _np_dtype(self.dtype)
+        eps = _clamp_eps(self.dtype)
+        u_ = min(max(self._param_np(self.u), T(eps)), T(1.0))
+        v_ = min(max(self._param_np(self.v), T(eps)), T(1.0))
+        u_, v_ = _separate(u_, v_, eps, T)
+        d = v_ - u_
+        b2 = (T(2.0) - T(3.0) * v_) / (T(6.0) * u_ * (-d))
+        b3 = (T(2.0) - T(3.0) * u_) / (T(6.0) * v_ * d)
+        b1 = T(1.0) - b2 - b3
+        w32 = v_ * (v_ - u_) / (u_ * (T(2.0) - T(3.0) * u_))
+        w31 = v_ - w32
+        return [T(0), u_, v_], [b1, b2, b3], [[T(0)], [u_, T(0)], [w31, w32, T(0)]], (u_, v_)
+
+    @property
+    def order(self):
+        return 3
+
+
+class RKOrder4Stage4(RKParametricSolver):
+    """One-parameter families u1/u2/u3 and the two-parameter family uv (rk_parametric_order4stage4.py:40-156)."""
+    n_stages, method = 4, "rk4"
+
+    def __init__(self, parameterization='u2', u0=1 / 3., v0=2 / 3., dtype=torch.float64, device='cpu', **kwargs):
+        super().__init__(**kwargs)
+        if parameterization not in ('u1', 'u2', 'u3', 'uv'):
+            raise ValueError('Unknown parameterization for RKOrder4Stage4 solver')
+        _init_params(self, parameterization, u0, v0, dtype, device, with_v=(parameterization == 'uv'))
+        self.build_ButcherTableau()
+
+    def _tableau_np(self):
+        T = _np_dtype(self.dtype)
+        eps = _clamp_eps(self.dtype)
+        u = self._param_np(self.u)
+        kind = self.parameterization
+        one, half = T(1.0), T(0.5)
+        if self.v is not None:
+            if u < half:
+                u_ = min(max(u, T(eps)), T(0.5 - eps))
+            else:
+                u_ = min(max(u, T(0.5 + eps)), T(1.0 - eps))
+            v_ = min(max(self._param_np(self.v), T(eps)), T(1.0 - eps))
+            u_, v_ = _separate(u_, v_, eps, T)
+        else:
+            u_, v_ = min(max(u, T(eps)), T(1.0 - eps)), None
+        sixth, two3 = T(1 / 6.), T(2 / 3.)
+        if kind == 'u1':
+            c2, c3 = half, T(0)
+            b1, b2, b3, b4 = sixth - u_, two3, u_, sixth
+        elif kind == 'u2':
+            c2, c3 = half, half
+            b1, b2, b3, b4 = sixth, two3 - u_, u_, sixth
+        elif kind == 'u3':
+            c2, c3 = one, half
+            b1, b2, b3, b4 = sixth, sixth - u_, two3, u_
+        else:
+            c2, c3 = u_, v_
+            su, sv, d = one - u_, one - v_, v_ - u_
+            b2 = (T(2.0) * v_ - one) / (T(12) * u_ * su * d)
+            b3 = (one - T(2) * u_) / (T(12) * v_ * sv * d)
+            b4 = (T(6.0) * u_ * v_ + T(3.0) - T(4.0) * u_ - T(4.0) * v_) / (T(12) * su * sv)
+            b1 = one - b2 - b3 - b4
+        c4 = one
+        # remaining order conditions: 2x2 linear system for (w32, w42), Cramer's rule (order4stage4.py:94-113)
+        w43 = b3 * (one - c3) / b4
+        a00, a01, a10, a11 = b3 * c3 * c2, b4 * c4 * c2, b3, b4
+        r0 = T(0.125) - b4 * c4 * c3 * w43
+        r1 = b2 * (one - c2)
+        det = a00 * a11 - a01 * a10
+        w32 = (r0 * a11 - r1 * a01) / det
+        w42 = (a00 * r1 - a10 * r0) / det
+        w41 = c4 - (w42 + w43)
+        w31 = c3 - w32
+        z = T(0)
+        return ([z, c2, c3, c4], [b1, b2, b3, b4],
+                [[z], [c2, z], [w31, w32, z], [w41, w42, w43, z]], (u_, v_))
+
+    @property
+    def order(self):
+        return 4

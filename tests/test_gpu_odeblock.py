@@ -1,0 +1,178 @@
+"""GPU parity tests: the CUDA ODE-block path (through the sopa API -> C ABI) against
+(a) golden vectors produced by the real reference and (b) the CPU oracle on seeded inputs.
+Tolerance: max|d|/max|ref| <= 1e-4 (BASELINE.json north_star), on outputs and on gradients."""
+import os
+import sys
+from argparse import Namespace
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import golden, max_rel, ROOT
+
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import make_golden_cases as cases  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _mods():
+    import metasolver_b200  # noqa: F401
+    from metasolver_b200.sopa.src.solvers.utils import create_solver
+    from metasolver_b200.sopa.src.models.odenet_cifar10.layers import MetaODEBlock, PreBasicBlock2, BasicBlock2
+    from metasolver_b200.sopa.src.models.odenet_cifar10.utils import Identity
+    return metasolver_b200, create_solver, MetaODEBlock, PreBasicBlock2, BasicBlock2, Identity
+
+
+def _engines(C, H, W):
+    import metasolver_b200
+    from metasolver_b200 import _cabi
+    eng = ["simt"]
+    if _cabi.lib().msb_shape_supports_tcgen05(C, H, W):
+        eng.append("tcgen05")
+    return eng
+
+
+def _run_block(case, engine, dev="cuda"):
+    msb, create_solver, MetaODEBlock, PreBasicBlock2, BasicBlock2, Identity = _mods()
+    name, C, H, W, B, kind, sv = case
+    x, w1, w2, r = [torch.from_numpy(a).to(dev) for a in cases.ode_case_inputs(C, H, W, B)]
+    cls = PreBasicBlock2 if kind == "preact" else BasicBlock2
+    blk = MetaODEBlock(cls(C, norm_layer=Identity, act_layer=F.gelu)).to(dev)
+    with torch.no_grad():
+        blk.rhs_func.conv1.weight.copy_(w1)
+        blk.rhs_func.conv2.weight.copy_(w2)
+    solver = create_solver(*sv, torch.float32, dev)
+    solver.freeze_params()
+    msb.set_default_engine(engine)
+    try:
+        x.requires_grad_(True)
+        y = blk(x, [solver], Namespace(solver_mode="standalone"))
+        (y * r).sum().backward()
+    finally:
+        msb.set_default_engine("auto")
+    torch.cuda.synchronize()
+    return (y.detach().cpu().numpy(), x.grad.cpu().numpy(), blk.rhs_func.conv1.weight.grad.cpu().numpy(),
+            blk.rhs_func.conv2.weight.grad.cpu().numpy(), blk.rhs_func.nfe)
+
+
+PRE_CASES = [c for c in cases.ODE_CASES if c[5] == "preact"]
+
+
+@pytest.mark.parametrize("case", PRE_CASES, ids=[c[0] for c in PRE_CASES])
+def test_ode_block_vs_reference_golden(case):
+    name, C, H, W, B, kind, sv = case
+    g = golden("ode_%s.npz" % name)
+    for engine in _engines(C, H, W):
+        y, gx, gw1, gw2, nfe = _run_block(case, engine)
+        assert nfe == int(g["nfe"])
+        assert max_rel(y, g["y"]) <= TOL, (engine, max_rel(y, g["y"]))
+        assert max_rel(gx, g["gx"]) <= TOL, (engine, max_rel(gx, g["gx"]))
+        assert max_rel(gw1.reshape(-1)[::cases.WG_STRIDE], g["gw1"]) <= TOL, engine
+        assert max_rel(gw2.reshape(-1)[::cases.WG_STRIDE], g["gw2"]) <= TOL, engine
+
+
+def test_unsupported_rhs_raises():
+    post = [c for c in cases.ODE_CASES if c[5] == "postact"][0]
+    with pytest.raises(RuntimeError):
+        _run_block(post, "simt")
+
+
+@pytest.mark.parametrize("C,H,W,B", [(64, 32, 32, 3), (128, 16, 16, 5), (64, 12, 32, 2), (32, 6, 6, 4)])
+def test_single_conv_and_wgrad_vs_cpu(C, H, W, B):
+    """Each GEMM kernel alone, through the C ABI, against fp64 CPU convolution of the same operands."""
+    from metasolver_b200 import ops
+    from oracle import det_normal, det_uniform
+    x = torch.from_numpy(det_normal((B, C, H, W), 5)).cuda().contiguous(memory_format=torch.channels_last)
+    go = torch.from_numpy(det_normal((B, C, H, W), 6)).cuda().contiguous(memory_format=torch.channels_last)
+    w = torch.from_numpy(det_uniform((C, C, 3, 3), 7, -0.05, 0.05)).cuda()
+    xs, _ = ops.act_split(x)
+    gs, _ = ops.act_split(go)
+    # what the kernels see: hi + lo
+    xeff = (xs[:, :, 0].float() + xs[:, :, 1].float()).permute(0, 3, 1, 2).double().cpu()
+    geff = (gs[:, :, 0].float() + gs[:, :, 1].float()).permute(0, 3, 1, 2).double().cpu()
+    assert max_rel(xeff.numpy(), x.cpu().numpy()) < 2 ** -16
+    wd = w.double().cpu()
+    ref_f = F.conv2d(xeff, wd, None, 1, 1)
+    ref_t = F.conv_transpose2d(geff, wd, None, 1, 1)
+    xr = xeff.clone().requires_grad_(True)
+    wr = wd.clone().requires_grad_(True)
+    (F.conv2d(xr, wr, None, 1, 1) * geff).sum().backward()
+    for engine in _engines(C, H, W):
+        out = ops.conv3x3(xs, w, False, engine)
+        assert max_rel(out.cpu().numpy(), ref_f.numpy()) < 2e-5, engine
+        out_t = ops.conv3x3(gs, w, True, engine)
+        assert max_rel(out_t.cpu().numpy(), ref_t.numpy()) < 2e-5, engine
+        gw = ops.wgrad3x3(gs, xs, engine)
+        assert max_rel(gw.cpu().numpy(), wr.grad.numpy()) < 2e-5, engine
+
+
+def test_regimes_vs_reference_golden():
+    msb, create_solver, MetaODEBlock, PreBasicBlock2, BasicBlock2, Identity = _mods()
+    g = golden("regimes.npz")
+    x, w1, w2, r = [torch.from_numpy(a).cuda() for a in cases.ode_case_inputs(64, 8, 32, 2)]
+    blk = MetaODEBlock(PreBasicBlock2(64, norm_layer=Identity, act_layer=F.gelu)).cuda()
+    with torch.no_grad():
+        blk.rhs_func.conv1.weight.copy_(w1)
+        blk.rhs_func.conv2.weight.copy_(w2)
+    solvers = [create_solver(*sv, torch.float32, "cuda") for sv in cases.REGIME_SOLVERS]
+    for s in solvers:
+        s.freeze_params()
+    with torch.no_grad():
+        np.random.seed(123)
+        ids = []
+        for rep in range(3):
+            opts = Namespace(solver_mode="switch", switch_probs=[0.1, 0.2, 0.3, 0.4])
+            y = blk(x, solvers, opts)
+            ids.append(opts.switch_solver_id)
+            assert max_rel(y.cpu().numpy(), g["switch_y%d" % rep]) <= TOL
+        assert ids == list(g["switch_ids"])
+        torch.manual_seed(5)
+        opts = Namespace(solver_mode="ensemble", ensemble_prob=1.0, ensemble_weights=[0.4, 0.3, 0.2, 0.1])
+        assert max_rel(blk(x, solvers, opts).cpu().numpy(), g["ens_weighted_y"]) <= TOL
+        opts = Namespace(solver_mode="ensemble", ensemble_prob=1.0, ensemble_weights=None)
+        assert max_rel(blk(x, solvers, opts).cpu().numpy(), g["ens_uniform_y"]) <= TOL
+        opts = Namespace(solver_mode="ensemble", ensemble_prob=0.0, ensemble_weights=None)
+        assert max_rel(blk(x, solvers, opts).cpu().numpy(), g["ens_tails_y"]) <= TOL
+
+
+def test_premetanode10_whole_model_vs_reference_golden():
+    """Published config (NF + GeLU, RK2 u=.5, 8 steps): logits, ODE-block outputs, gradients, argmax."""
+    msb, create_solver, *_ = _mods()
+    from metasolver_b200.sopa.src.models.odenet_cifar10.layers import premetanode10, MetaODEBlock
+    from metasolver_b200.sopa.src.models.odenet_cifar10.utils import Identity
+    from oracle import det_uniform
+    from oracle.models import det_premetanode10_params, CIFAR_MEAN, CIFAR_STD
+    g = golden("premetanode10.npz")
+    model = premetanode10((Identity,) * 3, (lambda x: x,) * 3, (F.gelu,) * 3, in_planes=64, is_odenet=True)
+    model.load_state_dict(det_premetanode10_params())
+    model = model.cuda().eval()
+    torch.backends.cudnn.allow_tf32 = False      # the non-ODE 5 % stays on PyTorch; keep it fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    img = torch.from_numpy(det_uniform((4, 3, 32, 32), 900, 0.0, 1.0))
+    mean = torch.tensor(CIFAR_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(CIFAR_STD).view(1, 3, 1, 1)
+    x = ((img - mean) / std).cuda().requires_grad_(True)
+    solver = create_solver("rk2", "u", 8, -1, 0.5, -1, torch.float32, "cuda")
+    solver.freeze_params()
+    taps = {}
+    for n, m in model.named_modules():
+        if isinstance(m, MetaODEBlock):
+            m.register_forward_hook(lambda mod, i, o, n=n: taps.__setitem__(n, o.detach().cpu().numpy()))
+    logits = model(x, [solver], Namespace(solver_mode="standalone"))
+    loss = F.cross_entropy(logits, torch.tensor([3, 1, 4, 1]).cuda())
+    loss.backward()
+    assert max_rel(logits.detach().cpu().numpy(), g["logits"]) <= TOL
+    assert (logits.argmax(1).cpu().numpy() == g["logits"].argmax(1)).all()
+    for k, v in taps.items():
+        assert max_rel(v, g["odeblock_" + k]) <= TOL, k
+    assert max_rel(x.grad.cpu().numpy(), g["gx"]) <= TOL
+    params = dict(model.named_parameters())
+    for k in g.files:
+        if k.startswith("g_"):
+            got = params[k[2:]].grad.cpu().numpy().reshape(-1)[::cases.WG_STRIDE]
+            assert max_rel(got, g[k]) <= TOL, (k, max_rel(got, g[k]))
+    assert model.nfe == 32

@@ -1,0 +1,104 @@
+"""CPU: host side of the product -- solver objects (tableaus, grids, smoothing API) and the C-ABI
+library (loads, exports every symbol the header declares).  No GPU compute here."""
+import copy
+import ctypes
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, ROOT
+
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import make_golden_cases as cases  # noqa: E402
+import metasolver_b200  # noqa: E402
+from metasolver_b200 import _cabi  # noqa: E402
+from metasolver_b200.sopa.src.solvers.utils import (create_solver, noise_params,  # noqa: E402
+                                                    create_solver_ensemble_by_noising_params)
+from metasolver_b200.sopa.src.solvers.rk_parametric_order2stage2 import RKOrder2Stage2  # noqa: E402
+
+
+@pytest.mark.parametrize("idx", range(len(cases.TABLEAU_CASES)))
+def test_solver_tableau_bit_exact_vs_reference(idx):
+    g = golden("tableaus.npz")
+    m, p, u0, v0 = cases.TABLEAU_CASES[idx]
+    for dt, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+        s = create_solver(m, p, 4, -1, u0, v0, dt, "cpu")
+        t = s.host_tableau()
+        assert np.array_equal(np.array(t["c"]), g["%d_%s_c" % (idx, tag)])
+        assert np.array_equal(np.array(t["b"]), g["%d_%s_b" % (idx, tag)])
+        assert np.array_equal(np.array(t["w"]), g["%d_%s_w" % (idx, tag)])
+        c, w, b = s.build_ButcherTableau(return_tableau=True)
+        assert len(c) == len(b) == len(w) == t["stages"]
+
+
+def test_time_grids_bit_exact_vs_reference():
+    g = golden("grids.npz")
+    t01 = torch.tensor([0, 1]).float()
+    for n in (1, 2, 3, 5, 7, 8, 10, 16):
+        s = create_solver("rk2", "u", n, -1, 0.5, -1, torch.float32, "cpu")
+        assert np.array_equal(s.host_time_grid(t01).numpy(), g["n%d" % n])
+    for ss in (0.3, 0.125, 0.4):
+        s = create_solver("rk2", "u", -1, ss, 0.5, -1, torch.float32, "cpu")
+        assert np.array_equal(s.host_time_grid(t01).numpy(), g["ss%g" % ss])
+    # grid_constructor stays externally assignable (sopa/src/models/odenet_mnist/metrics.py:35)
+    s.grid_constructor = s._grid_constructor_from_n_steps(5)
+    assert np.array_equal(s.host_time_grid(t01).numpy(), g["n5"])
+
+
+def test_solver_api_surface():
+    with pytest.raises(ValueError):
+        RKOrder2Stage2(parameterization="uv", u0=0.5, dtype=torch.float32, n_steps=2)
+    with pytest.raises(ValueError):
+        create_solver("rk2", "u", 4, 0.25, 0.5, -1, torch.float32, "cpu")     # n_steps and step_size together
+    s = create_solver("rk2", "u", 8, -1, 0.5, -1, torch.float32, "cpu")
+    assert s.order == 2 and isinstance(s.u, torch.nn.Parameter) and s.u.requires_grad
+    s.freeze_params()
+    assert not s.u.requires_grad and float(s.b2) == 1.0 and float(s.w21) == 0.5 and s.v is None
+    # solver smoothing (examples/cifar10/train_and_attack.py:266-273, 320-323)
+    torch.manual_seed(0)
+    s.u, s.v = noise_params(s.u0, s.v0, std=0.0125, bernoulli_p=1.0, noise_type="normal")
+    s.build_ButcherTableau()
+    u = float(s.u)
+    assert abs(u - 0.5) < 0.025 and abs(s.host_tableau()["b"][1] - np.float32(1.0) / (np.float32(2) * np.float32(u))) == 0
+    s.u, s.v = s.u0, s.v0
+    s.build_ButcherTableau()
+    assert s.host_tableau()["c"][1] == 0.5
+    ens = create_solver_ensemble_by_noising_params(s, 3, dict(std=0.2, noise_type="normal"))
+    assert len(ens) == 3 and ens[0] is s and ens[1].host_tableau()["c"][1] != 0.5
+    assert copy.deepcopy(s).host_tableau() == s.host_tableau()
+    assert create_solver("euler", None, 2, -1, -1, -1, torch.float32, "cpu").order == 1
+    assert create_solver("rk4", "uv", 2, -1, 1 / 3., 2 / 3., torch.float32, "cpu").order == 4
+
+
+def test_cpu_tensors_are_refused_loudly():
+    from metasolver_b200.sopa.src.models.odenet_cifar10.layers import MetaODEBlock, PreBasicBlock2
+    from metasolver_b200.sopa.src.models.odenet_cifar10.utils import Identity
+    import torch.nn.functional as F
+    from argparse import Namespace
+    blk = MetaODEBlock(PreBasicBlock2(64, norm_layer=Identity, act_layer=F.gelu))
+    s = create_solver("rk2", "u", 2, -1, 0.5, -1, torch.float32, "cpu")
+    s.freeze_params()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        blk(torch.zeros(1, 64, 4, 32), [s], Namespace(solver_mode="standalone"))
+    with pytest.raises(RuntimeError):
+        blk.rhs_func(0.0, torch.zeros(1, 64, 4, 32))
+
+
+def test_cabi_library_exports_header_symbols():
+    header = open(os.path.join(ROOT, "include", "metasolver_b200.h")).read()
+    declared = set(re.findall(r"\b(msb_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_cabi.EXPORTS), declared ^ set(_cabi.EXPORTS)
+    lib = _cabi.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.msb_abi_version() == 1
+    assert lib.msb_shape_supports_tcgen05(64, 32, 32) in (0, 1)
+    # descriptor validation is host-only: bad stage count must be refused with a message
+    d = _cabi.MsbOdeDesc()
+    d.stages = 9
+    assert lib.msb_odeblock_tape_bytes(ctypes.byref(d)) == 0
+    assert b"stages" in lib.msb_last_error() or b"rhs" in lib.msb_last_error()
