@@ -40,6 +40,7 @@ int launch_conv3x3_tc(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tile
                       ConvShape s, cudaStream_t st);
 
 // ---- wgrad_tc.cu ----
+bool wgrad_tc_supported(ConvShape s);
 int wgrad_tc_nparts(ConvShape s);
 int launch_wgrad3x3_tc(const __nv_bfloat16* split_gout, const __nv_bfloat16* split_in, float* partial,
                        int* nparts_out, ConvShape s, cudaStream_t st);

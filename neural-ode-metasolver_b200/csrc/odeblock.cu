@@ -113,13 +113,14 @@ void pack_w(int engine, const float* w, void* out, int C, int transpose, cudaStr
     if (engine == MSB_ENGINE_TCGEN05) launch_pack_w_tc(w, (__nv_bfloat16*)out, C, transpose, st);
     else launch_pack_w_simt(w, (float*)out, C, C, 0, transpose, st);
 }
+bool use_tc_wgrad(int engine, ConvShape s) { return engine == MSB_ENGINE_TCGEN05 && wgrad_tc_supported(s); }
 int wgrad_nparts(int engine, ConvShape s) {
-    return engine == MSB_ENGINE_TCGEN05 ? wgrad_tc_nparts(s) : wgrad_simt_nparts(s);
+    return use_tc_wgrad(engine, s) ? wgrad_tc_nparts(s) : wgrad_simt_nparts(s);
 }
 int run_wgrad(int engine, const __nv_bfloat16* gout, const __nv_bfloat16* in, float* partial, float* grad_w,
               int accumulate, ConvShape s, cudaStream_t st) {
     int nparts = 0, rc;
-    if (engine == MSB_ENGINE_TCGEN05) rc = launch_wgrad3x3_tc(gout, in, partial, &nparts, s, st);
+    if (use_tc_wgrad(engine, s)) rc = launch_wgrad3x3_tc(gout, in, partial, &nparts, s, st);
     else rc = launch_wgrad3x3_simt(gout, in, partial, &nparts, s, st);
     if (rc) return rc;
     launch_wgrad_reduce(partial, nparts, grad_w, s.C, accumulate, st);

@@ -104,7 +104,7 @@ class _OdeBlockFn(torch.autograd.Function):
         _check_inputs(x, w1, w2)
         lib = _cabi.lib()
         dev = x.device
-        need_grad = torch.is_grad_enabled() and (x.requires_grad or w1.requires_grad or w2.requires_grad)
+        need_grad = any(ctx.needs_input_grad[:3])     # (grad mode is always off inside Function.forward)
         with torch.cuda.device(dev):
             xc = x.detach().contiguous(memory_format=torch.channels_last)
             w1c, w2c = w1.detach().contiguous(), w2.detach().contiguous()
