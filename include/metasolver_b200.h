@@ -128,6 +128,15 @@ size_t msb_wgrad3x3_workspace_bytes(int channels, int engine);
 /* Number of kernels this library has launched since load (bench.py's `gpu_launches`). */
 uint64_t msb_launch_count(void);
 
+/* Optional per-launch timing for the roofline report: when enabled, CUDA events are recorded on the
+ * caller's stream around every convolution-engine launch.  msb_profile_read() waits for the recorded
+ * events and returns the summed duration, the summed algorithmic flops (2*M*N*K of the convolution)
+ * and the number of launches of one kind.  msb_profile_enable() also clears the records. */
+enum { MSB_PROF_CONV = 0,   /* forward / input-gradient convolutions */
+       MSB_PROF_WGRAD = 1   /* weight-gradient GEMMs */ };
+int msb_profile_enable(int on);
+int msb_profile_read(int kind, double* total_ms, double* total_flops, int64_t* count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,6 +7,7 @@ arithmetic of an ODE block runs in hand-written sm_100a CUDA kernels reached thr
 include/metasolver_b200.h (ctypes binding: _cabi.py).  There is no cuDNN, Triton or CPU path.
 """
 from . import _cabi  # noqa: F401
-from .ops import ode_block_integrate, input_grad_only, set_default_engine, launch_count  # noqa: F401
+from .ops import (ode_block_integrate, input_grad_only, set_default_engine, launch_count,  # noqa: F401
+                  profile_enable, profile_read)
 
 __version__ = "0.1.0"

@@ -19,7 +19,7 @@ EXPORTS = [
     "msb_abi_version", "msb_last_error", "msb_device_supports_tcgen05", "msb_shape_supports_tcgen05",
     "msb_odeblock_workspace_bytes", "msb_odeblock_tape_bytes", "msb_odeblock_bwd_workspace_bytes",
     "msb_odeblock_forward", "msb_odeblock_backward", "msb_act_split", "msb_conv3x3",
-    "msb_conv3x3_workspace_bytes", "msb_wgrad3x3", "msb_wgrad3x3_workspace_bytes", "msb_launch_count",
+    "msb_conv3x3_workspace_bytes", "msb_wgrad3x3", "msb_wgrad3x3_workspace_bytes", "msb_launch_count", "msb_profile_enable", "msb_profile_read",
 ]
 
 
@@ -67,6 +67,9 @@ def _declare(lib):
     lib.msb_wgrad3x3.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, sz, vp]
     lib.msb_wgrad3x3_workspace_bytes.argtypes = [i32, i32]
     lib.msb_wgrad3x3_workspace_bytes.restype = sz
+    lib.msb_profile_enable.argtypes = [i32]
+    lib.msb_profile_read.argtypes = [i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                     ctypes.POINTER(ctypes.c_int64)]
 
 
 def lib():

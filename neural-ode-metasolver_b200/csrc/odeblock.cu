@@ -45,6 +45,31 @@ int num_sms() {
     return cached[dev];
 }
 
+// ---- optional per-kernel timing (bench.py roofline): CUDA events around engine launches ----
+struct Prof {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;      // pairs (start, stop)
+    std::vector<int> kind;            // kind of each pair
+    std::vector<double> flops;        // algorithmic flops of each pair
+    size_t used = 0;
+};
+static Prof g_prof;
+static int prof_begin(int kind, double flops, cudaStream_t st) {
+    if (!g_prof.on) return -1;
+    if (g_prof.used + 2 > g_prof.ev.size()) {
+        for (int i = 0; i < 512; ++i) { cudaEvent_t e; cudaEventCreate(&e); g_prof.ev.push_back(e); }
+    }
+    int id = (int)(g_prof.used / 2);
+    g_prof.kind.resize(id + 1); g_prof.flops.resize(id + 1);
+    g_prof.kind[id] = kind; g_prof.flops[id] = flops;
+    cudaEventRecord(g_prof.ev[g_prof.used], st);
+    g_prof.used += 2;
+    return id;
+}
+static void prof_end(int id, cudaStream_t st) {
+    if (id >= 0) cudaEventRecord(g_prof.ev[2 * id + 1], st);
+}
+
 namespace {
 
 inline size_t align_up(size_t x, size_t a = 1024) { return (x + a - 1) / a * a; }
@@ -105,9 +130,14 @@ TapeSlot tape_slot(void* tape, size_t E, int slot) {
     return TapeSlot{(__nv_bfloat16*)p, (float*)(p + q), (__nv_bfloat16*)(p + 2 * q), (float*)(p + 3 * q)};
 }
 
+double conv_flops(ConvShape s) { return 2.0 * s.B * s.H * s.W * (double)s.C * 9.0 * s.C; }
 int run_conv(int engine, const __nv_bfloat16* in, const void* wpacked, const EpiParams& e, ConvShape s, cudaStream_t st) {
-    if (engine == MSB_ENGINE_TCGEN05) return launch_conv3x3_tc(in, (const __nv_bfloat16*)wpacked, e, s, st);
-    return launch_conv3x3_simt(in, (const float*)wpacked, e, s, st);
+    int id = prof_begin(MSB_PROF_CONV, conv_flops(s), st);
+    int rc;
+    if (engine == MSB_ENGINE_TCGEN05) rc = launch_conv3x3_tc(in, (const __nv_bfloat16*)wpacked, e, s, st);
+    else rc = launch_conv3x3_simt(in, (const float*)wpacked, e, s, st);
+    prof_end(id, st);
+    return rc;
 }
 void pack_w(int engine, const float* w, void* out, int C, int transpose, cudaStream_t st) {
     if (engine == MSB_ENGINE_TCGEN05) launch_pack_w_tc(w, (__nv_bfloat16*)out, C, transpose, st);
@@ -120,8 +150,10 @@ int wgrad_nparts(int engine, ConvShape s) {
 int run_wgrad(int engine, const __nv_bfloat16* gout, const __nv_bfloat16* in, float* partial, float* grad_w,
               int accumulate, ConvShape s, cudaStream_t st) {
     int nparts = 0, rc;
+    int id = prof_begin(MSB_PROF_WGRAD, conv_flops(s), st);
     if (use_tc_wgrad(engine, s)) rc = launch_wgrad3x3_tc(gout, in, partial, &nparts, s, st);
     else rc = launch_wgrad3x3_simt(gout, in, partial, &nparts, s, st);
+    prof_end(id, st);
     if (rc) return rc;
     launch_wgrad_reduce(partial, nparts, grad_w, s.C, accumulate, st);
     return check_cuda(cudaGetLastError(), "wgrad reduce launch");
@@ -137,6 +169,26 @@ extern "C" {
 int msb_abi_version(void) { return MSB_ABI_VERSION; }
 const char* msb_last_error(void) { return g_err.c_str(); }
 uint64_t msb_launch_count(void) { return g_launches.load(); }
+
+int msb_profile_enable(int on) {
+    g_prof.on = on != 0;
+    g_prof.used = 0;
+    return 0;
+}
+int msb_profile_read(int kind, double* total_ms, double* total_flops, int64_t* count) {
+    double ms = 0, fl = 0; int64_t n = 0;
+    for (size_t id = 0; id < g_prof.used / 2; ++id) {
+        if (g_prof.kind[id] != kind) continue;
+        if (cudaEventSynchronize(g_prof.ev[2 * id + 1]) != cudaSuccess) { set_error("profile event sync failed"); return -1; }
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, g_prof.ev[2 * id], g_prof.ev[2 * id + 1]) != cudaSuccess) { set_error("profile elapsed failed"); return -1; }
+        ms += t; fl += g_prof.flops[id]; ++n;
+    }
+    if (total_ms) *total_ms = ms;
+    if (total_flops) *total_flops = fl;
+    if (count) *count = n;
+    return 0;
+}
 
 int msb_device_supports_tcgen05(int device) {
     int major = 0;

@@ -32,6 +32,18 @@ def launch_count():
     return int(_cabi.lib().msb_launch_count())
 
 
+def profile_enable(on=True):
+    """Record CUDA events around every convolution-engine launch (clears earlier records)."""
+    _cabi.lib().msb_profile_enable(1 if on else 0)
+
+
+def profile_read(kind):
+    """kind 0 = fwd/dgrad convolutions, 1 = wgrad GEMMs -> (total ms, total algorithmic flops, launches)."""
+    ms, fl, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+    _cabi.check(_cabi.lib().msb_profile_read(kind, ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(n)), "profile_read")
+    return ms.value, fl.value, n.value
+
+
 @contextlib.contextmanager
 def input_grad_only():
     """Inside this context backward passes skip the weight gradients (FGSM / PGD input-gradient
