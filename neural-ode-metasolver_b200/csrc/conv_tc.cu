@@ -220,64 +220,99 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
         }
     } else if (warp >= kEpiWarp0) {
         // ===================== epilogue =====================
+        // Each thread owns one output channel and walks its share of the tile in chunks of 8
+        // pixels.  Operand loads for chunk i+1 (and for chunk 0 of the NEXT tile, before waiting
+        // for its accumulator) are in flight while chunk i is computed and stored.
         const int we = warp - kEpiWarp0;
         const int q = warp & 3;                       // TMEM lane quadrant this warp may read
         const int half = we >> 2;                     // which half of the tile's image rows
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         constexpr int RH = G::ROWS / 2;               // image rows per half
-        constexpr int PXCH = WIMG / 16;               // 16-pixel chunks per image row
+        constexpr int PX_PER_LD = (C == 64) ? 16 : 8; // pixels covered by one TMEM load step
+        constexpr int STEPS_PER_ROW = WIMG / PX_PER_LD;
+        constexpr int NCHUNK = RH * STEPS_PER_ROW;    // chunks (of 8 owned pixels) per tile per thread
+        const int sel = (C == 64) ? (lane >> 4) : 0;  // C=64: lanes l / l^16 split the 16 pixels of a step
+        const int c = (C == 64) ? (16 * q + (lane & 15)) : (32 * q + lane);
+        const size_t plane_stride = (size_t)WIMG * C;
+
+        // element index of owned pixel 0 of chunk `ch` in tile (n, h0)
+        auto chunk_pos = [&](int n, int h0, int ch, int& h, int& w0) {
+            const int rr = ch / STEPS_PER_ROW, stp = ch - rr * STEPS_PER_ROW;
+            h = h0 + half * RH + rr;
+            w0 = stp * PX_PER_LD + sel * 8;
+        };
+        EpiOperands<8> opsA, opsB;
         int acc = 0; uint32_t acc_ph = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int tile = blockIdx.x;
+        if (tile < num_tiles) {
+            const int n = tile / tiles_per_img, h0 = (tile - n * tiles_per_img) * G::ROWS;
+            int h, w0; chunk_pos(n, h0, 0, h, w0);
+            epi_prefetch<8>(epi, (((size_t)n * H + h) * WIMG + w0) * C + c, C, opsA);
+        }
+        for (; tile < num_tiles; tile += gridDim.x) {
             const int n = tile / tiles_per_img;
             const int h0 = (tile - n * tiles_per_img) * G::ROWS;
             ptx::mbar_wait(&bars->tmem_full[acc], acc_ph);
             ptx::tc_fence_after();
             const uint32_t t_acc = tmem_base + (uint32_t)acc * 256u + lane_addr;
-#pragma unroll 1
-            for (int rr = 0; rr < RH; ++rr) {
+            auto do_chunk = [&](const int ch, const EpiOperands<8>& cur, EpiOperands<8>& nxt) {
+                int h, w0; chunk_pos(n, h0, ch, h, w0);
+                const int rr = ch / STEPS_PER_ROW, stp = ch - rr * STEPS_PER_ROW;
                 const int rho = half * RH + rr;
-                const int h = h0 + rho;
-#pragma unroll 1
-                for (int pc = 0; pc < PXCH; ++pc) {
+                // ---- accumulator: hi + lo columns (and hi + lo weight rows for C = 64) ----
+                float v[8];
+                const uint32_t col = (uint32_t)(rho * 2 * WIMG + stp * PX_PER_LD);
+                if (C == 64) {
                     float hi[16], lo[16];
-                    const uint32_t col = (uint32_t)(rho * 2 * WIMG + pc * 16);
                     ptx::tmem_ld16(t_acc + col, hi);
                     ptx::tmem_ld16(t_acc + col + WIMG, lo);
                     ptx::tmem_ld_wait();
-                    if (rr == RH - 1 && pc == PXCH - 1) {
-                        // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
-                        ptx::tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) ptx::mbar_arrive(&bars->tmem_empty[acc]);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float a = hi[j] + lo[j];
+                        const float o = __shfl_xor_sync(0xffffffffu, a, 16);
+                        hi[j] = sel ? o + a : a + o;       // identical operand order in both lanes
                     }
-                    if (C == 64) {
-                        // lanes l and l^16 hold the W_hi-row and W_lo-row sums of the same output channel
-                        const int c = 16 * q + (lane & 15);
-                        const int sel = lane >> 4;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            float v = hi[j] + lo[j];
-                            float o = __shfl_xor_sync(0xffffffffu, v, 16);
-                            hi[j] = sel ? o + v : v + o;        // same operand order in both lanes
-                        }
+                    for (int j = 0; j < 8; ++j) v[j] = sel ? hi[8 + j] : hi[j];
+                } else {
+                    float hi[8], lo[8];
+                    ptx::tmem_ld8(t_acc + col, hi);
+                    ptx::tmem_ld8(t_acc + col + WIMG, lo);
+                    ptx::tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int w = pc * 16 + sel * 8 + j;
-                            const float v = sel ? hi[8 + j] : hi[j];
-                            const size_t idx = (((size_t)n * H + h) * WIMG + w) * C + c;
-                            epilogue_apply(epi, v, idx, n, h, w, c, H, WIMG, C);
-                        }
-                    } else {
-                        const int c = 32 * q + lane;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const int w = pc * 16 + j;
-                            const float v = hi[j] + lo[j];
-                            const size_t idx = (((size_t)n * H + h) * WIMG + w) * C + c;
-                            epilogue_apply(epi, v, idx, n, h, w, c, H, WIMG, C);
-                        }
+                    for (int j = 0; j < 8; ++j) v[j] = hi[j] + lo[j];
+                }
+                if (ch == NCHUNK - 1) {
+                    // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&bars->tmem_empty[acc]);
+                }
+                // ---- prefetch the operands of the next chunk (possibly of the next tile) ----
+                {
+                    int n2 = n, h02 = h0, ch2 = ch + 1;
+                    bool have = true;
+                    if (ch == NCHUNK - 1) {
+                        const int t2 = tile + gridDim.x;
+                        have = t2 < num_tiles;
+                        n2 = t2 / tiles_per_img; h02 = (t2 - n2 * tiles_per_img) * G::ROWS; ch2 = 0;
+                    }
+                    if (have) {
+                        int h2, w2; chunk_pos(n2, h02, ch2, h2, w2);
+                        epi_prefetch<8>(epi, (((size_t)n2 * H + h2) * WIMG + w2) * C + c, C, nxt);
                     }
                 }
+                // ---- fused RK epilogue on the 8 owned pixels ----
+                const size_t pix = ((size_t)n * H + h) * WIMG + w0;
+                const size_t split0 = (((size_t)n * H + h) * 2) * plane_stride + (size_t)w0 * C + c;
+                epi_finish<8>(epi, v, cur, pix * C + c, C, split0, plane_stride);
+            };
+            static_assert(NCHUNK % 2 == 0, "chunk pipeline is unrolled by two");
+#pragma unroll
+            for (int ch = 0; ch < NCHUNK; ch += 2) {
+                do_chunk(ch, opsA, opsB);
+                do_chunk(ch + 1, opsB, opsA);
             }
             if (++acc == 2) { acc = 0; acc_ph ^= 1; }
         }

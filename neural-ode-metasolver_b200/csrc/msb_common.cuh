@@ -151,4 +151,100 @@ __device__ __forceinline__ void epilogue_apply(const EpiParams& e, float acc, si
     }
 }
 
+
+// ---- pipelined form of the same epilogue (tensor-core engine) --------------------------------------
+// A thread owns N consecutive pixels of ONE channel (element j at idx0 + j*stride).  The operand
+// loads (prefetch) are issued a whole chunk ahead of their use so their HBM/L2 latency overlaps the
+// MMA of the tile and the math of the previous chunk; epi_finish() is the arithmetic of
+// epilogue_apply() on N elements.  (Bias terms are SIMT-engine only.)
+template <int N> struct EpiOperands {
+    float mul[N];
+    float base[N];
+    float src[3][N];
+};
+
+__device__ __forceinline__ float ldg_stream(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+template <int N>
+__device__ __forceinline__ void epi_prefetch(const EpiParams& e, size_t idx0, int stride, EpiOperands<N>& r) {
+    if (e.mul) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) r.mul[j] = ldg_stream(e.mul + idx0 + (size_t)j * stride);
+    }
+    if (e.base) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) r.base[j] = ldg_stream(e.base + idx0 + (size_t)j * stride);
+    }
+    if (e.nsrc > 0) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) r.src[0][j] = ldg_stream(e.src[0] + idx0 + (size_t)j * stride);
+    }
+    if (e.nsrc > 1) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) r.src[1][j] = ldg_stream(e.src[1] + idx0 + (size_t)j * stride);
+    }
+    if (e.nsrc > 2) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) r.src[2][j] = ldg_stream(e.src[2] + idx0 + (size_t)j * stride);
+    }
+}
+
+// split_idx0 = index of element 0 in the hi plane of out_split; lo plane is plane_stride further.
+template <int N>
+__device__ __forceinline__ void epi_finish(const EpiParams& e, const float* acc, const EpiOperands<N>& r, size_t idx0,
+                                           int stride, size_t split_idx0, size_t plane_stride) {
+    float out[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        float v = acc[j];
+        if (e.act_v != ACT_NONE) {
+            float a, d;
+            act_both(e.act_v, v, a, d);
+            if (e.dact_v_out) e.dact_v_out[idx0 + (size_t)j * stride] = d;
+            v = a;
+        }
+        if (e.mul) v = __fmul_rn(v, r.mul[j]);
+        if (e.v_out) e.v_out[idx0 + (size_t)j * stride] = v;
+        float s;
+        if (e.nsrc == 0) {
+            s = __fmul_rn(v, e.coef_v);
+        } else {
+            s = __fmul_rn(r.src[0][j], e.coef[0]);
+            if (e.nsrc > 1) s = __fadd_rn(s, __fmul_rn(r.src[1][j], e.coef[1]));
+            if (e.nsrc > 2) s = __fadd_rn(s, __fmul_rn(r.src[2][j], e.coef[2]));
+            s = __fadd_rn(s, __fmul_rn(v, e.coef_v));
+        }
+        float o = __fmul_rn(s, e.dt);
+        if (e.base) {
+            float bv = r.base[j];
+            if (!e.base_is_one) bv = __fmul_rn(bv, e.base_coef);
+            o = __fadd_rn(bv, o);
+        }
+        out[j] = o;
+    }
+    if (e.out_f32) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) e.out_f32[idx0 + (size_t)j * stride] = out[j];
+    }
+    if (e.out_split || e.dact_out) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            float a, d;
+            act_both(e.act, out[j], a, d);
+            if (e.dact_out) e.dact_out[idx0 + (size_t)j * stride] = d;
+            if (e.out_split) {
+                a = __fmul_rn(a, e.split_scale);
+                __nv_bfloat16 hi, lo;
+                split_bf16(a, hi, lo);
+                e.out_split[split_idx0 + (size_t)j * stride] = hi;
+                e.out_split[split_idx0 + plane_stride + (size_t)j * stride] = lo;
+            }
+        }
+    }
+}
+
 }  // namespace msb
