@@ -14,6 +14,9 @@ import torch.nn.functional as F
 
 from .utils import Identity
 from ..... import _cabi
+from .....ops import ode_block_integrate
+
+_EULER_STEP = dict(stages=1, c=[0.0], b=[1.0], w=[[0.0]])
 
 __all__ = ['MetaNODE', 'MetaODEBlock', 'MetaLayer', 'BasicBlock', 'PreBasicBlock', 'BasicBlock2', 'PreBasicBlock2',
            'metanode4', 'metanode6', 'metanode10', 'metanode18', 'metanode34',
@@ -77,7 +80,25 @@ class PreBasicBlock(nn.Module):
             self.shortcut = nn.Sequential(
                 param_norm(nn.Conv2d(in_planes, self.expansion * planes, kernel_size=1, stride=stride, bias=False)))
 
+    def _fusable(self, x):
+        """An identity-shortcut pre-activation block computes x + conv2(act(conv1(act(x)))): exactly ONE
+        explicit-Euler step (dt = 1) of the ODE right-hand side PreBasicBlock2 -- so it can run through the
+        same fused tcgen05 kernels (the non-ODE remainder becomes the Amdahl limit)."""
+        if not (x.is_cuda and x.dtype == torch.float32 and len(self.shortcut) == 0):
+            return False
+        if not (isinstance(self.bn1, Identity) and isinstance(self.bn2, Identity)):
+            return False
+        if self.act not in (F.gelu, F.relu) or type(self.conv1) is not nn.Conv2d or type(self.conv2) is not nn.Conv2d:
+            return False
+        if hasattr(self.conv1, "weight_orig") or hasattr(self.conv1, "weight_g"):
+            return False
+        B, C, H, W = x.shape
+        return self.conv1.stride == (1, 1) and bool(_cabi.lib().msb_shape_supports_tcgen05(C, H, W))
+
     def forward(self, x):
+        if self._fusable(x):
+            return ode_block_integrate(x, self.conv1.weight, self.conv2.weight, _EULER_STEP, (0.0, 1.0),
+                                       rhs_kind=_cabi.RHS_PREACT_NF, act=_act_code(self.act))
         out = self.conv1(self.act(self.bn1(x)))
         out = self.conv2(self.act(self.bn2(out)))
         return out + self.shortcut(x)
