@@ -111,7 +111,7 @@ struct __align__(8) Barriers {
     uint32_t tmem_base;
 };
 
-template <int C, int WIMG>
+template <int C, int WIMG, int ACT>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_w,
                   const EpiParams epi, const int H, const int num_tiles, const int tiles_per_img) {
@@ -306,7 +306,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
                 // ---- fused RK epilogue on the 8 owned pixels ----
                 const size_t pix = ((size_t)n * H + h) * WIMG + w0;
                 const size_t split0 = (((size_t)n * H + h) * 2) * plane_stride + (size_t)w0 * C + c;
-                epi_finish<8>(epi, v, cur, pix * C + c, C, split0, plane_stride);
+                epi_finish<8, ACT>(epi, v, cur, pix * C + c, C, split0, plane_stride);
             };
             static_assert(NCHUNK % 2 == 0, "chunk pipeline is unrolled by two");
 #pragma unroll
@@ -325,16 +325,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
     }
 }
 
-template <int C, int WIMG>
-int launch_impl(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, const EpiParams& epi, ConvShape s,
-                cudaStream_t st) {
+template <int C, int WIMG, int ACT>
+int launch_act(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, const EpiParams& epi, ConvShape s,
+               cudaStream_t st) {
     using G = TileGeom<WIMG>;
     CUtensorMap tm_act, tm_w;
     if (make_tmap_split5d(&tm_act, split_in, s.B, s.H, s.W, s.C, WIMG, G::ROWS + 2)) return -1;
     const size_t wrows = tc_packed_weight_bytes(C) / 128;
     if (make_tmap_rows64(&tm_w, w_tiles, wrows, 128)) return -1;
     const size_t smem = (size_t)kBStages * G::B_STAGE_BYTES + (size_t)kAStages * kATileBytes + sizeof(Barriers) + 1024;
-    auto kern = conv3x3_tc_kernel<C, WIMG>;
+    auto kern = conv3x3_tc_kernel<C, WIMG, ACT>;
     if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                    "cudaFuncSetAttribute(conv3x3_tc)"))
         return -1;
@@ -344,6 +344,16 @@ int launch_impl(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, con
     kern<<<grid, kNumThreads, smem, st>>>(tm_act, tm_w, epi, s.H, num_tiles, tiles_per_img);
     count_launch();
     return check_cuda(cudaGetLastError(), "conv3x3_tc launch");
+}
+
+template <int C, int WIMG>
+int launch_impl(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, const EpiParams& epi, ConvShape s,
+                cudaStream_t st) {
+    // the activation only matters when the epilogue emits act(out) / act'(out)
+    const int act = (epi.out_split || epi.dact_out) ? epi.act : ACT_NONE;
+    if (act == ACT_GELU) return launch_act<C, WIMG, ACT_GELU>(split_in, w_tiles, epi, s, st);
+    if (act == ACT_RELU) return launch_act<C, WIMG, ACT_RELU>(split_in, w_tiles, epi, s, st);
+    return launch_act<C, WIMG, ACT_NONE>(split_in, w_tiles, epi, s, st);
 }
 
 }  // namespace
