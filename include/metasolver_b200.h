@@ -49,7 +49,7 @@ enum { MSB_RHS_PREACT_NF = 0,   /* conv2(act(conv1(act(x))))          cifar10/la
 /* activations */
 enum { MSB_ACT_NONE = 0, MSB_ACT_GELU_ERF = 1, MSB_ACT_RELU = 2 };
 /* GEMM engines */
-enum { MSB_ENGINE_AUTO = 0,     /* tcgen05 when the shape is supported, else error unless allow_simt */
+enum { MSB_ENGINE_AUTO = 0,     /* tcgen05 when the shape is covered by it, else the SIMT CUDA engine */
        MSB_ENGINE_TCGEN05 = 1,  /* implicit-GEMM on tcgen05/TMEM fed by TMA (sm_100a) */
        MSB_ENGINE_SIMT = 2      /* plain fp32 FFMA CUDA kernels (any shape; validation / small shapes) */ };
 
