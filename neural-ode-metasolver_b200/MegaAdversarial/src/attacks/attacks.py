@@ -1,0 +1,195 @@
+"""FGSM, FGSM-random, PGD and the 2-model-ensemble FGSM (MegaAdversarial/src/attacks/{attack,base,fgsm,pgd}.py).
+
+Differences from the reference, none of which changes results:
+  * no torchvision dependency -- (inverse) normalisation is the same sub/div arithmetic on fp32 tensors;
+  * tensors follow `x.device` instead of a module-level global device;
+  * every randomised attack takes an optional `noise=` tensor so a test (or a multi-GPU run that must
+    reproduce single-process semantics) can supply host-generated randomness; without it the same
+    torch RNG calls as the reference are made;
+  * FGSM / PGD / FGSM2Ensemble differentiate w.r.t. the input only (pgd.py:44-46, fgsm.py:34-36), so
+    the ODE-block backward is run in input-gradient-only mode (`metasolver_b200.input_grad_only`).
+    FGSMRandom keeps `loss.backward()` (fgsm.py:98): parameter gradients DO accumulate there, which
+    the published training recipe relies on (examples/cifar10/train_and_attack.py:258-259, 290).
+"""
+import torch
+import torch.nn as nn
+
+from ....ops import input_grad_only
+
+
+def _chan(vals, like):
+    return torch.as_tensor(list(vals), dtype=like.dtype, device=like.device).view(1, -1, 1, 1)
+
+
+class _Normalizer:
+    def __init__(self, mean, std):
+        self.mean = tuple(mean) if mean is not None else (0., 0., 0.)
+        self.std = tuple(std) if std is not None else (1., 1., 1.)
+
+    def normalize(self, x):
+        return (x - _chan(self.mean, x)) / _chan(self.std, x)
+
+    def unnormalize(self, x):
+        # transforms.Normalize(mean=[-m/s], std=[1/s]) of fgsm.py:27 / pgd.py:28
+        inv_mean = [-m / s for m, s in zip(self.mean, self.std)]
+        inv_std = [1 / s for s in self.std]
+        return (x - _chan(inv_mean, x)) / _chan(inv_std, x)
+
+
+class Attack(nn.Module):
+    def __init__(self, model):
+        super().__init__()
+        self.model = model
+
+    def _project(self, x):
+        return torch.clamp(x, 0, 1)
+
+    def _clamp(self, x, min, max):
+        return torch.max(torch.min(x, max), min)
+
+    def _eval_mode(self, models):
+        was_training = models[0].training
+        if was_training:
+            for m in models:
+                m.eval()
+        return was_training
+
+    def forward(self, *args, **kwargs):
+        raise NotImplementedError
+
+
+class Attack2Ensemble(Attack):
+    def __init__(self, models):
+        nn.Module.__init__(self)
+        self.models = models
+
+
+class Clean(Attack):
+    def forward(self, x, y, kwargs):
+        return x, y
+
+
+class Clean2Ensemble(Attack2Ensemble):
+    def forward(self, x, y, kwargs_arr):
+        return x, y
+
+
+def _input_gradient(loss, x):
+    with input_grad_only():
+        return torch.autograd.grad([loss], [x], create_graph=False, retain_graph=False)[0]
+
+
+class FGSM(Attack):
+    """Single signed-gradient step of size eps in [0,1] image space (fgsm.py:8-43)."""
+
+    def __init__(self, model, eps=None, mean=None, std=None):
+        super().__init__(model)
+        self.eps = eps
+        self.loss_fn = nn.CrossEntropyLoss()
+        self.norm = _Normalizer(mean, std)
+
+    def forward(self, x, y, kwargs):
+        was_training = self._eval_mode([self.model])
+        x01 = self.norm.unnormalize(x)
+        xa = x01.clone().detach().requires_grad_(True)
+        loss = self.loss_fn(self.model(self.norm.normalize(xa), **kwargs), y)
+        grad = _input_gradient(loss, xa)
+        xa = self.norm.normalize(self._project(xa + self.eps * grad.sign())).detach()
+        if was_training:
+            self.model.train()
+        return xa, y
+
+
+def clamp(X, lower_limit, upper_limit):
+    if not isinstance(upper_limit, torch.Tensor):
+        upper_limit = torch.tensor(upper_limit, device=X.device, dtype=X.dtype)
+    if not isinstance(lower_limit, torch.Tensor):
+        lower_limit = torch.tensor(lower_limit, device=X.device, dtype=X.dtype)
+    return torch.max(torch.min(X, upper_limit), lower_limit)
+
+
+class FGSMRandom(Attack):
+    """Random start in the eps-ball + one signed step alpha, in normalised space (fgsm.py:54-106)."""
+
+    def __init__(self, model, alpha, epsilon=None, mu=None, std=None):
+        super().__init__(model)
+        self.scaled = (mu is not None) and (std is not None)
+        self.mu, self.std_, self.alpha_, self.epsilon_ = mu, std, alpha, epsilon
+        self.loss_fn = nn.CrossEntropyLoss()
+
+    def _limits(self, x):
+        if self.scaled:
+            mu, std = _chan(self.mu, x), _chan(self.std_, x)
+            return (0. - mu) / std, (1. - mu) / std, self.epsilon_ / std, self.alpha_ / std
+        return 0., 1., self.epsilon_, self.alpha_
+
+    def forward(self, x, y, kwargs, noise=None):
+        was_training = self._eval_mode([self.model])
+        lower, upper, epsilon, alpha = self._limits(x)
+        u01 = torch.rand_like(x) if noise is None else noise.to(x)
+        delta = epsilon - (2 * epsilon) * u01                        # Uniform[-eps, eps]
+        delta = clamp(delta, lower - x, upper - x).detach().requires_grad_(True)
+        loss = self.loss_fn(self.model(x + delta, **kwargs), y)
+        loss.backward()                                              # parameter grads accumulate too
+        grad = delta.grad.detach()
+        delta = clamp(delta.detach() + alpha * torch.sign(grad), -epsilon, epsilon)
+        delta = clamp(delta, lower - x, upper - x).detach()
+        if was_training:
+            self.model.train()
+        return x + delta, y
+
+
+class PGD(Attack):
+    """n_iter signed steps of size lr, clamped to the eps-ball around x and to [0,1] (pgd.py:8-57)."""
+
+    def __init__(self, model, eps=None, lr=None, n_iter=None, randomized_start=True, mean=None, std=None):
+        super().__init__(model)
+        self.eps, self.lr, self.n_iter, self.randomized_start = eps, lr, n_iter, randomized_start
+        self.loss_fn = nn.CrossEntropyLoss()
+        self.norm = _Normalizer(mean, std)
+
+    def forward(self, x, y, kwargs, noise=None):
+        was_training = self._eval_mode([self.model])
+        x01 = self.norm.unnormalize(x)
+        if self.randomized_start:
+            start = torch.zeros_like(x01).uniform_(-self.eps, self.eps) if noise is None else noise.to(x01)
+            xa = self._project(x01 + start).clone().detach()
+        else:
+            xa = x01.clone().detach()
+        for i in range(self.n_iter):
+            xa.requires_grad_(True)
+            loss = self.loss_fn(self.model(self.norm.normalize(xa), **kwargs), y)
+            grad = _input_gradient(loss, xa)
+            xa = self._project(self._clamp(xa + self.lr * grad.sign(), x01 - self.eps, x01 + self.eps))
+            if i == self.n_iter - 1:
+                xa = self.norm.normalize(xa)
+            xa = xa.detach()
+        if was_training:
+            self.model.train()
+        return xa, y
+
+
+class FGSM2Ensemble(Attack2Ensemble):
+    """FGSM on the NLL of the averaged softmax of several models / solvers (fgsm.py:109-155)."""
+
+    def __init__(self, models, eps=None, mean=None, std=None):
+        super().__init__(models)
+        self.eps = eps
+        self.loss_fn = nn.NLLLoss()
+        self.norm = _Normalizer(mean, std)
+
+    def forward(self, x, y, kwargs_arr):
+        was_training = self._eval_mode(list(self.models))
+        x01 = self.norm.unnormalize(x)
+        xa = x01.clone().detach().requires_grad_(True)
+        probs = 0
+        for model, kwargs in zip(self.models, kwargs_arr):
+            probs = probs + torch.softmax(model(self.norm.normalize(xa), **kwargs), dim=1)
+        probs = probs / len(self.models)
+        loss = self.loss_fn(torch.log(probs), y)
+        grad = _input_gradient(loss, xa)
+        xa = self.norm.normalize(self._project(xa + self.eps * grad.sign())).detach()
+        if was_training:
+            for m in self.models:
+                m.train()
+        return xa, y

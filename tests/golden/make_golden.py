@@ -192,6 +192,48 @@ def main():
             full["g_" + k] = p.grad.numpy().reshape(-1)[::WG_STRIDE].copy()
     np.savez(os.path.join(HERE, "premetanode10.npz"), **full)
     print("premetanode10 logits", logits[0])
+    # ---- G. attacks on the whole model (callers of the input-gradient backward) + FGSM-random train step
+    from MegaAdversarial.src.attacks import FGSM, FGSMRandom, PGD
+    import MegaAdversarial.src.attacks.attack as _att
+    _att.device = torch.device("cpu")
+    nb = 8
+    img = torch.from_numpy(det_uniform((nb, 3, 32, 32), 910, 0.0, 1.0))
+    xin = (img - mean) / std
+    labels = torch.tensor([3, 1, 4, 1, 5, 9, 2, 6])
+    kw = {"solvers": [solver], "solver_options": Namespace(solver_mode="standalone")}
+    mean_t, std_t = (0.4914, 0.4822, 0.4465), (0.2023, 0.1994, 0.2010)
+    att = {}
+    model.eval()
+    with torch.no_grad():
+        att["clean_logits"] = model(xin, **kw).numpy()
+    x_f, _ = FGSM(model, eps=8 / 255., mean=mean_t, std=std_t)(xin, labels, kw)
+    att["fgsm_x"] = x_f.numpy()
+    torch.manual_seed(77)
+    start = torch.zeros(nb, 3, 32, 32).uniform_(-8 / 255., 8 / 255.)
+    torch.manual_seed(77)
+    x_p, _ = PGD(model, eps=8 / 255., lr=2 / 255., n_iter=7, mean=mean_t, std=std_t)(xin, labels, kw)
+    att["pgd_start"] = start.numpy()
+    att["pgd_x"] = x_p.numpy()
+    with torch.no_grad():
+        att["fgsm_logits"] = model(x_f, **kw).numpy()
+        att["pgd_logits"] = model(x_p, **kw).numpy()
+    # FGSM-random training step (train_and_attack.py:246-327): zero_grad -> attack (backward #1) -> train pass
+    model.train()
+    model.zero_grad()
+    torch.manual_seed(78)
+    u01 = torch.rand(nb, 3, 32, 32)
+    torch.manual_seed(78)
+    x_r, _ = FGSMRandom(model, alpha=10 / 255., epsilon=8 / 255., mu=mean_t, std=std_t)(xin, labels, kw)
+    loss = F.cross_entropy(model(x_r, **kw), labels)
+    loss.backward()
+    att["fgsmr_u01"] = u01.numpy()
+    att["fgsmr_x"] = x_r.numpy()
+    att["train_loss"] = np.float64(loss.item())
+    for k, prm in model.named_parameters():
+        if "rhs_func" in k or k in ("conv1.weight", "fc_layers.2.weight"):
+            att["train_g_" + k] = prm.grad.numpy().reshape(-1)[::WG_STRIDE].copy()
+    np.savez(os.path.join(HERE, "attacks.npz"), **att)
+    print("attacks: clean pred", att["clean_logits"].argmax(1), "pgd pred", att["pgd_logits"].argmax(1))
     tot = sum(os.path.getsize(os.path.join(HERE, f)) for f in os.listdir(HERE) if f.endswith(".npz"))
     print("fixture bytes:", tot)
 

@@ -1,0 +1,94 @@
+"""GPU parity of the callers of the input-gradient backward (BASELINE configs 4 and 5):
+FGSM, PGD-7 and the FGSM-random training step on premetanode10 vs golden vectors from the real
+reference.  sign(grad) makes x_adv discontinuous in the gradient, so adversarial inputs are compared
+by the fraction of elements that differ; predictions / correct counts must be identical."""
+import os
+import sys
+from argparse import Namespace
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import golden, max_rel, ROOT
+
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import make_golden_cases as cases  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup():
+    import metasolver_b200  # noqa: F401
+    from metasolver_b200.sopa.src.solvers.utils import create_solver
+    from metasolver_b200.sopa.src.models.odenet_cifar10.layers import premetanode10
+    from metasolver_b200.sopa.src.models.odenet_cifar10.utils import Identity
+    from oracle import det_uniform
+    from oracle.models import det_premetanode10_params, CIFAR_MEAN, CIFAR_STD
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    model = premetanode10((Identity,) * 3, (lambda x: x,) * 3, (F.gelu,) * 3, in_planes=64, is_odenet=True)
+    model.load_state_dict(det_premetanode10_params())
+    model = model.cuda()
+    img = torch.from_numpy(det_uniform((8, 3, 32, 32), 910, 0.0, 1.0))
+    x = ((img - torch.tensor(CIFAR_MEAN).view(1, 3, 1, 1)) / torch.tensor(CIFAR_STD).view(1, 3, 1, 1)).cuda()
+    y = torch.tensor([3, 1, 4, 1, 5, 9, 2, 6]).cuda()
+    solver = create_solver("rk2", "u", 8, -1, 0.5, -1, torch.float32, "cuda")
+    solver.freeze_params()
+    kw = {"solvers": [solver], "solver_options": Namespace(solver_mode="standalone")}
+    return model, x, y, kw, CIFAR_MEAN, CIFAR_STD
+
+
+def _frac_diff(a, b, step):
+    """fraction of elements that differ by more than a small fraction of one attack step"""
+    return float((np.abs(a - b) > 0.25 * step).mean())
+
+
+def test_fgsm_and_pgd_vs_reference_golden():
+    from metasolver_b200.MegaAdversarial.src.attacks import FGSM, PGD
+    g = golden("attacks.npz")
+    model, x, y, kw, mean, std = _setup()
+    model.eval()
+    with torch.no_grad():
+        clean = model(x, **kw).cpu().numpy()
+    assert max_rel(clean, g["clean_logits"]) <= 1e-4
+    assert (clean.argmax(1) == g["clean_logits"].argmax(1)).all()
+    min_std = min(std)
+    xf, _ = FGSM(model, eps=8 / 255., mean=mean, std=std)(x, y, kw)
+    assert _frac_diff(xf.cpu().numpy(), g["fgsm_x"], (8 / 255.) / max(std)) < 5e-3
+    xp, _ = PGD(model, eps=8 / 255., lr=2 / 255., n_iter=7, mean=mean, std=std)(
+        x, y, kw, noise=torch.from_numpy(g["pgd_start"]))
+    assert _frac_diff(xp.cpu().numpy(), g["pgd_x"], (2 / 255.) / max(std)) < 2e-2
+    with torch.no_grad():
+        lf = model(xf, **kw).cpu().numpy()
+        lp = model(xp, **kw).cpu().numpy()
+    # robust-accuracy counts (what examples/cifar10/train_and_attack.py:233-239 accumulates) must be identical
+    yy = y.cpu().numpy()
+    assert (lf.argmax(1) == g["fgsm_logits"].argmax(1)).all()
+    assert (lp.argmax(1) == g["pgd_logits"].argmax(1)).all()
+    assert int((lp.argmax(1) == yy).sum()) == int((g["pgd_logits"].argmax(1) == yy).sum())
+    for prm in model.parameters():          # input-gradient-only mode: no parameter gradients were formed
+        assert prm.grad is None
+
+
+def test_fgsm_random_training_step_vs_reference_golden():
+    """zero_grad -> FGSMRandom (its backward accumulates parameter grads) -> train pass backward
+    (examples/cifar10/train_and_attack.py:256-311): applied gradient = sum of both passes."""
+    from metasolver_b200.MegaAdversarial.src.attacks import FGSMRandom
+    g = golden("attacks.npz")
+    model, x, y, kw, mean, std = _setup()
+    model.train()
+    model.zero_grad()
+    xr, _ = FGSMRandom(model, alpha=10 / 255., epsilon=8 / 255., mu=mean, std=std)(
+        x, y, kw, noise=torch.from_numpy(g["fgsmr_u01"]))
+    assert model.training
+    assert _frac_diff(xr.cpu().numpy(), g["fgsmr_x"], (10 / 255.) / max(std)) < 5e-3
+    loss = F.cross_entropy(model(xr, **kw), y)
+    loss.backward()
+    assert abs(float(loss) - float(g["train_loss"])) <= 1e-4 * abs(float(g["train_loss"]))
+    params = dict(model.named_parameters())
+    for k in g.files:
+        if k.startswith("train_g_"):
+            got = params[k[8:]].grad.cpu().numpy().reshape(-1)[::cases.WG_STRIDE]
+            assert max_rel(got, g[k]) <= 2e-3, (k, max_rel(got, g[k]))   # includes the effect of rare sign flips in x_adv

@@ -155,3 +155,37 @@ def test_numpy_direct_conv_pins_conv_semantics():
         for s in range(3):
             out += np.einsum("oc,nchw->nohw", w[:, :, r, s], xp[:, :, r:r + 5, s:s + 6])
     assert max_rel(out, ref) < 1e-14
+
+
+def test_attacks_and_fgsm_random_train_step_bit_exact():
+    """Oracle restatement of FGSM / PGD / FGSM-random + the published training step vs the real reference."""
+    from oracle import attacks as oa
+    g = golden("attacks.npz")
+    p = det_premetanode10_params()
+    for v in p.values():
+        v.requires_grad_(True)
+    img = torch.from_numpy(oracle.det_uniform((8, 3, 32, 32), 910, 0.0, 1.0))
+    mean = torch.tensor(CIFAR_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(CIFAR_STD).view(1, 3, 1, 1)
+    x = (img - mean) / std
+    y = torch.tensor([3, 1, 4, 1, 5, 9, 2, 6])
+    tab = butcher_tableau("rk2", "u", np.float32(0.5), None)
+    model = lambda inp: premetanode10_forward(p, inp, tab, dict(n_steps=8))
+    with torch.no_grad():
+        assert np.array_equal(model(x).numpy(), g["clean_logits"])
+    xf = oa.fgsm(model, x, y, 8 / 255., CIFAR_MEAN, CIFAR_STD)
+    assert np.array_equal(xf.numpy(), g["fgsm_x"])
+    xp = oa.pgd(model, x, y, 8 / 255., 2 / 255., 7, CIFAR_MEAN, CIFAR_STD, torch.from_numpy(g["pgd_start"]))
+    assert np.array_equal(xp.numpy(), g["pgd_x"])
+    with torch.no_grad():
+        assert np.array_equal(model(xp).numpy(), g["pgd_logits"])
+    for v in p.values():
+        v.grad = None
+    xr = oa.fgsm_random(model, x, y, 10 / 255., 8 / 255., CIFAR_MEAN, CIFAR_STD, torch.from_numpy(g["fgsmr_u01"]))
+    assert np.array_equal(xr.numpy(), g["fgsmr_x"])
+    loss = F.cross_entropy(model(xr), y)
+    loss.backward()
+    assert float(loss) == float(g["train_loss"])
+    for k in g.files:
+        if k.startswith("train_g_"):
+            assert np.array_equal(p[k[8:]].grad.numpy().reshape(-1)[::cases.WG_STRIDE], g[k]), k
