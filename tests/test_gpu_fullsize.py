@@ -1,0 +1,86 @@
+"""GPU: BASELINE.json full sizes (B=512), where the CPU oracle is too slow -- size-independent
+properties of the hot path:
+  * the tcgen05 engine and the independent SIMT engine agree (same operands, different GEMM engine);
+  * samples are independent: a batch of 512 gives, for any image, bit-identical results to running that
+    image in a different batch position / smaller batch (this is what makes batch sharding exact);
+  * runs are bitwise reproducible (deterministic split-K reduction, no atomics);
+  * linearity of the adjoint: the input gradient is linear in the output gradient.
+"""
+from argparse import Namespace
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import max_rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _block(C, seed=0):
+    import metasolver_b200  # noqa: F401
+    from metasolver_b200.sopa.src.solvers.utils import create_solver
+    from metasolver_b200.sopa.src.models.odenet_cifar10.layers import MetaODEBlock, PreBasicBlock2
+    from metasolver_b200.sopa.src.models.odenet_cifar10.utils import Identity
+    torch.manual_seed(seed)
+    blk = MetaODEBlock(PreBasicBlock2(C, norm_layer=Identity, act_layer=F.gelu)).cuda()
+    solver = create_solver("rk2", "u", 8, -1, 0.5, -1, torch.float32, "cuda")
+    solver.freeze_params()
+    return blk, solver, Namespace(solver_mode="standalone")
+
+
+@pytest.mark.parametrize("C,HW", [(64, 32), (128, 16)])
+def test_full_batch_engines_agree_and_samples_independent(C, HW):
+    import metasolver_b200
+    blk, solver, opts = _block(C)
+    torch.manual_seed(1)
+    x = torch.randn(512, C, HW, HW, device="cuda").contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        y = blk(x, [solver], opts)
+        y2 = blk(x, [solver], opts)
+        assert torch.equal(y, y2)                                   # reproducible
+        # sample independence / shard exactness: rows 100..131 alone, and reversed
+        sub = x[100:132].contiguous(memory_format=torch.channels_last)
+        ys = blk(sub, [solver], opts)
+        assert torch.equal(ys, y[100:132])
+        yr = blk(sub.flip(0).contiguous(memory_format=torch.channels_last), [solver], opts)
+        assert torch.equal(yr.flip(0), ys)
+        # independent engine on a slice (SIMT fp32 FFMA is slow: 16 images)
+        metasolver_b200.set_default_engine("simt")
+        try:
+            y_simt = blk(x[:16].contiguous(memory_format=torch.channels_last), [solver], opts)
+        finally:
+            metasolver_b200.set_default_engine("auto")
+    assert max_rel(y[:16].cpu().numpy(), y_simt.cpu().numpy()) < 1e-5
+    assert blk.rhs_func.nfe == 16 * 5
+
+
+def test_full_batch_backward_properties():
+    C, HW = 64, 32
+    blk, solver, opts = _block(C)
+    torch.manual_seed(2)
+    x = torch.randn(512, C, HW, HW, device="cuda").contiguous(memory_format=torch.channels_last)
+    g1 = torch.randn_like(x)
+    g2 = torch.randn_like(x)
+
+    def grads(g, xin):
+        xin = xin.clone().requires_grad_(True)
+        blk.zero_grad()
+        y = blk(xin, [solver], opts)
+        y.backward(g)
+        return xin.grad, blk.rhs_func.conv1.weight.grad.clone(), blk.rhs_func.conv2.weight.grad.clone()
+
+    gx1, gw1a, gw1b = grads(g1, x)
+    gx1r, gw1ar, gw1br = grads(g1, x)
+    assert torch.equal(gx1, gx1r) and torch.equal(gw1a, gw1ar) and torch.equal(gw1b, gw1br)   # deterministic
+    gx2, gw2a, _ = grads(g2, x)
+    gx12, gw12a, _ = grads(g1 + 2.0 * g2, x)
+    # adjoint linearity (up to the rounding of the bf16 hi/lo split of the gradient operand)
+    assert max_rel((gx1 + 2.0 * gx2).cpu().numpy(), gx12.cpu().numpy()) < 2e-5
+    assert max_rel((gw1a + 2.0 * gw2a).cpu().numpy(), gw12a.cpu().numpy()) < 2e-5
+    # weight gradient is a sum over samples: two half batches add up to the full batch
+    _, ha, hb = grads(g1[:256].contiguous(memory_format=torch.channels_last), x[:256].contiguous(memory_format=torch.channels_last))
+    _, ha2, hb2 = grads(g1[256:].contiguous(memory_format=torch.channels_last), x[256:].contiguous(memory_format=torch.channels_last))
+    assert max_rel((ha + ha2).cpu().numpy(), gw1a.cpu().numpy()) < 1e-4   # 5e5-term fp32 sums, different split-K partition
+    assert max_rel((hb + hb2).cpu().numpy(), gw1b.cpu().numpy()) < 1e-4
