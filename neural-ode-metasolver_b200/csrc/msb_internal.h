@@ -24,6 +24,11 @@ void launch_pack_w_simt(const float* w, float* out, int C, int Cin_total, int sk
 void launch_pack_w_tc(const float* w, __nv_bfloat16* out, int C, int transpose, cudaStream_t st);
 void launch_wgrad_reduce(const float* partial, int nparts, float* grad_w, int C, int accumulate, cudaStream_t st);
 
+// ---- groupnorm.cu (MNIST right-hand side) ----
+int launch_groupnorm_epi(const float* x, const float* gamma, const float* beta, const EpiParams& epi, ConvShape s,
+                         int groups, float eps, cudaStream_t st);
+void launch_time_tapmap(const float* w, float* tapmap, int H, int W, int C, cudaStream_t st);
+
 // ---- conv_simt.cu : plain fp32 FFMA engine (any C multiple of 4, any H, W) ----
 //   out-epilogue(conv3x3(split_in, w_packed[tap][ci][co]))
 int launch_conv3x3_simt(const __nv_bfloat16* split_in, const float* w_packed, const EpiParams& epi,

@@ -87,8 +87,12 @@ struct Carver {
 
 int validate(const MsbOdeDesc* d) {
     if (!d) { set_error("null descriptor"); return -1; }
-    if (d->rhs_kind != MSB_RHS_PREACT_NF) {
-        set_error("rhs_kind %d is not implemented by this entry point (supported: MSB_RHS_PREACT_NF)", d->rhs_kind);
+    if (d->rhs_kind != MSB_RHS_PREACT_NF && d->rhs_kind != MSB_RHS_MNIST_GN_T) {
+        set_error("rhs_kind %d is not implemented (supported: MSB_RHS_PREACT_NF, MSB_RHS_MNIST_GN_T forward)", d->rhs_kind);
+        return -1;
+    }
+    if (d->rhs_kind == MSB_RHS_MNIST_GN_T && d->save_tape) {
+        set_error("the MNIST (GroupNorm, time-dependent) right-hand side has no backward yet: save_tape must be 0");
         return -1;
     }
     if (d->act != MSB_ACT_GELU_ERF && d->act != MSB_ACT_RELU && d->act != MSB_ACT_NONE) {
@@ -108,6 +112,10 @@ int validate(const MsbOdeDesc* d) {
 // library (cuDNN) or CPU path to fall back to.
 int resolve_engine(const MsbOdeDesc* d) {
     bool tc_ok = tc_shape_supported(d->channels, d->height, d->width);
+    if (d->rhs_kind == MSB_RHS_MNIST_GN_T) {
+        if (d->engine == MSB_ENGINE_TCGEN05) { set_error("the MNIST right-hand side runs on the SIMT engine only"); return -1; }
+        return MSB_ENGINE_SIMT;
+    }
     if (d->engine == MSB_ENGINE_SIMT) return MSB_ENGINE_SIMT;
     if (d->engine == MSB_ENGINE_TCGEN05) {
         if (!tc_ok) { set_error("tcgen05 engine does not cover C=%d H=%d W=%d", d->channels, d->height, d->width); return -1; }
@@ -212,6 +220,8 @@ size_t msb_odeblock_workspace_bytes(const MsbOdeDesc* d) {
     n += 2 * align_up(E * 4);                                  // y ping-pong
     n += (size_t)(d->stages - 1) * align_up(E * 4);            // k_1 .. k_{s-1}
     n += 2 * align_up(E * 4);                                  // A / Hs split (inference)
+    if (d->rhs_kind == MSB_RHS_MNIST_GN_T)                     // conv output, stage input, 2 tapmaps
+        n += 2 * align_up(E * 4) + 2 * align_up((size_t)d->height * d->width * d->channels * 4);
     return n + 4096;
 }
 size_t msb_odeblock_tape_bytes(const MsbOdeDesc* d) {
@@ -233,11 +243,85 @@ size_t msb_odeblock_bwd_workspace_bytes(const MsbOdeDesc* d) {
     return n + 4096;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// MNIST right-hand side (forward):  f(t, x) = GN3(cconv2(t, relu(GN2(cconv1(t, relu(GN1(x)))))))
+// sopa/src/models/odenet_mnist/layers.py:158-171.  Five launches per evaluation; the RK stage
+// combination is the epilogue of the GN3 launch.  Stage time t_i = t_n + c_i*dt (`_get_t`).
+// ---------------------------------------------------------------------------------------------
+static int mnist_forward(const MsbOdeDesc* d, const float* x, const MsbMnistParams* mp, float* y_out, void* workspace,
+                         size_t workspace_bytes, cudaStream_t st) {
+    if (!mp) { set_error("MSB_RHS_MNIST_GN_T needs MsbMnistParams"); return -1; }
+    for (int i = 0; i < 3; ++i) if (!mp->norm_w[i] || !mp->norm_b[i]) { set_error("MNIST params: null norm pointer"); return -1; }
+    for (int i = 0; i < 2; ++i) if (!mp->conv_w[i] || !mp->conv_b[i]) { set_error("MNIST params: null conv pointer"); return -1; }
+    if (!x || !y_out || !workspace) { set_error("null pointer argument"); return -1; }
+    if (workspace_bytes < msb_odeblock_workspace_bytes(d)) { set_error("workspace too small"); return -1; }
+    const int S = d->stages, N = d->n_steps, C = d->channels;
+    const size_t E = state_elems(d);
+    ConvShape shp{d->batch, d->height, d->width, C};
+    Carver cv(workspace, workspace_bytes);
+    float* wp[2] = {cv.take<float>((size_t)9 * C * C * 4), cv.take<float>((size_t)9 * C * C * 4)};
+    float* ybuf[2] = {cv.take<float>(E * 4), cv.take<float>(E * 4)};
+    float* kbuf[MSB_MAX_STAGES] = {nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < S - 1; ++i) kbuf[i] = cv.take<float>(E * 4);
+    __nv_bfloat16* A = cv.take<__nv_bfloat16>(E * 4);
+    __nv_bfloat16* Hs = cv.take<__nv_bfloat16>(E * 4);
+    float* PQ = cv.take<float>(E * 4);
+    float* xbuf = cv.take<float>(E * 4);
+    float* tapmap[2] = {cv.take<float>((size_t)d->height * d->width * C * 4), cv.take<float>((size_t)d->height * d->width * C * 4)};
+    if (!cv.ok()) { set_error("internal: workspace carve overflow"); return -1; }
+    for (int k = 0; k < 2; ++k) {
+        launch_pack_w_simt(mp->conv_w[k], wp[k], C, C + 1, 1, 0, st);
+        launch_time_tapmap(mp->conv_w[k], tapmap[k], d->height, d->width, C, st);
+    }
+    const float* y_cur = x;
+    for (int n = 0; n < N; ++n) {
+        const float t0 = d->time_grid[n];
+        const float dt = d->time_grid[n + 1] - t0;
+        float* y_next = (n == N - 1) ? y_out : ybuf[n & 1];
+        for (int i = 0; i < S; ++i) {
+            volatile float cdt = d->c[i] * dt;                 // keep the reference's two roundings
+            const float ti = (i == 0) ? t0 : t0 + cdt;
+            const float* xi = (i == 0) ? y_cur : xbuf;
+            EpiParams g1 = epi_default();
+            g1.act = ACT_RELU; g1.out_split = A;
+            if (launch_groupnorm_epi(xi, mp->norm_w[0], mp->norm_b[0], g1, shp, mp->groups, mp->eps, st)) return -1;
+            EpiParams c1 = epi_default();
+            c1.chan_bias = mp->conv_b[0]; c1.pix_bias = tapmap[0]; c1.pix_bias_scale = ti; c1.out_f32 = PQ;
+            if (run_conv(MSB_ENGINE_SIMT, A, wp[0], c1, shp, st)) return -1;
+            EpiParams g2 = epi_default();
+            g2.act = ACT_RELU; g2.out_split = Hs;
+            if (launch_groupnorm_epi(PQ, mp->norm_w[1], mp->norm_b[1], g2, shp, mp->groups, mp->eps, st)) return -1;
+            EpiParams c2 = epi_default();
+            c2.chan_bias = mp->conv_b[1]; c2.pix_bias = tapmap[1]; c2.pix_bias_scale = ti; c2.out_f32 = PQ;
+            if (run_conv(MSB_ENGINE_SIMT, Hs, wp[1], c2, shp, st)) return -1;
+            EpiParams g3 = epi_default();                       // k_i = GN3(.) and the RK combination
+            g3.base = y_cur; g3.dt = dt;
+            if (i < S - 1) {
+                g3.v_out = kbuf[i];
+                g3.nsrc = i;
+                for (int j = 0; j < i; ++j) { g3.src[j] = kbuf[j]; g3.coef[j] = d->w[(i + 1) * MSB_MAX_STAGES + j]; }
+                g3.coef_v = d->w[(i + 1) * MSB_MAX_STAGES + i];
+                g3.out_f32 = xbuf;
+            } else {
+                g3.nsrc = S - 1;
+                for (int j = 0; j < S - 1; ++j) { g3.src[j] = kbuf[j]; g3.coef[j] = d->b[j]; }
+                g3.coef_v = d->b[S - 1];
+                g3.out_f32 = y_next;
+            }
+            if (launch_groupnorm_epi(PQ, mp->norm_w[2], mp->norm_b[2], g3, shp, mp->groups, mp->eps, st)) return -1;
+        }
+        y_cur = y_next;
+    }
+    return check_cuda(cudaGetLastError(), "odeblock forward (mnist)");
+}
+
 int msb_odeblock_forward(const MsbOdeDesc* d, const float* x, const float* w1, const float* w2,
                          const MsbMnistParams* mnist, float* y_out, void* workspace, size_t workspace_bytes,
                          void* tape, size_t tape_bytes, void* cuda_stream) {
     if (validate(d)) return -1;
-    (void)mnist;
+    if (d->rhs_kind == MSB_RHS_MNIST_GN_T)
+        return mnist_forward(d, x, mnist, y_out, workspace, workspace_bytes, (cudaStream_t)cuda_stream);
     int engine = resolve_engine(d);
     if (engine < 0) return -1;
     if (!x || !w1 || !w2 || !y_out || !workspace) { set_error("null pointer argument"); return -1; }

@@ -173,6 +173,41 @@ def ode_block_integrate(x, w1, w2, tableau, time_grid, rhs_kind=_cabi.RHS_PREACT
     return _OdeBlockFn.apply(x, w1, w2, prob)
 
 
+def ode_block_integrate_mnist(x, params, tableau, time_grid, groups, eps=1e-5):
+    """MNIST right-hand side (GroupNorm / ReLU / time-concatenated convs, mnist/layers.py:158-171).
+    `params`: dict(norm{1,2,3}_{w,b}, conv{1,2}_{w,b}) of fp32 CUDA tensors.  Forward only."""
+    if not x.is_cuda:
+        raise RuntimeError("metasolver_b200: the ODE-block path runs on CUDA only (got a %s tensor); "
+                           "there is no CPU fallback" % x.device)
+    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params.values())):
+        raise NotImplementedError("metasolver_b200: the backward of the MNIST (GroupNorm, time-dependent) right-hand "
+                                  "side is not implemented yet; run it under torch.no_grad()")
+    lib = _cabi.lib()
+    dev = x.device
+    prob = OdeProblem(_cabi.RHS_MNIST_GN_T, _cabi.ACT_RELU, tableau, time_grid, "simt")
+    with torch.cuda.device(dev):
+        xc = x.detach().contiguous(memory_format=torch.channels_last)
+        keep = {k: v.detach().contiguous() for k, v in params.items()}
+        mp = _cabi.MsbMnistParams()
+        for i in range(3):
+            mp.norm_w[i] = keep["norm%d_w" % (i + 1)].data_ptr()
+            mp.norm_b[i] = keep["norm%d_b" % (i + 1)].data_ptr()
+        for i in range(2):
+            mp.conv_w[i] = keep["conv%d_w" % (i + 1)].data_ptr()
+            mp.conv_b[i] = keep["conv%d_b" % (i + 1)].data_ptr()
+        mp.groups, mp.eps = groups, eps
+        d = prob.desc(tuple(x.shape), False)
+        ws_bytes = lib.msb_odeblock_workspace_bytes(ctypes.byref(d))
+        if ws_bytes == 0:
+            _cabi.check(-1, "odeblock workspace query")
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        y = torch.empty_like(xc)
+        rc = lib.msb_odeblock_forward(ctypes.byref(d), _ptr(xc), None, None, ctypes.byref(mp), _ptr(y), _ptr(ws),
+                                      ws_bytes, None, 0, _stream(dev))
+        _cabi.check(rc, "odeblock forward (mnist)")
+    return y
+
+
 # --------------------------------------------------------------------------- single-kernel entry points
 def act_split(x_cl, act=_cabi.ACT_NONE, want_dact=False):
     """x_cl: (B,C,H,W) channels_last fp32 -> (split uint16-view tensor [B,H,2,W,C], dact or None)."""

@@ -14,7 +14,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from ....ops import ode_block_integrate
+from ....ops import ode_block_integrate, ode_block_integrate_mnist
 from .... import _cabi
 
 
@@ -147,8 +147,12 @@ class RKParametricSolver(object, metaclass=abc.ABCMeta):
                                       "there is no unfused fallback" % type(rhs_func).__name__)
         spec = spec()
         grid = self.host_time_grid(t)
-        y = ode_block_integrate(x, spec["w1"], spec["w2"], self._host_tableau, grid.tolist(),
-                                rhs_kind=spec["rhs_kind"], act=spec["act"], engine=spec.get("engine"))
+        if spec["rhs_kind"] == _cabi.RHS_MNIST_GN_T:
+            y = ode_block_integrate_mnist(x, spec["params"], self._host_tableau, grid.tolist(), spec["groups"],
+                                          spec["eps"])
+        else:
+            y = ode_block_integrate(x, spec["w1"], spec["w2"], self._host_tableau, grid.tolist(),
+                                    rhs_kind=spec["rhs_kind"], act=spec["act"], engine=spec.get("engine"))
         rhs_func.nfe += self.n_stages * (len(grid) - 1)               # cifar10/layers.py:149
         return torch.stack((x, y))
 

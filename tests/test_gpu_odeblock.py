@@ -176,3 +176,42 @@ def test_premetanode10_whole_model_vs_reference_golden():
             got = params[k[2:]].grad.cpu().numpy().reshape(-1)[::cases.WG_STRIDE]
             assert max_rel(got, g[k]) <= TOL, (k, max_rel(got, g[k]))
     assert model.nfe == 32
+
+
+def test_mnist_ode_block_trained_weights_vs_reference_golden():
+    """BASELINE config 1: the MNIST ODE block (GN / ReLU / time-concatenated convs) with the trained weights
+    shipped by the reference, forward, against the reference's own outputs."""
+    import metasolver_b200  # noqa: F401
+    from metasolver_b200.sopa.src.solvers.utils import create_solver
+    from metasolver_b200.sopa.src.models.odenet_mnist.layers import MetaODEBlock, MetaNODE
+    w = golden("mnist_odeblock_weights.npz")
+    g = golden("mnist_odeblock.npz")
+    blk = MetaODEBlock()
+    rf = blk.rhs_func
+    with torch.no_grad():
+        for i in (1, 2, 3):
+            getattr(rf, "norm%d" % i).weight.copy_(torch.from_numpy(w["norm%d_w" % i]))
+            getattr(rf, "norm%d" % i).bias.copy_(torch.from_numpy(w["norm%d_b" % i]))
+        for i in (1, 2):
+            getattr(rf, "conv%d" % i)._layer.weight.copy_(torch.from_numpy(w["conv%d_w" % i]))
+            getattr(rf, "conv%d" % i)._layer.bias.copy_(torch.from_numpy(w["conv%d_b" % i]))
+    blk = blk.cuda()
+    x = torch.from_numpy(g["feat"]).cuda()
+    assert set(k for k in blk.state_dict()) == {
+        "rhs_func.norm1.weight", "rhs_func.norm1.bias", "rhs_func.conv1._layer.weight", "rhs_func.conv1._layer.bias",
+        "rhs_func.norm2.weight", "rhs_func.norm2.bias", "rhs_func.conv2._layer.weight", "rhs_func.conv2._layer.bias",
+        "rhs_func.norm3.weight", "rhs_func.norm3.bias"}
+    for tag, sv in (("rk2_u05_n8", ("rk2", "u", 8, -1, 0.5, -1)), ("rk4_u2_n2", ("rk4", "u2", 2, -1, 1 / 3., -1)),
+                    ("euler_n4", ("euler", None, 4, -1, -1, -1))):
+        solver = create_solver(*sv, torch.float32, "cuda")
+        solver.freeze_params()
+        with torch.no_grad():
+            y = blk(x, [solver], Namespace(solver_mode="standalone"))
+        assert max_rel(y.cpu().numpy(), g[tag + "_y"]) <= TOL, (tag, max_rel(y.cpu().numpy(), g[tag + "_y"]))
+    with pytest.raises(NotImplementedError):
+        blk(x.clone().requires_grad_(True), [solver], Namespace(solver_mode="standalone"))
+    # full model wiring (stem / head are PyTorch): shapes only
+    model = MetaNODE().cuda().eval()
+    with torch.no_grad():
+        out = model(torch.rand(4, 1, 28, 28, device="cuda"), [solver], Namespace(solver_mode="standalone"))
+    assert out.shape == (4, 10)
