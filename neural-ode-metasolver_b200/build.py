@@ -14,7 +14,7 @@ LIB = os.path.join(HERE, "libmetasolver_b200.so")
 SOURCES = ["odeblock.cu", "elementwise.cu", "conv_simt.cu", "conv_tc.cu", "wgrad_tc.cu", "groupnorm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",
-              "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+              "-I", os.path.join(ROOT, "include"), "-I", CSRC] + os.environ.get("MSB_NVCC_EXTRA", "").split()
 
 
 def _nvcc():

@@ -23,6 +23,10 @@
 #include "msb_internal.h"
 #include "msb_ptx.cuh"
 
+#ifndef MSB_B_STAGES
+#define MSB_B_STAGES 2
+#endif
+
 namespace msb {
 
 // ---------------------------------------------------------------------------------------------
@@ -90,33 +94,40 @@ size_t tc_packed_weight_bytes(int C) { return (size_t)((C == 64) ? 9 : 9 * (C / 
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-constexpr int kNumThreads = 384;
 constexpr int kEpiWarp0 = 4;
-constexpr int kNumEpiWarps = 8;
-constexpr int kAStages = 4;
-constexpr int kBStages = 3;
 constexpr int kATileBytes = 128 * 128;   // 128 rows x 64 bf16
 constexpr uint32_t kTmemCols = 512;
+constexpr int kMaxStages = 8;
 
-template <int WIMG> struct TileGeom {
+// Per-shape tuning.  C=64 has half the MMA time per output element of C=128, so its epilogue gets 16
+// warps (4-pixel chunks) and the weight ring is deepened at the cost of one activation stage:
+// the weight tiles turn over every 512 MMA cycles, far less than a loaded-L2 TMA round trip.
+template <int C, int WIMG> struct TileGeom {
     static constexpr int ROWS = 128 / WIMG;                       // image rows per 128-pixel tile
     static constexpr int B_STAGE_BYTES = (ROWS + 2) * 2 * WIMG * 128;
     static constexpr int ROW_PAIR_BYTES = 2 * WIMG * 128;         // one image row, both planes
+    static constexpr int EPI_WARPS = (C == 64) ? 16 : 8;          // multiple of 4 (one per TMEM lane quadrant)
+    static constexpr int THREADS = (kEpiWarp0 + EPI_WARPS) * 32;
+    static constexpr int PXO = (C == 64) ? 4 : 8;                 // pixels one epilogue thread owns per chunk
+    static constexpr int B_STAGES = MSB_B_STAGES;
+    static constexpr int A_STAGES = (212992 - B_STAGES * B_STAGE_BYTES) / kATileBytes > kMaxStages
+                                        ? kMaxStages : (212992 - B_STAGES * B_STAGE_BYTES) / kATileBytes;
 };
 
 struct __align__(8) Barriers {
-    uint64_t a_full[kAStages], a_empty[kAStages];
-    uint64_t b_full[kBStages], b_empty[kBStages];
+    uint64_t a_full[kMaxStages], a_empty[kMaxStages];
+    uint64_t b_full[kMaxStages], b_empty[kMaxStages];
     uint64_t tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
 };
 
 template <int C, int WIMG, int ACT>
-__global__ void __launch_bounds__(kNumThreads, 1)
+__global__ void __launch_bounds__((TileGeom<C, WIMG>::THREADS), 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_w,
                   const EpiParams epi, const int H, const int num_tiles, const int tiles_per_img) {
-    using G = TileGeom<WIMG>;
+    using G = TileGeom<C, WIMG>;
     constexpr int CHUNKS = C / 64;
+    constexpr int kAStages = G::A_STAGES, kBStages = G::B_STAGES, kNumEpiWarps = G::EPI_WARPS, kPXO = G::PXO;
     constexpr int PARTS = (C == 64) ? 1 : 2;          // weight tiles per (tap, chunk): C=64 packs hi/lo into one tile
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -225,29 +236,31 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
         // for its accumulator) are in flight while chunk i is computed and stored.
         const int we = warp - kEpiWarp0;
         const int q = warp & 3;                       // TMEM lane quadrant this warp may read
-        const int half = we >> 2;                     // which half of the tile's image rows
+        const int part = we >> 2;                     // which slice of the tile's image rows
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        constexpr int RH = G::ROWS / 2;               // image rows per half
-        constexpr int PX_PER_LD = (C == 64) ? 16 : 8; // pixels covered by one TMEM load step
+        constexpr int NPARTS = kNumEpiWarps / 4;
+        static_assert(G::ROWS % NPARTS == 0, "image rows of a tile must split evenly over the epilogue warp groups");
+        constexpr int RH = G::ROWS / NPARTS;          // image rows per warp group
+        constexpr int PX_PER_LD = (C == 64) ? 2 * kPXO : kPXO;   // pixels covered by one TMEM load step
         constexpr int STEPS_PER_ROW = WIMG / PX_PER_LD;
-        constexpr int NCHUNK = RH * STEPS_PER_ROW;    // chunks (of 8 owned pixels) per tile per thread
-        const int sel = (C == 64) ? (lane >> 4) : 0;  // C=64: lanes l / l^16 split the 16 pixels of a step
+        constexpr int NCHUNK = RH * STEPS_PER_ROW;    // chunks (of kPXO owned pixels) per tile per thread
+        const int sel = (C == 64) ? (lane >> 4) : 0;  // C=64: lanes l / l^16 split the pixels of a step
         const int c = (C == 64) ? (16 * q + (lane & 15)) : (32 * q + lane);
         const size_t plane_stride = (size_t)WIMG * C;
 
         // element index of owned pixel 0 of chunk `ch` in tile (n, h0)
         auto chunk_pos = [&](int n, int h0, int ch, int& h, int& w0) {
             const int rr = ch / STEPS_PER_ROW, stp = ch - rr * STEPS_PER_ROW;
-            h = h0 + half * RH + rr;
-            w0 = stp * PX_PER_LD + sel * 8;
+            h = h0 + part * RH + rr;
+            w0 = stp * PX_PER_LD + sel * kPXO;
         };
-        EpiOperands<8> opsA, opsB;
+        EpiOperands<kPXO> opsA, opsB;
         int acc = 0; uint32_t acc_ph = 0;
         int tile = blockIdx.x;
         if (tile < num_tiles) {
             const int n = tile / tiles_per_img, h0 = (tile - n * tiles_per_img) * G::ROWS;
             int h, w0; chunk_pos(n, h0, 0, h, w0);
-            epi_prefetch<8>(epi, (((size_t)n * H + h) * WIMG + w0) * C + c, C, opsA);
+            epi_prefetch<kPXO>(epi, (((size_t)n * H + h) * WIMG + w0) * C + c, C, opsA);
         }
         for (; tile < num_tiles; tile += gridDim.x) {
             const int n = tile / tiles_per_img;
@@ -255,33 +268,33 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
             ptx::mbar_wait(&bars->tmem_full[acc], acc_ph);
             ptx::tc_fence_after();
             const uint32_t t_acc = tmem_base + (uint32_t)acc * 256u + lane_addr;
-            auto do_chunk = [&](const int ch, const EpiOperands<8>& cur, EpiOperands<8>& nxt) {
+            auto do_chunk = [&](const int ch, const EpiOperands<kPXO>& cur, EpiOperands<kPXO>& nxt) {
                 int h, w0; chunk_pos(n, h0, ch, h, w0);
                 const int rr = ch / STEPS_PER_ROW, stp = ch - rr * STEPS_PER_ROW;
-                const int rho = half * RH + rr;
+                const int rho = part * RH + rr;
                 // ---- accumulator: hi + lo columns (and hi + lo weight rows for C = 64) ----
-                float v[8];
+                float v[kPXO];
                 const uint32_t col = (uint32_t)(rho * 2 * WIMG + stp * PX_PER_LD);
                 if (C == 64) {
-                    float hi[16], lo[16];
-                    ptx::tmem_ld16(t_acc + col, hi);
-                    ptx::tmem_ld16(t_acc + col + WIMG, lo);
+                    float hi[2 * kPXO], lo[2 * kPXO];
+                    ptx::tmem_ld<2 * kPXO>(t_acc + col, hi);
+                    ptx::tmem_ld<2 * kPXO>(t_acc + col + WIMG, lo);
                     ptx::tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
+                    for (int j = 0; j < 2 * kPXO; ++j) {
                         const float a = hi[j] + lo[j];
                         const float o = __shfl_xor_sync(0xffffffffu, a, 16);
                         hi[j] = sel ? o + a : a + o;       // identical operand order in both lanes
                     }
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = sel ? hi[8 + j] : hi[j];
+                    for (int j = 0; j < kPXO; ++j) v[j] = sel ? hi[kPXO + j] : hi[j];
                 } else {
-                    float hi[8], lo[8];
-                    ptx::tmem_ld8(t_acc + col, hi);
-                    ptx::tmem_ld8(t_acc + col + WIMG, lo);
+                    float hi[kPXO], lo[kPXO];
+                    ptx::tmem_ld<kPXO>(t_acc + col, hi);
+                    ptx::tmem_ld<kPXO>(t_acc + col + WIMG, lo);
                     ptx::tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = hi[j] + lo[j];
+                    for (int j = 0; j < kPXO; ++j) v[j] = hi[j] + lo[j];
                 }
                 if (ch == NCHUNK - 1) {
                     // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
@@ -300,13 +313,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
                     }
                     if (have) {
                         int h2, w2; chunk_pos(n2, h02, ch2, h2, w2);
-                        epi_prefetch<8>(epi, (((size_t)n2 * H + h2) * WIMG + w2) * C + c, C, nxt);
+                        epi_prefetch<kPXO>(epi, (((size_t)n2 * H + h2) * WIMG + w2) * C + c, C, nxt);
                     }
                 }
                 // ---- fused RK epilogue on the 8 owned pixels ----
                 const size_t pix = ((size_t)n * H + h) * WIMG + w0;
                 const size_t split0 = (((size_t)n * H + h) * 2) * plane_stride + (size_t)w0 * C + c;
-                epi_finish<8, ACT>(epi, v, cur, pix * C + c, C, split0, plane_stride);
+                epi_finish<kPXO, ACT>(epi, v, cur, pix * C + c, C, split0, plane_stride);
             };
             static_assert(NCHUNK % 2 == 0, "chunk pipeline is unrolled by two");
 #pragma unroll
@@ -328,7 +341,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
 template <int C, int WIMG, int ACT>
 int launch_act(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, const EpiParams& epi, ConvShape s,
                cudaStream_t st) {
-    using G = TileGeom<WIMG>;
+    using G = TileGeom<C, WIMG>;
+    constexpr int kAStages = G::A_STAGES, kBStages = G::B_STAGES;
     CUtensorMap tm_act, tm_w;
     if (make_tmap_split5d(&tm_act, split_in, s.B, s.H, s.W, s.C, WIMG, G::ROWS + 2)) return -1;
     const size_t wrows = tc_packed_weight_bytes(C) / 128;
@@ -341,7 +355,7 @@ int launch_act(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, cons
     const int tiles_per_img = s.H / G::ROWS;
     const int num_tiles = s.B * tiles_per_img;
     const int grid = std::min(num_tiles, num_sms());
-    kern<<<grid, kNumThreads, smem, st>>>(tm_act, tm_w, epi, s.H, num_tiles, tiles_per_img);
+    kern<<<grid, G::THREADS, smem, st>>>(tm_act, tm_w, epi, s.H, num_tiles, tiles_per_img);
     count_launch();
     return check_cuda(cudaGetLastError(), "conv3x3_tc launch");
 }

@@ -47,7 +47,8 @@ int launch_conv3x3_tc(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tile
 // ---- wgrad_tc.cu ----
 bool wgrad_tc_supported(ConvShape s);
 int wgrad_tc_nparts(ConvShape s);
+// accumulate != 0: partial[slot] += result (each CTA owns its slots: deterministic)
 int launch_wgrad3x3_tc(const __nv_bfloat16* split_gout, const __nv_bfloat16* split_in, float* partial,
-                       int* nparts_out, ConvShape s, cudaStream_t st);
+                       int* nparts_out, int accumulate, ConvShape s, cudaStream_t st);
 
 }  // namespace msb

@@ -112,6 +112,20 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
+    uint32_t r[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <int N> __device__ __forceinline__ void tmem_ld(uint32_t taddr, float* v) {
+    static_assert(N == 4 || N == 8 || N == 16, "supported TMEM load widths");
+    if (N == 4) tmem_ld4(taddr, v);
+    else if (N == 8) tmem_ld8(taddr, v);
+    else tmem_ld16(taddr, v);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- descriptors --------------------------------------------------------------------------------------

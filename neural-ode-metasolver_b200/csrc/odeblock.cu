@@ -155,15 +155,26 @@ bool use_tc_wgrad(int engine, ConvShape s) { return engine == MSB_ENGINE_TCGEN05
 int wgrad_nparts(int engine, ConvShape s) {
     return use_tc_wgrad(engine, s) ? wgrad_tc_nparts(s) : wgrad_simt_nparts(s);
 }
-int run_wgrad(int engine, const __nv_bfloat16* gout, const __nv_bfloat16* in, float* partial, float* grad_w,
-              int accumulate, ConvShape s, cudaStream_t st) {
+// Weight-gradient accumulation over the launches of one backward pass.
+//  tcgen05: every launch adds onto the CTA-private partial slots (first launch overwrites); ONE
+//           fixed-order reduction per weight tensor at the end (wgrad_finish).
+//  SIMT   : partials are reduced into grad_w after every launch.
+struct WgradAcc { float* partial; float* grad_w; int launches; int nparts; };
+int run_wgrad(int engine, const __nv_bfloat16* gout, const __nv_bfloat16* in, WgradAcc& acc, ConvShape s, cudaStream_t st) {
     int nparts = 0, rc;
     int id = prof_begin(MSB_PROF_WGRAD, conv_flops(s), st);
-    if (use_tc_wgrad(engine, s)) rc = launch_wgrad3x3_tc(gout, in, partial, &nparts, s, st);
-    else rc = launch_wgrad3x3_simt(gout, in, partial, &nparts, s, st);
+    const bool tc = use_tc_wgrad(engine, s);
+    if (tc) rc = launch_wgrad3x3_tc(gout, in, acc.partial, &nparts, acc.launches > 0, s, st);
+    else rc = launch_wgrad3x3_simt(gout, in, acc.partial, &nparts, s, st);
     prof_end(id, st);
     if (rc) return rc;
-    launch_wgrad_reduce(partial, nparts, grad_w, s.C, accumulate, st);
+    acc.nparts = nparts;
+    if (!tc) launch_wgrad_reduce(acc.partial, nparts, acc.grad_w, s.C, acc.launches > 0, st);
+    acc.launches++;
+    return check_cuda(cudaGetLastError(), "wgrad launch");
+}
+int wgrad_finish(int engine, WgradAcc& acc, ConvShape s, cudaStream_t st) {
+    if (use_tc_wgrad(engine, s) && acc.launches > 0) launch_wgrad_reduce(acc.partial, acc.nparts, acc.grad_w, s.C, 0, st);
     return check_cuda(cudaGetLastError(), "wgrad reduce launch");
 }
 
@@ -239,7 +250,7 @@ size_t msb_odeblock_bwd_workspace_bytes(const MsbOdeDesc* d) {
     n += 2 * align_up(E * 4);                                  // gbar ping-pong
     n += (size_t)(d->stages - 1) * align_up(E * 4);            // xbar_1 .. xbar_{s-1}
     n += 2 * align_up(E * 4);                                  // Kbar / DP split
-    n += align_up((size_t)wgrad_nparts(engine, s) * 9 * d->channels * d->channels * 4);
+    n += 2 * align_up((size_t)wgrad_nparts(engine, s) * 9 * d->channels * d->channels * 4);
     return n + 4096;
 }
 
@@ -415,7 +426,8 @@ int msb_odeblock_backward(const MsbOdeDesc* d, const float* grad_y, const float*
     for (int i = 1; i < S; ++i) xbar[i] = cv.take<float>(E * 4);
     __nv_bfloat16* Kbar = cv.take<__nv_bfloat16>(E * 4);
     __nv_bfloat16* DP = cv.take<__nv_bfloat16>(E * 4);
-    float* partial = cv.take<float>((size_t)wgrad_nparts(engine, shp) * 9 * C * C * 4);
+    const size_t part_bytes = (size_t)wgrad_nparts(engine, shp) * 9 * C * C * 4;
+    WgradAcc acc1{cv.take<float>(part_bytes), grad_w1, 0, 0}, acc2{cv.take<float>(part_bytes), grad_w2, 0, 0};
     if (!cv.ok()) { set_error("internal: workspace carve overflow"); return -1; }
 
     pack_w(engine, w1, wt1, C, 1, st);
@@ -425,21 +437,19 @@ int msb_odeblock_backward(const MsbOdeDesc* d, const float* grad_y, const float*
     // kbar_S of the last step = dt * b_S * gbar
     launch_act_split(grad_y, ACT_NONE, dt_of(N - 1) * d->b[S - 1], Kbar, nullptr, d->batch, d->height, d->width, C, st);
     const float* g_cur = grad_y;
-    int first_w = 1;
     for (int n = N - 1; n >= 0; --n) {
         const float dt = dt_of(n);
         float* g_next = (n == 0) ? grad_x : gbuf[n & 1];
         for (int i = S - 1; i >= 0; --i) {
             TapeSlot cur = tape_slot(const_cast<void*>(tape), E, n * S + i);
             // Kbar = split(kbar_i).   dW2 += kbar_i (x) Hs_i
-            if (need_w && run_wgrad(engine, Kbar, cur.Hs, partial, grad_w2, !first_w, shp, st)) return -1;
+            if (need_w && run_wgrad(engine, Kbar, cur.Hs, acc2, shp, st)) return -1;
             // dP = dgrad_W2(kbar_i) * act'(P_i)
             EpiParams e3 = epi_default();
             e3.mul = cur.G1; e3.out_split = DP;
             if (run_conv(engine, Kbar, wt2, e3, shp, st)) return -1;
             // dW1 += dP (x) A_i
-            if (need_w && run_wgrad(engine, DP, cur.A, partial, grad_w1, !first_w, shp, st)) return -1;
-            first_w = 0;
+            if (need_w && run_wgrad(engine, DP, cur.A, acc1, shp, st)) return -1;
             // xbar_i = dgrad_W1(dP) * act'(x_i), then the adjoint stage combination
             EpiParams e4 = epi_default();
             e4.mul = cur.G0; e4.base = g_cur;
@@ -465,6 +475,7 @@ int msb_odeblock_backward(const MsbOdeDesc* d, const float* grad_y, const float*
         }
         g_cur = g_next;
     }
+    if (need_w && (wgrad_finish(engine, acc1, shp, st) || wgrad_finish(engine, acc2, shp, st))) return -1;
     return check_cuda(cudaGetLastError(), "odeblock backward");
 }
 
@@ -520,8 +531,10 @@ int msb_wgrad3x3(const void* split_grad_out, const void* split_in, float* grad_w
         workspace_bytes < (size_t)wgrad_nparts(eng, s) * 9 * channels * channels * 4) {
         set_error("msb_wgrad3x3: bad arguments / workspace too small"); return -1;
     }
-    return run_wgrad(eng, (const __nv_bfloat16*)split_grad_out, (const __nv_bfloat16*)split_in, (float*)workspace,
-                     grad_w_oihw, 0, s, (cudaStream_t)cuda_stream);
+    WgradAcc acc{(float*)workspace, grad_w_oihw, 0, 0};
+    if (run_wgrad(eng, (const __nv_bfloat16*)split_grad_out, (const __nv_bfloat16*)split_in, acc, s, (cudaStream_t)cuda_stream))
+        return -1;
+    return wgrad_finish(eng, acc, s, (cudaStream_t)cuda_stream);
 }
 
 }  // extern "C"

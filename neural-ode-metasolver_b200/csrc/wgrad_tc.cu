@@ -13,7 +13,8 @@
 //   K = 16      : 16 consecutive pixels of one image row (two 8-pixel swizzle atoms, SBO = 1024 B)
 // All four hi/lo products are accumulated in fp32 in one TMEM accumulator (128 lanes x 192 cols),
 // which stays resident for ALL tiles of a CTA: the only global write is one 128x192 partial at the
-// end.  CTA = (group, part): group = (horizontal tap s, 64-wide c_in chunk), part = slice of the
+// end (optionally accumulated onto the CTA's own slot from earlier launches, so a whole backward pass
+// needs a single reduction per weight tensor).  CTA = (group, part): group = (horizontal tap s, 64-wide c_in chunk), part = slice of the
 // pixel tiles.  Partials are summed in a fixed order by wgrad_reduce_kernel (deterministic).
 // Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM alloc, 4..7 = final TMEM -> global.
 #include <cuda.h>
@@ -54,7 +55,8 @@ struct __align__(8) WBarriers {
 template <int C, int WIMG>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_go, const __grid_constant__ CUtensorMap tmap_in,
-                   float* __restrict__ partial, const int num_tiles, const int tiles_per_img, const int nparts) {
+                   float* __restrict__ partial, const int num_tiles, const int tiles_per_img, const int nparts,
+                   const int accumulate_partial) {
     using G = WG<C, WIMG>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -118,6 +120,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_go, const __grid_con
                                 go_base + rho * G::ROW_PAIR_BYTES + pa * G::PLANE_BYTES + px_off, a_lbo, 1024);
 #pragma unroll
                             for (int pb = 0; pb < 2; ++pb) {
+                                if (C != 64 && pa == 1 && pb == 1) continue;   // lo x lo (2^-18 relative) is dropped
                                 const uint64_t bdesc = ptx::make_smem_desc_sw128(
                                     in_base + rho * G::ROW_PAIR_BYTES + pb * G::PLANE_BYTES + px_off, G::ROW_PAIR_BYTES, 1024);
                                 ptx::umma_bf16(tmem_base, adesc, bdesc, idesc, accumulate);
@@ -151,7 +154,8 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_go, const __grid_con
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const int ci = ci_chunk * 64 + (cb & 63) + j;
-                dst[((size_t)tap * C + ci) * C + co] = v[j];
+                float* q = dst + ((size_t)tap * C + ci) * C + co;
+                *q = accumulate_partial ? *q + v[j] : v[j];        // CTA-private slot: deterministic
             }
         }
     }
@@ -174,8 +178,8 @@ int nparts_impl(ConvShape s) {
 }
 
 template <int C, int WIMG>
-int launch_impl(const __nv_bfloat16* gout, const __nv_bfloat16* in, float* partial, int* nparts_out, ConvShape s,
-                cudaStream_t st) {
+int launch_impl(const __nv_bfloat16* gout, const __nv_bfloat16* in, float* partial, int* nparts_out, int accumulate,
+                ConvShape s, cudaStream_t st) {
     using G = WG<C, WIMG>;
     CUtensorMap tm_go, tm_in;
     if (make_tmap_split5d(&tm_go, gout, s.B, s.H, s.W, s.C, WIMG, G::ROWS)) return -1;
@@ -188,7 +192,7 @@ int launch_impl(const __nv_bfloat16* gout, const __nv_bfloat16* in, float* parti
     const int tiles_per_img = s.H / G::ROWS;
     const int num_tiles = s.B * tiles_per_img;
     const int np = nparts_impl<C, WIMG>(s);
-    kern<<<np * G::GROUPS, kThreads, smem, st>>>(tm_go, tm_in, partial, num_tiles, tiles_per_img, np);
+    kern<<<np * G::GROUPS, kThreads, smem, st>>>(tm_go, tm_in, partial, num_tiles, tiles_per_img, np, accumulate);
     count_launch();
     *nparts_out = np * G::HALVES;
     return check_cuda(cudaGetLastError(), "wgrad3x3_tc launch");
@@ -205,13 +209,13 @@ int wgrad_tc_nparts(ConvShape s) {
     return nparts_impl<128, 16>(s);
 }
 
-int launch_wgrad3x3_tc(const __nv_bfloat16* gout, const __nv_bfloat16* in, float* partial, int* nparts_out, ConvShape s,
-                       cudaStream_t st) {
+int launch_wgrad3x3_tc(const __nv_bfloat16* gout, const __nv_bfloat16* in, float* partial, int* nparts_out,
+                       int accumulate, ConvShape s, cudaStream_t st) {
     if (!wgrad_tc_supported(s)) { set_error("tcgen05 wgrad: unsupported shape C=%d H=%d W=%d", s.C, s.H, s.W); return -1; }
-    if (s.C == 64 && s.W == 32) return launch_impl<64, 32>(gout, in, partial, nparts_out, s, st);
-    if (s.C == 64 && s.W == 16) return launch_impl<64, 16>(gout, in, partial, nparts_out, s, st);
-    if (s.C == 128 && s.W == 32) return launch_impl<128, 32>(gout, in, partial, nparts_out, s, st);
-    return launch_impl<128, 16>(gout, in, partial, nparts_out, s, st);
+    if (s.C == 64 && s.W == 32) return launch_impl<64, 32>(gout, in, partial, nparts_out, accumulate, s, st);
+    if (s.C == 64 && s.W == 16) return launch_impl<64, 16>(gout, in, partial, nparts_out, accumulate, s, st);
+    if (s.C == 128 && s.W == 32) return launch_impl<128, 32>(gout, in, partial, nparts_out, accumulate, s, st);
+    return launch_impl<128, 16>(gout, in, partial, nparts_out, accumulate, s, st);
 }
 
 }  // namespace msb
