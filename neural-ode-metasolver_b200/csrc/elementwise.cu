@@ -5,12 +5,12 @@
 namespace msb {
 
 // ---------------------------------------------------------------------------------------------
-// act_split: split[B][H][2][W][C] = hi/lo(act(x) * scale), dact = act'(x).   x fp32 NHWC.
+// act_split: split[B][H][2][W][C] = hi/lo(act(x) * mul * scale), dact = act'(x).   x, mul fp32 NHWC (mul optional).
 // One thread handles 4 consecutive channels (float4 in, 2 x 8-byte bf16x4 out).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) act_split_kernel(const float* __restrict__ x, int act, float scale,
-                                                        __nv_bfloat16* __restrict__ split, float* __restrict__ dact,
-                                                        size_t n_vec, int W, int C) {
+__global__ void __launch_bounds__(256) act_split_kernel(const float* __restrict__ x, const float* __restrict__ mul, int act,
+                                                        float scale, __nv_bfloat16* __restrict__ split,
+                                                        float* __restrict__ dact, size_t n_vec, int W, int C) {
     const int cv = C >> 2;  // float4 per pixel
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x) {
         size_t pix = i / cv;
@@ -23,6 +23,10 @@ __global__ void __launch_bounds__(256) act_split_kernel(const float* __restrict_
         act_both(act, v.y, a[1], d[1]);
         act_both(act, v.z, a[2], d[2]);
         act_both(act, v.w, a[3], d[3]);
+        if (mul) {
+            float4 m = reinterpret_cast<const float4*>(mul)[i];
+            a[0] = __fmul_rn(a[0], m.x); a[1] = __fmul_rn(a[1], m.y); a[2] = __fmul_rn(a[2], m.z); a[3] = __fmul_rn(a[3], m.w);
+        }
         __align__(8) __nv_bfloat16 hi[4], lo[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) split_bf16(__fmul_rn(a[k], scale), hi[k], lo[k]);
@@ -34,12 +38,12 @@ __global__ void __launch_bounds__(256) act_split_kernel(const float* __restrict_
     }
 }
 
-void launch_act_split(const float* x, int act, float scale, __nv_bfloat16* split, float* dact,
+void launch_act_split(const float* x, const float* mul, int act, float scale, __nv_bfloat16* split, float* dact,
                       int B, int H, int W, int C, cudaStream_t st) {
     size_t n_vec = (size_t)B * H * W * C / 4;
     int blocks = (int)std::min<size_t>((n_vec + 255) / 256, (size_t)num_sms() * 8);
     if (blocks < 1) blocks = 1;
-    act_split_kernel<<<blocks, 256, 0, st>>>(x, act, scale, split, dact, n_vec, W, C);
+    act_split_kernel<<<blocks, 256, 0, st>>>(x, mul, act, scale, split, dact, n_vec, W, C);
     count_launch();
 }
 

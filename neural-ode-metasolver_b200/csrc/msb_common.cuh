@@ -21,7 +21,8 @@ enum { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
 //   out = base*base_coef + s*dt                                exactly the reference's order
 //         (rk_parametric_order2stage2.py:91-93: x + k1*w21*dt ; (k1*b1 + k2*b2)*dt ; rk_parametric.py:106)
 //   out_f32[idx]   <- out
-//   out_split      <- hi/lo( (act ? act(out) : out) * split_scale )     operand of the next conv
+//   out_split      <- hi/lo( (act ? act(out) : out) * split_scale * split_mul[idx] )   operand of the next conv
+//                     (split_mul: post-activation RHS backward, kbar * act'(conv2 output))
 //   dact_out[idx]  <- act'(out)
 // ---------------------------------------------------------------------------------------------
 struct EpiParams {
@@ -35,6 +36,7 @@ struct EpiParams {
     float* dact_v_out;
     const float* chan_bias;
     const float* pix_bias;
+    const float* split_mul;
     float coef[3];
     float base_coef;
     float coef_v;
@@ -52,7 +54,7 @@ __host__ inline EpiParams epi_default() {
     e.mul = nullptr; e.v_out = nullptr; e.base = nullptr;
     e.src[0] = e.src[1] = e.src[2] = nullptr;
     e.out_f32 = nullptr; e.out_split = nullptr; e.dact_out = nullptr; e.dact_v_out = nullptr;
-    e.chan_bias = nullptr; e.pix_bias = nullptr;
+    e.chan_bias = nullptr; e.pix_bias = nullptr; e.split_mul = nullptr;
     e.coef[0] = e.coef[1] = e.coef[2] = 0.f;
     e.base_coef = 1.f; e.coef_v = 1.f; e.dt = 1.f; e.split_scale = 1.f; e.pix_bias_scale = 0.f;
     e.nsrc = 0; e.act = ACT_NONE; e.act_v = ACT_NONE; e.base_is_one = 1;
@@ -172,6 +174,7 @@ __device__ __forceinline__ void epilogue_apply(const EpiParams& e, float acc, si
         act_both(e.act, out, a, d);
         if (e.dact_out) e.dact_out[idx] = d;
         if (e.out_split) {
+            if (e.split_mul) a = __fmul_rn(a, e.split_mul[idx]);
             a = __fmul_rn(a, e.split_scale);
             __nv_bfloat16 hi, lo;
             split_bf16(a, hi, lo);
@@ -191,6 +194,7 @@ template <int N> struct EpiOperands {
     float mul[N];
     float base[N];
     float src[3][N];
+    float smul[N];
 };
 
 __device__ __forceinline__ float ldg_stream(const float* p) {
@@ -220,6 +224,10 @@ __device__ __forceinline__ void epi_prefetch(const EpiParams& e, size_t idx0, in
     if (e.nsrc > 2) {
 #pragma unroll
         for (int j = 0; j < N; ++j) r.src[2][j] = ldg_stream(e.src[2] + idx0 + (size_t)j * stride);
+    }
+    if (e.split_mul) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) r.smul[j] = ldg_stream(e.split_mul + idx0 + (size_t)j * stride);
     }
 }
 
@@ -290,6 +298,10 @@ __device__ __forceinline__ void epi_finish(const EpiParams& e, const float* acc,
             for (int j = 0; j < N; ++j) e.dact_out[idx0 + (size_t)j * stride] = d[j];
         }
         if (e.out_split) {
+            if (e.split_mul) {
+#pragma unroll
+                for (int j = 0; j < N; ++j) a[j] = __fmul_rn(a[j], r.smul[j]);
+            }
 #pragma unroll
             for (int j = 0; j < N; ++j) {
                 __nv_bfloat16 hi, lo;

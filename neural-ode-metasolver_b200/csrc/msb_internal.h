@@ -18,7 +18,7 @@ int check_cuda(cudaError_t e, const char* what);   // 0 if ok, else sets error a
 struct ConvShape { int B, H, W, C; };
 
 // ---- elementwise.cu ----
-void launch_act_split(const float* x, int act, float scale, __nv_bfloat16* split, float* dact,
+void launch_act_split(const float* x, const float* mul, int act, float scale, __nv_bfloat16* split, float* dact,
                       int B, int H, int W, int C, cudaStream_t st);
 void launch_pack_w_simt(const float* w, float* out, int C, int Cin_total, int skip_in, int transpose, cudaStream_t st);
 void launch_pack_w_tc(const float* w, __nv_bfloat16* out, int C, int transpose, cudaStream_t st);

@@ -87,8 +87,8 @@ struct Carver {
 
 int validate(const MsbOdeDesc* d) {
     if (!d) { set_error("null descriptor"); return -1; }
-    if (d->rhs_kind != MSB_RHS_PREACT_NF && d->rhs_kind != MSB_RHS_MNIST_GN_T) {
-        set_error("rhs_kind %d is not implemented (supported: MSB_RHS_PREACT_NF, MSB_RHS_MNIST_GN_T forward)", d->rhs_kind);
+    if (d->rhs_kind != MSB_RHS_PREACT_NF && d->rhs_kind != MSB_RHS_POSTACT_NF && d->rhs_kind != MSB_RHS_MNIST_GN_T) {
+        set_error("rhs_kind %d is not implemented (supported: PREACT_NF, POSTACT_NF, MNIST_GN_T forward)", d->rhs_kind);
         return -1;
     }
     if (d->rhs_kind == MSB_RHS_MNIST_GN_T && d->save_tape) {
@@ -361,10 +361,14 @@ int msb_odeblock_forward(const MsbOdeDesc* d, const float* x, const float* w1, c
         if (save) return tape_slot(tape, E, n * S + i);
         return TapeSlot{A_inf, nullptr, Hs_inf, nullptr};
     };
-    // prologue: operand of the very first conv1 = act(x)
-    {
+    // pre-activation RHS : f(x) = conv2(act(conv1(act(x))))   -> conv1 reads split(act(x_i)), G0 = act'(x_i)
+    // post-activation RHS: f(x) = act(conv2(act(conv1(x))))   -> conv1 reads split(x_i); the G0 slot of the
+    //                      tape holds G2 = act'(conv2 output), needed by the backward of k_i = act(.)
+    const bool post = d->rhs_kind == MSB_RHS_POSTACT_NF;
+    const int act_in = post ? ACT_NONE : d->act;
+    {   // prologue: operand of the very first conv1
         TapeSlot s0 = slot(0, 0);
-        launch_act_split(x, d->act, 1.f, s0.A, s0.G0, d->batch, d->height, d->width, C, st);
+        launch_act_split(x, nullptr, act_in, 1.f, s0.A, post ? nullptr : s0.G0, d->batch, d->height, d->width, C, st);
     }
     const float* y_cur = x;
     for (int n = 0; n < N; ++n) {
@@ -378,7 +382,8 @@ int msb_odeblock_forward(const MsbOdeDesc* d, const float* x, const float* w1, c
             if (run_conv(engine, cur.A, wp1, e1, shp, st)) return -1;
             // conv2: k_i = conv(Hs_i, W2) and the Runge-Kutta combination that follows it
             EpiParams e2 = epi_default();
-            e2.base = y_cur; e2.dt = dt; e2.act = d->act;
+            e2.base = y_cur; e2.dt = dt; e2.act = act_in;
+            if (post) { e2.act_v = d->act; e2.dact_v_out = cur.G0; }
             if (i < S - 1) {
                 // x_{i+1} = y + (sum_j k_j w[i+1][j]) dt          (order2stage2.py:91, order3stage3.py:100-101 ...)
                 e2.v_out = kbuf[i];
@@ -386,14 +391,14 @@ int msb_odeblock_forward(const MsbOdeDesc* d, const float* x, const float* w1, c
                 for (int j = 0; j < i; ++j) { e2.src[j] = kbuf[j]; e2.coef[j] = d->w[(i + 1) * MSB_MAX_STAGES + j]; }
                 e2.coef_v = d->w[(i + 1) * MSB_MAX_STAGES + i];
                 TapeSlot nx = slot(n, i + 1);
-                e2.out_split = nx.A; e2.dact_out = nx.G0;
+                e2.out_split = nx.A; e2.dact_out = post ? nullptr : nx.G0;
             } else {
                 // y1 = y0 + (sum_j k_j b_j) dt                     (order2stage2.py:93, rk_parametric.py:106)
                 e2.nsrc = S - 1;
                 for (int j = 0; j < S - 1; ++j) { e2.src[j] = kbuf[j]; e2.coef[j] = d->b[j]; }
                 e2.coef_v = d->b[S - 1];
                 e2.out_f32 = y_next;
-                if (n < N - 1) { TapeSlot nx = slot(n + 1, 0); e2.out_split = nx.A; e2.dact_out = nx.G0; }
+                if (n < N - 1) { TapeSlot nx = slot(n + 1, 0); e2.out_split = nx.A; e2.dact_out = post ? nullptr : nx.G0; }
             }
             if (run_conv(engine, cur.Hs, wp2, e2, shp, st)) return -1;
         }
@@ -434,8 +439,11 @@ int msb_odeblock_backward(const MsbOdeDesc* d, const float* grad_y, const float*
     pack_w(engine, w2, wt2, C, 1, st);
 
     auto dt_of = [&](int n) { return d->time_grid[n + 1] - d->time_grid[n]; };
-    // kbar_S of the last step = dt * b_S * gbar
-    launch_act_split(grad_y, ACT_NONE, dt_of(N - 1) * d->b[S - 1], Kbar, nullptr, d->batch, d->height, d->width, C, st);
+    // kbar_S of the last step = dt * b_S * gbar   (post-activation RHS: times act'(conv2 output) of that stage)
+    const bool post = d->rhs_kind == MSB_RHS_POSTACT_NF;
+    auto g2_of = [&](int n, int i) { return tape_slot(const_cast<void*>(tape), E, n * S + i).G0; };
+    launch_act_split(grad_y, post ? g2_of(N - 1, S - 1) : nullptr, ACT_NONE, dt_of(N - 1) * d->b[S - 1], Kbar, nullptr,
+                     d->batch, d->height, d->width, C, st);
     const float* g_cur = grad_y;
     for (int n = N - 1; n >= 0; --n) {
         const float dt = dt_of(n);
@@ -452,7 +460,7 @@ int msb_odeblock_backward(const MsbOdeDesc* d, const float* grad_y, const float*
             if (need_w && run_wgrad(engine, DP, cur.A, acc1, shp, st)) return -1;
             // xbar_i = dgrad_W1(dP) * act'(x_i), then the adjoint stage combination
             EpiParams e4 = epi_default();
-            e4.mul = cur.G0; e4.base = g_cur;
+            e4.mul = post ? nullptr : cur.G0; e4.base = g_cur;
             if (i > 0) {
                 // kbar_{i-1} = dt b_{i-1} gbar + dt sum_{j >= i} w[j][i-1] xbar_j
                 e4.v_out = xbar[i];
@@ -463,13 +471,17 @@ int msb_odeblock_backward(const MsbOdeDesc* d, const float* grad_y, const float*
                 e4.coef_v = d->w[i * MSB_MAX_STAGES + (i - 1)];
                 e4.dt = dt;
                 e4.out_split = Kbar;
+                if (post) e4.split_mul = g2_of(n, i - 1);
             } else {
                 // ybar = gbar + sum_i xbar_i ; and kbar_S of the previous step
                 int ns = 0;
                 for (int j = S - 1; j > 0; --j) { e4.src[ns] = xbar[j]; e4.coef[ns] = 1.f; ++ns; }
                 e4.nsrc = ns;
                 e4.out_f32 = g_next;
-                if (n > 0) { e4.out_split = Kbar; e4.split_scale = dt_of(n - 1) * d->b[S - 1]; }
+                if (n > 0) {
+                    e4.out_split = Kbar; e4.split_scale = dt_of(n - 1) * d->b[S - 1];
+                    if (post) e4.split_mul = g2_of(n - 1, S - 1);
+                }
             }
             if (run_conv(engine, DP, wt1, e4, shp, st)) return -1;
         }
@@ -482,7 +494,7 @@ int msb_odeblock_backward(const MsbOdeDesc* d, const float* grad_y, const float*
 int msb_act_split(const float* x, int act, void* split_out, float* dact_out, int batch, int height, int width,
                   int channels, void* cuda_stream) {
     if (!x || !split_out || channels % 4) { set_error("msb_act_split: bad arguments"); return -1; }
-    launch_act_split(x, act, 1.f, (__nv_bfloat16*)split_out, dact_out, batch, height, width, channels, (cudaStream_t)cuda_stream);
+    launch_act_split(x, nullptr, act, 1.f, (__nv_bfloat16*)split_out, dact_out, batch, height, width, channels, (cudaStream_t)cuda_stream);
     return check_cuda(cudaGetLastError(), "act_split");
 }
 

@@ -59,7 +59,7 @@ def _run_block(case, engine, dev="cuda"):
             blk.rhs_func.conv2.weight.grad.cpu().numpy(), blk.rhs_func.nfe)
 
 
-PRE_CASES = [c for c in cases.ODE_CASES if c[5] == "preact"]
+PRE_CASES = list(cases.ODE_CASES)     # pre-activation (PreBasicBlock2) and post-activation (BasicBlock2) families
 
 
 @pytest.mark.parametrize("case", PRE_CASES, ids=[c[0] for c in PRE_CASES])
@@ -75,10 +75,23 @@ def test_ode_block_vs_reference_golden(case):
         assert max_rel(gw2.reshape(-1)[::cases.WG_STRIDE], g["gw2"]) <= TOL, engine
 
 
-def test_unsupported_rhs_raises():
-    post = [c for c in cases.ODE_CASES if c[5] == "postact"][0]
-    with pytest.raises(RuntimeError):
-        _run_block(post, "simt")
+def test_unsupported_configurations_raise():
+    msb, create_solver, MetaODEBlock, PreBasicBlock2, BasicBlock2, Identity = _mods()
+    x = torch.zeros(1, 64, 4, 32, device="cuda")
+    solver = create_solver("rk2", "u", 2, -1, 0.5, -1, torch.float32, "cuda")
+    solver.freeze_params()
+    opts = Namespace(solver_mode="standalone")
+    with pytest.raises(NotImplementedError):        # normalisation other than NF inside an ODE block
+        MetaODEBlock(PreBasicBlock2(64, norm_layer=torch.nn.BatchNorm2d, act_layer=F.gelu)).cuda()(x, [solver], opts)
+    with pytest.raises(NotImplementedError):        # activation the fused epilogue does not know
+        MetaODEBlock(PreBasicBlock2(64, norm_layer=Identity, act_layer=F.softsign)).cuda()(x, [solver], opts)
+    blk = MetaODEBlock(PreBasicBlock2(64, norm_layer=Identity, act_layer=F.gelu)).cuda()
+    solver.unfreeze_params()
+    with pytest.raises(NotImplementedError):        # d/du is not implemented
+        blk(x, [solver], opts)
+    solver.freeze_params()
+    with pytest.raises(NotImplementedError):        # intermediate output times
+        solver.integrate(blk.rhs_func, x, torch.tensor([0., 0.5, 1.]))
 
 
 @pytest.mark.parametrize("C,H,W,B", [(64, 32, 32, 3), (128, 16, 16, 5), (64, 12, 32, 2), (32, 6, 6, 4)])
