@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define MSB_ABI_VERSION 1
+#define MSB_ABI_VERSION 2
 #define MSB_MAX_STAGES 4
 
 /* right-hand-side families */
@@ -52,6 +52,14 @@ enum { MSB_ACT_NONE = 0, MSB_ACT_GELU_ERF = 1, MSB_ACT_RELU = 2 };
 enum { MSB_ENGINE_AUTO = 0,     /* tcgen05 when the shape is covered by it, else the SIMT CUDA engine */
        MSB_ENGINE_TCGEN05 = 1,  /* implicit-GEMM on tcgen05/TMEM fed by TMA (sm_100a) */
        MSB_ENGINE_SIMT = 2      /* plain fp32 FFMA CUDA kernels (any shape; validation / small shapes) */ };
+
+/* Butcher tableau of one solver of a stacked solver axis (same meaning as MsbOdeDesc.c/b/w). */
+typedef struct MsbTableau {
+    float c[MSB_MAX_STAGES];
+    float b[MSB_MAX_STAGES];
+    float w[MSB_MAX_STAGES * MSB_MAX_STAGES];
+} MsbTableau;
+#define MSB_MAX_SOLVERS 8
 
 /* One ODE-block integration problem.  All scalar arrays are HOST values, read during the call. */
 typedef struct MsbOdeDesc {
@@ -66,7 +74,12 @@ typedef struct MsbOdeDesc {
     float w[MSB_MAX_STAGES * MSB_MAX_STAGES]; /* row-major lower-triangular stage matrix w[i][j] */
     const float* time_grid;           /* HOST pointer, n_steps+1 grid points (rk_parametric.py:93-96) */
     int32_t save_tape;                /* 1: record what backward needs into `tape` */
-    int32_t reserved;
+    /* Stacked solver axis (solver ensembling, cifar10/layers.py:190-205; model ensembling, fgsm.py:135-143):
+     * n_solvers = K > 1 integrates K equal slices of the batch, slice s (images [s*batch/K, (s+1)*batch/K))
+     * with tableau solver_tableaus[s], in the SAME launches -- all solvers share stages, n_steps and time_grid.
+     * 0 or 1: one solver, tableau = c/b/w above. */
+    int32_t n_solvers;
+    const MsbTableau* solver_tableaus; /* HOST pointer, n_solvers entries; ignored when n_solvers <= 1 */
 } MsbOdeDesc;
 
 /* Extra parameters of the MNIST RHS (device pointers, fp32). */

@@ -169,6 +169,36 @@ class PGD(Attack):
         return xa, y
 
 
+def ensemble_logits(models, x, kwargs_arr):
+    """[model_i(x, **kwargs_i)] for the model-ensembling loop of fgsm.py:135-137.
+
+    When every entry is the SAME network in the standalone regime and only the solver differs (how the
+    reference's notebooks build solver ensembles of one trained model), the K forward passes are folded into
+    ONE pass over a K-fold batch with a stacked solver axis in every ODE block (`solver_mode='stacked'`):
+    slice k of the batch is integrated by solver k inside the same kernel launches."""
+    from argparse import Namespace
+    from ....sopa.src.solvers.rk_parametric import RKParametricSolver
+    K = len(models)
+    same_model = all(m is models[0] for m in models)
+    solvers = []
+    for kw in kwargs_arr:
+        so, sv = kw.get("solver_options"), kw.get("solvers")
+        if (set(kw) != {"solvers", "solver_options"} or getattr(so, "solver_mode", None) != "standalone"
+                or not sv or not isinstance(sv[0], RKParametricSolver)):
+            solvers = None
+            break
+        solvers.append(sv[0])
+    stackable = (same_model and solvers is not None and 2 <= K <= 8 and x.is_cuda
+                 and all(s.n_stages == solvers[0].n_stages for s in solvers)
+                 and all(torch.equal(s.host_time_grid(torch.tensor([0., 1.])), solvers[0].host_time_grid(torch.tensor([0., 1.])))
+                         for s in solvers))
+    if not stackable:
+        return [m(x, **kw) for m, kw in zip(models, kwargs_arr)]
+    xs = x.unsqueeze(0).expand(K, *x.shape).reshape(K * x.shape[0], *x.shape[1:])
+    logits = models[0](xs, solvers=solvers, solver_options=Namespace(solver_mode="stacked"))
+    return list(logits.view(K, x.shape[0], -1).unbind(0))
+
+
 class FGSM2Ensemble(Attack2Ensemble):
     """FGSM on the NLL of the averaged softmax of several models / solvers (fgsm.py:109-155)."""
 
@@ -183,8 +213,8 @@ class FGSM2Ensemble(Attack2Ensemble):
         x01 = self.norm.unnormalize(x)
         xa = x01.clone().detach().requires_grad_(True)
         probs = 0
-        for model, kwargs in zip(self.models, kwargs_arr):
-            probs = probs + torch.softmax(model(self.norm.normalize(xa), **kwargs), dim=1)
+        for logits in ensemble_logits(list(self.models), self.norm.normalize(xa), kwargs_arr):
+            probs = probs + torch.softmax(logits, dim=1)
         probs = probs / len(self.models)
         loss = self.loss_fn(torch.log(probs), y)
         grad = _input_gradient(loss, xa)

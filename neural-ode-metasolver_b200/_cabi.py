@@ -10,6 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmetasolver_b200.so")
 
 MSB_MAX_STAGES = 4
+ABI_VERSION = 2
 RHS_PREACT_NF, RHS_POSTACT_NF, RHS_MNIST_GN_T = 0, 1, 2
 ACT_NONE, ACT_GELU_ERF, ACT_RELU = 0, 1, 2
 ENGINE_AUTO, ENGINE_TCGEN05, ENGINE_SIMT = 0, 1, 2
@@ -23,6 +24,14 @@ EXPORTS = [
 ]
 
 
+MSB_MAX_SOLVERS = 8
+
+
+class MsbTableau(ctypes.Structure):
+    _fields_ = [("c", ctypes.c_float * MSB_MAX_STAGES), ("b", ctypes.c_float * MSB_MAX_STAGES),
+                ("w", ctypes.c_float * (MSB_MAX_STAGES * MSB_MAX_STAGES))]
+
+
 class MsbOdeDesc(ctypes.Structure):
     _fields_ = [
         ("rhs_kind", ctypes.c_int32), ("act", ctypes.c_int32), ("engine", ctypes.c_int32),
@@ -31,7 +40,8 @@ class MsbOdeDesc(ctypes.Structure):
         ("c", ctypes.c_float * MSB_MAX_STAGES), ("b", ctypes.c_float * MSB_MAX_STAGES),
         ("w", ctypes.c_float * (MSB_MAX_STAGES * MSB_MAX_STAGES)),
         ("time_grid", ctypes.POINTER(ctypes.c_float)),
-        ("save_tape", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("save_tape", ctypes.c_int32), ("n_solvers", ctypes.c_int32),
+        ("solver_tableaus", ctypes.POINTER(MsbTableau)),
     ]
 
 
@@ -84,7 +94,7 @@ def lib():
                         "(or __graft_entry__.build()). There is no CPU / cuDNN path to fall back to." % LIB_PATH)
                 l = ctypes.CDLL(LIB_PATH)
                 _declare(l)
-                if l.msb_abi_version() != 1:
+                if l.msb_abi_version() != ABI_VERSION:
                     raise RuntimeError("metasolver_b200: ABI version mismatch")
                 _lib = l
     return _lib

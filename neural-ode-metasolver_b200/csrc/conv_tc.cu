@@ -319,7 +319,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
                 // ---- fused RK epilogue on the 8 owned pixels ----
                 const size_t pix = ((size_t)n * H + h) * WIMG + w0;
                 const size_t split0 = (((size_t)n * H + h) * 2) * plane_stride + (size_t)w0 * C + c;
-                epi_finish<kPXO, ACT>(epi, v, cur, pix * C + c, C, split0, plane_stride);
+                epi_finish<kPXO, ACT>(epi, epi_coef(epi, n), v, cur, pix * C + c, C, split0, plane_stride);
             };
             static_assert(NCHUNK % 2 == 0, "chunk pipeline is unrolled by two");
 #pragma unroll

@@ -8,8 +8,10 @@ namespace msb {
 // act_split: split[B][H][2][W][C] = hi/lo(act(x) * mul * scale), dact = act'(x).   x, mul fp32 NHWC (mul optional).
 // One thread handles 4 consecutive channels (float4 in, 2 x 8-byte bf16x4 out).
 // ---------------------------------------------------------------------------------------------
+struct SliceScales { float s[kMaxSlices]; };
 __global__ void __launch_bounds__(256) act_split_kernel(const float* __restrict__ x, const float* __restrict__ mul, int act,
-                                                        float scale, __nv_bfloat16* __restrict__ split,
+                                                        SliceScales scales, size_t vec_per_slice,
+                                                        __nv_bfloat16* __restrict__ split,
                                                         float* __restrict__ dact, size_t n_vec, int W, int C) {
     const int cv = C >> 2;  // float4 per pixel
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x) {
@@ -18,6 +20,7 @@ __global__ void __launch_bounds__(256) act_split_kernel(const float* __restrict_
         size_t row = pix / W;  // = n*H + h
         int w = (int)(pix - row * W);
         float4 v = reinterpret_cast<const float4*>(x)[i];
+        const float scale = scales.s[vec_per_slice ? i / vec_per_slice : 0];
         float a[4], d[4];
         act_both(act, v.x, a[0], d[0]);
         act_both(act, v.y, a[1], d[1]);
@@ -40,10 +43,19 @@ __global__ void __launch_bounds__(256) act_split_kernel(const float* __restrict_
 
 void launch_act_split(const float* x, const float* mul, int act, float scale, __nv_bfloat16* split, float* dact,
                       int B, int H, int W, int C, cudaStream_t st) {
+    launch_act_split_sliced(x, mul, act, &scale, 1, split, dact, B, H, W, C, st);
+}
+
+// per-slice scale: the batch is n_slices equal slices (stacked solver axis), slice s is scaled by scales[s]
+void launch_act_split_sliced(const float* x, const float* mul, int act, const float* scales_host, int n_slices,
+                             __nv_bfloat16* split, float* dact, int B, int H, int W, int C, cudaStream_t st) {
+    SliceScales scales;
+    for (int i = 0; i < kMaxSlices; ++i) scales.s[i] = scales_host[i < n_slices ? i : 0];
     size_t n_vec = (size_t)B * H * W * C / 4;
+    size_t vec_per_slice = n_slices > 1 ? n_vec / n_slices : 0;
     int blocks = (int)std::min<size_t>((n_vec + 255) / 256, (size_t)num_sms() * 8);
     if (blocks < 1) blocks = 1;
-    act_split_kernel<<<blocks, 256, 0, st>>>(x, mul, act, scale, split, dact, n_vec, W, C);
+    act_split_kernel<<<blocks, 256, 0, st>>>(x, mul, act, scales, vec_per_slice, split, dact, n_vec, W, C);
     count_launch();
 }
 

@@ -25,6 +25,17 @@ enum { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
 //                     (split_mul: post-activation RHS backward, kbar * act'(conv2 output))
 //   dact_out[idx]  <- act'(out)
 // ---------------------------------------------------------------------------------------------
+// Scalar coefficients of one epilogue.  With a stacked solver axis (solver ensembling: K solvers
+// integrate K copies of the batch in one launch) every slice of the batch has its own set.
+constexpr int kMaxSlices = 8;
+struct EpiCoef {
+    float coef[3];
+    float coef_v;
+    float dt;
+    float base_coef;
+    float split_scale;
+};
+
 struct EpiParams {
     const float* mul;
     float* v_out;
@@ -37,12 +48,9 @@ struct EpiParams {
     const float* chan_bias;
     const float* pix_bias;
     const float* split_mul;
-    float coef[3];
-    float base_coef;
-    float coef_v;
-    float dt;
-    float split_scale;
+    EpiCoef k[kMaxSlices];     // k[0] unless slice_batch > 0: then slice = image index / slice_batch
     float pix_bias_scale;
+    int slice_batch;
     int nsrc;
     int act;
     int act_v;
@@ -55,10 +63,17 @@ __host__ inline EpiParams epi_default() {
     e.src[0] = e.src[1] = e.src[2] = nullptr;
     e.out_f32 = nullptr; e.out_split = nullptr; e.dact_out = nullptr; e.dact_v_out = nullptr;
     e.chan_bias = nullptr; e.pix_bias = nullptr; e.split_mul = nullptr;
-    e.coef[0] = e.coef[1] = e.coef[2] = 0.f;
-    e.base_coef = 1.f; e.coef_v = 1.f; e.dt = 1.f; e.split_scale = 1.f; e.pix_bias_scale = 0.f;
+    for (int i = 0; i < kMaxSlices; ++i) {
+        e.k[i].coef[0] = e.k[i].coef[1] = e.k[i].coef[2] = 0.f;
+        e.k[i].base_coef = 1.f; e.k[i].coef_v = 1.f; e.k[i].dt = 1.f; e.k[i].split_scale = 1.f;
+    }
+    e.pix_bias_scale = 0.f; e.slice_batch = 0;
     e.nsrc = 0; e.act = ACT_NONE; e.act_v = ACT_NONE; e.base_is_one = 1;
     return e;
+}
+
+__device__ __forceinline__ const EpiCoef& epi_coef(const EpiParams& e, int n) {
+    return e.k[e.slice_batch > 0 ? n / e.slice_batch : 0];
 }
 
 // ---- activations -----------------------------------------------------------------------------
@@ -142,6 +157,7 @@ __device__ __forceinline__ size_t split_index(int n, int h, int plane, int w, in
 // idx = NHWC linear index of the element, (n,h,w,c) its coordinates.
 __device__ __forceinline__ void epilogue_apply(const EpiParams& e, float acc, size_t idx,
                                                int n, int h, int w, int c, int H, int W, int C) {
+    const EpiCoef& k = epi_coef(e, n);
     float v = acc;
     if (e.chan_bias) v = __fadd_rn(v, e.chan_bias[c]);
     if (e.pix_bias) v = __fadd_rn(v, __fmul_rn(e.pix_bias_scale, e.pix_bias[((size_t)h * W + w) * C + c]));
@@ -155,17 +171,17 @@ __device__ __forceinline__ void epilogue_apply(const EpiParams& e, float acc, si
     if (e.v_out) e.v_out[idx] = v;
     float s;
     if (e.nsrc == 0) {
-        s = __fmul_rn(v, e.coef_v);
+        s = __fmul_rn(v, k.coef_v);
     } else {
-        s = __fmul_rn(e.src[0][idx], e.coef[0]);
-        if (e.nsrc > 1) s = __fadd_rn(s, __fmul_rn(e.src[1][idx], e.coef[1]));
-        if (e.nsrc > 2) s = __fadd_rn(s, __fmul_rn(e.src[2][idx], e.coef[2]));
-        s = __fadd_rn(s, __fmul_rn(v, e.coef_v));
+        s = __fmul_rn(e.src[0][idx], k.coef[0]);
+        if (e.nsrc > 1) s = __fadd_rn(s, __fmul_rn(e.src[1][idx], k.coef[1]));
+        if (e.nsrc > 2) s = __fadd_rn(s, __fmul_rn(e.src[2][idx], k.coef[2]));
+        s = __fadd_rn(s, __fmul_rn(v, k.coef_v));
     }
-    float out = __fmul_rn(s, e.dt);
+    float out = __fmul_rn(s, k.dt);
     if (e.base) {
         float bv = e.base[idx];
-        if (!e.base_is_one) bv = __fmul_rn(bv, e.base_coef);
+        if (!e.base_is_one) bv = __fmul_rn(bv, k.base_coef);
         out = __fadd_rn(bv, out);
     }
     if (e.out_f32) e.out_f32[idx] = out;
@@ -175,7 +191,7 @@ __device__ __forceinline__ void epilogue_apply(const EpiParams& e, float acc, si
         if (e.dact_out) e.dact_out[idx] = d;
         if (e.out_split) {
             if (e.split_mul) a = __fmul_rn(a, e.split_mul[idx]);
-            a = __fmul_rn(a, e.split_scale);
+            a = __fmul_rn(a, k.split_scale);
             __nv_bfloat16 hi, lo;
             split_bf16(a, hi, lo);
             e.out_split[split_index(n, h, 0, w, c, H, W, C)] = hi;
@@ -235,8 +251,8 @@ __device__ __forceinline__ void epi_prefetch(const EpiParams& e, size_t idx0, in
 // ACT = the activation `e.act` as a compile-time constant.  Every phase is a fully unrolled,
 // straight-line loop over the N independent elements (uniform flags are tested outside the loops).
 template <int N, int ACT>
-__device__ __forceinline__ void epi_finish(const EpiParams& e, const float* acc, const EpiOperands<N>& r, size_t idx0,
-                                           int stride, size_t split_idx0, size_t plane_stride) {
+__device__ __forceinline__ void epi_finish(const EpiParams& e, const EpiCoef& k, const float* acc, const EpiOperands<N>& r,
+                                           size_t idx0, int stride, size_t split_idx0, size_t plane_stride) {
     float v[N], o[N];
 #pragma unroll
     for (int j = 0; j < N; ++j) v[j] = acc[j];
@@ -259,30 +275,30 @@ __device__ __forceinline__ void epi_finish(const EpiParams& e, const float* acc,
     }
     if (e.nsrc == 0) {
 #pragma unroll
-        for (int j = 0; j < N; ++j) o[j] = __fmul_rn(v[j], e.coef_v);
+        for (int j = 0; j < N; ++j) o[j] = __fmul_rn(v[j], k.coef_v);
     } else {
 #pragma unroll
-        for (int j = 0; j < N; ++j) o[j] = __fmul_rn(r.src[0][j], e.coef[0]);
+        for (int j = 0; j < N; ++j) o[j] = __fmul_rn(r.src[0][j], k.coef[0]);
         if (e.nsrc > 1) {
 #pragma unroll
-            for (int j = 0; j < N; ++j) o[j] = __fadd_rn(o[j], __fmul_rn(r.src[1][j], e.coef[1]));
+            for (int j = 0; j < N; ++j) o[j] = __fadd_rn(o[j], __fmul_rn(r.src[1][j], k.coef[1]));
         }
         if (e.nsrc > 2) {
 #pragma unroll
-            for (int j = 0; j < N; ++j) o[j] = __fadd_rn(o[j], __fmul_rn(r.src[2][j], e.coef[2]));
+            for (int j = 0; j < N; ++j) o[j] = __fadd_rn(o[j], __fmul_rn(r.src[2][j], k.coef[2]));
         }
 #pragma unroll
-        for (int j = 0; j < N; ++j) o[j] = __fadd_rn(o[j], __fmul_rn(v[j], e.coef_v));
+        for (int j = 0; j < N; ++j) o[j] = __fadd_rn(o[j], __fmul_rn(v[j], k.coef_v));
     }
 #pragma unroll
-    for (int j = 0; j < N; ++j) o[j] = __fmul_rn(o[j], e.dt);
+    for (int j = 0; j < N; ++j) o[j] = __fmul_rn(o[j], k.dt);
     if (e.base) {
         if (e.base_is_one) {
 #pragma unroll
             for (int j = 0; j < N; ++j) o[j] = __fadd_rn(r.base[j], o[j]);
         } else {
 #pragma unroll
-            for (int j = 0; j < N; ++j) o[j] = __fadd_rn(__fmul_rn(r.base[j], e.base_coef), o[j]);
+            for (int j = 0; j < N; ++j) o[j] = __fadd_rn(__fmul_rn(r.base[j], k.base_coef), o[j]);
         }
     }
     if (e.out_f32) {
@@ -305,7 +321,7 @@ __device__ __forceinline__ void epi_finish(const EpiParams& e, const float* acc,
 #pragma unroll
             for (int j = 0; j < N; ++j) {
                 __nv_bfloat16 hi, lo;
-                split_bf16(__fmul_rn(a[j], e.split_scale), hi, lo);
+                split_bf16(__fmul_rn(a[j], k.split_scale), hi, lo);
                 e.out_split[split_idx0 + (size_t)j * stride] = hi;
                 e.out_split[split_idx0 + plane_stride + (size_t)j * stride] = lo;
             }

@@ -20,6 +20,8 @@ struct ConvShape { int B, H, W, C; };
 // ---- elementwise.cu ----
 void launch_act_split(const float* x, const float* mul, int act, float scale, __nv_bfloat16* split, float* dact,
                       int B, int H, int W, int C, cudaStream_t st);
+void launch_act_split_sliced(const float* x, const float* mul, int act, const float* scales_host, int n_slices,
+                             __nv_bfloat16* split, float* dact, int B, int H, int W, int C, cudaStream_t st);
 void launch_pack_w_simt(const float* w, float* out, int C, int Cin_total, int skip_in, int transpose, cudaStream_t st);
 void launch_pack_w_tc(const float* w, __nv_bfloat16* out, int C, int transpose, cudaStream_t st);
 void launch_wgrad_reduce(const float* partial, int nparts, float* grad_w, int C, int accumulate, cudaStream_t st);

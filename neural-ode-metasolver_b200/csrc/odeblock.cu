@@ -15,6 +15,7 @@
 
 namespace msb {
 
+static_assert(kMaxSlices == MSB_MAX_SOLVERS, "EpiParams slice table must match the ABI");
 static thread_local std::string g_err;
 static std::atomic<uint64_t> g_launches{0};
 
@@ -105,7 +106,32 @@ int validate(const MsbOdeDesc* d) {
         return -1;
     }
     if (!d->time_grid) { set_error("time_grid is NULL"); return -1; }
+    if (d->n_solvers < 0 || d->n_solvers > kMaxSlices) { set_error("n_solvers must be 0..%d (got %d)", kMaxSlices, d->n_solvers); return -1; }
+    if (d->n_solvers > 1) {
+        if (!d->solver_tableaus) { set_error("n_solvers = %d but solver_tableaus is NULL", d->n_solvers); return -1; }
+        if (d->batch % d->n_solvers) { set_error("batch %d is not divisible into %d solver slices", d->batch, d->n_solvers); return -1; }
+        if (d->rhs_kind == MSB_RHS_MNIST_GN_T) { set_error("the stacked solver axis is not implemented for the MNIST right-hand side"); return -1; }
+    }
     return 0;
+}
+
+// Tableau of every solver slice (one entry when there is no stacked solver axis).
+struct Tabs {
+    int K;
+    MsbTableau t[kMaxSlices];
+    int slice_batch;     // images per slice, 0 when K == 1 (EpiParams::slice_batch)
+};
+Tabs make_tabs(const MsbOdeDesc* d) {
+    Tabs r;
+    r.K = d->n_solvers > 1 ? d->n_solvers : 1;
+    if (r.K == 1) {
+        memcpy(r.t[0].c, d->c, sizeof(d->c)); memcpy(r.t[0].b, d->b, sizeof(d->b)); memcpy(r.t[0].w, d->w, sizeof(d->w));
+        r.slice_batch = 0;
+    } else {
+        for (int s = 0; s < r.K; ++s) r.t[s] = d->solver_tableaus[s];
+        r.slice_batch = d->batch / r.K;
+    }
+    return r;
 }
 
 // Resolve MSB_ENGINE_AUTO.  Both engines are this library's own CUDA kernels; there is no
@@ -307,17 +333,17 @@ static int mnist_forward(const MsbOdeDesc* d, const float* x, const MsbMnistPara
             c2.chan_bias = mp->conv_b[1]; c2.pix_bias = tapmap[1]; c2.pix_bias_scale = ti; c2.out_f32 = PQ;
             if (run_conv(MSB_ENGINE_SIMT, Hs, wp[1], c2, shp, st)) return -1;
             EpiParams g3 = epi_default();                       // k_i = GN3(.) and the RK combination
-            g3.base = y_cur; g3.dt = dt;
+            g3.base = y_cur; g3.k[0].dt = dt;
             if (i < S - 1) {
                 g3.v_out = kbuf[i];
                 g3.nsrc = i;
-                for (int j = 0; j < i; ++j) { g3.src[j] = kbuf[j]; g3.coef[j] = d->w[(i + 1) * MSB_MAX_STAGES + j]; }
-                g3.coef_v = d->w[(i + 1) * MSB_MAX_STAGES + i];
+                for (int j = 0; j < i; ++j) { g3.src[j] = kbuf[j]; g3.k[0].coef[j] = d->w[(i + 1) * MSB_MAX_STAGES + j]; }
+                g3.k[0].coef_v = d->w[(i + 1) * MSB_MAX_STAGES + i];
                 g3.out_f32 = xbuf;
             } else {
                 g3.nsrc = S - 1;
-                for (int j = 0; j < S - 1; ++j) { g3.src[j] = kbuf[j]; g3.coef[j] = d->b[j]; }
-                g3.coef_v = d->b[S - 1];
+                for (int j = 0; j < S - 1; ++j) { g3.src[j] = kbuf[j]; g3.k[0].coef[j] = d->b[j]; }
+                g3.k[0].coef_v = d->b[S - 1];
                 g3.out_f32 = y_next;
             }
             if (launch_groupnorm_epi(PQ, mp->norm_w[2], mp->norm_b[2], g3, shp, mp->groups, mp->eps, st)) return -1;
@@ -356,6 +382,7 @@ int msb_odeblock_forward(const MsbOdeDesc* d, const float* x, const float* w1, c
 
     pack_w(engine, w1, wp1, C, 0, st);
     pack_w(engine, w2, wp2, C, 0, st);
+    const Tabs tabs = make_tabs(d);
 
     auto slot = [&](int n, int i) {
         if (save) return tape_slot(tape, E, n * S + i);
@@ -382,21 +409,28 @@ int msb_odeblock_forward(const MsbOdeDesc* d, const float* x, const float* w1, c
             if (run_conv(engine, cur.A, wp1, e1, shp, st)) return -1;
             // conv2: k_i = conv(Hs_i, W2) and the Runge-Kutta combination that follows it
             EpiParams e2 = epi_default();
-            e2.base = y_cur; e2.dt = dt; e2.act = act_in;
+            e2.base = y_cur; e2.act = act_in; e2.slice_batch = tabs.slice_batch;
+            for (int q = 0; q < tabs.K; ++q) e2.k[q].dt = dt;
             if (post) { e2.act_v = d->act; e2.dact_v_out = cur.G0; }
             if (i < S - 1) {
                 // x_{i+1} = y + (sum_j k_j w[i+1][j]) dt          (order2stage2.py:91, order3stage3.py:100-101 ...)
                 e2.v_out = kbuf[i];
                 e2.nsrc = i;
-                for (int j = 0; j < i; ++j) { e2.src[j] = kbuf[j]; e2.coef[j] = d->w[(i + 1) * MSB_MAX_STAGES + j]; }
-                e2.coef_v = d->w[(i + 1) * MSB_MAX_STAGES + i];
+                for (int j = 0; j < i; ++j) e2.src[j] = kbuf[j];
+                for (int q = 0; q < tabs.K; ++q) {
+                    for (int j = 0; j < i; ++j) e2.k[q].coef[j] = tabs.t[q].w[(i + 1) * MSB_MAX_STAGES + j];
+                    e2.k[q].coef_v = tabs.t[q].w[(i + 1) * MSB_MAX_STAGES + i];
+                }
                 TapeSlot nx = slot(n, i + 1);
                 e2.out_split = nx.A; e2.dact_out = post ? nullptr : nx.G0;
             } else {
                 // y1 = y0 + (sum_j k_j b_j) dt                     (order2stage2.py:93, rk_parametric.py:106)
                 e2.nsrc = S - 1;
-                for (int j = 0; j < S - 1; ++j) { e2.src[j] = kbuf[j]; e2.coef[j] = d->b[j]; }
-                e2.coef_v = d->b[S - 1];
+                for (int j = 0; j < S - 1; ++j) e2.src[j] = kbuf[j];
+                for (int q = 0; q < tabs.K; ++q) {
+                    for (int j = 0; j < S - 1; ++j) e2.k[q].coef[j] = tabs.t[q].b[j];
+                    e2.k[q].coef_v = tabs.t[q].b[S - 1];
+                }
                 e2.out_f32 = y_next;
                 if (n < N - 1) { TapeSlot nx = slot(n + 1, 0); e2.out_split = nx.A; e2.dact_out = post ? nullptr : nx.G0; }
             }
@@ -437,13 +471,18 @@ int msb_odeblock_backward(const MsbOdeDesc* d, const float* grad_y, const float*
 
     pack_w(engine, w1, wt1, C, 1, st);
     pack_w(engine, w2, wt2, C, 1, st);
+    const Tabs tabs = make_tabs(d);
 
     auto dt_of = [&](int n) { return d->time_grid[n + 1] - d->time_grid[n]; };
     // kbar_S of the last step = dt * b_S * gbar   (post-activation RHS: times act'(conv2 output) of that stage)
     const bool post = d->rhs_kind == MSB_RHS_POSTACT_NF;
     auto g2_of = [&](int n, int i) { return tape_slot(const_cast<void*>(tape), E, n * S + i).G0; };
-    launch_act_split(grad_y, post ? g2_of(N - 1, S - 1) : nullptr, ACT_NONE, dt_of(N - 1) * d->b[S - 1], Kbar, nullptr,
-                     d->batch, d->height, d->width, C, st);
+    {
+        float scales[kMaxSlices];
+        for (int q = 0; q < tabs.K; ++q) scales[q] = dt_of(N - 1) * tabs.t[q].b[S - 1];
+        launch_act_split_sliced(grad_y, post ? g2_of(N - 1, S - 1) : nullptr, ACT_NONE, scales, tabs.K, Kbar, nullptr,
+                                d->batch, d->height, d->width, C, st);
+    }
     const float* g_cur = grad_y;
     for (int n = N - 1; n >= 0; --n) {
         const float dt = dt_of(n);
@@ -460,26 +499,34 @@ int msb_odeblock_backward(const MsbOdeDesc* d, const float* grad_y, const float*
             if (need_w && run_wgrad(engine, DP, cur.A, acc1, shp, st)) return -1;
             // xbar_i = dgrad_W1(dP) * act'(x_i), then the adjoint stage combination
             EpiParams e4 = epi_default();
-            e4.mul = post ? nullptr : cur.G0; e4.base = g_cur;
+            e4.mul = post ? nullptr : cur.G0; e4.base = g_cur; e4.slice_batch = tabs.slice_batch;
             if (i > 0) {
                 // kbar_{i-1} = dt b_{i-1} gbar + dt sum_{j >= i} w[j][i-1] xbar_j
                 e4.v_out = xbar[i];
-                e4.base_coef = dt * d->b[i - 1]; e4.base_is_one = 0;
+                e4.base_is_one = 0;
                 int ns = 0;
-                for (int j = S - 1; j > i; --j) { e4.src[ns] = xbar[j]; e4.coef[ns] = d->w[j * MSB_MAX_STAGES + (i - 1)]; ++ns; }
+                for (int j = S - 1; j > i; --j) e4.src[ns++] = xbar[j];
                 e4.nsrc = ns;
-                e4.coef_v = d->w[i * MSB_MAX_STAGES + (i - 1)];
-                e4.dt = dt;
+                for (int q = 0; q < tabs.K; ++q) {
+                    EpiCoef& k = e4.k[q];
+                    k.base_coef = dt * tabs.t[q].b[i - 1];
+                    int m = 0;
+                    for (int j = S - 1; j > i; --j) k.coef[m++] = tabs.t[q].w[j * MSB_MAX_STAGES + (i - 1)];
+                    k.coef_v = tabs.t[q].w[i * MSB_MAX_STAGES + (i - 1)];
+                    k.dt = dt;
+                }
                 e4.out_split = Kbar;
                 if (post) e4.split_mul = g2_of(n, i - 1);
             } else {
                 // ybar = gbar + sum_i xbar_i ; and kbar_S of the previous step
                 int ns = 0;
-                for (int j = S - 1; j > 0; --j) { e4.src[ns] = xbar[j]; e4.coef[ns] = 1.f; ++ns; }
+                for (int j = S - 1; j > 0; --j) e4.src[ns++] = xbar[j];
                 e4.nsrc = ns;
+                for (int q = 0; q < tabs.K; ++q) e4.k[q].coef[0] = e4.k[q].coef[1] = e4.k[q].coef[2] = 1.f;
                 e4.out_f32 = g_next;
                 if (n > 0) {
-                    e4.out_split = Kbar; e4.split_scale = dt_of(n - 1) * d->b[S - 1];
+                    e4.out_split = Kbar;
+                    for (int q = 0; q < tabs.K; ++q) e4.k[q].split_scale = dt_of(n - 1) * tabs.t[q].b[S - 1];
                     if (post) e4.split_mul = g2_of(n - 1, S - 1);
                 }
             }

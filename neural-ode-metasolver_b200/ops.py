@@ -62,7 +62,14 @@ class OdeProblem:
     def __init__(self, rhs_kind, act, tableau, time_grid, engine=None):
         self.rhs_kind = rhs_kind
         self.act = act
-        self.tableau = tableau              # dict(stages, c, b, w) of python floats
+        # dict(stages, c, b, w) of python floats -- or a list of them (stacked solver axis: slice s of
+        # the batch is integrated with tableau s; all must share the number of stages)
+        self.tableaus = list(tableau) if isinstance(tableau, (list, tuple)) else [tableau]
+        self.tableau = self.tableaus[0]
+        if len(self.tableaus) > _cabi.MSB_MAX_SOLVERS:
+            raise ValueError("at most %d stacked solvers per launch" % _cabi.MSB_MAX_SOLVERS)
+        if any(t["stages"] != self.tableau["stages"] for t in self.tableaus):
+            raise ValueError("stacked solvers must have the same number of stages")
         self.time_grid = [float(v) for v in time_grid]
         self.engine = _cabi.ENGINES[engine or _default_engine[0]]
         if len(self.time_grid) < 2:
@@ -84,7 +91,21 @@ class OdeProblem:
         grid = (ctypes.c_float * len(self.time_grid))(*self.time_grid)
         d.time_grid = ctypes.cast(grid, ctypes.POINTER(ctypes.c_float))
         d.save_tape = 1 if save_tape else 0
-        d._keepalive = grid
+        d._keepalive = [grid]
+        K = len(self.tableaus)
+        if K > 1:
+            if B % K:
+                raise ValueError("batch %d is not divisible into %d solver slices" % (B, K))
+            tabs = (_cabi.MsbTableau * K)()
+            for q, t in enumerate(self.tableaus):
+                for i in range(s):
+                    tabs[q].c[i] = t["c"][i]
+                    tabs[q].b[i] = t["b"][i]
+                    for j in range(s):
+                        tabs[q].w[i * _cabi.MSB_MAX_STAGES + j] = t["w"][i][j]
+            d.n_solvers = K
+            d.solver_tableaus = ctypes.cast(tabs, ctypes.POINTER(_cabi.MsbTableau))
+            d._keepalive.append(tabs)
         return d
 
 
@@ -168,9 +189,23 @@ class _OdeBlockFn(torch.autograd.Function):
 def ode_block_integrate(x, w1, w2, tableau, time_grid, rhs_kind=_cabi.RHS_PREACT_NF, act=_cabi.ACT_GELU_ERF,
                         engine=None):
     """y(t_end) of dy/dt = f(y) with f = conv2(act(conv1(act(y)))) integrated on `time_grid`
-    by the explicit RK method `tableau`; differentiable w.r.t. x, w1, w2."""
+    by the explicit RK method `tableau`; differentiable w.r.t. x, w1, w2.
+
+    `tableau` may be a list of K tableaus (same stage count): the batch is then K equal slices along
+    dim 0 and slice s is integrated by solver s, all inside the same kernel launches (stacked solver axis)."""
     prob = OdeProblem(rhs_kind, act, tableau, time_grid, engine)
     return _OdeBlockFn.apply(x, w1, w2, prob)
+
+
+def ode_block_integrate_stacked(x, w1, w2, tableaus, time_grid, rhs_kind=_cabi.RHS_PREACT_NF,
+                                act=_cabi.ACT_GELU_ERF, engine=None):
+    """Solver ensembling on a stacked solver axis: integrate the SAME state x (B,C,H,W) with each of the K
+    solvers in one batched set of launches -> (K, B, C, H, W).  Replaces the reference's sequential loop over
+    solvers (cifar10/layers.py:198-203); each slice is bit-identical to the one-solver call."""
+    K = len(tableaus)
+    xs = x.unsqueeze(0).expand(K, *x.shape).reshape(K * x.shape[0], *x.shape[1:])
+    y = ode_block_integrate(xs, w1, w2, list(tableaus), time_grid, rhs_kind=rhs_kind, act=act, engine=engine)
+    return y.view(K, *x.shape)
 
 
 def ode_block_integrate_mnist(x, params, tableau, time_grid, groups, eps=1e-5):

@@ -15,6 +15,7 @@ import torch.nn.functional as F
 from .utils import Identity
 from ..... import _cabi
 from .....ops import ode_block_integrate
+from ...solvers.rk_parametric import can_stack, integrate_stacked
 
 _EULER_STEP = dict(stages=1, c=[0.0], b=[1.0], w=[[0.0]])
 
@@ -183,11 +184,23 @@ class MetaODEBlock(nn.Module):
                 if weights is None:
                     weights = [1. / n for _ in range(n)]
                 y = None
+                if can_stack(solvers, self.rhs_func, t):
+                    # stacked solver axis: the N solvers' stage evaluations are ONE batched set of launches
+                    ys = integrate_stacked(solvers, self.rhs_func, x, t)
+                    for k, wi in enumerate(weights):
+                        yi = wi * ys[k]
+                        y = yi if y is None else y + yi
+                    return y
                 for wi, solver in zip(weights, solvers):
                     yi = wi * solver.integrate(self.rhs_func, x=x, t=t)
                     y = yi if y is None else y + yi
             else:
                 y = solvers[0].integrate(self.rhs_func, x=x, t=t)
+        elif mode == 'stacked':
+            # extension (not in the reference): the batch holds len(solvers) equal slices, slice k is
+            # integrated by solvers[k] -- K model copies that differ only in their solver, evaluated as one
+            # model on a K-fold batch (model ensembling, MegaAdversarial/src/attacks/fgsm.py:135-143)
+            return integrate_stacked(solvers, self.rhs_func, x, t, replicate=False)
         else:
             raise ValueError("unknown solver_mode %r" % (mode,))
         return y[-1, :, :, :, :]

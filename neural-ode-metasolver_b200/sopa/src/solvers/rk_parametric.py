@@ -14,7 +14,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from ....ops import ode_block_integrate, ode_block_integrate_mnist
+from ....ops import ode_block_integrate, ode_block_integrate_mnist, ode_block_integrate_stacked
 from .... import _cabi
 
 
@@ -135,6 +135,18 @@ class RKParametricSolver(object, metaclass=abc.ABCMeta):
 
     def integrate(self, rhs_func, x, t):
         """-> Tensor[len(t), B, C, H, W]; differentiable w.r.t. x and rhs_func's conv weights."""
+        spec, grid = self._fused_args(rhs_func, t)
+        if spec["rhs_kind"] == _cabi.RHS_MNIST_GN_T:
+            y = ode_block_integrate_mnist(x, spec["params"], self._host_tableau, grid.tolist(), spec["groups"],
+                                          spec["eps"])
+        else:
+            y = ode_block_integrate(x, spec["w1"], spec["w2"], self._host_tableau, grid.tolist(),
+                                    rhs_kind=spec["rhs_kind"], act=spec["act"], engine=spec.get("engine"))
+        rhs_func.nfe += self.n_stages * (len(grid) - 1)               # cifar10/layers.py:149
+        return torch.stack((x, y))
+
+    def _fused_args(self, rhs_func, t):
+        """Checks shared by integrate() and integrate_stacked(); -> (rhs spec, host time grid)."""
         if len(t) != 2:
             raise NotImplementedError("metasolver_b200: integrate() returns the solution at t[0] and t[-1] only "
                                       "(MetaODEBlock uses t=[0,1]); intermediate output times are not supported")
@@ -145,22 +157,51 @@ class RKParametricSolver(object, metaclass=abc.ABCMeta):
         if spec is None:
             raise NotImplementedError("metasolver_b200: %s is not a right-hand side the fused CUDA path knows; "
                                       "there is no unfused fallback" % type(rhs_func).__name__)
-        spec = spec()
-        grid = self.host_time_grid(t)
-        if spec["rhs_kind"] == _cabi.RHS_MNIST_GN_T:
-            y = ode_block_integrate_mnist(x, spec["params"], self._host_tableau, grid.tolist(), spec["groups"],
-                                          spec["eps"])
-        else:
-            y = ode_block_integrate(x, spec["w1"], spec["w2"], self._host_tableau, grid.tolist(),
-                                    rhs_kind=spec["rhs_kind"], act=spec["act"], engine=spec.get("engine"))
-        rhs_func.nfe += self.n_stages * (len(grid) - 1)               # cifar10/layers.py:149
-        return torch.stack((x, y))
+        return spec(), self.host_time_grid(t)
 
     def print_is_requires_grad(self):
         print('\nIs requires grad? (RK solver)')
         for name, p in self.__dict__.items():
             if hasattr(p, 'requires_grad'):
                 print(name, p.requires_grad)
+
+
+def can_stack(solvers, rhs_func, t):
+    """True when `solvers` can share one set of launches on a stacked solver axis: same stage count,
+    bit-identical time grids, a CIFAR-family right-hand side, at most MSB_MAX_SOLVERS of them."""
+    if not (2 <= len(solvers) <= _cabi.MSB_MAX_SOLVERS):
+        return False
+    spec = getattr(rhs_func, "fused_rhs_spec", None)
+    if spec is None or spec()["rhs_kind"] == _cabi.RHS_MNIST_GN_T:
+        return False
+    if any(s.n_stages != solvers[0].n_stages for s in solvers):
+        return False
+    g0 = solvers[0].host_time_grid(t)
+    return all(torch.equal(s.host_time_grid(t), g0) for s in solvers[1:])
+
+
+def integrate_stacked(solvers, rhs_func, x, t, replicate=True):
+    """Stacked solver axis: every solver's stage evaluations run in the SAME kernel launches.
+
+    replicate=True  (solver ensembling, cifar10/layers.py:198-203): x is (B,C,H,W); every solver integrates
+                    the same x -> Tensor[K,B,C,H,W] of end states, slice k bit-identical to
+                    solvers[k].integrate(rhs_func, x, t)[-1].
+    replicate=False (model ensembling, fgsm.py:135-143, with the K model copies folded into the batch):
+                    x is (K*B,C,H,W), slice k along dim 0 is integrated by solvers[k] -> Tensor[K*B,C,H,W]."""
+    if not can_stack(solvers, rhs_func, t):
+        raise ValueError("metasolver_b200: these solvers cannot share a stacked solver axis "
+                         "(need equal stage counts and identical time grids, 2..%d solvers)" % _cabi.MSB_MAX_SOLVERS)
+    spec, grid = solvers[0]._fused_args(rhs_func, t)
+    for s in solvers[1:]:
+        s._fused_args(rhs_func, t)
+    tabs = [s.host_tableau() for s in solvers]
+    kw = dict(rhs_kind=spec["rhs_kind"], act=spec["act"], engine=spec.get("engine"))
+    if replicate:
+        y = ode_block_integrate_stacked(x, spec["w1"], spec["w2"], tabs, grid.tolist(), **kw)
+    else:
+        y = ode_block_integrate(x, spec["w1"], spec["w2"], tabs, grid.tolist(), **kw)
+    rhs_func.nfe += sum(s.n_stages for s in solvers) * (len(grid) - 1)
+    return y
 
 
 def _init_params(self, parameterization, u0, v0, dtype, device, with_v):

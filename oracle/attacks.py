@@ -71,3 +71,18 @@ def pgd(model, x, y, eps, lr, n_iter, mean, std, start_noise=None):
             xa = normalize(xa, mean, std)
         xa = xa.detach()
     return xa
+
+
+def fgsm_2ensemble(models, x, y, eps, mean, std):
+    """FGSM2Ensemble, fgsm.py:128-155: FGSM on NLL(log(mean_i softmax(model_i(x)))).
+    `models` = list of callables x -> logits (same network, different solvers, in the reference's use)."""
+    x01 = unnormalize(x, mean, std)
+    xa = x01.clone().detach().requires_grad_(True)
+    probs = 0
+    for m in models:
+        probs = probs + torch.softmax(m(normalize(xa, mean, std)), dim=1)
+    probs = probs / len(models)
+    loss = F.nll_loss(torch.log(probs), y)
+    grad = torch.autograd.grad([loss], [xa])[0]
+    xa = torch.clamp(xa + eps * grad.sign(), 0, 1)
+    return normalize(xa, mean, std).detach()

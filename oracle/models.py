@@ -14,7 +14,7 @@ import torch
 import torch.nn.functional as F
 
 from .detrand import det_uniform
-from .rk import integrate, rhs_preact
+from .rk import integrate, rhs_preact, ode_block_forward
 
 PREMETANODE10_KEYS = [
     ("conv1.weight", (64, 3, 3, 3)),
@@ -60,8 +60,10 @@ def _pre_basic_block(x, w1, w2, w_sc, stride):
     return out
 
 
-def premetanode10_forward(p, x, tableau, grid, counters=None, taps=None):
-    """x: normalised images (B,3,32,32) -> logits (B,10).  `taps` (dict) collects ODE-block outputs."""
+def premetanode10_forward(p, x, tableau, grid, counters=None, taps=None, ensemble_weights=None):
+    """x: normalised images (B,3,32,32) -> logits (B,10).  `taps` (dict) collects ODE-block outputs.
+    `tableau` / `grid` may be lists: every ODE block then runs the solver-ensemble regime
+    (ensemble_prob = 1, cifar10/layers.py:190-203) with `ensemble_weights` (None = uniform)."""
     t = torch.tensor([0, 1]).float()
     out = F.gelu(F.conv2d(x, p["conv1.weight"], None, 1, 1))                       # :411-413
     for li, stride in ((1, 1), (2, 2)):
@@ -70,7 +72,11 @@ def premetanode10_forward(p, x, tableau, grid, counters=None, taps=None):
                                p.get(pre + "blocks_res.0.shortcut.0.weight"), stride)
         rhs = rhs_preact(p[pre + "blocks_ode.0.rhs_func.conv1.weight"], p[pre + "blocks_ode.0.rhs_func.conv2.weight"],
                          "gelu", None if counters is None else counters[li - 1])
-        out = integrate(tableau, rhs, out, t, **grid)[-1]                           # MetaODEBlock :176-177,207
+        if isinstance(tableau, (list, tuple)):
+            out = ode_block_forward(out, rhs, list(tableau), list(grid), "ensemble", ensemble_prob=1.0,
+                                    ensemble_weights=ensemble_weights, t=t)
+        else:
+            out = integrate(tableau, rhs, out, t, **grid)[-1]                       # MetaODEBlock :176-177,207
         if taps is not None:
             taps[pre + "blocks_ode.0"] = out
     out = F.adaptive_avg_pool2d(out, (1, 1)).flatten(1)                             # :390-392, 425

@@ -53,3 +53,9 @@ def ode_case_inputs(C, H, W, B, seed=0):
 
 REGIME_SOLVERS = [("rk2", "u", 4, -1, 0.3, -1), ("rk2", "u", 4, -1, 0.5, -1), ("rk2", "u", 2, -1, 2 / 3., -1),
                   ("rk4", "u2", 2, -1, 1 / 3., -1)]
+
+# BASELINE config 3: solver ensembling / model ensembling over 4 RK2 u values (and RK4), 8 steps each
+C3_RK2_SOLVERS = [("rk2", "u", 8, -1, 0.3, -1), ("rk2", "u", 8, -1, 0.5, -1), ("rk2", "u", 8, -1, 2 / 3., -1),
+                  ("rk2", "u", 8, -1, 1.0, -1)]
+C3_RK4_SOLVERS = [("rk4", "u2", 8, -1, 1 / 3., -1), ("rk4", "uv", 8, -1, 1 / 3., 2 / 3.)]
+C3_WEIGHTS = [0.4, 0.3, 0.2, 0.1]

@@ -189,3 +189,65 @@ def test_attacks_and_fgsm_random_train_step_bit_exact():
     for k in g.files:
         if k.startswith("train_g_"):
             assert np.array_equal(p[k[8:]].grad.numpy().reshape(-1)[::cases.WG_STRIDE], g[k]), k
+
+
+# ---------------------------------------------------------------- BASELINE config 3: ensembles
+def _c3_tabs(svs):
+    tabs = []
+    for s in svs:
+        v = None if s[5] == -1 else np.float32(s[5])
+        tabs.append(butcher_tableau(s[0], s[1], np.float32(s[4]), v))
+    return tabs, [_grid(s) for s in svs]
+
+
+@pytest.mark.parametrize("tag,shape,svs,weights", [
+    ("c64_rk2x4_uniform", (64, 8, 32, 2), cases.C3_RK2_SOLVERS, None),
+    ("c64_rk2x4_weighted", (64, 8, 32, 2), cases.C3_RK2_SOLVERS, cases.C3_WEIGHTS),
+    ("c64_rk4x2_uniform", (64, 8, 32, 2), cases.C3_RK4_SOLVERS, None),
+    ("c128_rk2x4_uniform", (128, 8, 16, 1), cases.C3_RK2_SOLVERS, None)])
+def test_solver_ensemble_block_bit_exact(tag, shape, svs, weights):
+    g = golden("ensemble_c3.npz")
+    x, w1, w2, r = [torch.from_numpy(a) for a in cases.ode_case_inputs(*shape)]
+    x.requires_grad_(True); w1.requires_grad_(True); w2.requires_grad_(True)
+    tabs, grids = _c3_tabs(svs)
+    cnt = RhsCounter()
+    y = oracle.ode_block_forward(x, rhs_preact(w1, w2, counter=cnt), tabs, grids, "ensemble", ensemble_prob=1.0,
+                                 ensemble_weights=weights)
+    (y * r).sum().backward()
+    assert np.array_equal(y.detach().numpy(), g[tag + "_y"])
+    assert np.array_equal(x.grad.numpy(), g[tag + "_gx"])
+    assert np.array_equal(w1.grad.numpy().reshape(-1)[::cases.WG_STRIDE], g[tag + "_gw1"])
+    assert np.array_equal(w2.grad.numpy().reshape(-1)[::cases.WG_STRIDE], g[tag + "_gw2"])
+    assert cnt.nfe == int(g[tag + "_nfe"])
+
+
+def test_model_solver_and_model_ensembling_bit_exact():
+    from oracle import attacks as oa
+    g = golden("ensemble_c3.npz")
+    p = det_premetanode10_params()
+    for v in p.values():
+        v.requires_grad_(True)
+    img = torch.from_numpy(oracle.det_uniform((4, 3, 32, 32), 920, 0.0, 1.0))
+    mean = torch.tensor(CIFAR_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(CIFAR_STD).view(1, 3, 1, 1)
+    labels = torch.tensor([3, 1, 4, 1])
+    tabs, grids = _c3_tabs(cases.C3_RK2_SOLVERS)
+    x = ((img - mean) / std).requires_grad_(True)
+    logits = premetanode10_forward(p, x, tabs, grids)
+    F.cross_entropy(logits, labels).backward()
+    assert np.array_equal(logits.detach().numpy(), g["model_solver_ens_logits"])
+    assert np.array_equal(x.grad.numpy(), g["model_solver_ens_gx"])
+    for k in g.files:
+        if k.startswith("model_solver_ens_g_"):
+            name = k[len("model_solver_ens_g_"):]
+            assert np.array_equal(p[name].grad.numpy().reshape(-1)[::cases.WG_STRIDE], g[k]), k
+    # model ensembling: the same network under each of the 4 solvers, softmax-averaged (fgsm.py:135-143)
+    x = (img - mean) / std
+    models = [lambda inp, t=t, gr=gr: premetanode10_forward(p, inp, t, gr) for t, gr in zip(tabs, grids)]
+    with torch.no_grad():
+        probs = 0
+        for m in models:
+            probs = probs + torch.softmax(m(x), dim=1)
+        assert np.array_equal((probs / len(models)).numpy(), g["model_ens_probs"])
+    xa = oa.fgsm_2ensemble(models, x, labels, 8 / 255., CIFAR_MEAN, CIFAR_STD)
+    assert np.array_equal(xa.numpy(), g["model_ens_fgsm_x"])
