@@ -119,6 +119,40 @@ int msb_odeblock_backward(const MsbOdeDesc* d, const float* grad_y, const float*
                           const void* tape, size_t tape_bytes, float* grad_x, float* grad_w1, float* grad_w2,
                           void* workspace, size_t workspace_bytes, void* cuda_stream);
 
+/* ---- non-ODE layers of the CIFAR networks on the same engines ------------------------
+ * Stem: y = act(conv3x3(x, w)), 3 input channels -> `channels`, stride 1, pad 1, no bias
+ * (MetaNODE.forward, sopa/src/models/odenet_cifar10/layers.py:411-413).  x: fp32 NHWC (B,H,W,3);
+ * y, dact_out (= act'(pre-activation), NULL when no backward will follow): fp32 NHWC (B,H,W,channels). */
+int msb_stem_forward(const float* x_nhwc, const float* w_oihw, int act, float* y, float* dact_out,
+                     int batch, int height, int width, int channels, void* cuda_stream);
+size_t msb_stem_backward_workspace_bytes(int channels);
+/* grad_w (OIHW, overwritten) may be NULL (input-gradient-only attacks); grad_x (NHWC, 3 channels) may be NULL. */
+int msb_stem_backward(const float* grad_y, const float* dact, const float* x_nhwc, const float* w_oihw,
+                      float* grad_w, float* grad_x, int batch, int height, int width, int channels,
+                      void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* Strided pre-activation residual block  y = conv2(act(conv1_s2(act(x)))) + conv1x1_s2(x)
+ * (PreBasicBlock with stride 2 and the 1x1 shortcut, layers.py:54-81, NF norm): in_channels -> out_channels
+ * = 2*in_channels, (H,W) -> (H/2,W/2).  w1: (Co,Ci,3,3), w2: (Co,Co,3,3), wsc: (Co,Ci,1,1), fp32 OIHW. */
+typedef struct MsbDownDesc {
+    int32_t act;                      /* MSB_ACT_* */
+    int32_t engine;                   /* MSB_ENGINE_* */
+    int32_t batch, height, width;     /* input size (even height and width) */
+    int32_t in_channels, out_channels;
+    int32_t save_tape;
+} MsbDownDesc;
+size_t msb_downblock_workspace_bytes(const MsbDownDesc* d);
+size_t msb_downblock_tape_bytes(const MsbDownDesc* d);
+size_t msb_downblock_bwd_workspace_bytes(const MsbDownDesc* d);
+int msb_downblock_forward(const MsbDownDesc* d, const float* x, const float* w1, const float* w2, const float* wsc,
+                          float* y_out, void* workspace, size_t workspace_bytes, void* tape, size_t tape_bytes,
+                          void* cuda_stream);
+/* grad_w1 / grad_w2 / grad_wsc: all given (overwritten) or all NULL (input-gradient only). */
+int msb_downblock_backward(const MsbDownDesc* d, const float* grad_y, const float* w1, const float* w2,
+                           const float* wsc, const void* tape, size_t tape_bytes, float* grad_x, float* grad_w1,
+                           float* grad_w2, float* grad_wsc, void* workspace, size_t workspace_bytes,
+                           void* cuda_stream);
+
 /* ---- building blocks, exported so the parity tests can exercise each kernel through the C ABI ---- */
 
 /* split[B][H][2][W][C] = hi/lo(act(x)) ; dact (optional, fp32 NHWC) = act'(x). */

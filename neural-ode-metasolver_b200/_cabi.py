@@ -20,6 +20,9 @@ EXPORTS = [
     "msb_abi_version", "msb_last_error", "msb_device_supports_tcgen05", "msb_shape_supports_tcgen05",
     "msb_odeblock_workspace_bytes", "msb_odeblock_tape_bytes", "msb_odeblock_bwd_workspace_bytes",
     "msb_odeblock_forward", "msb_odeblock_backward", "msb_act_split", "msb_conv3x3",
+    "msb_stem_forward", "msb_stem_backward_workspace_bytes", "msb_stem_backward",
+    "msb_downblock_workspace_bytes", "msb_downblock_tape_bytes", "msb_downblock_bwd_workspace_bytes",
+    "msb_downblock_forward", "msb_downblock_backward",
     "msb_conv3x3_workspace_bytes", "msb_wgrad3x3", "msb_wgrad3x3_workspace_bytes", "msb_launch_count", "msb_profile_enable", "msb_profile_read",
 ]
 
@@ -43,6 +46,12 @@ class MsbOdeDesc(ctypes.Structure):
         ("save_tape", ctypes.c_int32), ("n_solvers", ctypes.c_int32),
         ("solver_tableaus", ctypes.POINTER(MsbTableau)),
     ]
+
+
+class MsbDownDesc(ctypes.Structure):
+    _fields_ = [("act", ctypes.c_int32), ("engine", ctypes.c_int32), ("batch", ctypes.c_int32),
+                ("height", ctypes.c_int32), ("width", ctypes.c_int32), ("in_channels", ctypes.c_int32),
+                ("out_channels", ctypes.c_int32), ("save_tape", ctypes.c_int32)]
 
 
 class MsbMnistParams(ctypes.Structure):
@@ -70,6 +79,16 @@ def _declare(lib):
         f.restype = sz
     lib.msb_odeblock_forward.argtypes = [dp, vp, vp, vp, ctypes.POINTER(MsbMnistParams), vp, vp, sz, vp, sz, vp]
     lib.msb_odeblock_backward.argtypes = [dp, vp, vp, vp, vp, sz, vp, vp, vp, vp, sz, vp]
+    lib.msb_stem_forward.argtypes = [vp, vp, i32, vp, vp, i32, i32, i32, i32, vp]
+    lib.msb_stem_backward_workspace_bytes.argtypes = [i32]
+    lib.msb_stem_backward_workspace_bytes.restype = sz
+    lib.msb_stem_backward.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, sz, vp]
+    ddp = ctypes.POINTER(MsbDownDesc)
+    for f in (lib.msb_downblock_workspace_bytes, lib.msb_downblock_tape_bytes, lib.msb_downblock_bwd_workspace_bytes):
+        f.argtypes = [ddp]
+        f.restype = sz
+    lib.msb_downblock_forward.argtypes = [ddp, vp, vp, vp, vp, vp, vp, sz, vp, sz, vp]
+    lib.msb_downblock_backward.argtypes = [ddp, vp, vp, vp, vp, vp, sz, vp, vp, vp, vp, vp, sz, vp]
     lib.msb_act_split.argtypes = [vp, i32, vp, vp, i32, i32, i32, i32, vp]
     lib.msb_conv3x3.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, sz, vp]
     lib.msb_conv3x3_workspace_bytes.argtypes = [i32]

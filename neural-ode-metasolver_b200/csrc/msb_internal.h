@@ -31,6 +31,21 @@ int launch_groupnorm_epi(const float* x, const float* gamma, const float* beta, 
                          int groups, float eps, cudaStream_t st);
 void launch_time_tapmap(const float* w, float* tapmap, int H, int W, int C, cudaStream_t st);
 
+// ---- netlayers.cu (stem, strided residual block re-indexing) ----
+int launch_stem_fwd(const float* x, const float* w, int act, float* y, float* dact, int B, int H, int W, int C,
+                    cudaStream_t st);
+int stem_wgrad_blocks();
+int launch_stem_wgrad(const float* gy, const float* dact, const float* x, float* partial, float* gw, int B, int H, int W,
+                      int C, cudaStream_t st);
+int launch_stem_dgrad(const float* gy, const float* dact, const float* w, float* gx, int B, int H, int W, int C,
+                      cudaStream_t st);
+void launch_s2d_act_split(const float* x, int act, __nv_bfloat16* T0, __nv_bfloat16* T1, __nv_bfloat16* Tsc, float* G0,
+                          int B, int H, int W, int Ci, cudaStream_t st);
+void launch_d2s_grad(const float* gT0, const float* gT1, const float* gTsc, const float* G0, float* gx, int B, int H, int W,
+                     int Ci, cudaStream_t st);
+void launch_down_weights_build(const float* w1, const float* wsc, float* Wd, int Ci, int Co, cudaStream_t st);
+void launch_down_weights_gather(const float* gWd, float* gw1, float* gwsc, int Ci, int Co, cudaStream_t st);
+
 // ---- conv_simt.cu : plain fp32 FFMA engine (any C multiple of 4, any H, W) ----
 //   out-epilogue(conv3x3(split_in, w_packed[tap][ci][co]))
 int launch_conv3x3_simt(const __nv_bfloat16* split_in, const float* w_packed, const EpiParams& epi,

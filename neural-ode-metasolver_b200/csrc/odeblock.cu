@@ -12,6 +12,7 @@
 
 #include "metasolver_b200.h"
 #include "msb_internal.h"
+#include "msb_host.h"
 
 namespace msb {
 
@@ -71,20 +72,62 @@ static void prof_end(int id, cudaStream_t st) {
     if (id >= 0) cudaEventRecord(g_prof.ev[2 * id + 1], st);
 }
 
-namespace {
-
-inline size_t align_up(size_t x, size_t a = 1024) { return (x + a - 1) / a * a; }
-
-struct Carver {
-    char* base; size_t off, cap;
-    Carver(void* p, size_t c) : base((char*)p), off(0), cap(c) {}
-    template <typename T> T* take(size_t bytes) {
-        size_t o = align_up(off);
-        off = o + bytes;
-        return (T*)(base + o);
+// ---- host helpers shared with blocks.cu (declared in msb_host.h) ----
+size_t packed_w_bytes(int engine, int C) {
+    return engine == MSB_ENGINE_TCGEN05 ? tc_packed_weight_bytes(C) : (size_t)9 * C * C * sizeof(float);
+}
+int resolve_engine_shape(int engine, int C, int H, int W) {
+    const bool tc_ok = tc_shape_supported(C, H, W);
+    if (engine == MSB_ENGINE_SIMT) return MSB_ENGINE_SIMT;
+    if (engine == MSB_ENGINE_TCGEN05) {
+        if (!tc_ok) { set_error("tcgen05 engine does not cover C=%d H=%d W=%d", C, H, W); return -1; }
+        return MSB_ENGINE_TCGEN05;
     }
-    bool ok() const { return off <= cap; }
-};
+    if (engine == MSB_ENGINE_AUTO) return tc_ok ? MSB_ENGINE_TCGEN05 : MSB_ENGINE_SIMT;
+    set_error("unknown engine %d", engine);
+    return -1;
+}
+double conv_flops(ConvShape s) { return 2.0 * s.B * s.H * s.W * (double)s.C * 9.0 * s.C; }
+int run_conv(int engine, const __nv_bfloat16* in, const void* wpacked, const EpiParams& e, ConvShape s, cudaStream_t st) {
+    int id = prof_begin(MSB_PROF_CONV, conv_flops(s), st);
+    int rc;
+    if (engine == MSB_ENGINE_TCGEN05) rc = launch_conv3x3_tc(in, (const __nv_bfloat16*)wpacked, e, s, st);
+    else rc = launch_conv3x3_simt(in, (const float*)wpacked, e, s, st);
+    prof_end(id, st);
+    return rc;
+}
+void pack_w(int engine, const float* w, void* out, int C, int transpose, cudaStream_t st) {
+    if (engine == MSB_ENGINE_TCGEN05) launch_pack_w_tc(w, (__nv_bfloat16*)out, C, transpose, st);
+    else launch_pack_w_simt(w, (float*)out, C, C, 0, transpose, st);
+}
+bool use_tc_wgrad(int engine, ConvShape s) { return engine == MSB_ENGINE_TCGEN05 && wgrad_tc_supported(s); }
+int wgrad_nparts(int engine, ConvShape s) {
+    return use_tc_wgrad(engine, s) ? wgrad_tc_nparts(s) : wgrad_simt_nparts(s);
+}
+// Weight-gradient accumulation over the launches of one backward pass.
+//  tcgen05: every launch adds onto the CTA-private partial slots (first launch overwrites); ONE
+//           fixed-order reduction per weight tensor at the end (wgrad_finish).
+//  SIMT   : partials are reduced into grad_w after every launch.
+int run_wgrad(int engine, const __nv_bfloat16* gout, const __nv_bfloat16* in, WgradAcc& acc, ConvShape s, cudaStream_t st) {
+    int nparts = 0, rc;
+    int id = prof_begin(MSB_PROF_WGRAD, conv_flops(s), st);
+    const bool tc = use_tc_wgrad(engine, s);
+    if (tc) rc = launch_wgrad3x3_tc(gout, in, acc.partial, &nparts, acc.launches > 0, s, st);
+    else rc = launch_wgrad3x3_simt(gout, in, acc.partial, &nparts, s, st);
+    prof_end(id, st);
+    if (rc) return rc;
+    acc.nparts = nparts;
+    if (!tc) launch_wgrad_reduce(acc.partial, nparts, acc.grad_w, s.C, acc.launches > 0, st);
+    acc.launches++;
+    return check_cuda(cudaGetLastError(), "wgrad launch");
+}
+int wgrad_finish(int engine, WgradAcc& acc, ConvShape s, cudaStream_t st) {
+    if (use_tc_wgrad(engine, s) && acc.launches > 0) launch_wgrad_reduce(acc.partial, acc.nparts, acc.grad_w, s.C, 0, st);
+    return check_cuda(cudaGetLastError(), "wgrad reduce launch");
+}
+
+
+namespace {
 
 int validate(const MsbOdeDesc* d) {
     if (!d) { set_error("null descriptor"); return -1; }
@@ -142,19 +185,10 @@ int resolve_engine(const MsbOdeDesc* d) {
         if (d->engine == MSB_ENGINE_TCGEN05) { set_error("the MNIST right-hand side runs on the SIMT engine only"); return -1; }
         return MSB_ENGINE_SIMT;
     }
-    if (d->engine == MSB_ENGINE_SIMT) return MSB_ENGINE_SIMT;
-    if (d->engine == MSB_ENGINE_TCGEN05) {
-        if (!tc_ok) { set_error("tcgen05 engine does not cover C=%d H=%d W=%d", d->channels, d->height, d->width); return -1; }
-        return MSB_ENGINE_TCGEN05;
-    }
-    if (d->engine == MSB_ENGINE_AUTO) return tc_ok ? MSB_ENGINE_TCGEN05 : MSB_ENGINE_SIMT;
-    set_error("unknown engine %d", d->engine);
-    return -1;
+    (void)tc_ok;
+    return resolve_engine_shape(d->engine, d->channels, d->height, d->width);
 }
 
-size_t packed_w_bytes(int engine, int C) {
-    return engine == MSB_ENGINE_TCGEN05 ? tc_packed_weight_bytes(C) : (size_t)9 * C * C * sizeof(float);
-}
 size_t state_elems(const MsbOdeDesc* d) { return (size_t)d->batch * d->height * d->width * d->channels; }
 
 struct TapeSlot { __nv_bfloat16* A; float* G0; __nv_bfloat16* Hs; float* G1; };
@@ -162,46 +196,6 @@ TapeSlot tape_slot(void* tape, size_t E, int slot) {
     char* p = (char*)tape + (size_t)slot * 4 * align_up(E * 4);
     size_t q = align_up(E * 4);
     return TapeSlot{(__nv_bfloat16*)p, (float*)(p + q), (__nv_bfloat16*)(p + 2 * q), (float*)(p + 3 * q)};
-}
-
-double conv_flops(ConvShape s) { return 2.0 * s.B * s.H * s.W * (double)s.C * 9.0 * s.C; }
-int run_conv(int engine, const __nv_bfloat16* in, const void* wpacked, const EpiParams& e, ConvShape s, cudaStream_t st) {
-    int id = prof_begin(MSB_PROF_CONV, conv_flops(s), st);
-    int rc;
-    if (engine == MSB_ENGINE_TCGEN05) rc = launch_conv3x3_tc(in, (const __nv_bfloat16*)wpacked, e, s, st);
-    else rc = launch_conv3x3_simt(in, (const float*)wpacked, e, s, st);
-    prof_end(id, st);
-    return rc;
-}
-void pack_w(int engine, const float* w, void* out, int C, int transpose, cudaStream_t st) {
-    if (engine == MSB_ENGINE_TCGEN05) launch_pack_w_tc(w, (__nv_bfloat16*)out, C, transpose, st);
-    else launch_pack_w_simt(w, (float*)out, C, C, 0, transpose, st);
-}
-bool use_tc_wgrad(int engine, ConvShape s) { return engine == MSB_ENGINE_TCGEN05 && wgrad_tc_supported(s); }
-int wgrad_nparts(int engine, ConvShape s) {
-    return use_tc_wgrad(engine, s) ? wgrad_tc_nparts(s) : wgrad_simt_nparts(s);
-}
-// Weight-gradient accumulation over the launches of one backward pass.
-//  tcgen05: every launch adds onto the CTA-private partial slots (first launch overwrites); ONE
-//           fixed-order reduction per weight tensor at the end (wgrad_finish).
-//  SIMT   : partials are reduced into grad_w after every launch.
-struct WgradAcc { float* partial; float* grad_w; int launches; int nparts; };
-int run_wgrad(int engine, const __nv_bfloat16* gout, const __nv_bfloat16* in, WgradAcc& acc, ConvShape s, cudaStream_t st) {
-    int nparts = 0, rc;
-    int id = prof_begin(MSB_PROF_WGRAD, conv_flops(s), st);
-    const bool tc = use_tc_wgrad(engine, s);
-    if (tc) rc = launch_wgrad3x3_tc(gout, in, acc.partial, &nparts, acc.launches > 0, s, st);
-    else rc = launch_wgrad3x3_simt(gout, in, acc.partial, &nparts, s, st);
-    prof_end(id, st);
-    if (rc) return rc;
-    acc.nparts = nparts;
-    if (!tc) launch_wgrad_reduce(acc.partial, nparts, acc.grad_w, s.C, acc.launches > 0, st);
-    acc.launches++;
-    return check_cuda(cudaGetLastError(), "wgrad launch");
-}
-int wgrad_finish(int engine, WgradAcc& acc, ConvShape s, cudaStream_t st) {
-    if (use_tc_wgrad(engine, s) && acc.launches > 0) launch_wgrad_reduce(acc.partial, acc.nparts, acc.grad_w, s.C, 0, st);
-    return check_cuda(cudaGetLastError(), "wgrad reduce launch");
 }
 
 }  // namespace

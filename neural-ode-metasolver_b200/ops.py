@@ -243,6 +243,134 @@ def ode_block_integrate_mnist(x, params, tableau, time_grid, groups, eps=1e-5):
     return y
 
 
+# --------------------------------------------------------------------------- non-ODE layers
+def _input_only():
+    return getattr(_state, "input_only", False)
+
+
+class _StemFn(torch.autograd.Function):
+    """y = act(conv3x3(x, w)), 3 -> C channels (MetaNODE stem, cifar10/layers.py:411-413)."""
+
+    @staticmethod
+    def forward(ctx, x, w, act):
+        lib = _cabi.lib()
+        dev = x.device
+        need_grad = any(ctx.needs_input_grad[:2])
+        B, _, H, W = x.shape
+        C = w.shape[0]
+        with torch.cuda.device(dev):
+            xc = x.detach().contiguous(memory_format=torch.channels_last)
+            wc = w.detach().contiguous()
+            y = torch.empty((B, C, H, W), dtype=torch.float32, device=dev).contiguous(memory_format=torch.channels_last)
+            dact = torch.empty_like(y) if need_grad else None
+            _cabi.check(lib.msb_stem_forward(_ptr(xc), _ptr(wc), act, _ptr(y), _ptr(dact), B, H, W, C, _stream(dev)),
+                        "stem forward")
+        ctx.save_for_backward(xc, wc, dact)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _cabi.lib()
+        xc, wc, dact = ctx.saved_tensors
+        dev = gy.device
+        B, _, H, W = xc.shape
+        C = wc.shape[0]
+        need_w = ctx.needs_input_grad[1] and not _input_only()
+        need_x = ctx.needs_input_grad[0]
+        with torch.cuda.device(dev):
+            gyc = gy.contiguous(memory_format=torch.channels_last)
+            ws_bytes = lib.msb_stem_backward_workspace_bytes(C)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            gw = torch.empty_like(wc) if need_w else None
+            gx = torch.empty_like(xc) if need_x else None
+            _cabi.check(lib.msb_stem_backward(_ptr(gyc), _ptr(dact), _ptr(xc), _ptr(wc), _ptr(gw), _ptr(gx), B, H, W, C,
+                                              _ptr(ws), ws_bytes, _stream(dev)), "stem backward")
+        return gx, gw, None
+
+
+def stem_conv_act(x, w, act=_cabi.ACT_GELU_ERF):
+    """act(conv2d(x, w, stride 1, padding 1)) for a 3-channel input; differentiable w.r.t. x and w."""
+    if not x.is_cuda:
+        raise RuntimeError("metasolver_b200: CUDA tensors required (got %s)" % x.device)
+    if x.dtype != torch.float32 or w.dtype != torch.float32 or x.dim() != 4 or x.shape[1] != 3 \
+            or tuple(w.shape[1:]) != (3, 3, 3):
+        raise RuntimeError("metasolver_b200: stem expects fp32 (B,3,H,W) input and (C,3,3,3) weight")
+    return _StemFn.apply(x, w, act)
+
+
+class _DownBlockFn(torch.autograd.Function):
+    """Strided pre-activation residual block (PreBasicBlock, stride 2, 1x1 shortcut; cifar10/layers.py:54-81)."""
+
+    @staticmethod
+    def _desc(x_shape, co, act, engine, save):
+        d = _cabi.MsbDownDesc()
+        d.act, d.engine = act, engine
+        d.batch, d.in_channels, d.height, d.width = x_shape
+        d.out_channels = co
+        d.save_tape = 1 if save else 0
+        return d
+
+    @staticmethod
+    def forward(ctx, x, w1, w2, wsc, act, engine):
+        lib = _cabi.lib()
+        dev = x.device
+        need_grad = any(ctx.needs_input_grad[:4])
+        B, Ci, H, W = x.shape
+        Co = w1.shape[0]
+        with torch.cuda.device(dev):
+            xc = x.detach().contiguous(memory_format=torch.channels_last)
+            ws_ = [w.detach().contiguous() for w in (w1, w2, wsc)]
+            d = _DownBlockFn._desc(tuple(x.shape), Co, act, engine, need_grad)
+            ws_bytes = lib.msb_downblock_workspace_bytes(ctypes.byref(d))
+            if ws_bytes == 0:
+                _cabi.check(-1, "downblock workspace query")
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            tape, tape_bytes = None, 0
+            if need_grad:
+                tape_bytes = lib.msb_downblock_tape_bytes(ctypes.byref(d))
+                tape = torch.empty(tape_bytes, dtype=torch.uint8, device=dev)
+            y = torch.empty((B, Co, H // 2, W // 2), dtype=torch.float32, device=dev).contiguous(
+                memory_format=torch.channels_last)
+            _cabi.check(lib.msb_downblock_forward(ctypes.byref(d), _ptr(xc), _ptr(ws_[0]), _ptr(ws_[1]), _ptr(ws_[2]),
+                                                  _ptr(y), _ptr(ws), ws_bytes, _ptr(tape), tape_bytes, _stream(dev)),
+                        "downblock forward")
+        ctx.tape, ctx.tape_bytes, ctx.shape, ctx.co, ctx.act, ctx.engine = tape, tape_bytes, tuple(x.shape), Co, act, engine
+        ctx.save_for_backward(*ws_)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _cabi.lib()
+        w1, w2, wsc = ctx.saved_tensors
+        if ctx.tape is None:
+            raise RuntimeError("metasolver_b200: backward called but no tape was recorded")
+        dev = gy.device
+        need_w = any(ctx.needs_input_grad[1:4]) and not _input_only()
+        with torch.cuda.device(dev):
+            gyc = gy.contiguous(memory_format=torch.channels_last)
+            d = _DownBlockFn._desc(ctx.shape, ctx.co, ctx.act, ctx.engine, True)
+            ws_bytes = lib.msb_downblock_bwd_workspace_bytes(ctypes.byref(d))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            B, Ci, H, W = ctx.shape
+            gx = torch.empty((B, Ci, H, W), dtype=torch.float32, device=dev).contiguous(memory_format=torch.channels_last)
+            gws = [torch.empty_like(w) if need_w else None for w in (w1, w2, wsc)]
+            _cabi.check(lib.msb_downblock_backward(ctypes.byref(d), _ptr(gyc), _ptr(w1), _ptr(w2), _ptr(wsc), _ptr(ctx.tape),
+                                                   ctx.tape_bytes, _ptr(gx), _ptr(gws[0]), _ptr(gws[1]), _ptr(gws[2]),
+                                                   _ptr(ws), ws_bytes, _stream(dev)), "downblock backward")
+        ctx.tape = None
+        return gx, gws[0], gws[1], gws[2], None, None
+
+
+def resblock_down(x, w1, w2, wsc, act=_cabi.ACT_GELU_ERF, engine=None):
+    """conv2(act(conv1_stride2(act(x)))) + conv1x1_stride2(x); w1 (2C,C,3,3), w2 (2C,2C,3,3), wsc (2C,C,1,1)."""
+    if not x.is_cuda:
+        raise RuntimeError("metasolver_b200: CUDA tensors required (got %s)" % x.device)
+    C = x.shape[1]
+    if tuple(w1.shape) != (2 * C, C, 3, 3) or tuple(w2.shape) != (2 * C, 2 * C, 3, 3) or tuple(wsc.shape) != (2 * C, C, 1, 1):
+        raise RuntimeError("metasolver_b200: strided block weight shapes do not match a %d -> %d block" % (C, 2 * C))
+    return _DownBlockFn.apply(x, w1, w2, wsc, act, _cabi.ENGINES[engine or _default_engine[0]])
+
+
 # --------------------------------------------------------------------------- single-kernel entry points
 def act_split(x_cl, act=_cabi.ACT_NONE, want_dact=False):
     """x_cl: (B,C,H,W) channels_last fp32 -> (split uint16-view tensor [B,H,2,W,C], dact or None)."""

@@ -14,7 +14,7 @@ import torch.nn.functional as F
 
 from .utils import Identity
 from ..... import _cabi
-from .....ops import ode_block_integrate
+from .....ops import ode_block_integrate, resblock_down, stem_conv_act
 from ...solvers.rk_parametric import can_stack, integrate_stacked
 
 _EULER_STEP = dict(stages=1, c=[0.0], b=[1.0], w=[[0.0]])
@@ -96,10 +96,29 @@ class PreBasicBlock(nn.Module):
         B, C, H, W = x.shape
         return self.conv1.stride == (1, 1) and bool(_cabi.lib().msb_shape_supports_tcgen05(C, H, W))
 
+    def _fusable_down(self, x):
+        """Stride-2 block with the 1x1 stride-2 shortcut, C -> 2C: runs on the library's own convolution
+        engines after a space-to-depth re-indexing (ops.resblock_down) instead of cuDNN."""
+        if not (x.is_cuda and x.dtype == torch.float32 and len(self.shortcut) == 1):
+            return False
+        if not (isinstance(self.bn1, Identity) and isinstance(self.bn2, Identity)):
+            return False
+        convs = (self.conv1, self.conv2, self.shortcut[0])
+        if self.act not in (F.gelu, F.relu) or any(type(c) is not nn.Conv2d for c in convs):
+            return False
+        if any(hasattr(c, "weight_orig") or hasattr(c, "weight_g") for c in convs):
+            return False
+        B, C, H, W = x.shape
+        return (self.conv1.stride == (2, 2) and self.conv1.out_channels == 2 * C and H % 2 == 0 and W % 2 == 0
+                and C % 4 == 0 and self.shortcut[0].stride == (2, 2))
+
     def forward(self, x):
         if self._fusable(x):
             return ode_block_integrate(x, self.conv1.weight, self.conv2.weight, _EULER_STEP, (0.0, 1.0),
                                        rhs_kind=_cabi.RHS_PREACT_NF, act=_act_code(self.act))
+        if self._fusable_down(x):
+            return resblock_down(x, self.conv1.weight, self.conv2.weight, self.shortcut[0].weight,
+                                 act=_act_code(self.act))
         out = self.conv1(self.act(self.bn1(x)))
         out = self.conv2(self.act(self.bn2(out)))
         return out + self.shortcut(x)
@@ -276,6 +295,13 @@ class MetaNODE(nn.Module):
         self.fc_layers = nn.Sequential(nn.AdaptiveAvgPool2d((1, 1)), Flatten(),
                                        nn.Linear(self.n_features_linear * resblock.expansion, num_classes))
 
+    def _fusable_stem(self, x):
+        c = self.conv1
+        return (x.is_cuda and x.dtype == torch.float32 and not self.is_preactivation and isinstance(self.bn1, Identity)
+                and self.act in (F.gelu, F.relu) and type(c) is nn.Conv2d and not hasattr(c, "weight_orig")
+                and not hasattr(c, "weight_g") and c.in_channels == 3 and c.out_channels % 64 == 0
+                and c.out_channels <= 256 and c.stride == (1, 1))
+
     def _layers(self):
         return [getattr(self, 'layer%d' % i) for i in range(1, self.n_layers + 1)]
 
@@ -290,9 +316,12 @@ class MetaNODE(nn.Module):
 
     def forward(self, x, solvers=None, solver_options=None, loss_options=None):
         self.ss_loss = 0
-        out = self.conv1(x)
-        if not self.is_preactivation:
-            out = self.act(self.bn1(out))
+        if self._fusable_stem(x):
+            out = stem_conv_act(x, self.conv1.weight, _act_code(self.act))
+        else:
+            out = self.conv1(x)
+            if not self.is_preactivation:
+                out = self.act(self.bn1(out))
         for layer in self._layers():
             out = layer(out, solvers=solvers, solver_options=solver_options, loss_options=loss_options)
             self.ss_loss += layer.ss_loss

@@ -251,3 +251,22 @@ def test_model_solver_and_model_ensembling_bit_exact():
         assert np.array_equal((probs / len(models)).numpy(), g["model_ens_probs"])
     xa = oa.fgsm_2ensemble(models, x, labels, 8 / 255., CIFAR_MEAN, CIFAR_STD)
     assert np.array_equal(xa.numpy(), g["model_ens_fgsm_x"])
+
+
+def test_non_ode_layer_gradients_bit_exact():
+    """stem pre-activation, strided residual block output and the gradients of both residual blocks."""
+    g = golden("premetanode10_resgrads.npz")
+    p = det_premetanode10_params()
+    for v in p.values():
+        v.requires_grad_(True)
+    img = torch.from_numpy(oracle.det_uniform((4, 3, 32, 32), 900, 0.0, 1.0))
+    mean = torch.tensor(CIFAR_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(CIFAR_STD).view(1, 3, 1, 1)
+    x = ((img - mean) / std)
+    tab = butcher_tableau("rk2", "u", np.float32(0.5), None)
+    logits = premetanode10_forward(p, x, tab, dict(n_steps=8))
+    F.cross_entropy(logits, torch.tensor([3, 1, 4, 1])).backward()
+    assert np.array_equal(F.conv2d(x, p["conv1.weight"], None, 1, 1).detach().numpy(), g["stem_preact"])
+    for k in g.files:
+        if k.startswith("g_"):
+            assert np.array_equal(p[k[2:]].grad.numpy().reshape(-1)[::cases.WG_STRIDE], g[k]), k
