@@ -237,7 +237,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
         const int we = warp - kEpiWarp0;
         const int q = warp & 3;                       // TMEM lane quadrant this warp may read
         const int part = we >> 2;                     // which slice of the tile's image rows
-        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        asm volatile("" : "+r"(lane_addr));           // keep it in a register (else S2R + shifts are redone per chunk)
         constexpr int NPARTS = kNumEpiWarps / 4;
         static_assert(G::ROWS % NPARTS == 0, "image rows of a tile must split evenly over the epilogue warp groups");
         constexpr int RH = G::ROWS / NPARTS;          // image rows per warp group

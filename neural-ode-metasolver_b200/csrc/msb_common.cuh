@@ -77,36 +77,43 @@ __device__ __forceinline__ const EpiCoef& epi_coef(const EpiParams& e, int n) {
 }
 
 // ---- activations -----------------------------------------------------------------------------
-// Branch-free single-precision erf (both minimax branches of the classic |x| <> 0.927734375 split are
-// evaluated and selected; max abs error 5.8e-8 vs fp64 erf, checked offline).  No divergence and no
-// control flow, so the compiler can interleave the independent elements of an unrolled epilogue.
-__device__ __forceinline__ float erf_fast(float a) {
-    const float t = fabsf(a);
-    const float s = a * a;
-    float r = fmaf(-1.72853470e-5f, t, 3.83197126e-4f);
-    float u = fmaf(-3.88396438e-3f, t, 2.42546219e-2f);
-    r = fmaf(r, s, u);
-    r = fmaf(r, t, -1.06777877e-1f);
-    r = fmaf(r, t, -6.34846687e-1f);
-    r = fmaf(r, t, -1.28717512e-1f);
-    r = fmaf(r, t, -t);
-    const float big = copysignf(1.0f - __expf(r), a);
-    float q = -5.96761703e-4f;
-    q = fmaf(q, s, 4.99119423e-3f);
-    q = fmaf(q, s, -2.67681349e-2f);
-    q = fmaf(q, s, 1.12819925e-1f);
-    q = fmaf(q, s, -3.76125336e-1f);
-    q = fmaf(q, s, 1.28379166e-1f);
-    const float small = fmaf(q, a, a);
-    return t > 0.927734375f ? big : small;
+// GeLU (exact-erf form, cifar10/utils.py:67-68) and its derivative from ONE exponential:
+//   Phi(x) = 1 - h (x >= 0),  h (x < 0),   h = 0.5 * erfc(|x| / sqrt 2) = Q(t) * E,
+//   E = exp(-x^2 / 2),  t = 1 / (1 + p |x| / sqrt 2),  Q = degree-7 polynomial in t without constant term
+// (same shape as Abramowitz-Stegun 7.1.26 but refitted: p = 0.45, minimax on the absolute error of erf,
+// approximation error 1e-9; evaluated in fp32 the max abs error is 1.8e-7 on Phi and 1.9e-7 on gelu',
+// checked offline against fp64 over [-13, 13]).  E is also the Gaussian of the derivative
+// gelu'(x) = Phi(x) + x * E / sqrt(2 pi).  Branch-free: 2 MUFU + ~17 FMA-pipe instructions per element.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void gelu_both(float x, float& a, float& d) {
+    const float ax = fabsf(x);
+    const float E = ex2_approx((x * x) * -0.72134752044448170368f);        // exp(-x^2/2)
+    const float t = rcp_approx(fmaf(ax, 0.31819805153394638f, 1.0f));      // 0.45 / sqrt 2
+    float q = 0.04628484081253973f;                                        // 0.5 * c7
+    q = fmaf(q, t, -0.2470522577736345f);
+    q = fmaf(q, t, 0.4285840718840338f);
+    q = fmaf(q, t, -0.18790157886011314f);
+    q = fmaf(q, t, 0.23008541295425833f);
+    q = fmaf(q, t, 0.1005046642482306f);
+    q = fmaf(q, t, 0.12949484725821528f);
+    const float h = (q * t) * E;
+    const float cdf = x >= 0.f ? 1.0f - h : h;
+    a = x * cdf;
+    d = fmaf(x, E * 0.39894228040143267794f, cdf);
 }
 template <int ACT>
 __device__ __forceinline__ void act_both_t(float x, float& a, float& d) {
-    if (ACT == 1) {                      // ACT_GELU (exact-erf form)
-        const float cdf = fmaf(0.5f, erf_fast(x * 0.70710678118654752440f), 0.5f);
-        const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-        a = x * cdf;
-        d = fmaf(x, pdf, cdf);
+    if (ACT == 1) {                      // ACT_GELU
+        gelu_both(x, a, d);
     } else if (ACT == 2) {               // ACT_RELU
         a = x > 0.f ? x : 0.f;
         d = x > 0.f ? 1.f : 0.f;
@@ -115,27 +122,19 @@ __device__ __forceinline__ void act_both_t(float x, float& a, float& d) {
     }
 }
 
-// Exact-erf GeLU as torch.nn.functional.gelu (cifar10/utils.py:67-68): x * 0.5 * (1 + erf(x / sqrt 2)).
-__device__ __forceinline__ float gelu_f(float x) {
-    return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-}
-// d/dx gelu = Phi(x) + x * phi(x)
-__device__ __forceinline__ float dgelu_f(float x) {
-    float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-    float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-    return cdf + x * pdf;
-}
 __device__ __forceinline__ float act_f(int act, float x) {
-    if (act == ACT_GELU) return gelu_f(x);
+    float a, d;
+    if (act == ACT_GELU) { act_both_t<1>(x, a, d); return a; }
     if (act == ACT_RELU) return x > 0.f ? x : 0.f;
     return x;
 }
 __device__ __forceinline__ float dact_f(int act, float x) {
-    if (act == ACT_GELU) return dgelu_f(x);
+    float a, d;
+    if (act == ACT_GELU) { act_both_t<1>(x, a, d); return d; }
     if (act == ACT_RELU) return x > 0.f ? 1.f : 0.f;
     return 1.f;
 }
-// value and derivative together (shares the erf)
+// value and derivative together (shares the exponential)
 __device__ __forceinline__ void act_both(int act, float x, float& a, float& d) {
     if (act == ACT_GELU) act_both_t<1>(x, a, d);
     else if (act == ACT_RELU) act_both_t<2>(x, a, d);

@@ -15,9 +15,11 @@ namespace msb {
 
 // ---------------------------------------------------------------------------------------------
 // stem forward:  y = act(conv3x3(x, w)),  dact = act'(conv3x3(x, w)).   x: (B,H,W,3), w: (C,3,3,3) OIHW
-// thread = one pixel x 16 output channels; weights transposed to [27][C] in shared memory.
+// thread = 4 consecutive pixels of one image row x 16 output channels (each weight read from shared
+// memory feeds 4 FMAs); weights transposed to [27][C] in shared memory.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, int act,
+constexpr int kStemPX = 4;
+__global__ void __launch_bounds__(128) stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, int act,
                                                        float* __restrict__ y, float* __restrict__ dact, int B, int H, int W,
                                                        int C) {
     extern __shared__ float sw[];                      // [27][C]
@@ -27,100 +29,120 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__
     }
     __syncthreads();
     const int groups = C / 16;
-    const long long P = (long long)B * H * W;
+    const int wgroups = (W + kStemPX - 1) / kStemPX;
+    const long long total = (long long)B * H * wgroups * groups;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long pix = t / groups;
-    const int cg = (int)(t - pix * groups);
-    if (pix >= P) return;
-    const int wq = (int)(pix % W);
-    const long long rest = pix / W;
-    const int h = (int)(rest % H);
-    const long long n = rest / H;
-    float xin[27];
+    if (t >= total) return;
+    const int cg = (int)(t % groups);
+    long long pg = t / groups;
+    const int w0 = (int)(pg % wgroups) * kStemPX; pg /= wgroups;
+    const int h = (int)(pg % H);
+    const long long n = pg / H;
+    float patch[3][kStemPX + 2][3];
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int s = 0; s < 3; ++s) {
-            const int ih = h + r - 1, iw = wq + s - 1;
+        for (int cc = 0; cc < kStemPX + 2; ++cc) {
+            const int ih = h + r - 1, iw = w0 + cc - 1;
             const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
             const float* p = x + (((size_t)n * H + (ok ? ih : 0)) * W + (ok ? iw : 0)) * 3;
 #pragma unroll
-            for (int ci = 0; ci < 3; ++ci) xin[ci * 9 + r * 3 + s] = ok ? p[ci] : 0.f;
+            for (int ci = 0; ci < 3; ++ci) patch[r][cc][ci] = ok ? p[ci] : 0.f;
         }
-    float acc[16];
+    float acc[kStemPX][16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    for (int px = 0; px < kStemPX; ++px)
 #pragma unroll
-    for (int k = 0; k < 27; ++k) {
-        const float4* wr = reinterpret_cast<const float4*>(sw + k * C + cg * 16);
+        for (int j = 0; j < 16; ++j) acc[px][j] = 0.f;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 wv = wr[q];
-            acc[4 * q + 0] = fmaf(xin[k], wv.x, acc[4 * q + 0]);
-            acc[4 * q + 1] = fmaf(xin[k], wv.y, acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(xin[k], wv.z, acc[4 * q + 2]);
-            acc[4 * q + 3] = fmaf(xin[k], wv.w, acc[4 * q + 3]);
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const float4* wr = reinterpret_cast<const float4*>(sw + (ci * 9 + r * 3 + s) * C + cg * 16);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 wv = wr[q];
+#pragma unroll
+                    for (int px = 0; px < kStemPX; ++px) {
+                        const float xv = patch[r][px + s][ci];
+                        acc[px][4 * q + 0] = fmaf(xv, wv.x, acc[px][4 * q + 0]);
+                        acc[px][4 * q + 1] = fmaf(xv, wv.y, acc[px][4 * q + 1]);
+                        acc[px][4 * q + 2] = fmaf(xv, wv.z, acc[px][4 * q + 2]);
+                        acc[px][4 * q + 3] = fmaf(xv, wv.w, acc[px][4 * q + 3]);
+                    }
+                }
+            }
+#pragma unroll
+    for (int px = 0; px < kStemPX; ++px) {
+        if (w0 + px >= W) break;
+        const size_t pix = ((size_t)n * H + h) * W + w0 + px;
+        float a[16], d[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) act_both(act, acc[px][j], a[j], d[j]);
+        float4* yo = reinterpret_cast<float4*>(y + pix * C + cg * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) yo[q] = make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+        if (dact) {
+            float4* dq = reinterpret_cast<float4*>(dact + pix * C + cg * 16);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dq[q] = make_float4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]);
         }
-    }
-    float a[16], d[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) act_both(act, acc[j], a[j], d[j]);
-    float4* yo = reinterpret_cast<float4*>(y + (size_t)pix * C + cg * 16);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) yo[q] = make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
-    if (dact) {
-        float4* dq = reinterpret_cast<float4*>(dact + (size_t)pix * C + cg * 16);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) dq[q] = make_float4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]);
     }
 }
 
 int launch_stem_fwd(const float* x, const float* w, int act, float* y, float* dact, int B, int H, int W, int C,
                     cudaStream_t st) {
     if (C % 16 || C > 256) { set_error("stem: output channels must be a multiple of 16, <= 256 (got %d)", C); return -1; }
-    const long long threads = (long long)B * H * W * (C / 16);
-    stem_fwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 27 * C * sizeof(float), st>>>(x, w, act, y, dact, B, H, W, C);
+    const long long threads = (long long)B * H * ((W + kStemPX - 1) / kStemPX) * (C / 16);
+    stem_fwd_kernel<<<(unsigned)((threads + 127) / 128), 128, 27 * C * sizeof(float), st>>>(x, w, act, y, dact, B, H, W, C);
     count_launch();
     return check_cuda(cudaGetLastError(), "stem forward launch");
 }
 
 // ---------------------------------------------------------------------------------------------
 // stem weight gradient:  partial[block][k][co] = sum over the block's pixels of gpre[p][co] * patch[p][k],
-// gpre = gy * dact.  Block = 256 threads = (co 0..63) x (4 k-groups of 7 taps, 27 padded to 28); C == 64 * n
-// handled by a channel-block loop.  Deterministic: fixed pixel order per block + fixed-order reduction.
+// gpre = gy * dact.  Thread = 4 output channels x 7 taps (27 padded to 28) x one quarter of the staged
+// pixels; the four pixel quarters are summed through shared memory in a fixed order.  Deterministic: fixed
+// pixel order per block + fixed-order reduction over blocks.
 // ---------------------------------------------------------------------------------------------
 constexpr int kStemPix = 32;   // pixels staged per iteration
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ gy, const float* __restrict__ dact,
                                                          const float* __restrict__ x, float* __restrict__ partial, int B,
                                                          int H, int W, int C, long long pix_per_block) {
-    __shared__ float sg[kStemPix][64];
-    __shared__ float sx[kStemPix][28];
-    const int co_l = threadIdx.x & 63, kg = threadIdx.x >> 6;
+    __shared__ __align__(16) float sg[kStemPix][64];
+    __shared__ __align__(16) float sx[kStemPix][32];       // [pixel][k-group 0..3][8]: 7 taps + 1 pad per group
+    __shared__ float sred[3][64][28];
+    const int co4 = threadIdx.x & 15, kg = (threadIdx.x >> 4) & 3, ps = threadIdx.x >> 6;
     const long long P = (long long)B * H * W;
     const long long p_beg = (long long)blockIdx.x * pix_per_block;
     const long long p_end = p_beg + pix_per_block < P ? p_beg + pix_per_block : P;
     for (int cb = 0; cb < C; cb += 64) {
-        float acc[7];
+        float acc[4][7];
 #pragma unroll
-        for (int j = 0; j < 7; ++j) acc[j] = 0.f;
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 7; ++j) acc[i][j] = 0.f;
         for (long long p0 = p_beg; p0 < p_end; p0 += kStemPix) {
-            // stage gpre: kStemPix x 64 values, 8 per thread
-            for (int i = threadIdx.x; i < kStemPix * 64; i += 256) {
-                const int pl = i >> 6, c = i & 63;
+            for (int i = threadIdx.x; i < kStemPix * 16; i += 256) {          // gpre: 32 pixels x 16 float4
+                const int pl = i >> 4, c4 = i & 15;
                 const long long pix = p0 + pl;
-                float v = 0.f;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (pix < p_end) {
-                    const size_t idx = (size_t)pix * C + cb + c;
-                    v = gy[idx] * dact[idx];
+                    const size_t idx = (size_t)pix * C + cb + c4 * 4;
+                    const float4 g = *reinterpret_cast<const float4*>(gy + idx);
+                    const float4 d = *reinterpret_cast<const float4*>(dact + idx);
+                    v = make_float4(g.x * d.x, g.y * d.y, g.z * d.z, g.w * d.w);
                 }
-                sg[pl][c] = v;
+                *reinterpret_cast<float4*>(&sg[pl][c4 * 4]) = v;
             }
-            // stage input patches: kStemPix x 27 (+1 zero pad)
-            for (int i = threadIdx.x; i < kStemPix * 28; i += 256) {
-                const int pl = i / 28, k = i - pl * 28;
+            for (int i = threadIdx.x; i < kStemPix * 32; i += 256) {          // input patches
+                const int pl = i >> 5, slot = i & 31;
+                const int k = (slot >> 3) * 7 + (slot & 7);
                 const long long pix = p0 + pl;
                 float v = 0.f;
-                if (pix < p_end && k < 27) {
+                if (pix < p_end && (slot & 7) < 7 && k < 27) {
                     const int ci = k / 9, r = (k % 9) / 3, s = k % 3;
                     const int wq = (int)(pix % W);
                     const long long rest = pix / W;
@@ -129,22 +151,43 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
                     const int ih = h + r - 1, iw = wq + s - 1;
                     if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = x[(((size_t)n * H + ih) * W + iw) * 3 + ci];
                 }
-                sx[pl][k] = v;
+                sx[pl][slot] = v;
             }
             __syncthreads();
-#pragma unroll 8
-            for (int pl = 0; pl < kStemPix; ++pl) {
-                const float g = sg[pl][co_l];
 #pragma unroll
-                for (int j = 0; j < 7; ++j) acc[j] = fmaf(g, sx[pl][kg * 7 + j], acc[j]);
+            for (int q = 0; q < kStemPix / 4; ++q) {
+                const int pl = ps * (kStemPix / 4) + q;
+                const float4 g = *reinterpret_cast<const float4*>(&sg[pl][co4 * 4]);
+                const float4 xa = *reinterpret_cast<const float4*>(&sx[pl][kg * 8]);
+                const float4 xb = *reinterpret_cast<const float4*>(&sx[pl][kg * 8 + 4]);
+                const float gg[4] = {g.x, g.y, g.z, g.w};
+                const float xx[7] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 7; ++j) acc[i][j] = fmaf(gg[i], xx[j], acc[i][j]);
             }
             __syncthreads();
         }
+        // sum the four pixel quarters in the fixed order 0 + 1 + 2 + 3
+        if (ps > 0) {
 #pragma unroll
-        for (int j = 0; j < 7; ++j) {
-            const int k = kg * 7 + j;
-            if (k < 27) partial[((size_t)blockIdx.x * 27 + k) * C + cb + co_l] = acc[j];
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 7; ++j) sred[ps - 1][co4 * 4 + i][kg * 7 + j] = acc[i][j];
         }
+        __syncthreads();
+        if (ps == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 7; ++j) {
+                    const int k = kg * 7 + j, co = co4 * 4 + i;
+                    const float v = ((acc[i][j] + sred[0][co][k]) + sred[1][co][k]) + sred[2][co][k];
+                    if (k < 27) partial[((size_t)blockIdx.x * 27 + k) * C + cb + co] = v;
+                }
+        }
+        __syncthreads();
     }
 }
 

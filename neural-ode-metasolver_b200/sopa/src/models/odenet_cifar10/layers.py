@@ -187,14 +187,14 @@ class MetaODEBlock(nn.Module):
         mode = solver_options.solver_mode
         n = len(solvers)
         if mode == 'standalone':
-            y = solvers[0].integrate(self.rhs_func, x=x, t=t)
+            return solvers[0].integrate_end(self.rhs_func, x, t)
         elif mode == 'switch':
             probs = solver_options.switch_probs
             if probs is None:
                 probs = [1. / n for _ in range(n)]
             solver_id = np.random.choice(range(n), p=probs)          # numpy global RNG, drawn per block call
             solver_options.switch_solver_id = solver_id
-            y = solvers[solver_id].integrate(self.rhs_func, x=x, t=t)
+            return solvers[solver_id].integrate_end(self.rhs_func, x, t)
         elif mode == 'ensemble':
             coin_flip = torch.bernoulli(torch.tensor((1,)), solver_options.ensemble_prob)
             solver_options.ensemble_coin_flip = coin_flip
@@ -211,10 +211,10 @@ class MetaODEBlock(nn.Module):
                         y = yi if y is None else y + yi
                     return y
                 for wi, solver in zip(weights, solvers):
-                    yi = wi * solver.integrate(self.rhs_func, x=x, t=t)
+                    yi = wi * solver.integrate_end(self.rhs_func, x, t)
                     y = yi if y is None else y + yi
-            else:
-                y = solvers[0].integrate(self.rhs_func, x=x, t=t)
+                return y
+            return solvers[0].integrate_end(self.rhs_func, x, t)
         elif mode == 'stacked':
             # extension (not in the reference): the batch holds len(solvers) equal slices, slice k is
             # integrated by solvers[k] -- K model copies that differ only in their solver, evaluated as one
@@ -222,7 +222,6 @@ class MetaODEBlock(nn.Module):
             return integrate_stacked(solvers, self.rhs_func, x, t, replicate=False)
         else:
             raise ValueError("unknown solver_mode %r" % (mode,))
-        return y[-1, :, :, :, :]
 
     def ss_loss(self, y, solvers, solver_options):
         raise NotImplementedError("metasolver_b200: the steady-state regulariser is not implemented "

@@ -135,6 +135,11 @@ class RKParametricSolver(object, metaclass=abc.ABCMeta):
 
     def integrate(self, rhs_func, x, t):
         """-> Tensor[len(t), B, C, H, W]; differentiable w.r.t. x and rhs_func's conv weights."""
+        return torch.stack((x, self.integrate_end(rhs_func, x, t)))
+
+    def integrate_end(self, rhs_func, x, t):
+        """The end state y(t[-1]) alone, (B, C, H, W): what MetaODEBlock keeps of integrate()'s result
+        (`y[-1]`, cifar10/layers.py:207) -- without materialising the stacked [x, y] copy."""
         spec, grid = self._fused_args(rhs_func, t)
         if spec["rhs_kind"] == _cabi.RHS_MNIST_GN_T:
             y = ode_block_integrate_mnist(x, spec["params"], self._host_tableau, grid.tolist(), spec["groups"],
@@ -143,7 +148,7 @@ class RKParametricSolver(object, metaclass=abc.ABCMeta):
             y = ode_block_integrate(x, spec["w1"], spec["w2"], self._host_tableau, grid.tolist(),
                                     rhs_kind=spec["rhs_kind"], act=spec["act"], engine=spec.get("engine"))
         rhs_func.nfe += self.n_stages * (len(grid) - 1)               # cifar10/layers.py:149
-        return torch.stack((x, y))
+        return y
 
     def _fused_args(self, rhs_func, t):
         """Checks shared by integrate() and integrate_stacked(); -> (rhs spec, host time grid)."""
