@@ -98,7 +98,7 @@ def run_reference(args):
                 config=dict(workload=WORKLOAD, batch_per_step=args.cpu_batch),
                 cpu_baseline=dict(value=val, unit="images/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=val, unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------ clocks
@@ -263,12 +263,26 @@ def run_ours(args):
         line["cpu_baseline"] = dict(value=args.cpu_batch / best, unit="images/s", cores=torch.get_num_threads(),
                                     kind="port", sample="best of 3 steps of a %d-image batch (oracle port of the reference, "
                                     "torch CPU fp32, all host threads); %.1f s of CPU work" % (args.cpu_batch, sum(ts)))
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _claim_stdout():
+    """Libraries (NCCL prints its version banner) write to fd 1; the contract is ONE JSON line on stdout.
+    Point fd 1 at stderr for the duration of the run and keep the real stdout for the result line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return real
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 if __name__ == "__main__":
+    _REAL_STDOUT = _claim_stdout()
     a = parse()
     if a.impl == "reference":
         run_reference(a)

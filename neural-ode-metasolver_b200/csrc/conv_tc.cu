@@ -66,6 +66,21 @@ int make_tmap_split5d(CUtensorMap* m, const void* base, int B, int H, int W, int
     return 0;
 }
 
+// same tensor, ONE plane per box: box = {64 ch, box_w, 1, box_h, 1} (pixel-major engine: smem = [row][pixel] per plane)
+int make_tmap_split_plane(CUtensorMap* m, const void* base, int B, int H, int W, int C, int box_w, int box_h) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return -1;
+    cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, 2, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)2 * W * C * 2, (cuuint64_t)H * 2 * W * C * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)box_w, 1, (cuuint32_t)box_h, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(split plane) failed with %d", (int)r); return -1; }
+    return 0;
+}
+
 // row-major [rows][64] bf16 tiles, box = {64, box_rows}
 int make_tmap_rows64(CUtensorMap* m, const void* base, size_t rows, int box_rows) {
     EncodeTiledFn fn = get_encode_fn();
@@ -80,6 +95,19 @@ int make_tmap_rows64(CUtensorMap* m, const void* base, size_t rows, int box_rows
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(rows64) failed with %d", (int)r); return -1; }
     return 0;
 }
+
+#ifdef MSB_CONV_DEBUG
+int tcp_debug_set(int flags);
+int tcp_debug_hint(unsigned ns);
+extern "C" int msb_debug_suspend_hint(unsigned ns) {
+    if (tcp_debug_hint(ns)) return -1;
+    return cudaMemcpyToSymbol(ptx::g_suspend_hint, &ns, sizeof(ns)) == cudaSuccess ? 0 : -1;
+}
+extern "C" int msb_debug_conv_flags(int flags) {
+    if (tcp_debug_set(flags)) return -1;
+    return cudaMemcpyToSymbol(g_conv_debug, &flags, sizeof(int)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 bool tc_shape_supported(int C, int H, int W) {
     if (C != 64 && C != 128) return false;
@@ -165,9 +193,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
                 for (int chunk = 0; chunk < CHUNKS; ++chunk)
                     for (int s = 0; s < 3; ++s) {
                         ptx::mbar_wait(&bars->b_empty[st], ph ^ 1);
+                        if (MSB_DBG(8)) { ptx::mbar_arrive(&bars->b_full[st]); }
+                        else {
                         ptx::mbar_arrive_expect_tx(&bars->b_full[st], G::B_STAGE_BYTES);
                         ptx::tma_load_5d(smem_b + st * G::B_STAGE_BYTES, &tmap_act, &bars->b_full[st],
                                          chunk * 64, s - 1, 0, h0 - 1, n);
+                        }
                         if (++st == kBStages) { st = 0; ph ^= 1; }
                     }
             }
@@ -184,8 +215,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
                                 const int tap = r * 3 + s;
                                 const int wt = (C == 64) ? tap : ((tap * CHUNKS + chunk) * 2 + part);
                                 ptx::mbar_wait(&bars->a_empty[st], ph ^ 1);
+                                if (MSB_DBG(4)) { ptx::mbar_arrive(&bars->a_full[st]); }
+                                else {
                                 ptx::mbar_arrive_expect_tx(&bars->a_full[st], kATileBytes);
                                 ptx::tma_load_2d(smem_a + st * kATileBytes, &tmap_w, &bars->a_full[st], 0, wt * 128);
+                                }
                                 if (++st == kAStages) { st = 0; ph ^= 1; }
                             }
             }
@@ -216,7 +250,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
                                     const uint64_t adesc = ptx::make_smem_desc_sw128(a_base + k * 32, 16, 1024);
                                     const uint64_t bdesc =
                                         ptx::make_smem_desc_sw128(b_base + r * G::ROW_PAIR_BYTES + k * 32, 16, 1024);
-                                    ptx::umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
+                                    if (!MSB_DBG(2)) ptx::umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
                                     accumulate = 1;
                                 }
                                 ptx::umma_commit(&bars->a_empty[ast]);
@@ -269,6 +303,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
             ptx::mbar_wait(&bars->tmem_full[acc], acc_ph);
             ptx::tc_fence_after();
             const uint32_t t_acc = tmem_base + (uint32_t)acc * 256u + lane_addr;
+            const EpiCoef coef = epi_coef(epi, n);          // one image per tile: the slice is tile-uniform
+            if (MSB_DBG(1)) {
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&bars->tmem_empty[acc]);
+                if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+                continue;
+            }
             auto do_chunk = [&](const int ch, const EpiOperands<kPXO>& cur, EpiOperands<kPXO>& nxt) {
                 int h, w0; chunk_pos(n, h0, ch, h, w0);
                 const int rr = ch / STEPS_PER_ROW, stp = ch - rr * STEPS_PER_ROW;
@@ -320,7 +362,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
                 // ---- fused RK epilogue on the 8 owned pixels ----
                 const size_t pix = ((size_t)n * H + h) * WIMG + w0;
                 const size_t split0 = (((size_t)n * H + h) * 2) * plane_stride + (size_t)w0 * C + c;
-                epi_finish<kPXO, ACT>(epi, epi_coef(epi, n), v, cur, pix * C + c, C, split0, plane_stride);
+                epi_finish<kPXO, ACT>(epi, coef, v, cur, pix * C + c, C, split0, plane_stride);
             };
             static_assert(NCHUNK % 2 == 0, "chunk pipeline is unrolled by two");
 #pragma unroll

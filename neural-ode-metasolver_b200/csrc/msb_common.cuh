@@ -8,6 +8,17 @@ namespace msb {
 
 enum { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
 
+// Bottleneck-decomposition switches (scripts/conv_bottleneck.py), compiled in only with -DMSB_CONV_DEBUG; one
+// copy of the flag word per translation unit, all set by msb_debug_conv_flags().
+//   1: epilogue skipped (accumulator barriers still cycle)   2: no MMAs issued   4: no weight TMA
+//   8: no activation TMA   16: epilogue global stores off   32: epilogue global loads off
+#ifdef MSB_CONV_DEBUG
+static __device__ int g_conv_debug = 0;
+#define MSB_DBG(bit) (g_conv_debug & (bit))
+#else
+#define MSB_DBG(bit) 0
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // Fused epilogue applied to every accumulator element of a convolution.  One struct covers the
 // forward RK stage combinations, the activation that feeds the next convolution, and the
@@ -324,6 +335,134 @@ __device__ __forceinline__ void epi_finish(const EpiParams& e, const EpiCoef& k,
                 e.out_split[split_idx0 + (size_t)j * stride] = hi;
                 e.out_split[split_idx0 + plane_stride + (size_t)j * stride] = lo;
             }
+        }
+    }
+}
+
+}  // namespace msb
+
+// ---- channel-vector form of the same epilogue (pixel-major tensor-core engine, conv_tcp.cu) ------------
+// A thread owns 8 CONSECUTIVE CHANNELS of one pixel: element j at idx0 + j.  Global accesses are whole
+// 32-byte sectors (256-bit loads / stores, sm_100+), bf16 hi/lo planes get one 16-byte store each.
+// Arithmetic and evaluation order are those of epilogue_apply() / epi_finish().
+namespace msb {
+
+struct EpiVec8 {
+    float mul[8];
+    float base[8];
+    float src[3][8];
+    float smul[8];
+};
+
+__device__ __forceinline__ void ldg256_stream(const float* p, float* v) {
+#ifdef MSB_CONV_DEBUG
+    if (g_conv_debug & 32) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 1.f;
+        return;
+    }
+#endif
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void stg256(float* p, const float* v) {
+#ifdef MSB_CONV_DEBUG
+    if ((g_conv_debug & 16) && v[0] != 123.456f) return;
+#endif
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+
+__device__ __forceinline__ void epi_prefetch_vec8(const EpiParams& e, size_t idx0, EpiVec8& r) {
+    if (e.mul) ldg256_stream(e.mul + idx0, r.mul);
+    if (e.base) ldg256_stream(e.base + idx0, r.base);
+    if (e.nsrc > 0) ldg256_stream(e.src[0] + idx0, r.src[0]);
+    if (e.nsrc > 1) ldg256_stream(e.src[1] + idx0, r.src[1]);
+    if (e.nsrc > 2) ldg256_stream(e.src[2] + idx0, r.src[2]);
+    if (e.split_mul) ldg256_stream(e.split_mul + idx0, r.smul);
+}
+
+// split_idx0 = index of element 0 in the hi plane of out_split; the lo plane is plane_stride further.
+template <int ACT>
+__device__ __forceinline__ void epi_finish_vec8(const EpiParams& e, const EpiCoef& k, const float* acc, const EpiVec8& r,
+                                                size_t idx0, size_t split_idx0, size_t plane_stride) {
+    constexpr int N = 8;
+    float v[N], o[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) v[j] = acc[j];
+    if (e.act_v != ACT_NONE) {            // post-activation RHS only (rare): generic path
+        float d[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            float a;
+            act_both(e.act_v, v[j], a, d[j]);
+            v[j] = a;
+        }
+        if (e.dact_v_out) stg256(e.dact_v_out + idx0, d);
+    }
+    if (e.mul) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) v[j] = __fmul_rn(v[j], r.mul[j]);
+    }
+    if (e.v_out) stg256(e.v_out + idx0, v);
+    if (e.nsrc == 0) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) o[j] = __fmul_rn(v[j], k.coef_v);
+    } else {
+#pragma unroll
+        for (int j = 0; j < N; ++j) o[j] = __fmul_rn(r.src[0][j], k.coef[0]);
+        if (e.nsrc > 1) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) o[j] = __fadd_rn(o[j], __fmul_rn(r.src[1][j], k.coef[1]));
+        }
+        if (e.nsrc > 2) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) o[j] = __fadd_rn(o[j], __fmul_rn(r.src[2][j], k.coef[2]));
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j) o[j] = __fadd_rn(o[j], __fmul_rn(v[j], k.coef_v));
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) o[j] = __fmul_rn(o[j], k.dt);
+    if (e.base) {
+        if (e.base_is_one) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) o[j] = __fadd_rn(r.base[j], o[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < N; ++j) o[j] = __fadd_rn(__fmul_rn(r.base[j], k.base_coef), o[j]);
+        }
+    }
+    if (e.out_f32) stg256(e.out_f32 + idx0, o);
+    if (e.out_split || e.dact_out) {
+        float a[N], d[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) act_both_t<ACT>(o[j], a[j], d[j]);
+        if (e.dact_out) stg256(e.dact_out + idx0, d);
+        if (e.out_split) {
+            if (e.split_mul) {
+#pragma unroll
+                for (int j = 0; j < N; ++j) a[j] = __fmul_rn(a[j], r.smul[j]);
+            }
+            uint32_t hi[N / 2], lo[N / 2];
+#pragma unroll
+            for (int j = 0; j < N; j += 2) {
+                const float x0 = __fmul_rn(a[j], k.split_scale), x1 = __fmul_rn(a[j + 1], k.split_scale);
+                // packed round-to-nearest bf16 pair (element j in the low half = lower address)
+                uint32_t h;
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
+                const float h0 = __uint_as_float(h << 16), h1 = __uint_as_float(h & 0xffff0000u);
+                uint32_t l;
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(x1 - h1), "f"(x0 - h0));
+                hi[j / 2] = h; lo[j / 2] = l;
+            }
+#ifdef MSB_CONV_DEBUG
+            if ((g_conv_debug & 16) && hi[0] != 0x12345678u) return;
+#endif
+            *reinterpret_cast<uint4*>(e.out_split + split_idx0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(e.out_split + split_idx0 + plane_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
     }
 }

@@ -61,6 +61,14 @@ size_t tc_packed_weight_bytes(int C);
 int launch_conv3x3_tc(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, const EpiParams& epi,
                       ConvShape s, cudaStream_t st);
 
+// ---- conv_tcp.cu : the same engine in pixel-major form (pixels on M, 3 hi/lo products, vector epilogue) ----
+size_t tcp_packed_weight_bytes(int C);
+void launch_pack_w_tcp(const float* w, __nv_bfloat16* out, int C, int transpose, cudaStream_t st);
+int launch_conv3x3_tcp(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, const EpiParams& epi,
+                       ConvShape s, cudaStream_t st);
+// which form MSB_ENGINE_TCGEN05 runs for C channels (odeblock.cu; env MSB_TC_CONV=cm|pm forces one)
+bool tc_pixel_major(int C);
+
 // ---- wgrad_tc.cu ----
 bool wgrad_tc_supported(ConvShape s);
 int wgrad_tc_nparts(ConvShape s);

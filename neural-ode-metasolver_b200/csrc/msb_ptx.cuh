@@ -23,24 +23,35 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+constexpr uint32_t kSuspendHintNs = 20000;
+#ifdef MSB_CONV_DEBUG
+static __device__ uint32_t g_suspend_hint = kSuspendHintNs;
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
+#ifdef MSB_CONV_DEBUG
+    const uint32_t hint = g_suspend_hint;
+#else
+    const uint32_t hint = kSuspendHintNs;
+#endif
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(hint)
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug traps (-> CUDA error) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (-> CUDA error) instead of hanging the GPU.  The suspend-time hint lets
+// the hardware park the waiting thread (it is woken by the phase completion), so waiting roles do not
+// compete with the epilogue warps for issue slots.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) __trap();
+        if (++spins > (1u << 22)) __trap();
     }
 }
 

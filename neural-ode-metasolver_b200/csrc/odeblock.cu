@@ -73,8 +73,22 @@ static void prof_end(int id, cudaStream_t st) {
 }
 
 // ---- host helpers shared with blocks.cu (declared in msb_host.h) ----
+// Which form of the tcgen05 convolution runs for C channels.  Measured on B200 (profiles/conv_forms_r1.txt):
+// the pixel-major form (3 hi/lo products) wins for C = 128, where the channel-major form is MMA-bound; for
+// C = 64 its N = 128 / N = 64 MMAs are shared-memory-operand-bound and the channel-major form (N = 256) wins.
+// MSB_TC_CONV=cm|pm forces one form for every shape (A/B runs).
+bool tc_pixel_major(int C) {
+    static int forced = -2;
+    if (forced == -2) {
+        const char* e = getenv("MSB_TC_CONV");
+        forced = !e ? -1 : (strcmp(e, "cm") == 0 ? 0 : (strcmp(e, "pm") == 0 ? 1 : -1));
+    }
+    if (forced >= 0) return forced == 1;
+    return C >= 128;
+}
 size_t packed_w_bytes(int engine, int C) {
-    return engine == MSB_ENGINE_TCGEN05 ? tc_packed_weight_bytes(C) : (size_t)9 * C * C * sizeof(float);
+    if (engine != MSB_ENGINE_TCGEN05) return (size_t)9 * C * C * sizeof(float);
+    return tc_pixel_major(C) ? tcp_packed_weight_bytes(C) : tc_packed_weight_bytes(C);
 }
 int resolve_engine_shape(int engine, int C, int H, int W) {
     const bool tc_ok = tc_shape_supported(C, H, W);
@@ -91,14 +105,18 @@ double conv_flops(ConvShape s) { return 2.0 * s.B * s.H * s.W * (double)s.C * 9.
 int run_conv(int engine, const __nv_bfloat16* in, const void* wpacked, const EpiParams& e, ConvShape s, cudaStream_t st) {
     int id = prof_begin(MSB_PROF_CONV, conv_flops(s), st);
     int rc;
-    if (engine == MSB_ENGINE_TCGEN05) rc = launch_conv3x3_tc(in, (const __nv_bfloat16*)wpacked, e, s, st);
+    if (engine == MSB_ENGINE_TCGEN05)
+        rc = tc_pixel_major(s.C) ? launch_conv3x3_tcp(in, (const __nv_bfloat16*)wpacked, e, s, st)
+                              : launch_conv3x3_tc(in, (const __nv_bfloat16*)wpacked, e, s, st);
     else rc = launch_conv3x3_simt(in, (const float*)wpacked, e, s, st);
     prof_end(id, st);
     return rc;
 }
 void pack_w(int engine, const float* w, void* out, int C, int transpose, cudaStream_t st) {
-    if (engine == MSB_ENGINE_TCGEN05) launch_pack_w_tc(w, (__nv_bfloat16*)out, C, transpose, st);
-    else launch_pack_w_simt(w, (float*)out, C, C, 0, transpose, st);
+    if (engine == MSB_ENGINE_TCGEN05) {
+        if (tc_pixel_major(C)) launch_pack_w_tcp(w, (__nv_bfloat16*)out, C, transpose, st);
+        else launch_pack_w_tc(w, (__nv_bfloat16*)out, C, transpose, st);
+    } else launch_pack_w_simt(w, (float*)out, C, C, 0, transpose, st);
 }
 bool use_tc_wgrad(int engine, ConvShape s) { return engine == MSB_ENGINE_TCGEN05 && wgrad_tc_supported(s); }
 int wgrad_nparts(int engine, ConvShape s) {
@@ -540,7 +558,7 @@ int msb_act_split(const float* x, int act, void* split_out, float* dact_out, int
 }
 
 size_t msb_conv3x3_workspace_bytes(int channels) {
-    size_t a = tc_packed_weight_bytes(channels), b = (size_t)9 * channels * channels * 4;
+    size_t a = std::max(tc_packed_weight_bytes(channels), tcp_packed_weight_bytes(channels)), b = (size_t)9 * channels * channels * 4;
     return align_up(a > b ? a : b) + 1024;
 }
 
