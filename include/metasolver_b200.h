@@ -183,6 +183,9 @@ enum { MSB_PROF_CONV = 0,   /* forward / input-gradient convolutions */
        MSB_PROF_WGRAD = 1   /* weight-gradient GEMMs */ };
 int msb_profile_enable(int on);
 int msb_profile_read(int kind, double* total_ms, double* total_flops, int64_t* count);
+/* Tensor-core flops actually EXECUTED by the recorded launches of `kind`: algorithmic flops x the number of
+ * bf16 hi/lo products the engine forms (3 or 4 on the tcgen05 engine, 1 on the SIMT engine). */
+int msb_profile_read_executed(int kind, double* executed_flops);
 
 #ifdef __cplusplus
 }

@@ -53,17 +53,18 @@ struct Prof {
     std::vector<cudaEvent_t> ev;      // pairs (start, stop)
     std::vector<int> kind;            // kind of each pair
     std::vector<double> flops;        // algorithmic flops of each pair
+    std::vector<double> exec;         // executed tensor-core flops of each pair (hi/lo products formed)
     size_t used = 0;
 };
 static Prof g_prof;
-static int prof_begin(int kind, double flops, cudaStream_t st) {
+static int prof_begin(int kind, double flops, double products, cudaStream_t st) {
     if (!g_prof.on) return -1;
     if (g_prof.used + 2 > g_prof.ev.size()) {
         for (int i = 0; i < 512; ++i) { cudaEvent_t e; cudaEventCreate(&e); g_prof.ev.push_back(e); }
     }
     int id = (int)(g_prof.used / 2);
-    g_prof.kind.resize(id + 1); g_prof.flops.resize(id + 1);
-    g_prof.kind[id] = kind; g_prof.flops[id] = flops;
+    g_prof.kind.resize(id + 1); g_prof.flops.resize(id + 1); g_prof.exec.resize(id + 1);
+    g_prof.kind[id] = kind; g_prof.flops[id] = flops; g_prof.exec[id] = flops * products;
     cudaEventRecord(g_prof.ev[g_prof.used], st);
     g_prof.used += 2;
     return id;
@@ -103,7 +104,8 @@ int resolve_engine_shape(int engine, int C, int H, int W) {
 }
 double conv_flops(ConvShape s) { return 2.0 * s.B * s.H * s.W * (double)s.C * 9.0 * s.C; }
 int run_conv(int engine, const __nv_bfloat16* in, const void* wpacked, const EpiParams& e, ConvShape s, cudaStream_t st) {
-    int id = prof_begin(MSB_PROF_CONV, conv_flops(s), st);
+    const double products = engine != MSB_ENGINE_TCGEN05 ? 1.0 : (tc_pixel_major(s.C) ? 3.0 : 4.0);
+    int id = prof_begin(MSB_PROF_CONV, conv_flops(s), products, st);
     int rc;
     if (engine == MSB_ENGINE_TCGEN05)
         rc = tc_pixel_major(s.C) ? launch_conv3x3_tcp(in, (const __nv_bfloat16*)wpacked, e, s, st)
@@ -128,8 +130,8 @@ int wgrad_nparts(int engine, ConvShape s) {
 //  SIMT   : partials are reduced into grad_w after every launch.
 int run_wgrad(int engine, const __nv_bfloat16* gout, const __nv_bfloat16* in, WgradAcc& acc, ConvShape s, cudaStream_t st) {
     int nparts = 0, rc;
-    int id = prof_begin(MSB_PROF_WGRAD, conv_flops(s), st);
     const bool tc = use_tc_wgrad(engine, s);
+    int id = prof_begin(MSB_PROF_WGRAD, conv_flops(s), tc ? (s.C == 64 ? 4.0 : 3.0) : 1.0, st);
     if (tc) rc = launch_wgrad3x3_tc(gout, in, acc.partial, &nparts, acc.launches > 0, s, st);
     else rc = launch_wgrad3x3_simt(gout, in, acc.partial, &nparts, s, st);
     prof_end(id, st);
@@ -244,6 +246,14 @@ int msb_profile_read(int kind, double* total_ms, double* total_flops, int64_t* c
     if (total_ms) *total_ms = ms;
     if (total_flops) *total_flops = fl;
     if (count) *count = n;
+    return 0;
+}
+
+int msb_profile_read_executed(int kind, double* executed_flops) {
+    double fl = 0;
+    for (size_t id = 0; id < g_prof.used / 2; ++id)
+        if (g_prof.kind[id] == kind) fl += g_prof.exec[id];
+    if (executed_flops) *executed_flops = fl;
     return 0;
 }
 

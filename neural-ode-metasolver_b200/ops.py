@@ -44,6 +44,13 @@ def profile_read(kind):
     return ms.value, fl.value, n.value
 
 
+def profile_read_executed(kind):
+    """Executed tensor-core flops (algorithmic x hi/lo products formed) of the recorded launches of `kind`."""
+    fl = ctypes.c_double()
+    _cabi.check(_cabi.lib().msb_profile_read_executed(kind, ctypes.byref(fl)), "profile_read_executed")
+    return fl.value
+
+
 @contextlib.contextmanager
 def input_grad_only():
     """Inside this context backward passes skip the weight gradients (FGSM / PGD input-gradient
