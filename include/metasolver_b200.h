@@ -92,6 +92,14 @@ typedef struct MsbMnistParams {
     float eps;                        /* 1e-5 */
 } MsbMnistParams;
 
+/* Gradients of the MNIST right-hand-side parameters (device pointers, fp32, shapes of MsbMnistParams; overwritten). */
+typedef struct MsbMnistGrads {
+    float* norm_w[3];
+    float* norm_b[3];
+    float* conv_w[2];                 /* [C][C+1][3][3], incl. the time channel */
+    float* conv_b[2];
+} MsbMnistGrads;
+
 int         msb_abi_version(void);
 const char* msb_last_error(void);
 /* 1 if `device` can run the tcgen05 engine (compute capability 10.x), 0 if not, <0 on error. */
@@ -118,6 +126,12 @@ int msb_odeblock_forward(const MsbOdeDesc* d, const float* x, const float* w1, c
 int msb_odeblock_backward(const MsbOdeDesc* d, const float* grad_y, const float* w1, const float* w2,
                           const void* tape, size_t tape_bytes, float* grad_x, float* grad_w1, float* grad_w2,
                           void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* Same for MSB_RHS_MNIST_GN_T (tape recorded by msb_odeblock_forward with save_tape = 1).  `grads` NULL = input
+ * gradient only.  Replaces torch.autograd through ODEfunc / ConcatConv2d / GroupNorm, mnist/layers.py:158-171, 250-253. */
+int msb_odeblock_backward_mnist(const MsbOdeDesc* d, const float* grad_y, const MsbMnistParams* mnist, const void* tape,
+                                size_t tape_bytes, float* grad_x, const MsbMnistGrads* grads, void* workspace,
+                                size_t workspace_bytes, void* cuda_stream);
 
 /* ---- non-ODE layers of the CIFAR networks on the same engines ------------------------
  * Stem: y = act(conv3x3(x, w)), 3 input channels -> `channels`, stride 1, pad 1, no bias

@@ -19,7 +19,7 @@ ENGINES = {"auto": ENGINE_AUTO, "tcgen05": ENGINE_TCGEN05, "simt": ENGINE_SIMT}
 EXPORTS = [
     "msb_abi_version", "msb_last_error", "msb_device_supports_tcgen05", "msb_shape_supports_tcgen05",
     "msb_odeblock_workspace_bytes", "msb_odeblock_tape_bytes", "msb_odeblock_bwd_workspace_bytes",
-    "msb_odeblock_forward", "msb_odeblock_backward", "msb_act_split", "msb_conv3x3",
+    "msb_odeblock_forward", "msb_odeblock_backward", "msb_odeblock_backward_mnist", "msb_act_split", "msb_conv3x3",
     "msb_stem_forward", "msb_stem_backward_workspace_bytes", "msb_stem_backward",
     "msb_downblock_workspace_bytes", "msb_downblock_tape_bytes", "msb_downblock_bwd_workspace_bytes",
     "msb_downblock_forward", "msb_downblock_backward",
@@ -62,6 +62,13 @@ class MsbMnistParams(ctypes.Structure):
     ]
 
 
+class MsbMnistGrads(ctypes.Structure):
+    _fields_ = [
+        ("norm_w", ctypes.c_void_p * 3), ("norm_b", ctypes.c_void_p * 3),
+        ("conv_w", ctypes.c_void_p * 2), ("conv_b", ctypes.c_void_p * 2),
+    ]
+
+
 _lib = None
 _lock = threading.Lock()
 
@@ -79,6 +86,8 @@ def _declare(lib):
         f.restype = sz
     lib.msb_odeblock_forward.argtypes = [dp, vp, vp, vp, ctypes.POINTER(MsbMnistParams), vp, vp, sz, vp, sz, vp]
     lib.msb_odeblock_backward.argtypes = [dp, vp, vp, vp, vp, sz, vp, vp, vp, vp, sz, vp]
+    lib.msb_odeblock_backward_mnist.argtypes = [dp, vp, ctypes.POINTER(MsbMnistParams), vp, sz, vp,
+                                                ctypes.POINTER(MsbMnistGrads), vp, sz, vp]
     lib.msb_stem_forward.argtypes = [vp, vp, i32, vp, vp, i32, i32, i32, i32, vp]
     lib.msb_stem_backward_workspace_bytes.argtypes = [i32]
     lib.msb_stem_backward_workspace_bytes.restype = sz

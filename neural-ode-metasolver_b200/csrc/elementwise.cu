@@ -138,23 +138,28 @@ void launch_pack_w_tc(const float* w, __nv_bfloat16* out, int C, int transpose, 
 // wgrad finalisation: grad_w[O][I][3][3] (+)= sum_{p < nparts} partial[p][tap][ci][co]
 // Deterministic (fixed summation order), one thread per weight.
 // ---------------------------------------------------------------------------------------------
+// grad_w may have more input channels than the GEMM (`cin_total` > C: ConcatConv2d, whose first `skip_in`
+// input channels are handled elsewhere): element (co, ci, r, s) goes to grad_w[co][ci + skip_in][r][s].
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nparts, float* __restrict__ grad_w,
-                                    int C, int accumulate) {
+                                    int C, int accumulate, int cin_total, int skip_in) {
     int total = 9 * C * C;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        // i indexes OIHW
+        // i indexes OIHW of the C x C x 3 x 3 GEMM result
         int s = i % 3, r = (i / 3) % 3;
         int ci = (i / 9) % C, co = i / (9 * C);
         size_t src = ((size_t)(r * 3 + s) * C + ci) * C + co;
         float acc = 0.f;
         for (int p = 0; p < nparts; ++p) acc += partial[(size_t)p * total + src];
-        grad_w[i] = accumulate ? grad_w[i] + acc : acc;
+        float* q = grad_w + (((size_t)co * cin_total + ci + skip_in) * 3 + r) * 3 + s;
+        *q = accumulate ? *q + acc : acc;
     }
 }
 
-void launch_wgrad_reduce(const float* partial, int nparts, float* grad_w, int C, int accumulate, cudaStream_t st) {
+void launch_wgrad_reduce(const float* partial, int nparts, float* grad_w, int C, int accumulate, cudaStream_t st,
+                         int cin_total, int skip_in) {
     int total = 9 * C * C;
-    wgrad_reduce_kernel<<<(total + 127) / 128, 128, 0, st>>>(partial, nparts, grad_w, C, accumulate);
+    wgrad_reduce_kernel<<<(total + 127) / 128, 128, 0, st>>>(partial, nparts, grad_w, C, accumulate,
+                                                             cin_total > 0 ? cin_total : C, skip_in);
     count_launch();
 }
 

@@ -24,11 +24,17 @@ void launch_act_split_sliced(const float* x, const float* mul, int act, const fl
                              __nv_bfloat16* split, float* dact, int B, int H, int W, int C, cudaStream_t st);
 void launch_pack_w_simt(const float* w, float* out, int C, int Cin_total, int skip_in, int transpose, cudaStream_t st);
 void launch_pack_w_tc(const float* w, __nv_bfloat16* out, int C, int transpose, cudaStream_t st);
-void launch_wgrad_reduce(const float* partial, int nparts, float* grad_w, int C, int accumulate, cudaStream_t st);
+void launch_wgrad_reduce(const float* partial, int nparts, float* grad_w, int C, int accumulate, cudaStream_t st,
+                         int cin_total = 0, int skip_in = 0);
 
 // ---- groupnorm.cu (MNIST right-hand side) ----
 int launch_groupnorm_epi(const float* x, const float* gamma, const float* beta, const EpiParams& epi, ConvShape s,
                          int groups, float eps, cudaStream_t st);
+int launch_groupnorm_bwd_epi(const float* x, const float* gamma, const float* beta, const float* dy, float dy_scale, int relu,
+                             const EpiParams& epi, float* dgamma_part, float* dbeta_part, int accumulate, ConvShape s,
+                             int groups, float eps, cudaStream_t st);
+void launch_sum_over_batch(const float* part, float* out, int B, int C, cudaStream_t st);
+void launch_concat_aux_grad(const float* dP, float t, float* gw, float* gb, int accumulate, ConvShape s, cudaStream_t st);
 void launch_time_tapmap(const float* w, float* tapmap, int H, int W, int C, cudaStream_t st);
 
 // ---- netlayers.cu (stem, strided residual block re-indexing) ----

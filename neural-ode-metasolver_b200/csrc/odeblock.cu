@@ -155,10 +155,6 @@ int validate(const MsbOdeDesc* d) {
         set_error("rhs_kind %d is not implemented (supported: PREACT_NF, POSTACT_NF, MNIST_GN_T forward)", d->rhs_kind);
         return -1;
     }
-    if (d->rhs_kind == MSB_RHS_MNIST_GN_T && d->save_tape) {
-        set_error("the MNIST (GroupNorm, time-dependent) right-hand side has no backward yet: save_tape must be 0");
-        return -1;
-    }
     if (d->act != MSB_ACT_GELU_ERF && d->act != MSB_ACT_RELU && d->act != MSB_ACT_NONE) {
         set_error("unsupported activation %d", d->act); return -1;
     }
@@ -285,13 +281,24 @@ size_t msb_odeblock_workspace_bytes(const MsbOdeDesc* d) {
 }
 size_t msb_odeblock_tape_bytes(const MsbOdeDesc* d) {
     if (validate(d)) return 0;
-    return (size_t)d->n_steps * d->stages * 4 * align_up(state_elems(d) * 4);
+    const int per_slot = d->rhs_kind == MSB_RHS_MNIST_GN_T ? 5 : 4;      // MNIST: X, P1, P2, A, Hs
+    return (size_t)d->n_steps * d->stages * per_slot * align_up(state_elems(d) * 4);
 }
 size_t msb_odeblock_bwd_workspace_bytes(const MsbOdeDesc* d) {
     if (validate(d)) return 0;
     int engine = resolve_engine(d);
     if (engine < 0) return 0;
     size_t E = state_elems(d);
+    if (d->rhs_kind == MSB_RHS_MNIST_GN_T) {
+        ConvShape s{d->batch, d->height, d->width, d->channels};
+        size_t n = 2 * align_up((size_t)9 * d->channels * d->channels * 4);      // transposed packed weights
+        n += 2 * align_up(E * 4);                                                // gbar ping-pong
+        n += (size_t)(d->stages - 1) * align_up(E * 4);                          // xbar_1 .. xbar_{s-1}
+        n += 4 * align_up(E * 4);                                                // kbar, dP, dH (fp32), Dsplit
+        n += align_up((size_t)wgrad_simt_nparts(s) * 9 * d->channels * d->channels * 4);
+        n += 6 * align_up((size_t)d->batch * d->channels * 4);                   // per-sample dgamma / dbeta partials
+        return n + 4096;
+    }
     ConvShape s{d->batch, d->height, d->width, d->channels};
     size_t n = 0;
     n += 2 * align_up(packed_w_bytes(engine, d->channels));
@@ -308,8 +315,24 @@ size_t msb_odeblock_bwd_workspace_bytes(const MsbOdeDesc* d) {
 // sopa/src/models/odenet_mnist/layers.py:158-171.  Five launches per evaluation; the RK stage
 // combination is the epilogue of the GN3 launch.  Stage time t_i = t_n + c_i*dt (`_get_t`).
 // ---------------------------------------------------------------------------------------------
+struct MnistSlot { float *X, *P1, *P2; __nv_bfloat16 *A, *Hs; };
+static MnistSlot mnist_slot(void* tape, size_t E, int slot) {
+    const size_t q = align_up(E * 4);
+    char* p = (char*)tape + (size_t)slot * 5 * q;
+    return MnistSlot{(float*)p, (float*)(p + q), (float*)(p + 2 * q), (__nv_bfloat16*)(p + 3 * q), (__nv_bfloat16*)(p + 4 * q)};
+}
+// stage time t_n + c_i*dt with the reference's two roundings (`_get_t`)
+static float mnist_stage_time(const MsbOdeDesc* d, int n, int i) {
+    const float t0 = d->time_grid[n];
+    const float dt = d->time_grid[n + 1] - t0;
+    volatile float cdt = d->c[i] * dt;
+    return (i == 0) ? t0 : t0 + cdt;
+}
+
 static int mnist_forward(const MsbOdeDesc* d, const float* x, const MsbMnistParams* mp, float* y_out, void* workspace,
-                         size_t workspace_bytes, cudaStream_t st) {
+                         size_t workspace_bytes, void* tape, size_t tape_bytes, cudaStream_t st) {
+    const bool save = d->save_tape != 0;
+    if (save && (!tape || tape_bytes < msb_odeblock_tape_bytes(d))) { set_error("tape missing or too small"); return -1; }
     if (!mp) { set_error("MSB_RHS_MNIST_GN_T needs MsbMnistParams"); return -1; }
     for (int i = 0; i < 3; ++i) if (!mp->norm_w[i] || !mp->norm_b[i]) { set_error("MNIST params: null norm pointer"); return -1; }
     for (int i = 0; i < 2; ++i) if (!mp->conv_w[i] || !mp->conv_b[i]) { set_error("MNIST params: null conv pointer"); return -1; }
@@ -333,27 +356,34 @@ static int mnist_forward(const MsbOdeDesc* d, const float* x, const MsbMnistPara
         launch_pack_w_simt(mp->conv_w[k], wp[k], C, C + 1, 1, 0, st);
         launch_time_tapmap(mp->conv_w[k], tapmap[k], d->height, d->width, C, st);
     }
+    // With a tape every intermediate a backward pass needs is written straight into its slot: the stage input X,
+    // the two convolution outputs P1 / P2 (GroupNorm inputs) and the two convolution operands A / Hs.
     const float* y_cur = x;
+    if (save) {
+        MnistSlot s0 = mnist_slot(tape, E, 0);
+        if (check_cuda(cudaMemcpyAsync(s0.X, x, E * 4, cudaMemcpyDeviceToDevice, st), "copy x to tape")) return -1;
+        y_cur = s0.X;
+    }
     for (int n = 0; n < N; ++n) {
-        const float t0 = d->time_grid[n];
-        const float dt = d->time_grid[n + 1] - t0;
-        float* y_next = (n == N - 1) ? y_out : ybuf[n & 1];
+        const float dt = d->time_grid[n + 1] - d->time_grid[n];
+        float* y_next = (n == N - 1) ? y_out : (save ? mnist_slot(tape, E, (n + 1) * S).X : ybuf[n & 1]);
         for (int i = 0; i < S; ++i) {
-            volatile float cdt = d->c[i] * dt;                 // keep the reference's two roundings
-            const float ti = (i == 0) ? t0 : t0 + cdt;
-            const float* xi = (i == 0) ? y_cur : xbuf;
+            const float ti = mnist_stage_time(d, n, i);
+            MnistSlot sl = save ? mnist_slot(tape, E, n * S + i) : MnistSlot{nullptr, PQ, PQ, A, Hs};
+            const float* xi = (i == 0) ? y_cur : (save ? sl.X : xbuf);
             EpiParams g1 = epi_default();
-            g1.act = ACT_RELU; g1.out_split = A;
+            g1.act = ACT_RELU; g1.out_split = sl.A;
             if (launch_groupnorm_epi(xi, mp->norm_w[0], mp->norm_b[0], g1, shp, mp->groups, mp->eps, st)) return -1;
             EpiParams c1 = epi_default();
-            c1.chan_bias = mp->conv_b[0]; c1.pix_bias = tapmap[0]; c1.pix_bias_scale = ti; c1.out_f32 = PQ;
-            if (run_conv(MSB_ENGINE_SIMT, A, wp[0], c1, shp, st)) return -1;
+            c1.chan_bias = mp->conv_b[0]; c1.pix_bias = tapmap[0]; c1.pix_bias_scale = ti; c1.out_f32 = sl.P1;
+            if (run_conv(MSB_ENGINE_SIMT, sl.A, wp[0], c1, shp, st)) return -1;
             EpiParams g2 = epi_default();
-            g2.act = ACT_RELU; g2.out_split = Hs;
-            if (launch_groupnorm_epi(PQ, mp->norm_w[1], mp->norm_b[1], g2, shp, mp->groups, mp->eps, st)) return -1;
+            g2.act = ACT_RELU; g2.out_split = sl.Hs;
+            if (launch_groupnorm_epi(sl.P1, mp->norm_w[1], mp->norm_b[1], g2, shp, mp->groups, mp->eps, st)) return -1;
             EpiParams c2 = epi_default();
-            c2.chan_bias = mp->conv_b[1]; c2.pix_bias = tapmap[1]; c2.pix_bias_scale = ti; c2.out_f32 = PQ;
-            if (run_conv(MSB_ENGINE_SIMT, Hs, wp[1], c2, shp, st)) return -1;
+            c2.chan_bias = mp->conv_b[1]; c2.pix_bias = tapmap[1]; c2.pix_bias_scale = ti; c2.out_f32 = sl.P2;
+            if (run_conv(MSB_ENGINE_SIMT, sl.Hs, wp[1], c2, shp, st)) return -1;
+            float* const PQ2 = sl.P2;
             EpiParams g3 = epi_default();                       // k_i = GN3(.) and the RK combination
             g3.base = y_cur; g3.k[0].dt = dt;
             if (i < S - 1) {
@@ -361,14 +391,14 @@ static int mnist_forward(const MsbOdeDesc* d, const float* x, const MsbMnistPara
                 g3.nsrc = i;
                 for (int j = 0; j < i; ++j) { g3.src[j] = kbuf[j]; g3.k[0].coef[j] = d->w[(i + 1) * MSB_MAX_STAGES + j]; }
                 g3.k[0].coef_v = d->w[(i + 1) * MSB_MAX_STAGES + i];
-                g3.out_f32 = xbuf;
+                g3.out_f32 = save ? mnist_slot(tape, E, n * S + i + 1).X : xbuf;
             } else {
                 g3.nsrc = S - 1;
                 for (int j = 0; j < S - 1; ++j) { g3.src[j] = kbuf[j]; g3.k[0].coef[j] = d->b[j]; }
                 g3.k[0].coef_v = d->b[S - 1];
                 g3.out_f32 = y_next;
             }
-            if (launch_groupnorm_epi(PQ, mp->norm_w[2], mp->norm_b[2], g3, shp, mp->groups, mp->eps, st)) return -1;
+            if (launch_groupnorm_epi(PQ2, mp->norm_w[2], mp->norm_b[2], g3, shp, mp->groups, mp->eps, st)) return -1;
         }
         y_cur = y_next;
     }
@@ -380,7 +410,7 @@ int msb_odeblock_forward(const MsbOdeDesc* d, const float* x, const float* w1, c
                          void* tape, size_t tape_bytes, void* cuda_stream) {
     if (validate(d)) return -1;
     if (d->rhs_kind == MSB_RHS_MNIST_GN_T)
-        return mnist_forward(d, x, mnist, y_out, workspace, workspace_bytes, (cudaStream_t)cuda_stream);
+        return mnist_forward(d, x, mnist, y_out, workspace, workspace_bytes, tape, tape_bytes, (cudaStream_t)cuda_stream);
     int engine = resolve_engine(d);
     if (engine < 0) return -1;
     if (!x || !w1 || !w2 || !y_out || !workspace) { set_error("null pointer argument"); return -1; }
@@ -467,6 +497,7 @@ int msb_odeblock_backward(const MsbOdeDesc* d, const float* grad_y, const float*
                           const void* tape, size_t tape_bytes, float* grad_x, float* grad_w1, float* grad_w2,
                           void* workspace, size_t workspace_bytes, void* cuda_stream) {
     if (validate(d)) return -1;
+    if (d->rhs_kind == MSB_RHS_MNIST_GN_T) { set_error("use msb_odeblock_backward_mnist for the MNIST right-hand side"); return -1; }
     int engine = resolve_engine(d);
     if (engine < 0) return -1;
     if (!grad_y || !w1 || !w2 || !tape || !grad_x || !workspace) { set_error("null pointer argument"); return -1; }
@@ -558,6 +589,118 @@ int msb_odeblock_backward(const MsbOdeDesc* d, const float* grad_y, const float*
     }
     if (need_w && (wgrad_finish(engine, acc1, shp, st) || wgrad_finish(engine, acc2, shp, st))) return -1;
     return check_cuda(cudaGetLastError(), "odeblock backward");
+}
+
+// ---------------------------------------------------------------------------------------------
+// MNIST right-hand side, backward: the adjoint of mnist_forward, stage by stage in reverse.
+//   kbar_i --GN3'--> dP2 --conv2^T--> . --ReLU', GN2'--> dP1 --conv1^T--> . --ReLU', GN1'--> xbar_i
+// with the Runge-Kutta adjoint combination as the epilogue of the GN1' launch, and the parameter gradients
+// (x-channel weights: wgrad GEMM; time channel + bias: concat_aux_grad; gamma / beta: per-sample partials).
+// ---------------------------------------------------------------------------------------------
+int msb_odeblock_backward_mnist(const MsbOdeDesc* d, const float* grad_y, const MsbMnistParams* mp, const void* tape,
+                                size_t tape_bytes, float* grad_x, const MsbMnistGrads* grads, void* workspace,
+                                size_t workspace_bytes, void* cuda_stream) {
+    if (validate(d)) return -1;
+    if (d->rhs_kind != MSB_RHS_MNIST_GN_T) { set_error("msb_odeblock_backward_mnist: rhs_kind must be MSB_RHS_MNIST_GN_T"); return -1; }
+    if (!grad_y || !mp || !tape || !grad_x || !workspace) { set_error("null pointer argument"); return -1; }
+    for (int i = 0; i < 3; ++i) if (!mp->norm_w[i] || !mp->norm_b[i]) { set_error("MNIST params: null norm pointer"); return -1; }
+    for (int i = 0; i < 2; ++i) if (!mp->conv_w[i] || !mp->conv_b[i]) { set_error("MNIST params: null conv pointer"); return -1; }
+    if (tape_bytes < msb_odeblock_tape_bytes(d)) { set_error("tape too small"); return -1; }
+    if (workspace_bytes < msb_odeblock_bwd_workspace_bytes(d)) { set_error("workspace too small"); return -1; }
+    const bool need_w = grads != nullptr;
+    if (need_w) {
+        for (int i = 0; i < 3; ++i) if (!grads->norm_w[i] || !grads->norm_b[i]) { set_error("MNIST grads: null norm pointer"); return -1; }
+        for (int i = 0; i < 2; ++i) if (!grads->conv_w[i] || !grads->conv_b[i]) { set_error("MNIST grads: null conv pointer"); return -1; }
+    }
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int S = d->stages, N = d->n_steps, C = d->channels;
+    const size_t E = state_elems(d);
+    ConvShape shp{d->batch, d->height, d->width, C};
+    Carver cv(workspace, workspace_bytes);
+    float* wt[2] = {cv.take<float>((size_t)9 * C * C * 4), cv.take<float>((size_t)9 * C * C * 4)};
+    float* gbuf[2] = {cv.take<float>(E * 4), cv.take<float>(E * 4)};
+    float* xbar[MSB_MAX_STAGES] = {nullptr, nullptr, nullptr, nullptr};
+    for (int i = 1; i < S; ++i) xbar[i] = cv.take<float>(E * 4);
+    float* kbar = cv.take<float>(E * 4);
+    float* dP = cv.take<float>(E * 4);
+    float* dH = cv.take<float>(E * 4);
+    __nv_bfloat16* Dsplit = cv.take<__nv_bfloat16>(E * 4);
+    float* wpart = cv.take<float>((size_t)wgrad_simt_nparts(shp) * 9 * C * C * 4);
+    float* gnpart[6];
+    for (int i = 0; i < 6; ++i) gnpart[i] = cv.take<float>((size_t)d->batch * C * 4);     // (dgamma_k, dbeta_k), k = 1..3
+    if (!cv.ok()) { set_error("internal: workspace carve overflow"); return -1; }
+    for (int k = 0; k < 2; ++k) launch_pack_w_simt(mp->conv_w[k], wt[k], C, C + 1, 1, 1, st);
+
+    auto dt_of = [&](int n) { return d->time_grid[n + 1] - d->time_grid[n]; };
+    int evals = 0;                                   // stage evaluations processed so far (first one overwrites the accumulators)
+    const float* g_cur = grad_y;
+    for (int n = N - 1; n >= 0; --n) {
+        const float dt = dt_of(n);
+        float* g_next = (n == 0) ? grad_x : gbuf[n & 1];
+        for (int i = S - 1; i >= 0; --i) {
+            const MnistSlot sl = mnist_slot(const_cast<void*>(tape), E, n * S + i);
+            const float ti = mnist_stage_time(d, n, i);
+            const int acc = evals > 0;
+            // kbar_S = dt b_S gbar (folded into the scale of dy); kbar_i (i < S) was formed by the previous GN1' epilogue
+            const float* dy3 = (i == S - 1) ? g_cur : kbar;
+            const float sc3 = (i == S - 1) ? dt * d->b[S - 1] : 1.f;
+            EpiParams e = epi_default();
+            e.out_f32 = dP; e.out_split = Dsplit;
+            if (launch_groupnorm_bwd_epi(sl.P2, mp->norm_w[2], mp->norm_b[2], dy3, sc3, 0, e, need_w ? gnpart[4] : nullptr,
+                                         need_w ? gnpart[5] : nullptr, acc, shp, mp->groups, mp->eps, st)) return -1;
+            if (need_w) {
+                int np = 0;
+                if (launch_wgrad3x3_simt(Dsplit, sl.Hs, wpart, &np, shp, st)) return -1;
+                launch_wgrad_reduce(wpart, np, grads->conv_w[1], C, acc, st, C + 1, 1);
+                launch_concat_aux_grad(dP, ti, grads->conv_w[1], grads->conv_b[1], acc, shp, st);
+            }
+            e = epi_default();
+            e.out_f32 = dH;
+            if (run_conv(MSB_ENGINE_SIMT, Dsplit, wt[1], e, shp, st)) return -1;
+            e = epi_default();
+            e.out_f32 = dP; e.out_split = Dsplit;
+            if (launch_groupnorm_bwd_epi(sl.P1, mp->norm_w[1], mp->norm_b[1], dH, 1.f, 1, e, need_w ? gnpart[2] : nullptr,
+                                         need_w ? gnpart[3] : nullptr, acc, shp, mp->groups, mp->eps, st)) return -1;
+            if (need_w) {
+                int np = 0;
+                if (launch_wgrad3x3_simt(Dsplit, sl.A, wpart, &np, shp, st)) return -1;
+                launch_wgrad_reduce(wpart, np, grads->conv_w[0], C, acc, st, C + 1, 1);
+                launch_concat_aux_grad(dP, ti, grads->conv_w[0], grads->conv_b[0], acc, shp, st);
+            }
+            e = epi_default();
+            e.out_f32 = dH;
+            if (run_conv(MSB_ENGINE_SIMT, Dsplit, wt[0], e, shp, st)) return -1;
+            // xbar_i = GN1'(ReLU'(.)) and the adjoint stage combination (same algebra as the CIFAR path)
+            EpiParams e4 = epi_default();
+            e4.base = g_cur;
+            if (i > 0) {
+                e4.v_out = xbar[i];
+                e4.base_is_one = 0;
+                e4.k[0].base_coef = dt * d->b[i - 1];
+                int ns = 0;
+                for (int j = S - 1; j > i; --j) { e4.src[ns] = xbar[j]; e4.k[0].coef[ns] = d->w[j * MSB_MAX_STAGES + (i - 1)]; ++ns; }
+                e4.nsrc = ns;
+                e4.k[0].coef_v = d->w[i * MSB_MAX_STAGES + (i - 1)];
+                e4.k[0].dt = dt;
+                e4.out_f32 = kbar;
+            } else {
+                int ns = 0;
+                for (int j = S - 1; j > 0; --j) { e4.src[ns] = xbar[j]; e4.k[0].coef[ns] = 1.f; ++ns; }
+                e4.nsrc = ns;
+                e4.out_f32 = g_next;
+            }
+            if (launch_groupnorm_bwd_epi(sl.X, mp->norm_w[0], mp->norm_b[0], dH, 1.f, 1, e4, need_w ? gnpart[0] : nullptr,
+                                         need_w ? gnpart[1] : nullptr, acc, shp, mp->groups, mp->eps, st)) return -1;
+            ++evals;
+        }
+        g_cur = g_next;
+    }
+    if (need_w)
+        for (int k = 0; k < 3; ++k) {
+            launch_sum_over_batch(gnpart[2 * k], grads->norm_w[k], d->batch, C, st);
+            launch_sum_over_batch(gnpart[2 * k + 1], grads->norm_b[k], d->batch, C, st);
+        }
+    return check_cuda(cudaGetLastError(), "odeblock backward (mnist)");
 }
 
 int msb_act_split(const float* x, int act, void* split_out, float* dact_out, int batch, int height, int width,

@@ -215,39 +215,92 @@ def ode_block_integrate_stacked(x, w1, w2, tableaus, time_grid, rhs_kind=_cabi.R
     return y.view(K, *x.shape)
 
 
+_MNIST_KEYS = ("norm1_w", "norm1_b", "norm2_w", "norm2_b", "norm3_w", "norm3_b", "conv1_w", "conv1_b", "conv2_w", "conv2_b")
+
+
+def _mnist_params_struct(keep, groups, eps):
+    mp = _cabi.MsbMnistParams()
+    for i in range(3):
+        mp.norm_w[i] = keep["norm%d_w" % (i + 1)].data_ptr()
+        mp.norm_b[i] = keep["norm%d_b" % (i + 1)].data_ptr()
+    for i in range(2):
+        mp.conv_w[i] = keep["conv%d_w" % (i + 1)].data_ptr()
+        mp.conv_b[i] = keep["conv%d_b" % (i + 1)].data_ptr()
+    mp.groups, mp.eps = groups, eps
+    return mp
+
+
+class _MnistOdeBlockFn(torch.autograd.Function):
+    """ODE block with the MNIST right-hand side; backward = fused discretize-then-optimize pass
+    (msb_odeblock_backward_mnist): gradients w.r.t. x and all ten RHS parameters."""
+
+    @staticmethod
+    def forward(ctx, x, prob, groups, eps, *params):
+        lib = _cabi.lib()
+        dev = x.device
+        need_grad = ctx.needs_input_grad[0] or any(ctx.needs_input_grad[4:])
+        with torch.cuda.device(dev):
+            xc = x.detach().contiguous(memory_format=torch.channels_last)
+            keep = {k: v.detach().contiguous() for k, v in zip(_MNIST_KEYS, params)}
+            mp = _mnist_params_struct(keep, groups, eps)
+            d = prob.desc(tuple(x.shape), need_grad)
+            ws_bytes = lib.msb_odeblock_workspace_bytes(ctypes.byref(d))
+            if ws_bytes == 0:
+                _cabi.check(-1, "odeblock workspace query")
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            tape, tape_bytes = None, 0
+            if need_grad:
+                tape_bytes = lib.msb_odeblock_tape_bytes(ctypes.byref(d))
+                tape = torch.empty(tape_bytes, dtype=torch.uint8, device=dev)
+            y = torch.empty_like(xc)
+            rc = lib.msb_odeblock_forward(ctypes.byref(d), _ptr(xc), None, None, ctypes.byref(mp), _ptr(y), _ptr(ws),
+                                          ws_bytes, _ptr(tape), tape_bytes, _stream(dev))
+            _cabi.check(rc, "odeblock forward (mnist)")
+        ctx.prob, ctx.groups, ctx.eps, ctx.tape, ctx.tape_bytes, ctx.shape = prob, groups, eps, tape, tape_bytes, tuple(x.shape)
+        ctx.save_for_backward(*[keep[k] for k in _MNIST_KEYS])
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _cabi.lib()
+        if ctx.tape is None:
+            raise RuntimeError("metasolver_b200: backward called but no tape was recorded")
+        keep = dict(zip(_MNIST_KEYS, ctx.saved_tensors))
+        dev = gy.device
+        need_w = any(ctx.needs_input_grad[4:]) and not getattr(_state, "input_only", False)
+        with torch.cuda.device(dev):
+            gyc = gy.contiguous(memory_format=torch.channels_last)
+            mp = _mnist_params_struct(keep, ctx.groups, ctx.eps)
+            d = ctx.prob.desc(ctx.shape, True)
+            ws_bytes = lib.msb_odeblock_bwd_workspace_bytes(ctypes.byref(d))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            gx = torch.empty_like(gyc)
+            grads, gstruct = None, None
+            if need_w:
+                grads = {k: torch.zeros_like(v) for k, v in keep.items()}
+                gstruct = _cabi.MsbMnistGrads()
+                for i in range(3):
+                    gstruct.norm_w[i] = grads["norm%d_w" % (i + 1)].data_ptr()
+                    gstruct.norm_b[i] = grads["norm%d_b" % (i + 1)].data_ptr()
+                for i in range(2):
+                    gstruct.conv_w[i] = grads["conv%d_w" % (i + 1)].data_ptr()
+                    gstruct.conv_b[i] = grads["conv%d_b" % (i + 1)].data_ptr()
+            rc = lib.msb_odeblock_backward_mnist(ctypes.byref(d), _ptr(gyc), ctypes.byref(mp), _ptr(ctx.tape), ctx.tape_bytes,
+                                                 _ptr(gx), ctypes.byref(gstruct) if need_w else None, _ptr(ws), ws_bytes,
+                                                 _stream(dev))
+            _cabi.check(rc, "odeblock backward (mnist)")
+        ctx.tape = None
+        return (gx, None, None, None) + (tuple(grads[k] for k in _MNIST_KEYS) if need_w else (None,) * len(_MNIST_KEYS))
+
+
 def ode_block_integrate_mnist(x, params, tableau, time_grid, groups, eps=1e-5):
     """MNIST right-hand side (GroupNorm / ReLU / time-concatenated convs, mnist/layers.py:158-171).
-    `params`: dict(norm{1,2,3}_{w,b}, conv{1,2}_{w,b}) of fp32 CUDA tensors.  Forward only."""
+    `params`: dict(norm{1,2,3}_{w,b}, conv{1,2}_{w,b}) of fp32 CUDA tensors.  Differentiable w.r.t. x and all params."""
     if not x.is_cuda:
         raise RuntimeError("metasolver_b200: the ODE-block path runs on CUDA only (got a %s tensor); "
                            "there is no CPU fallback" % x.device)
-    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params.values())):
-        raise NotImplementedError("metasolver_b200: the backward of the MNIST (GroupNorm, time-dependent) right-hand "
-                                  "side is not implemented yet; run it under torch.no_grad()")
-    lib = _cabi.lib()
-    dev = x.device
     prob = OdeProblem(_cabi.RHS_MNIST_GN_T, _cabi.ACT_RELU, tableau, time_grid, "simt")
-    with torch.cuda.device(dev):
-        xc = x.detach().contiguous(memory_format=torch.channels_last)
-        keep = {k: v.detach().contiguous() for k, v in params.items()}
-        mp = _cabi.MsbMnistParams()
-        for i in range(3):
-            mp.norm_w[i] = keep["norm%d_w" % (i + 1)].data_ptr()
-            mp.norm_b[i] = keep["norm%d_b" % (i + 1)].data_ptr()
-        for i in range(2):
-            mp.conv_w[i] = keep["conv%d_w" % (i + 1)].data_ptr()
-            mp.conv_b[i] = keep["conv%d_b" % (i + 1)].data_ptr()
-        mp.groups, mp.eps = groups, eps
-        d = prob.desc(tuple(x.shape), False)
-        ws_bytes = lib.msb_odeblock_workspace_bytes(ctypes.byref(d))
-        if ws_bytes == 0:
-            _cabi.check(-1, "odeblock workspace query")
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        y = torch.empty_like(xc)
-        rc = lib.msb_odeblock_forward(ctypes.byref(d), _ptr(xc), None, None, ctypes.byref(mp), _ptr(y), _ptr(ws),
-                                      ws_bytes, None, 0, _stream(dev))
-        _cabi.check(rc, "odeblock forward (mnist)")
-    return y
+    return _MnistOdeBlockFn.apply(x, prob, groups, eps, *[params[k] for k in _MNIST_KEYS])
 
 
 # --------------------------------------------------------------------------- non-ODE layers (SURVEY 8(f-1))
