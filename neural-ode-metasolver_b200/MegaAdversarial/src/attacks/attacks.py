@@ -17,8 +17,19 @@ import torch.nn as nn
 from ....ops import input_grad_only
 
 
+_CHAN_CACHE = {}
+
+
 def _chan(vals, like):
-    return torch.as_tensor(list(vals), dtype=like.dtype, device=like.device).view(1, -1, 1, 1)
+    """Per-channel constant as a (1,C,1,1) tensor on `like`'s device.  Cached: the attacks call this several
+    times per iteration, and a fresh host->device copy each time would serialise the loop on the host (and
+    cannot be captured into a CUDA graph)."""
+    key = (tuple(float(v) for v in vals), like.dtype, like.device)
+    t = _CHAN_CACHE.get(key)
+    if t is None:
+        t = torch.as_tensor(list(vals), dtype=like.dtype, device=like.device).view(1, -1, 1, 1)
+        _CHAN_CACHE[key] = t
+    return t
 
 
 class _Normalizer:

@@ -208,6 +208,26 @@ int resolve_engine(const MsbOdeDesc* d) {
 size_t state_elems(const MsbOdeDesc* d) { return (size_t)d->batch * d->height * d->width * d->channels; }
 
 struct TapeSlot { __nv_bfloat16* A; float* G0; __nv_bfloat16* Hs; float* G1; };
+// the same slot, advanced to the images [b0, ...) of the batch (`off` = b0 * H*W*C state elements)
+TapeSlot slot_at(TapeSlot t, size_t off) {
+    t.A += 2 * off; t.Hs += 2 * off;              // split tensors hold two bf16 planes per state element
+    if (t.G0) t.G0 += off;
+    if (t.G1) t.G1 += off;
+    return t;
+}
+// Micro-batching (L2 locality): an ODE block is a chain of launches in which every tensor is consumed by the launch
+// right after the one that wrote it.  At B = 512 a state tensor is 134 MB (> the 126 MB L2), so every hand-off
+// round-trips HBM.  Integrating the batch in slices of `MSB_MICROBATCH` images, each slice taken through all steps
+// before the next one starts, keeps those hand-offs L2-resident; samples are independent, results are unchanged.
+int microbatch_images(const MsbOdeDesc* d, int n_slices) {
+    static int env = -2;
+    if (env == -2) { const char* e = getenv("MSB_MICROBATCH"); env = e ? atoi(e) : -1; }
+    if (n_slices > 1) return d->batch;              // stacked solver axis: one launch covers every slice
+    int mb = env;
+    if (mb < 0) mb = 0;                              // default: off (see DESIGN.md for the measured trade-off)
+    if (mb <= 0 || mb >= d->batch || d->batch % mb) return d->batch;   // equal slices only (wgrad partial slots)
+    return mb;
+}
 TapeSlot tape_slot(void* tape, size_t E, int slot) {
     char* p = (char*)tape + (size_t)slot * 4 * align_up(E * 4);
     size_t q = align_up(E * 4);
@@ -420,7 +440,6 @@ int msb_odeblock_forward(const MsbOdeDesc* d, const float* x, const float* w1, c
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const int S = d->stages, N = d->n_steps, C = d->channels;
     const size_t E = state_elems(d);
-    ConvShape shp{d->batch, d->height, d->width, C};
 
     Carver cv(workspace, workspace_bytes);
     void* wp1 = cv.take<char>(packed_w_bytes(engine, C));
@@ -436,7 +455,7 @@ int msb_odeblock_forward(const MsbOdeDesc* d, const float* x, const float* w1, c
     pack_w(engine, w2, wp2, C, 0, st);
     const Tabs tabs = make_tabs(d);
 
-    auto slot = [&](int n, int i) {
+    auto slot_full = [&](int n, int i) {
         if (save) return tape_slot(tape, E, n * S + i);
         return TapeSlot{A_inf, nullptr, Hs_inf, nullptr};
     };
@@ -445,14 +464,20 @@ int msb_odeblock_forward(const MsbOdeDesc* d, const float* x, const float* w1, c
     //                      tape holds G2 = act'(conv2 output), needed by the backward of k_i = act(.)
     const bool post = d->rhs_kind == MSB_RHS_POSTACT_NF;
     const int act_in = post ? ACT_NONE : d->act;
+    const int MB = microbatch_images(d, tabs.K);
+    const size_t img_elems = (size_t)d->height * d->width * C;
+    for (int b0 = 0; b0 < d->batch; b0 += MB) {
+    const size_t off = (size_t)b0 * img_elems;
+    const ConvShape shp{std::min(MB, d->batch - b0), d->height, d->width, C};
+    auto slot = [&](int n, int i) { return slot_at(slot_full(n, i), off); };
     {   // prologue: operand of the very first conv1
         TapeSlot s0 = slot(0, 0);
-        launch_act_split(x, nullptr, act_in, 1.f, s0.A, post ? nullptr : s0.G0, d->batch, d->height, d->width, C, st);
+        launch_act_split(x + off, nullptr, act_in, 1.f, s0.A, post ? nullptr : s0.G0, shp.B, d->height, d->width, C, st);
     }
-    const float* y_cur = x;
+    const float* y_cur = x + off;
     for (int n = 0; n < N; ++n) {
         const float dt = d->time_grid[n + 1] - d->time_grid[n];      // fp32, as `t1 - t0` (rk_parametric.py:105)
-        float* y_next = (n == N - 1) ? y_out : ybuf[n & 1];
+        float* y_next = ((n == N - 1) ? y_out : ybuf[n & 1]) + off;
         for (int i = 0; i < S; ++i) {
             TapeSlot cur = slot(n, i);
             // conv1: P = conv(A_i, W1);  Hs_i = split(act(P)),  G1_i = act'(P)
@@ -466,9 +491,9 @@ int msb_odeblock_forward(const MsbOdeDesc* d, const float* x, const float* w1, c
             if (post) { e2.act_v = d->act; e2.dact_v_out = cur.G0; }
             if (i < S - 1) {
                 // x_{i+1} = y + (sum_j k_j w[i+1][j]) dt          (order2stage2.py:91, order3stage3.py:100-101 ...)
-                e2.v_out = kbuf[i];
+                e2.v_out = kbuf[i] + off;
                 e2.nsrc = i;
-                for (int j = 0; j < i; ++j) e2.src[j] = kbuf[j];
+                for (int j = 0; j < i; ++j) e2.src[j] = kbuf[j] + off;
                 for (int q = 0; q < tabs.K; ++q) {
                     for (int j = 0; j < i; ++j) e2.k[q].coef[j] = tabs.t[q].w[(i + 1) * MSB_MAX_STAGES + j];
                     e2.k[q].coef_v = tabs.t[q].w[(i + 1) * MSB_MAX_STAGES + i];
@@ -478,7 +503,7 @@ int msb_odeblock_forward(const MsbOdeDesc* d, const float* x, const float* w1, c
             } else {
                 // y1 = y0 + (sum_j k_j b_j) dt                     (order2stage2.py:93, rk_parametric.py:106)
                 e2.nsrc = S - 1;
-                for (int j = 0; j < S - 1; ++j) e2.src[j] = kbuf[j];
+                for (int j = 0; j < S - 1; ++j) e2.src[j] = kbuf[j] + off;
                 for (int q = 0; q < tabs.K; ++q) {
                     for (int j = 0; j < S - 1; ++j) e2.k[q].coef[j] = tabs.t[q].b[j];
                     e2.k[q].coef_v = tabs.t[q].b[S - 1];
@@ -490,6 +515,7 @@ int msb_odeblock_forward(const MsbOdeDesc* d, const float* x, const float* w1, c
         }
         y_cur = y_next;
     }
+    }   // micro-batches
     return check_cuda(cudaGetLastError(), "odeblock forward");
 }
 
@@ -516,9 +542,9 @@ int msb_odeblock_backward(const MsbOdeDesc* d, const float* grad_y, const float*
     float* gbuf[2] = {cv.take<float>(E * 4), cv.take<float>(E * 4)};
     float* xbar[MSB_MAX_STAGES] = {nullptr, nullptr, nullptr, nullptr};   // xbar[i], i = 1..S-1
     for (int i = 1; i < S; ++i) xbar[i] = cv.take<float>(E * 4);
-    __nv_bfloat16* Kbar = cv.take<__nv_bfloat16>(E * 4);
-    __nv_bfloat16* DP = cv.take<__nv_bfloat16>(E * 4);
-    const size_t part_bytes = (size_t)wgrad_nparts(engine, shp) * 9 * C * C * 4;
+    __nv_bfloat16* Kbar_full = cv.take<__nv_bfloat16>(E * 4);
+    __nv_bfloat16* DP_full = cv.take<__nv_bfloat16>(E * 4);
+    const size_t part_bytes = (size_t)wgrad_nparts(engine, ConvShape{d->batch, d->height, d->width, C}) * 9 * C * C * 4;
     WgradAcc acc1{cv.take<float>(part_bytes), grad_w1, 0, 0}, acc2{cv.take<float>(part_bytes), grad_w2, 0, 0};
     if (!cv.ok()) { set_error("internal: workspace carve overflow"); return -1; }
 
@@ -529,19 +555,27 @@ int msb_odeblock_backward(const MsbOdeDesc* d, const float* grad_y, const float*
     auto dt_of = [&](int n) { return d->time_grid[n + 1] - d->time_grid[n]; };
     // kbar_S of the last step = dt * b_S * gbar   (post-activation RHS: times act'(conv2 output) of that stage)
     const bool post = d->rhs_kind == MSB_RHS_POSTACT_NF;
-    auto g2_of = [&](int n, int i) { return tape_slot(const_cast<void*>(tape), E, n * S + i).G0; };
+    const int MB = microbatch_images(d, tabs.K);
+    const size_t img_elems = (size_t)d->height * d->width * C;
+    for (int b0 = 0; b0 < d->batch; b0 += MB) {
+    const size_t off = (size_t)b0 * img_elems;
+    const ConvShape shp{std::min(MB, d->batch - b0), d->height, d->width, C};
+    __nv_bfloat16* const Kbar = Kbar_full + 2 * off;
+    __nv_bfloat16* const DP = DP_full + 2 * off;
+    auto slot = [&](int n, int i) { return slot_at(tape_slot(const_cast<void*>(tape), E, n * S + i), off); };
+    auto g2_of = [&](int n, int i) { return slot(n, i).G0; };
     {
         float scales[kMaxSlices];
         for (int q = 0; q < tabs.K; ++q) scales[q] = dt_of(N - 1) * tabs.t[q].b[S - 1];
-        launch_act_split_sliced(grad_y, post ? g2_of(N - 1, S - 1) : nullptr, ACT_NONE, scales, tabs.K, Kbar, nullptr,
-                                d->batch, d->height, d->width, C, st);
+        launch_act_split_sliced(grad_y + off, post ? g2_of(N - 1, S - 1) : nullptr, ACT_NONE, scales, tabs.K, Kbar, nullptr,
+                                shp.B, d->height, d->width, C, st);
     }
-    const float* g_cur = grad_y;
+    const float* g_cur = grad_y + off;
     for (int n = N - 1; n >= 0; --n) {
         const float dt = dt_of(n);
-        float* g_next = (n == 0) ? grad_x : gbuf[n & 1];
+        float* g_next = ((n == 0) ? grad_x : gbuf[n & 1]) + off;
         for (int i = S - 1; i >= 0; --i) {
-            TapeSlot cur = tape_slot(const_cast<void*>(tape), E, n * S + i);
+            TapeSlot cur = slot(n, i);
             // Kbar = split(kbar_i).   dW2 += kbar_i (x) Hs_i
             if (need_w && run_wgrad(engine, Kbar, cur.Hs, acc2, shp, st)) return -1;
             // dP = dgrad_W2(kbar_i) * act'(P_i)
@@ -555,10 +589,10 @@ int msb_odeblock_backward(const MsbOdeDesc* d, const float* grad_y, const float*
             e4.mul = post ? nullptr : cur.G0; e4.base = g_cur; e4.slice_batch = tabs.slice_batch;
             if (i > 0) {
                 // kbar_{i-1} = dt b_{i-1} gbar + dt sum_{j >= i} w[j][i-1] xbar_j
-                e4.v_out = xbar[i];
+                e4.v_out = xbar[i] + off;
                 e4.base_is_one = 0;
                 int ns = 0;
-                for (int j = S - 1; j > i; --j) e4.src[ns++] = xbar[j];
+                for (int j = S - 1; j > i; --j) e4.src[ns++] = xbar[j] + off;
                 e4.nsrc = ns;
                 for (int q = 0; q < tabs.K; ++q) {
                     EpiCoef& k = e4.k[q];
@@ -573,7 +607,7 @@ int msb_odeblock_backward(const MsbOdeDesc* d, const float* grad_y, const float*
             } else {
                 // ybar = gbar + sum_i xbar_i ; and kbar_S of the previous step
                 int ns = 0;
-                for (int j = S - 1; j > 0; --j) e4.src[ns++] = xbar[j];
+                for (int j = S - 1; j > 0; --j) e4.src[ns++] = xbar[j] + off;
                 e4.nsrc = ns;
                 for (int q = 0; q < tabs.K; ++q) e4.k[q].coef[0] = e4.k[q].coef[1] = e4.k[q].coef[2] = 1.f;
                 e4.out_f32 = g_next;
@@ -587,6 +621,7 @@ int msb_odeblock_backward(const MsbOdeDesc* d, const float* grad_y, const float*
         }
         g_cur = g_next;
     }
+    }   // micro-batches
     if (need_w && (wgrad_finish(engine, acc1, shp, st) || wgrad_finish(engine, acc2, shp, st))) return -1;
     return check_cuda(cudaGetLastError(), "odeblock backward");
 }
