@@ -84,3 +84,37 @@ def test_full_batch_backward_properties():
     _, ha2, hb2 = grads(g1[256:].contiguous(memory_format=torch.channels_last), x[256:].contiguous(memory_format=torch.channels_last))
     assert max_rel((ha + ha2).cpu().numpy(), gw1a.cpu().numpy()) < 1e-4   # 5e5-term fp32 sums, different split-K partition
     assert max_rel((hb + hb2).cpu().numpy(), gw1b.cpu().numpy()) < 1e-4
+
+
+def test_cuda_graph_replay_equals_eager_step():
+    """metasolver_b200.GraphedStep: a captured forward+backward of premetanode10 replays to the same loss and
+    gradients as the eager step (every launch is a plain stream-ordered kernel with its scalars in the parameters)."""
+    from argparse import Namespace
+    import torch.nn.functional as F
+    import metasolver_b200 as msb
+    from metasolver_b200.sopa.src.solvers.utils import create_solver
+    from metasolver_b200.sopa.src.models.odenet_cifar10.layers import premetanode10
+    from metasolver_b200.sopa.src.models.odenet_cifar10.utils import Identity
+    torch.manual_seed(3)
+    model = premetanode10((Identity,) * 3, (lambda x: x,) * 3, (F.gelu,) * 3, in_planes=64, is_odenet=True).cuda()
+    model = model.to(memory_format=torch.channels_last)
+    solver = create_solver("rk2", "u", 4, -1, 0.5, -1, torch.float32, "cuda")
+    solver.freeze_params()
+    opts = Namespace(solver_mode="standalone")
+    x = torch.randn(16, 3, 32, 32, device="cuda").contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 10, (16,), device="cuda")
+
+    def step(xx, yy):
+        model.zero_grad(set_to_none=True)
+        loss = F.cross_entropy(model(xx, [solver], opts), yy)
+        loss.backward()
+        return loss
+    loss_e = step(x, y).item()
+    grads_e = {k: p.grad.clone() for k, p in model.named_parameters()}
+    g = msb.GraphedStep(step, (x, y))
+    x2 = torch.randn_like(x)
+    g(x2, y)                                   # different batch through the same graph ...
+    loss_g = g(x, y).item()                    # ... and back: replay must reproduce the eager numbers exactly
+    assert loss_g == loss_e
+    for k, p in model.named_parameters():
+        assert torch.equal(p.grad, grads_e[k]), k
