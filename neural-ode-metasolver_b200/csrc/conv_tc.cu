@@ -130,7 +130,11 @@ constexpr int kMaxStages = 8;
 // Per-shape tuning.  C=64 has half the MMA time per output element of C=128, so its epilogue gets 16
 // warps (4-pixel chunks) and the weight ring is deepened at the cost of one activation stage:
 // the weight tiles turn over every 512 MMA cycles, far less than a loaded-L2 TMA round trip.
-template <int C, int WIMG> struct TileGeom {
+// RES: all weight tiles stay resident in shared memory for the whole kernel (C = 64 only: 9 x 16 KB), loaded once
+// per CTA instead of once per tile -- the weight stream was half of the L2 -> SM traffic (profiles/).  To make room
+// the tile is 8 rows x 16 pixels (two 40 KB activation stages) also on 32-pixel-wide images: WIMG is the TILE width,
+// the image width is a runtime parameter (a multiple of WIMG).
+template <int C, int WIMG, bool RES = false> struct TileGeom {
     static constexpr int ROWS = 128 / WIMG;                       // image rows per 128-pixel tile
     static constexpr int B_STAGE_BYTES = (ROWS + 2) * 2 * WIMG * 128;
     static constexpr int ROW_PAIR_BYTES = 2 * WIMG * 128;         // one image row, both planes
@@ -138,8 +142,10 @@ template <int C, int WIMG> struct TileGeom {
     static constexpr int THREADS = (kEpiWarp0 + EPI_WARPS) * 32;
     static constexpr int PXO = (C == 64) ? 4 : 8;                 // pixels one epilogue thread owns per chunk
     static constexpr int B_STAGES = MSB_B_STAGES;
-    static constexpr int A_STAGES = (212992 - B_STAGES * B_STAGE_BYTES) / kATileBytes > kMaxStages
-                                        ? kMaxStages : (212992 - B_STAGES * B_STAGE_BYTES) / kATileBytes;
+    static constexpr int A_RING = (212992 - B_STAGES * B_STAGE_BYTES) / kATileBytes > kMaxStages
+                                      ? kMaxStages : (212992 - B_STAGES * B_STAGE_BYTES) / kATileBytes;
+    static constexpr int A_STAGES = RES ? 9 : A_RING;             // smem weight tiles
+    static_assert(!RES || C == 64, "resident weights: C = 64 only");
 };
 
 struct __align__(8) Barriers {
@@ -149,11 +155,20 @@ struct __align__(8) Barriers {
     uint32_t tmem_base;
 };
 
-template <int C, int WIMG, int ACT>
-__global__ void __launch_bounds__((TileGeom<C, WIMG>::THREADS), 1)
+template <int C, int WIMG, int ACT, bool RES>
+__global__ void __launch_bounds__((TileGeom<C, WIMG, RES>::THREADS), 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_w,
-                  const EpiParams epi, const int H, const int num_tiles, const int tiles_per_img) {
-    using G = TileGeom<C, WIMG>;
+                  const EpiParams epi, const int H, const int Wimg, const int num_tiles, const int tiles_per_img) {
+    using G = TileGeom<C, WIMG, RES>;
+    const int cols = Wimg / WIMG;                                  // tile columns per image
+    // tile -> (image n, first row h0, first pixel column w_off); neighbouring tiles are neighbouring columns
+    auto tile_coords = [&](int tile, int& n, int& h0, int& w_off) {
+        n = tile / tiles_per_img;
+        const int t = tile - n * tiles_per_img;
+        const int band = t / cols;
+        h0 = band * G::ROWS;
+        w_off = (t - band * cols) * WIMG;
+    };
     constexpr int CHUNKS = C / 64;
     constexpr int kAStages = G::A_STAGES, kBStages = G::B_STAGES, kNumEpiWarps = G::EPI_WARPS, kPXO = G::PXO;
     constexpr int PARTS = (C == 64) ? 1 : 2;          // weight tiles per (tap, chunk): C=64 packs hi/lo into one tile
@@ -188,8 +203,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
         if (lane == 0) {
             int st = 0; uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int n = tile / tiles_per_img;
-                const int h0 = (tile - n * tiles_per_img) * G::ROWS;
+                int n, h0, w_off;
+                tile_coords(tile, n, h0, w_off);
                 for (int chunk = 0; chunk < CHUNKS; ++chunk)
                     for (int s = 0; s < 3; ++s) {
                         ptx::mbar_wait(&bars->b_empty[st], ph ^ 1);
@@ -197,7 +212,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
                         else {
                         ptx::mbar_arrive_expect_tx(&bars->b_full[st], G::B_STAGE_BYTES);
                         ptx::tma_load_5d(smem_b + st * G::B_STAGE_BYTES, &tmap_act, &bars->b_full[st],
-                                         chunk * 64, s - 1, 0, h0 - 1, n);
+                                         chunk * 64, w_off + s - 1, 0, h0 - 1, n);
                         }
                         if (++st == kBStages) { st = 0; ph ^= 1; }
                     }
@@ -205,7 +220,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
         }
     } else if (warp == 3) {
         // ===================== weight producer =====================
-        if (lane == 0) {
+        if (lane == 0 && RES) {
+            // resident weights: all 9 tiles once, one barrier
+            ptx::mbar_arrive_expect_tx(&bars->a_full[0], 9 * kATileBytes);
+            for (int wt = 0; wt < 9; ++wt)
+                ptx::tma_load_2d(smem_a + wt * kATileBytes, &tmap_w, &bars->a_full[0], 0, wt * 128);
+        } else if (lane == 0) {
             int st = 0; uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 for (int chunk = 0; chunk < CHUNKS; ++chunk)
@@ -230,6 +250,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
             constexpr uint32_t idesc = ptx::make_idesc_bf16(128, 256, 0, 0);
             int ast = 0, bst = 0; uint32_t aph = 0, bph = 0;
             int acc = 0; uint32_t acc_ph = 0;
+            if (RES) { ptx::mbar_wait(&bars->a_full[0], 0); ptx::tc_fence_after(); }
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 ptx::mbar_wait(&bars->tmem_empty[acc], acc_ph ^ 1);
                 ptx::tc_fence_after();
@@ -242,8 +263,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
                         const uint32_t b_base = ptx::smem_u32(smem_b + bst * G::B_STAGE_BYTES);
                         for (int r = 0; r < 3; ++r)
                             for (int part = 0; part < PARTS; ++part) {
-                                ptx::mbar_wait(&bars->a_full[ast], aph);
-                                ptx::tc_fence_after();
+                                if (RES) ast = r * 3 + s;
+                                else { ptx::mbar_wait(&bars->a_full[ast], aph); ptx::tc_fence_after(); }
                                 const uint32_t a_base = ptx::smem_u32(smem_a + ast * kATileBytes);
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
@@ -253,8 +274,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
                                     if (!MSB_DBG(2)) ptx::umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
                                     accumulate = 1;
                                 }
-                                ptx::umma_commit(&bars->a_empty[ast]);
-                                if (++ast == kAStages) { ast = 0; aph ^= 1; }
+                                if (!RES) {
+                                    ptx::umma_commit(&bars->a_empty[ast]);
+                                    if (++ast == kAStages) { ast = 0; aph ^= 1; }
+                                }
                             }
                         ptx::umma_commit(&bars->b_empty[bst]);
                         if (++bst == kBStages) { bst = 0; bph ^= 1; }
@@ -281,25 +304,26 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
         constexpr int NCHUNK = RH * STEPS_PER_ROW;    // chunks (of kPXO owned pixels) per tile per thread
         const int sel = (C == 64) ? (lane >> 4) : 0;  // C=64: lanes l / l^16 split the pixels of a step
         const int c = (C == 64) ? (16 * q + (lane & 15)) : (32 * q + lane);
-        const size_t plane_stride = (size_t)WIMG * C;
+        const size_t plane_stride = (size_t)Wimg * C;
 
-        // element index of owned pixel 0 of chunk `ch` in tile (n, h0)
-        auto chunk_pos = [&](int n, int h0, int ch, int& h, int& w0) {
+        // image row and image column of owned pixel 0 of chunk `ch` in the tile at (h0, w_off)
+        auto chunk_pos = [&](int h0, int w_off, int ch, int& h, int& w0) {
             const int rr = ch / STEPS_PER_ROW, stp = ch - rr * STEPS_PER_ROW;
             h = h0 + part * RH + rr;
-            w0 = stp * PX_PER_LD + sel * kPXO;
+            w0 = w_off + stp * PX_PER_LD + sel * kPXO;
         };
         EpiOperands<kPXO> opsA, opsB;
         int acc = 0; uint32_t acc_ph = 0;
         int tile = blockIdx.x;
         if (tile < num_tiles) {
-            const int n = tile / tiles_per_img, h0 = (tile - n * tiles_per_img) * G::ROWS;
-            int h, w0; chunk_pos(n, h0, 0, h, w0);
-            epi_prefetch<kPXO>(epi, (((size_t)n * H + h) * WIMG + w0) * C + c, C, opsA);
+            int n, h0, w_off;
+            tile_coords(tile, n, h0, w_off);
+            int h, w0; chunk_pos(h0, w_off, 0, h, w0);
+            epi_prefetch<kPXO>(epi, (((size_t)n * H + h) * Wimg + w0) * C + c, C, opsA);
         }
         for (; tile < num_tiles; tile += gridDim.x) {
-            const int n = tile / tiles_per_img;
-            const int h0 = (tile - n * tiles_per_img) * G::ROWS;
+            int n, h0, w_off;
+            tile_coords(tile, n, h0, w_off);
             ptx::mbar_wait(&bars->tmem_full[acc], acc_ph);
             ptx::tc_fence_after();
             const uint32_t t_acc = tmem_base + (uint32_t)acc * 256u + lane_addr;
@@ -312,7 +336,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
                 continue;
             }
             auto do_chunk = [&](const int ch, const EpiOperands<kPXO>& cur, EpiOperands<kPXO>& nxt) {
-                int h, w0; chunk_pos(n, h0, ch, h, w0);
+                int h, w0; chunk_pos(h0, w_off, ch, h, w0);
                 const int rr = ch / STEPS_PER_ROW, stp = ch - rr * STEPS_PER_ROW;
                 const int rho = part * RH + rr;
                 // ---- accumulator: hi + lo columns (and hi + lo weight rows for C = 64) ----
@@ -347,20 +371,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
                 }
                 // ---- prefetch the operands of the next chunk (possibly of the next tile) ----
                 {
-                    int n2 = n, h02 = h0, ch2 = ch + 1;
+                    int n2 = n, h02 = h0, woff2 = w_off, ch2 = ch + 1;
                     bool have = true;
                     if (ch == NCHUNK - 1) {
                         const int t2 = tile + gridDim.x;
                         have = t2 < num_tiles;
-                        n2 = t2 / tiles_per_img; h02 = (t2 - n2 * tiles_per_img) * G::ROWS; ch2 = 0;
+                        tile_coords(t2, n2, h02, woff2); ch2 = 0;
                     }
                     if (have) {
-                        int h2, w2; chunk_pos(n2, h02, ch2, h2, w2);
-                        epi_prefetch<kPXO>(epi, (((size_t)n2 * H + h2) * WIMG + w2) * C + c, C, nxt);
+                        int h2, w2; chunk_pos(h02, woff2, ch2, h2, w2);
+                        epi_prefetch<kPXO>(epi, (((size_t)n2 * H + h2) * Wimg + w2) * C + c, C, nxt);
                     }
                 }
                 // ---- fused RK epilogue on the 8 owned pixels ----
-                const size_t pix = ((size_t)n * H + h) * WIMG + w0;
+                const size_t pix = ((size_t)n * H + h) * Wimg + w0;
                 const size_t split0 = (((size_t)n * H + h) * 2) * plane_stride + (size_t)w0 * C + c;
                 epi_finish<kPXO, ACT>(epi, coef, v, cur, pix * C + c, C, split0, plane_stride);
             };
@@ -381,36 +405,46 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
     }
 }
 
-template <int C, int WIMG, int ACT>
+template <int C, int WIMG, int ACT, bool RES>
 int launch_act(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, const EpiParams& epi, ConvShape s,
                cudaStream_t st) {
-    using G = TileGeom<C, WIMG>;
+    using G = TileGeom<C, WIMG, RES>;
     constexpr int kAStages = G::A_STAGES, kBStages = G::B_STAGES;
     CUtensorMap tm_act, tm_w;
     if (make_tmap_split5d(&tm_act, split_in, s.B, s.H, s.W, s.C, WIMG, G::ROWS + 2)) return -1;
     const size_t wrows = tc_packed_weight_bytes(C) / 128;
     if (make_tmap_rows64(&tm_w, w_tiles, wrows, 128)) return -1;
     const size_t smem = (size_t)kBStages * G::B_STAGE_BYTES + (size_t)kAStages * kATileBytes + sizeof(Barriers) + 1024;
-    auto kern = conv3x3_tc_kernel<C, WIMG, ACT>;
+    auto kern = conv3x3_tc_kernel<C, WIMG, ACT, RES>;
     if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                    "cudaFuncSetAttribute(conv3x3_tc)"))
         return -1;
-    const int tiles_per_img = s.H / G::ROWS;
+    const int tiles_per_img = (s.H / G::ROWS) * (s.W / WIMG);
     const int num_tiles = s.B * tiles_per_img;
     const int grid = std::min(num_tiles, num_sms());
-    kern<<<grid, G::THREADS, smem, st>>>(tm_act, tm_w, epi, s.H, num_tiles, tiles_per_img);
+    kern<<<grid, G::THREADS, smem, st>>>(tm_act, tm_w, epi, s.H, s.W, num_tiles, tiles_per_img);
     count_launch();
     return check_cuda(cudaGetLastError(), "conv3x3_tc launch");
 }
 
-template <int C, int WIMG>
+template <int C, int WIMG, bool RES = false>
 int launch_impl(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, const EpiParams& epi, ConvShape s,
                 cudaStream_t st) {
     // the activation only matters when the epilogue emits act(out) / act'(out)
     const int act = (epi.out_split || epi.dact_out) ? epi.act : ACT_NONE;
-    if (act == ACT_GELU) return launch_act<C, WIMG, ACT_GELU>(split_in, w_tiles, epi, s, st);
-    if (act == ACT_RELU) return launch_act<C, WIMG, ACT_RELU>(split_in, w_tiles, epi, s, st);
-    return launch_act<C, WIMG, ACT_NONE>(split_in, w_tiles, epi, s, st);
+    if (act == ACT_GELU) return launch_act<C, WIMG, ACT_GELU, RES>(split_in, w_tiles, epi, s, st);
+    if (act == ACT_RELU) return launch_act<C, WIMG, ACT_RELU, RES>(split_in, w_tiles, epi, s, st);
+    return launch_act<C, WIMG, ACT_NONE, RES>(split_in, w_tiles, epi, s, st);
+}
+
+// MSB_TC_RESIDENT=1 selects the resident-weight variant.  Measured (profiles/conv_forms_r1.txt): it halves the
+// L2 -> SM traffic and speeds the MMA + TMA side up by 17 % (110 vs 133 us without the epilogue), but the full
+// kernel is unchanged within noise (155.6 vs 151.6 us per launch) -- the epilogue's HBM traffic, not the operand
+// feed, is what the MMAs wait for.  Off by default; kept as the starting point for the round-2 epilogue work.
+bool resident_weights_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MSB_TC_RESIDENT"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
 }
 
 }  // namespace
@@ -421,6 +455,8 @@ int launch_conv3x3_tc(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tile
         set_error("tcgen05 conv: unsupported shape C=%d H=%d W=%d", s.C, s.H, s.W);
         return -1;
     }
+    if (s.C == 64 && s.H % 8 == 0 && resident_weights_enabled())       // 8 x 16 tiles, weights resident in shared memory
+        return launch_impl<64, 16, true>(split_in, w_tiles, epi, s, st);
     if (s.C == 64 && s.W == 32) return launch_impl<64, 32>(split_in, w_tiles, epi, s, st);
     if (s.C == 64 && s.W == 16) return launch_impl<64, 16>(split_in, w_tiles, epi, s, st);
     if (s.C == 128 && s.W == 32) return launch_impl<128, 32>(split_in, w_tiles, epi, s, st);

@@ -224,6 +224,7 @@ template <int N> struct EpiOperands {
 };
 
 __device__ __forceinline__ float ldg_stream(const float* p) {
+    if (MSB_DBG(32)) return 1.f;
     float v;
     asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
@@ -261,8 +262,17 @@ __device__ __forceinline__ void epi_prefetch(const EpiParams& e, size_t idx0, in
 // ACT = the activation `e.act` as a compile-time constant.  Every phase is a fully unrolled,
 // straight-line loop over the N independent elements (uniform flags are tested outside the loops).
 template <int N, int ACT>
-__device__ __forceinline__ void epi_finish(const EpiParams& e, const EpiCoef& k, const float* acc, const EpiOperands<N>& r,
+__device__ __forceinline__ void epi_finish(const EpiParams& e_in, const EpiCoef& k, const float* acc, const EpiOperands<N>& r,
                                            size_t idx0, int stride, size_t split_idx0, size_t plane_stride) {
+#ifdef MSB_CONV_DEBUG
+    EpiParams e = e_in;
+    if (MSB_DBG(16)) {       // stores off: keep the math alive through one predicated-off path
+        const bool keep = acc[0] == 123.456f;
+        if (!keep) { e.v_out = nullptr; e.out_f32 = nullptr; e.dact_out = nullptr; e.dact_v_out = nullptr; e.out_split = nullptr; }
+    }
+#else
+    const EpiParams& e = e_in;
+#endif
     float v[N], o[N];
 #pragma unroll
     for (int j = 0; j < N; ++j) v[j] = acc[j];
