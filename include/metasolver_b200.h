@@ -102,6 +102,9 @@ typedef struct MsbMnistGrads {
 
 int         msb_abi_version(void);
 const char* msb_last_error(void);
+/* sizeof() of the ABI structs as this library was compiled (0 MsbOdeDesc, 1 MsbTableau, 2 MsbMnistParams,
+ * 3 MsbMnistGrads, 4 MsbDownDesc): lets a foreign-language binding verify its struct layout at load time. */
+size_t      msb_sizeof(int which);
 /* 1 if `device` can run the tcgen05 engine (compute capability 10.x), 0 if not, <0 on error. */
 int         msb_device_supports_tcgen05(int device);
 /* 1 if (C,H,W) is covered by the tcgen05 engine. */

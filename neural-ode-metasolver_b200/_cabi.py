@@ -17,7 +17,7 @@ ENGINE_AUTO, ENGINE_TCGEN05, ENGINE_SIMT = 0, 1, 2
 ENGINES = {"auto": ENGINE_AUTO, "tcgen05": ENGINE_TCGEN05, "simt": ENGINE_SIMT}
 
 EXPORTS = [
-    "msb_abi_version", "msb_last_error", "msb_device_supports_tcgen05", "msb_shape_supports_tcgen05",
+    "msb_abi_version", "msb_sizeof", "msb_last_error", "msb_device_supports_tcgen05", "msb_shape_supports_tcgen05",
     "msb_odeblock_workspace_bytes", "msb_odeblock_tape_bytes", "msb_odeblock_bwd_workspace_bytes",
     "msb_odeblock_forward", "msb_odeblock_backward", "msb_odeblock_backward_mnist", "msb_act_split", "msb_conv3x3",
     "msb_stem_forward", "msb_stem_backward_workspace_bytes", "msb_stem_backward",
@@ -77,6 +77,8 @@ def _declare(lib):
     vp, sz, i32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
     dp = ctypes.POINTER(MsbOdeDesc)
     lib.msb_abi_version.restype = i32
+    lib.msb_sizeof.argtypes = [i32]
+    lib.msb_sizeof.restype = sz
     lib.msb_last_error.restype = ctypes.c_char_p
     lib.msb_launch_count.restype = ctypes.c_uint64
     lib.msb_device_supports_tcgen05.argtypes = [i32]
@@ -125,6 +127,10 @@ def lib():
                 _declare(l)
                 if l.msb_abi_version() != ABI_VERSION:
                     raise RuntimeError("metasolver_b200: ABI version mismatch")
+                for which, cls in enumerate((MsbOdeDesc, MsbTableau, MsbMnistParams, MsbMnistGrads, MsbDownDesc)):
+                    if l.msb_sizeof(which) != ctypes.sizeof(cls):
+                        raise RuntimeError("metasolver_b200: struct %s is %d bytes in the binding but %d in the library"
+                                           % (cls.__name__, ctypes.sizeof(cls), l.msb_sizeof(which)))
                 _lib = l
     return _lib
 

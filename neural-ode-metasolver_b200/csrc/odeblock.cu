@@ -242,6 +242,16 @@ using namespace msb;
 extern "C" {
 
 int msb_abi_version(void) { return MSB_ABI_VERSION; }
+size_t msb_sizeof(int which) {
+    switch (which) {
+        case 0: return sizeof(MsbOdeDesc);
+        case 1: return sizeof(MsbTableau);
+        case 2: return sizeof(MsbMnistParams);
+        case 3: return sizeof(MsbMnistGrads);
+        case 4: return sizeof(MsbDownDesc);
+        default: return 0;
+    }
+}
 const char* msb_last_error(void) { return g_err.c_str(); }
 uint64_t msb_launch_count(void) { return g_launches.load(); }
 

@@ -118,3 +118,67 @@ def test_cuda_graph_replay_equals_eager_step():
     assert loss_g == loss_e
     for k, p in model.named_parameters():
         assert torch.equal(p.grad, grads_e[k]), k
+
+
+def test_full_batch_whole_network_shard_exactness_and_determinism():
+    """B = 512 through the whole premetanode10 (own stem, Euler residual block, strided block, both ODE blocks):
+    a shard of the batch gives bit-identical logits and input gradients to the same images inside the full
+    batch (what makes data-parallel sharding exact), weight gradients are bitwise reproducible, and the
+    weight gradient of the full batch equals the sum of the shards' weight gradients up to fp32 summation order."""
+    from metasolver_b200.sopa.src.solvers.utils import create_solver
+    from metasolver_b200.sopa.src.models.odenet_cifar10.layers import premetanode10
+    from metasolver_b200.sopa.src.models.odenet_cifar10.utils import Identity
+    torch.manual_seed(5)
+    model = premetanode10((Identity,) * 3, (lambda x: x,) * 3, (F.gelu,) * 3, in_planes=64, is_odenet=True).cuda()
+    model = model.to(memory_format=torch.channels_last)
+    solver = create_solver("rk2", "u", 8, -1, 0.5, -1, torch.float32, "cuda")
+    solver.freeze_params()
+    opts = Namespace(solver_mode="standalone")
+    x = torch.randn(512, 3, 32, 32, device="cuda").contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 10, (512,), device="cuda")
+
+    def run(xx, yy):
+        model.zero_grad(set_to_none=True)
+        xx = xx.clone().requires_grad_(True)
+        logits = model(xx, [solver], opts)
+        F.cross_entropy(logits, yy, reduction="sum").backward()
+        return logits.detach(), xx.grad, {k: p.grad.clone() for k, p in model.named_parameters()}
+    lg, gx, gw = run(x, y)
+    lg2, gx2, gw2 = run(x, y)
+    assert torch.equal(lg, lg2) and torch.equal(gx, gx2)
+    for k in gw:
+        assert torch.equal(gw[k], gw2[k]), k                     # deterministic reductions everywhere
+    acc = None
+    for lo in (0, 256):
+        ls, gs, ws = run(x[lo:lo + 256].contiguous(memory_format=torch.channels_last), y[lo:lo + 256])
+        assert torch.equal(ls, lg[lo:lo + 256])                   # shard == slice of the full batch, bit for bit
+        assert torch.equal(gs, gx[lo:lo + 256])
+        acc = ws if acc is None else {k: acc[k] + ws[k] for k in ws}
+    for k in gw:
+        assert max_rel(acc[k].cpu().numpy(), gw[k].cpu().numpy()) < 2e-5, k
+
+
+def test_full_batch_stacked_solver_axis_slices():
+    """Config 3 at full size: 4 RK2 solvers x 128 images in one set of launches; every slice is bit-identical to
+    its solver run alone, for the forward and for the input gradient."""
+    from metasolver_b200.sopa.src.solvers.utils import create_solver
+    from metasolver_b200.sopa.src.solvers.rk_parametric import integrate_stacked
+    blk, _, _ = _block(64, seed=2)
+    solvers = [create_solver("rk2", "u", 8, -1, u, -1, torch.float32, "cuda") for u in (0.3, 0.5, 2 / 3., 1.0)]
+    for s in solvers:
+        s.freeze_params()
+    torch.manual_seed(3)
+    x = torch.randn(128, 64, 32, 32, device="cuda").contiguous(memory_format=torch.channels_last)
+    r = torch.randn(4, 128, 64, 32, 32, device="cuda")
+    t = torch.tensor([0., 1.])
+    xs = x.clone().requires_grad_(True)
+    ys = integrate_stacked(solvers, blk.rhs_func, xs, t)          # (4, 128, 64, 32, 32): B = 512 per launch
+    (ys * r).sum().backward()
+    gsum = torch.zeros_like(x)
+    for k, s in enumerate(solvers):
+        xk = x.clone().requires_grad_(True)
+        yk = s.integrate_end(blk.rhs_func, xk, t)
+        assert torch.equal(yk, ys[k]), k
+        gk, = torch.autograd.grad((yk * r[k]).sum(), [xk])
+        gsum += gk
+    assert max_rel(xs.grad.cpu().numpy(), gsum.cpu().numpy()) < 1e-6

@@ -102,3 +102,38 @@ def test_cabi_library_exports_header_symbols():
     d.stages = 9
     assert lib.msb_odeblock_tape_bytes(ctypes.byref(d)) == 0
     assert b"stages" in lib.msb_last_error() or b"rhs" in lib.msb_last_error()
+
+
+def test_binding_struct_layouts_match_the_library():
+    lib = _cabi.lib()
+    for which, cls in enumerate((_cabi.MsbOdeDesc, _cabi.MsbTableau, _cabi.MsbMnistParams, _cabi.MsbMnistGrads,
+                                 _cabi.MsbDownDesc)):
+        assert lib.msb_sizeof(which) == ctypes.sizeof(cls), cls.__name__
+    assert lib.msb_sizeof(99) == 0
+
+
+def test_descriptor_validation_is_host_side_and_loud():
+    """Bad descriptors are refused before any CUDA call (size queries return 0 and set the error text)."""
+    lib = _cabi.lib()
+    d = _cabi.MsbDownDesc()
+    d.act, d.engine, d.batch, d.height, d.width, d.in_channels, d.out_channels = 1, 2, 4, 32, 32, 64, 96
+    assert lib.msb_downblock_workspace_bytes(ctypes.byref(d)) == 0
+    assert b"out_channels" in lib.msb_last_error()
+    d.out_channels, d.height = 128, 31
+    assert lib.msb_downblock_tape_bytes(ctypes.byref(d)) == 0
+    assert b"even" in lib.msb_last_error()
+    d.height = 32
+    assert lib.msb_downblock_tape_bytes(ctypes.byref(d)) > 0
+    o = _cabi.MsbOdeDesc()
+    o.rhs_kind, o.act, o.engine, o.batch, o.height, o.width, o.channels, o.n_steps, o.stages = 0, 1, 2, 6, 8, 8, 16, 2, 2
+    grid = (ctypes.c_float * 3)(0.0, 0.5, 1.0)
+    o.time_grid = ctypes.cast(grid, ctypes.POINTER(ctypes.c_float))
+    assert lib.msb_odeblock_tape_bytes(ctypes.byref(o)) > 0
+    o.n_solvers = 4                                   # 6 images do not split into 4 solver slices; no tableaus given
+    assert lib.msb_odeblock_tape_bytes(ctypes.byref(o)) == 0
+    assert b"solver" in lib.msb_last_error()
+    o.n_solvers, o.rhs_kind = 0, 2                    # MNIST tape: five tensors per stage evaluation
+    mn = lib.msb_odeblock_tape_bytes(ctypes.byref(o))
+    o.rhs_kind = 0
+    assert mn * 4 == lib.msb_odeblock_tape_bytes(ctypes.byref(o)) * 5
+    assert lib.msb_stem_backward_workspace_bytes(64) > 0
