@@ -10,13 +10,14 @@ against the reference keep working unchanged.
 """
 import contextlib
 import ctypes
-import threading
 
 import torch
 
 from . import _cabi
 
-_state = threading.local()
+# input-gradient-only mode is PROCESS-global on purpose: autograd runs Function.backward on its own engine
+# thread, where a thread-local set by the caller of autograd.grad() would not be visible.
+_input_only_depth = [0]
 _default_engine = ["auto"]
 
 
@@ -55,12 +56,11 @@ def profile_read_executed(kind):
 def input_grad_only():
     """Inside this context backward passes skip the weight gradients (FGSM / PGD input-gradient
     mode, MegaAdversarial/src/attacks/pgd.py:44-46 uses autograd.grad w.r.t. the input only)."""
-    prev = getattr(_state, "input_only", False)
-    _state.input_only = True
+    _input_only_depth[0] += 1
     try:
         yield
     finally:
-        _state.input_only = prev
+        _input_only_depth[0] -= 1
 
 
 class OdeProblem:
@@ -176,7 +176,7 @@ class _OdeBlockFn(torch.autograd.Function):
         if ctx.tape is None:
             raise RuntimeError("metasolver_b200: backward called but no tape was recorded")
         dev = gy.device
-        need_w = (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]) and not getattr(_state, "input_only", False)
+        need_w = (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]) and not (_input_only_depth[0] > 0)
         with torch.cuda.device(dev):
             gyc = gy.contiguous(memory_format=torch.channels_last)
             d = ctx.prob.desc(ctx.shape, True)
@@ -267,7 +267,7 @@ class _MnistOdeBlockFn(torch.autograd.Function):
             raise RuntimeError("metasolver_b200: backward called but no tape was recorded")
         keep = dict(zip(_MNIST_KEYS, ctx.saved_tensors))
         dev = gy.device
-        need_w = any(ctx.needs_input_grad[4:]) and not getattr(_state, "input_only", False)
+        need_w = any(ctx.needs_input_grad[4:]) and not (_input_only_depth[0] > 0)
         with torch.cuda.device(dev):
             gyc = gy.contiguous(memory_format=torch.channels_last)
             mp = _mnist_params_struct(keep, ctx.groups, ctx.eps)
@@ -305,7 +305,7 @@ def ode_block_integrate_mnist(x, params, tableau, time_grid, groups, eps=1e-5):
 
 # --------------------------------------------------------------------------- non-ODE layers
 def _input_only():
-    return getattr(_state, "input_only", False)
+    return (_input_only_depth[0] > 0)
 
 
 class _StemFn(torch.autograd.Function):

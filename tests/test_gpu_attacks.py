@@ -92,3 +92,36 @@ def test_fgsm_random_training_step_vs_reference_golden():
         if k.startswith("train_g_"):
             got = params[k[8:]].grad.cpu().numpy().reshape(-1)[::cases.WG_STRIDE]
             assert max_rel(got, g[k]) <= 2e-3, (k, max_rel(got, g[k]))   # includes the effect of rare sign flips in x_adv
+
+
+def test_input_gradient_only_mode_forms_no_weight_gradients():
+    """FGSM / PGD differentiate w.r.t. the input only (pgd.py:44-46): inside `input_grad_only()` the backward must not
+    launch a single weight-gradient kernel (autograd runs backward on its own thread: the switch is process-global)."""
+    import metasolver_b200 as msb
+    model, x, y, kw, mean, std = _setup()
+    model.eval()
+
+    def launches(input_only):
+        xa = x.clone().requires_grad_(True)
+        loss = F.cross_entropy(model(xa, **kw), y)
+        torch.cuda.synchronize()
+        before = msb.launch_count()
+        if input_only:
+            with msb.input_grad_only():
+                g, = torch.autograd.grad([loss], [xa])
+        else:
+            g, = torch.autograd.grad([loss], [xa])
+        torch.cuda.synchronize()
+        return msb.launch_count() - before, g
+    n_full, g_full = launches(False)
+    n_in, g_in = launches(True)
+    assert torch.equal(g_full, g_in)
+    # per ODE stage evaluation the full backward adds 2 wgrad launches to the 2 dgrad launches
+    assert n_in < 0.62 * n_full, (n_in, n_full)
+    msb.profile_enable(True)
+    with msb.input_grad_only():
+        xa = x.clone().requires_grad_(True)
+        torch.autograd.grad([F.cross_entropy(model(xa, **kw), y)], [xa])
+    _, _, n_wgrad = msb.profile_read(1)
+    msb.profile_enable(False)
+    assert n_wgrad == 0
