@@ -192,6 +192,18 @@ size_t msb_wgrad3x3_workspace_bytes(int channels, int engine);
 /* Number of kernels this library has launched since load (bench.py's `gpu_launches`). */
 uint64_t msb_launch_count(void);
 
+/* Tuning options (process-wide; defaults are the measured best).  Names:
+ *   "epi_l2_prefetch"  distance, in tiles, at which the tcgen05 convolutions bulk-prefetch their epilogue
+ *                      operands (y, k_j, act') into L2; 0 = off          (env MSB_EPI_L2_PREFETCH)
+ *   "tc_resident"      1 = channel-major C=64 convolution keeps its weights resident in shared memory
+ *                                                                        (env MSB_TC_RESIDENT)
+ *   "tcp_epi_warps"    epilogue warps of the pixel-major convolution, 8 or 16      (env MSB_TCP_EPI_WARPS)
+ *   "tc_form_c64"      tcgen05 convolution form for 64 channels: 0 = channel-major (4 hi/lo products),
+ *                      1 = pixel-major (3 products)                      (env MSB_TC_FORM_C64)
+ * Results do not depend on any option.  Returns 0, or -1 for an unknown name. */
+int msb_set_option(const char* name, int value);
+int msb_get_option(const char* name, int* value);
+
 /* Optional per-launch timing for the roofline report: when enabled, CUDA events are recorded on the
  * caller's stream around every convolution-engine launch.  msb_profile_read() waits for the recorded
  * events and returns the summed duration, the summed algorithmic flops (2*M*N*K of the convolution)

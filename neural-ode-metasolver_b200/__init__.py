@@ -8,7 +8,7 @@ include/metasolver_b200.h (ctypes binding: _cabi.py).  There is no cuDNN, Triton
 """
 from . import _cabi  # noqa: F401
 from .ops import (ode_block_integrate, input_grad_only, set_default_engine, launch_count,  # noqa: F401
-                  profile_enable, profile_read, profile_read_executed)
+                  profile_enable, profile_read, profile_read_executed, set_option, get_option)
 from .graphs import GraphedStep  # noqa: F401
 
 __version__ = "0.1.0"

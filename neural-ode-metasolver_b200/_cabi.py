@@ -24,6 +24,7 @@ EXPORTS = [
     "msb_downblock_workspace_bytes", "msb_downblock_tape_bytes", "msb_downblock_bwd_workspace_bytes",
     "msb_downblock_forward", "msb_downblock_backward",
     "msb_conv3x3_workspace_bytes", "msb_wgrad3x3", "msb_wgrad3x3_workspace_bytes", "msb_launch_count", "msb_profile_enable", "msb_profile_read", "msb_profile_read_executed",
+    "msb_set_option", "msb_get_option",
 ]
 
 
@@ -107,6 +108,8 @@ def _declare(lib):
     lib.msb_wgrad3x3.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, sz, vp]
     lib.msb_wgrad3x3_workspace_bytes.argtypes = [i32, i32]
     lib.msb_wgrad3x3_workspace_bytes.restype = sz
+    lib.msb_set_option.argtypes = [ctypes.c_char_p, i32]
+    lib.msb_get_option.argtypes = [ctypes.c_char_p, ctypes.POINTER(i32)]
     lib.msb_profile_enable.argtypes = [i32]
     lib.msb_profile_read_executed.argtypes = [i32, ctypes.POINTER(ctypes.c_double)]
     lib.msb_profile_read.argtypes = [i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),

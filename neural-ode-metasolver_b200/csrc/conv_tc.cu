@@ -158,7 +158,8 @@ struct __align__(8) Barriers {
 template <int C, int WIMG, int ACT, bool RES>
 __global__ void __launch_bounds__((TileGeom<C, WIMG, RES>::THREADS), 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_w,
-                  const EpiParams epi, const int H, const int Wimg, const int num_tiles, const int tiles_per_img) {
+                  const EpiParams epi, const int H, const int Wimg, const int num_tiles, const int tiles_per_img,
+                  const int l2pf_dist) {
     using G = TileGeom<C, WIMG, RES>;
     const int cols = Wimg / WIMG;                                  // tile columns per image
     // tile -> (image n, first row h0, first pixel column w_off); neighbouring tiles are neighbouring columns
@@ -201,10 +202,34 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
     if (warp == 0) {
         // ===================== activation producer =====================
         if (lane == 0) {
+            // The epilogue's operands (y, k_j, act' ... of the SAME pixels, fp32 NHWC) are pulled into L2 by bulk
+            // prefetches issued here, l2pf_dist tiles ahead of the activation loads: the epilogue threads hold only
+            // one chunk of loads in flight, which at HBM latency caps them far below the HBM bandwidth; from L2
+            // the same loads are ~3x shorter (profiles/epi_l2_prefetch_r1.txt).
+            const bool pf_n = l2pf_dist > 0;
+            auto l2_prefetch_tile = [&](int t) {
+                if (t >= num_tiles) return;
+                int n, h0, w_off;
+                tile_coords(t, n, h0, w_off);
+#pragma unroll
+                for (int i = 0; i < kEpiLoadSlots; ++i) {
+                    const float* p = epi_load_operand(epi, i);
+                    if (!p) continue;
+                    if (cols == 1) {
+                        ptx::l2_prefetch_bulk(p + ((size_t)n * H + h0) * Wimg * C, G::ROWS * WIMG * C * 4);
+                    } else {
+                        for (int rr = 0; rr < G::ROWS; ++rr)
+                            ptx::l2_prefetch_bulk(p + (((size_t)n * H + h0 + rr) * Wimg + w_off) * C, WIMG * C * 4);
+                    }
+                }
+            };
+            if (pf_n)
+                for (int d = 0; d + 1 < l2pf_dist; ++d) l2_prefetch_tile(blockIdx.x + d * gridDim.x);
             int st = 0; uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 int n, h0, w_off;
                 tile_coords(tile, n, h0, w_off);
+                if (pf_n) l2_prefetch_tile(tile + (l2pf_dist - 1) * gridDim.x);
                 for (int chunk = 0; chunk < CHUNKS; ++chunk)
                     for (int s = 0; s < 3; ++s) {
                         ptx::mbar_wait(&bars->b_empty[st], ph ^ 1);
@@ -422,7 +447,8 @@ int launch_act(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, cons
     const int tiles_per_img = (s.H / G::ROWS) * (s.W / WIMG);
     const int num_tiles = s.B * tiles_per_img;
     const int grid = std::min(num_tiles, num_sms());
-    kern<<<grid, G::THREADS, smem, st>>>(tm_act, tm_w, epi, s.H, s.W, num_tiles, tiles_per_img);
+    kern<<<grid, G::THREADS, smem, st>>>(tm_act, tm_w, epi, s.H, s.W, num_tiles, tiles_per_img,
+                                         tune_get(TUNE_EPI_L2_PREFETCH));
     count_launch();
     return check_cuda(cudaGetLastError(), "conv3x3_tc launch");
 }
@@ -441,11 +467,7 @@ int launch_impl(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, con
 // L2 -> SM traffic and speeds the MMA + TMA side up by 17 % (110 vs 133 us without the epilogue), but the full
 // kernel is unchanged within noise (155.6 vs 151.6 us per launch) -- the epilogue's HBM traffic, not the operand
 // feed, is what the MMAs wait for.  Off by default; kept as the starting point for the round-2 epilogue work.
-bool resident_weights_enabled() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("MSB_TC_RESIDENT"); v = (e && e[0] == '1') ? 1 : 0; }
-    return v == 1;
-}
+bool resident_weights_enabled() { return tune_get(TUNE_TC_RESIDENT) == 1; }
 
 }  // namespace
 

@@ -44,21 +44,27 @@ int tcp_debug_hint(unsigned ns) { return cudaMemcpyToSymbol(ptx::g_suspend_hint,
 namespace {
 
 constexpr int kEpiWarp0 = 4;
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;
+// EW = epilogue warps, 8 or 16.  With 8 (2 per scheduler) each thread software-pipelines its operand loads one chunk
+// ahead in registers (2 x 48 registers of buffers; 160 registers / thread).  With 16 (4 per scheduler, 640 threads,
+// <= 102 registers) the loads are issued at the top of their own chunk instead and the latency is covered by the other
+// warps of the scheduler plus the L2 prefetch of the operands (the epilogue at 8 warps was latency-, not issue-bound:
+// 29 % issue utilisation, profiles/).
 constexpr uint32_t kTmemCols = 512;
 constexpr int kMaxStages = 8;
-constexpr int kSmemBudget = 212992;
+constexpr int kSmemBudget = 212992;        // 8 epilogue warps: operand rings only
+constexpr int kSmemBudget16 = 230400;      // 16 epilogue warps: rings + 64 KB of transpose staging (227 KB max per CTA)
+constexpr int kStageBytesPerWarp = 4096;   // 32 pixels x 32 channels fp32
 
-template <int C, int WIMG> struct Geom {
+template <int C, int WIMG, int EW = 8> struct Geom {
     static constexpr int ROWS = 128 / WIMG;                          // image rows per 128-pixel tile
     static constexpr int PLANE_BYTES = (ROWS + 2) * WIMG * 128;      // one plane of the halo box
     static constexpr int X_STAGE_BYTES = 2 * PLANE_BYTES;
     static constexpr int ROW_BYTES = WIMG * 128;                     // one image row of one plane
     static constexpr int W_TILE_BYTES = 2 * C * 128;                 // [W_hi ; W_lo] x 64 k
     static constexpr int X_STAGES = 2;
-    static constexpr int W_STAGES = (kSmemBudget - X_STAGES * X_STAGE_BYTES) / W_TILE_BYTES > kMaxStages
-                                        ? kMaxStages : (kSmemBudget - X_STAGES * X_STAGE_BYTES) / W_TILE_BYTES;
+    static constexpr int STAGE_BYTES = (EW == 16) ? 16 * kStageBytesPerWarp : 0;
+    static constexpr int RING_BUDGET = (EW == 16 ? kSmemBudget16 : kSmemBudget) - STAGE_BYTES - X_STAGES * X_STAGE_BYTES;
+    static constexpr int W_STAGES = RING_BUDGET / W_TILE_BYTES > kMaxStages ? kMaxStages : RING_BUDGET / W_TILE_BYTES;
     static constexpr int ACC_COLS = 2 * C;                           // fp32 accumulator columns per tile
     static constexpr int ACC_BUFS = (C == 64) ? 4 : 2;
     static_assert(ACC_COLS * ACC_BUFS <= 512, "TMEM");
@@ -72,18 +78,20 @@ struct __align__(8) Barriers {
     uint32_t tmem_base;
 };
 
-template <int C, int WIMG, int ACT>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int C, int WIMG, int ACT, int EW>
+__global__ void __launch_bounds__((kEpiWarp0 + EW) * 32, 1)
 conv3x3_tcp_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_w,
-                   const EpiParams epi, const int H, const int num_tiles, const int tiles_per_img) {
-    using G = Geom<C, WIMG>;
+                   const EpiParams epi, const int H, const int num_tiles, const int tiles_per_img, const int l2pf_dist) {
+    using G = Geom<C, WIMG, EW>;
     constexpr int CHUNKS = C / 64;
     constexpr int kWStages = G::W_STAGES, kXStages = G::X_STAGES, kAccBufs = G::ACC_BUFS;
+    constexpr int kEpiWarps = EW;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_x = smem;                                          // kXStages x X_STAGE_BYTES
     uint8_t* smem_w = smem + kXStages * G::X_STAGE_BYTES;            // kWStages x W_TILE_BYTES
-    Barriers* bars = reinterpret_cast<Barriers*>(smem_w + kWStages * G::W_TILE_BYTES);
+    uint8_t* smem_stage = smem_w + kWStages * G::W_TILE_BYTES;       // EW == 16: 4 KB per epilogue warp
+    Barriers* bars = reinterpret_cast<Barriers*>(smem_stage + G::STAGE_BYTES);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -93,7 +101,7 @@ conv3x3_tcp_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
         ptx::prefetch_tmap(&tmap_w);
         for (int i = 0; i < kWStages; ++i) { ptx::mbar_init(&bars->w_full[i], 1); ptx::mbar_init(&bars->w_empty[i], 1); }
         for (int i = 0; i < kXStages; ++i) { ptx::mbar_init(&bars->x_full[i], 1); ptx::mbar_init(&bars->x_empty[i], 1); }
-        for (int i = 0; i < kAccBufs; ++i) { ptx::mbar_init(&bars->tmem_full[i], 1); ptx::mbar_init(&bars->tmem_empty[i], kEpiWarps); }
+        for (int i = 0; i < kAccBufs; ++i) { ptx::mbar_init(&bars->tmem_full[i], 1); ptx::mbar_init(&bars->tmem_empty[i], EW == 16 ? 4 * (C / 32) : kEpiWarps); }
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
@@ -108,10 +116,26 @@ conv3x3_tcp_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
     if (warp == 0) {
         // ===================== activation producer =====================
         if (lane == 0) {
+            // bulk L2 prefetch of the epilogue's operands, l2pf_dist tiles ahead (see conv_tc.cu); a tile is
+            // ROWS full image rows = one contiguous 128 x C fp32 range of every operand
+            const bool pf_n = l2pf_dist > 0;
+            auto l2_prefetch_tile = [&](int t) {
+                if (t >= num_tiles) return;
+                const int n = t / tiles_per_img;
+                const int h0 = (t - n * tiles_per_img) * G::ROWS;
+#pragma unroll
+                for (int i = 0; i < kEpiLoadSlots; ++i) {
+                    const float* p = epi_load_operand(epi, i);
+                    if (p) ptx::l2_prefetch_bulk(p + ((size_t)n * H + h0) * WIMG * C, 128 * C * 4);
+                }
+            };
+            if (pf_n)
+                for (int d = 0; d + 1 < l2pf_dist; ++d) l2_prefetch_tile(blockIdx.x + d * gridDim.x);
             int st = 0; uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int n = tile / tiles_per_img;
                 const int h0 = (tile - n * tiles_per_img) * G::ROWS;
+                if (pf_n) l2_prefetch_tile(tile + (l2pf_dist - 1) * gridDim.x);
                 for (int chunk = 0; chunk < CHUNKS; ++chunk)
                     for (int s = 0; s < 3; ++s) {
                         ptx::mbar_wait(&bars->x_empty[st], ph ^ 1);
@@ -206,13 +230,104 @@ conv3x3_tcp_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
         const int rr = p / WIMG, wq = p - rr * WIMG;
         const size_t plane_stride = (size_t)WIMG * C;
 
-        EpiVec8 opsA, opsB;
         int acc = 0; uint32_t acc_ph = 0;
         int tile = blockIdx.x;
         auto pix_of = [&](int t) {
             const int n = t / tiles_per_img, h0 = (t - n * tiles_per_img) * G::ROWS;
             return ((size_t)n * H + h0 + rr) * WIMG + wq;
         };
+        if (EW == 16) {
+            // ---- 16 warps, transposed ownership ----------------------------------------------------------------
+            // A TMEM lane is a pixel, so a thread reading its own accumulator row owns 32 B of a pixel and the 32
+            // lanes of a warp-wide global access touch 32 different 128-byte lines: measured (profiles/
+            // power_probe_r1*.log) the epilogue's stores then cost 45-70 us per launch EVEN WHEN THEY HIT L2 --
+            // the SM's load/store path (one line per cycle), not DRAM, was the limiter.  Here a warp (32 pixels x
+            // 32 channels) passes its accumulators through a private, XOR-swizzled 4 KB shared-memory stage and
+            // reads them back transposed within each quad of lanes: lane 4i+k then owns channels 8k..8k+7 of the
+            // four pixels 4i..4i+3, so the four lanes of a quad cover one whole 128-byte line per access (8 lines
+            // instead of 32 per warp instruction, for loads and stores alike).  The accumulator buffer is handed
+            // back to the MMA warp as soon as it is copied out.  C = 64: 8 warps per tile, the two groups of 8
+            // take alternate tiles; C = 128: all 16 warps on every tile.
+            constexpr int NG = C / 32;                 // channel groups of 32 per tile
+            constexpr int WPT = 4 * NG;                // warps per tile
+            constexpr int TG = 16 / WPT;               // tile groups
+            static_assert(TG >= 1 && 16 % WPT == 0, "16 epilogue warps must split evenly");
+            const int tg = we / WPT, wi = we % WPT;
+            const int cb = (wi >> 2) * 32;             // first channel of this warp's group
+            const uint32_t stage = ptx::smem_u32(smem_stage + we * kStageBytesPerWarp);
+            const int k4 = lane & 3, quad = lane >> 2;
+            // owned element block j (j = 0..3): pixel 32q + 4*quad + j of the tile, channels cb + 8*k4 .. +7
+            // (row0 = first image row of the tile counted over the whole batch: n * H + h0)
+            auto owned = [&](size_t row0, int j, size_t& idx, size_t& sidx) {
+                const int pp = q * 32 + quad * 4 + j;
+                const int r2 = pp / WIMG, w2 = pp - r2 * WIMG;
+                idx = ((row0 + r2) * WIMG + w2) * C + cb + 8 * k4;
+                sidx = ((row0 + r2) * 2) * plane_stride + (size_t)w2 * C + cb + 8 * k4;
+            };
+            auto row0_of = [&](int t) {
+                const int n = t / tiles_per_img;
+                return (size_t)n * H + (size_t)(t - n * tiles_per_img) * G::ROWS;
+            };
+            int it = tg;
+            tile = blockIdx.x + tg * gridDim.x;
+            EpiVec8 ops;
+            if (tile < num_tiles) { size_t i0, s0; owned(row0_of(tile), 0, i0, s0); epi_prefetch_vec8(epi, i0, ops); }
+            for (; tile < num_tiles; tile += TG * gridDim.x, it += TG) {
+                const int acc16 = it % kAccBufs;
+                const uint32_t ph16 = (uint32_t)(it / kAccBufs) & 1u;
+                const EpiCoef coef = epi_coef(epi, tile / tiles_per_img);
+                const size_t row0 = row0_of(tile);
+                ptx::mbar_wait(&bars->tmem_full[acc16], ph16);
+                ptx::tc_fence_after();
+                if (MSB_DBG(1)) {
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&bars->tmem_empty[acc16]);
+                    continue;
+                }
+                const uint32_t t_acc = tmem_base + (uint32_t)(acc16 * G::ACC_COLS) + lane_addr + (uint32_t)cb;
+                __syncwarp();                          // every lane is done reading the previous tile's stage
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {       // 8 channels = two 16-byte units of this lane's 128-byte row
+                    float a[8], b[8];
+                    ptx::tmem_ld<8>(t_acc + c8 * 8, a);
+                    ptx::tmem_ld<8>(t_acc + C + c8 * 8, b);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const uint32_t addr = stage + lane * 128 + (((c8 * 2 + u) ^ (lane & 7)) << 4);
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a[4 * u] + b[4 * u]),
+                                     "f"(a[4 * u + 1] + b[4 * u + 1]), "f"(a[4 * u + 2] + b[4 * u + 2]),
+                                     "f"(a[4 * u + 3] + b[4 * u + 3]) : "memory");
+                    }
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&bars->tmem_empty[acc16]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int row = quad * 4 + j;
+                    float v[8];
+                    {
+                        const uint32_t base = stage + row * 128;
+                        const uint32_t a0 = base + (((2 * k4) ^ (row & 7)) << 4), a1 = base + (((2 * k4 + 1) ^ (row & 7)) << 4);
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a0));
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(a1));
+                    }
+                    size_t idx, sidx;
+                    owned(row0, j, idx, sidx);
+                    epi_finish_vec8<ACT>(epi, coef, v, ops, idx, sidx, plane_stride);
+                    if (j < 3) {
+                        owned(row0, j + 1, idx, sidx);
+                        epi_prefetch_vec8(epi, idx, ops);
+                    } else {
+                        const int t2 = tile + TG * gridDim.x;
+                        if (t2 < num_tiles) { owned(row0_of(t2), 0, idx, sidx); epi_prefetch_vec8(epi, idx, ops); }
+                    }
+                }
+            }
+        } else {
+        EpiVec8 opsA, opsB;
         if (tile < num_tiles) epi_prefetch_vec8(epi, pix_of(tile) * C + cbase, opsA);
         for (; tile < num_tiles; tile += gridDim.x) {
             const int n = tile / tiles_per_img;
@@ -259,6 +374,7 @@ conv3x3_tcp_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
             }
             if (++acc == kAccBufs) { acc = 0; acc_ph ^= 1; }
         }
+        }
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -268,24 +384,35 @@ conv3x3_tcp_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
     }
 }
 
-template <int C, int WIMG, int ACT>
-int launch_act(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, const EpiParams& epi, ConvShape s,
+template <int C, int WIMG, int ACT, int EW>
+int launch_act_ew(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, const EpiParams& epi, ConvShape s,
                cudaStream_t st) {
-    using G = Geom<C, WIMG>;
+    using G = Geom<C, WIMG, EW>;
     CUtensorMap tm_act, tm_w;
     if (make_tmap_split_plane(&tm_act, split_in, s.B, s.H, s.W, s.C, WIMG, G::ROWS + 2)) return -1;
     if (make_tmap_rows64(&tm_w, w_tiles, tcp_packed_weight_bytes(C) / 128, 2 * C)) return -1;
-    const size_t smem = (size_t)G::X_STAGES * G::X_STAGE_BYTES + (size_t)G::W_STAGES * G::W_TILE_BYTES + sizeof(Barriers) + 1024;
-    auto kern = conv3x3_tcp_kernel<C, WIMG, ACT>;
+    const size_t smem = (size_t)G::X_STAGES * G::X_STAGE_BYTES + (size_t)G::W_STAGES * G::W_TILE_BYTES + G::STAGE_BYTES +
+                        sizeof(Barriers) + 1024;
+    static_assert(G::X_STAGES * G::X_STAGE_BYTES + G::W_STAGES * G::W_TILE_BYTES + G::STAGE_BYTES + sizeof(Barriers) + 1024 <= 232448,
+                  "shared memory per CTA");
+    auto kern = conv3x3_tcp_kernel<C, WIMG, ACT, EW>;
+    constexpr int kThreads = (kEpiWarp0 + EW) * 32;
     if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                    "cudaFuncSetAttribute(conv3x3_tcp)"))
         return -1;
     const int tiles_per_img = s.H / G::ROWS;
     const int num_tiles = s.B * tiles_per_img;
     const int grid = std::min(num_tiles, num_sms());
-    kern<<<grid, kThreads, smem, st>>>(tm_act, tm_w, epi, s.H, num_tiles, tiles_per_img);
+    kern<<<grid, kThreads, smem, st>>>(tm_act, tm_w, epi, s.H, num_tiles, tiles_per_img, tune_get(TUNE_EPI_L2_PREFETCH));
     count_launch();
     return check_cuda(cudaGetLastError(), "conv3x3_tcp launch");
+}
+
+template <int C, int WIMG, int ACT>
+int launch_act(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, const EpiParams& epi, ConvShape s,
+               cudaStream_t st) {
+    if (tune_get(TUNE_TCP_EPI_WARPS) == 16) return launch_act_ew<C, WIMG, ACT, 16>(split_in, w_tiles, epi, s, st);
+    return launch_act_ew<C, WIMG, ACT, 8>(split_in, w_tiles, epi, s, st);
 }
 
 template <int C, int WIMG>

@@ -12,11 +12,17 @@ enum { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
 // copy of the flag word per translation unit, all set by msb_debug_conv_flags().
 //   1: epilogue skipped (accumulator barriers still cycle)   2: no MMAs issued   4: no weight TMA
 //   8: no activation TMA   16: epilogue global stores off   32: epilogue global loads off
+//   64: epilogue loads wrapped into the first 1 MB of each array (L2 hits: isolates the loads' DRAM latency)
+//   128: epilogue stores wrapped into the first 1 MB of each array (isolates the stores' DRAM traffic)
 #ifdef MSB_CONV_DEBUG
 static __device__ int g_conv_debug = 0;
 #define MSB_DBG(bit) (g_conv_debug & (bit))
+#define MSB_DBG_LD(idx) ((g_conv_debug & 64) ? ((idx) & (size_t)0x3FFF8) : (idx))
+#define MSB_DBG_ST(idx) ((g_conv_debug & 128) ? ((idx) & (size_t)0x3FFF8) : (idx))
 #else
 #define MSB_DBG(bit) 0
+#define MSB_DBG_LD(idx) (idx)
+#define MSB_DBG_ST(idx) (idx)
 #endif
 
 // ---------------------------------------------------------------------------------------------
@@ -81,6 +87,20 @@ __host__ inline EpiParams epi_default() {
     e.pix_bias_scale = 0.f; e.slice_batch = 0;
     e.nsrc = 0; e.act = ACT_NONE; e.act_v = ACT_NONE; e.base_is_one = 1;
     return e;
+}
+
+// The fp32 NHWC arrays an epilogue READS (all indexed like the output): candidates for an L2 prefetch.
+// Slot i of the fixed list (null = not read); callers unroll over kEpiLoadSlots.
+constexpr int kEpiLoadSlots = 6;
+__device__ __forceinline__ const float* epi_load_operand(const EpiParams& e, int i) {
+    switch (i) {
+        case 0: return e.mul;
+        case 1: return e.base;
+        case 2: return e.nsrc > 0 ? e.src[0] : nullptr;
+        case 3: return e.nsrc > 1 ? e.src[1] : nullptr;
+        case 4: return e.nsrc > 2 ? e.src[2] : nullptr;
+        default: return e.split_mul;
+    }
 }
 
 __device__ __forceinline__ const EpiCoef& epi_coef(const EpiParams& e, int n) {
@@ -385,7 +405,8 @@ __device__ __forceinline__ void stg256(float* p, const float* v) {
                  : "memory");
 }
 
-__device__ __forceinline__ void epi_prefetch_vec8(const EpiParams& e, size_t idx0, EpiVec8& r) {
+__device__ __forceinline__ void epi_prefetch_vec8(const EpiParams& e, size_t idx0_in, EpiVec8& r) {
+    const size_t idx0 = MSB_DBG_LD(idx0_in);
     if (e.mul) ldg256_stream(e.mul + idx0, r.mul);
     if (e.base) ldg256_stream(e.base + idx0, r.base);
     if (e.nsrc > 0) ldg256_stream(e.src[0] + idx0, r.src[0]);
@@ -397,8 +418,9 @@ __device__ __forceinline__ void epi_prefetch_vec8(const EpiParams& e, size_t idx
 // split_idx0 = index of element 0 in the hi plane of out_split; the lo plane is plane_stride further.
 template <int ACT>
 __device__ __forceinline__ void epi_finish_vec8(const EpiParams& e, const EpiCoef& k, const float* acc, const EpiVec8& r,
-                                                size_t idx0, size_t split_idx0, size_t plane_stride) {
+                                                size_t idx0_in, size_t split_idx0_in, size_t plane_stride) {
     constexpr int N = 8;
+    const size_t idx0 = MSB_DBG_ST(idx0_in), split_idx0 = MSB_DBG_ST(split_idx0_in);
     float v[N], o[N];
 #pragma unroll
     for (int j = 0; j < N; ++j) v[j] = acc[j];

@@ -15,6 +15,14 @@ void count_launch(int n = 1);
 void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);   // 0 if ok, else sets error and returns -1
 
+// tuning options: process-wide ints, set by msb_set_option() or the environment (MSB_EPI_L2_PREFETCH, MSB_TC_RESIDENT)
+enum { TUNE_EPI_L2_PREFETCH = 0,   // conv epilogue operands: bulk L2 prefetch distance in tiles (0 = off)
+       TUNE_TC_RESIDENT = 1,       // channel-major C=64 conv: weights resident in shared memory
+       TUNE_TCP_EPI_WARPS = 2,     // pixel-major conv: epilogue warps (8 or 16)
+       TUNE_TC_FORM_C64 = 3,       // tcgen05 conv form for C = 64: 0 = channel-major, 1 = pixel-major
+       TUNE_COUNT };
+int tune_get(int which);
+
 struct ConvShape { int B, H, W, C; };
 
 // ---- elementwise.cu ----

@@ -74,6 +74,11 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+// Bulk prefetch of a contiguous global range into L2 (fire and forget; bytes a multiple of 16).
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(p)), "r"(bytes) : "memory");
+}
+
 // ---- tcgen05 ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols)

@@ -34,6 +34,22 @@ int check_cuda(cudaError_t e, const char* what) {
     return -1;
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+// ---- tuning options (msb_set_option / environment MSB_<NAME>) ----
+static std::atomic<int> g_tune[TUNE_COUNT];
+static std::atomic<bool> g_tune_init{false};
+static const char* const kTuneNames[TUNE_COUNT] = {"epi_l2_prefetch", "tc_resident", "tcp_epi_warps", "tc_form_c64"};
+static const char* const kTuneEnv[TUNE_COUNT] = {"MSB_EPI_L2_PREFETCH", "MSB_TC_RESIDENT", "MSB_TCP_EPI_WARPS", "MSB_TC_FORM_C64"};
+static const int kTuneDefault[TUNE_COUNT] = {0, 0, 8, 0};
+static void tune_init() {
+    if (g_tune_init.load(std::memory_order_acquire)) return;
+    for (int i = 0; i < TUNE_COUNT; ++i) {
+        const char* e = getenv(kTuneEnv[i]);
+        g_tune[i].store(e ? atoi(e) : kTuneDefault[i]);
+    }
+    g_tune_init.store(true, std::memory_order_release);
+}
+int tune_get(int which) { tune_init(); return g_tune[which].load(std::memory_order_relaxed); }
 int num_sms() {
     static int cached[64] = {0};
     int dev = 0;
@@ -85,7 +101,7 @@ bool tc_pixel_major(int C) {
         forced = !e ? -1 : (strcmp(e, "cm") == 0 ? 0 : (strcmp(e, "pm") == 0 ? 1 : -1));
     }
     if (forced >= 0) return forced == 1;
-    return C >= 128;
+    return C >= 128 || tune_get(TUNE_TC_FORM_C64) == 1;
 }
 size_t packed_w_bytes(int engine, int C) {
     if (engine != MSB_ENGINE_TCGEN05) return (size_t)9 * C * C * sizeof(float);
@@ -254,6 +270,21 @@ size_t msb_sizeof(int which) {
 }
 const char* msb_last_error(void) { return g_err.c_str(); }
 uint64_t msb_launch_count(void) { return g_launches.load(); }
+int msb_set_option(const char* name, int value) {
+    if (!name) { set_error("msb_set_option: null name"); return -1; }
+    tune_init();
+    for (int i = 0; i < TUNE_COUNT; ++i)
+        if (strcmp(name, kTuneNames[i]) == 0) { g_tune[i].store(value); return 0; }
+    set_error("msb_set_option: unknown option '%s'", name);
+    return -1;
+}
+int msb_get_option(const char* name, int* value) {
+    if (!name || !value) { set_error("msb_get_option: null argument"); return -1; }
+    for (int i = 0; i < TUNE_COUNT; ++i)
+        if (strcmp(name, kTuneNames[i]) == 0) { *value = tune_get(i); return 0; }
+    set_error("msb_get_option: unknown option '%s'", name);
+    return -1;
+}
 
 int msb_profile_enable(int on) {
     g_prof.on = on != 0;

@@ -33,6 +33,17 @@ def launch_count():
     return int(_cabi.lib().msb_launch_count())
 
 
+def set_option(name, value):
+    """Set a process-wide tuning option of the library (include/metasolver_b200.h: msb_set_option)."""
+    _cabi.check(_cabi.lib().msb_set_option(name.encode(), int(value)), "set_option")
+
+
+def get_option(name):
+    v = ctypes.c_int()
+    _cabi.check(_cabi.lib().msb_get_option(name.encode(), ctypes.byref(v)), "get_option")
+    return v.value
+
+
 def profile_enable(on=True):
     """Record CUDA events around every convolution-engine launch (clears earlier records)."""
     _cabi.lib().msb_profile_enable(1 if on else 0)

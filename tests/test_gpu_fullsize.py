@@ -182,3 +182,41 @@ def test_full_batch_stacked_solver_axis_slices():
         gk, = torch.autograd.grad((yk * r[k]).sum(), [xk])
         gsum += gk
     assert max_rel(xs.grad.cpu().numpy(), gsum.cpu().numpy()) < 1e-6
+
+
+@pytest.mark.parametrize("C,HW", [(64, 32), (128, 16)])
+def test_tuning_options_do_not_change_results(C, HW):
+    """msb_set_option knobs (L2 prefetch distance of the epilogue operands, resident weights) move data
+    earlier or keep it on chip; outputs and all gradients must stay bit-identical."""
+    import metasolver_b200
+    blk, solver, opts = _block(C)
+    torch.manual_seed(3)
+    x0 = torch.randn(64, C, HW, HW, device="cuda").contiguous(memory_format=torch.channels_last)
+    r = torch.randn_like(x0)
+
+    def run():
+        x = x0.clone().requires_grad_(True)
+        for p in blk.parameters():
+            p.grad = None
+        y = blk(x, [solver], opts)
+        (y * r).sum().backward()
+        return [y.detach().clone(), x.grad.clone()] + [p.grad.clone() for p in blk.parameters()]
+
+    names = ("epi_l2_prefetch", "tc_resident", "tcp_epi_warps")
+    defaults = {k: metasolver_b200.get_option(k) for k in names + ("tc_form_c64",)}
+    try:
+        for form in (0, 1):           # the two conv forms differ in the products they form: compare within a form
+            metasolver_b200.set_option("tc_form_c64", form)
+            for k, v in zip(names, (0, 0, 8)):
+                metasolver_b200.set_option(k, v)
+            base = run()
+            for vals in ((1, 0, 8), (2, 0, 16), (3, 1, 16), (0, 1, 8), (0, 0, 16)):
+                for k, v in zip(names, vals):
+                    metasolver_b200.set_option(k, v)
+                for a, b in zip(base, run()):
+                    assert torch.equal(a, b), (form, vals)
+        with pytest.raises(RuntimeError):
+            metasolver_b200.set_option("no_such_option", 1)
+    finally:
+        for k, v in defaults.items():
+            metasolver_b200.set_option(k, v)
