@@ -1,0 +1,334 @@
+// tcgen05 engine, pixel-major form on a CTA PAIR (tcgen05.mma.cta_group::2): the 3x3 convolution of conv_tcp.cu with
+// M = 256 -- two 128-pixel tiles, one per CTA of a 2-CTA cluster -- so that the weight operand is SHARED by the pair.
+//
+//   D[pixel][c_out] = sum_{tap, c_in} X[pixel + tap][c_in] * W[c_out][tap][c_in]
+//
+//   A (M = 256)  = activations: each CTA supplies ITS 128 pixels (one bf16 plane, K-major) from its own shared memory
+//   B (N rows)   = weights [W_hi ; W_lo]: each CTA holds HALF of the N rows (rank 0: W_hi, rank 1: W_lo for the N = 2C
+//                  product; rank r: rows r*C/2.. of W_hi for the N = C product X_lo * W_hi)
+//   D            = 128 TMEM lanes (own pixels) x 2C fp32 columns in each CTA, same layout as the single-CTA kernel
+//
+// Why: with both operands in shared memory a single-CTA MMA is limited by the shared-memory operand feed (~72 B/clk):
+// per k-step the single-CTA form reads 128 + 2C and 128 + C operand rows, the pair form 128 + C and 128 + C/2 -- for
+// C = 64: 448 -> 352 rows (the N = 128 / N = 64 MMAs were the slowest point of the engine, profiles/conv_forms_r1.txt);
+// and every weight tile crosses L2 -> SM once per PAIR instead of once per CTA.  Three hi/lo products as in conv_tcp.cu.
+//
+// Protocol (rank 0 = leader issues every MMA for the pair):
+//   full barriers (x_full, w_full) live in the LEADER; both CTAs' TMA loads complete_tx on them
+//       (cp.async.bulk.tensor...cta_group::2 with the leader's barrier address), the leader's producer arms them with
+//       the bytes of both CTAs
+//   empty barriers (x_empty, w_empty) and tmem_full are local to each CTA and signalled by the leader's
+//       tcgen05.commit.cta_group::2 ... multicast::cluster (mask 0b11)
+//   tmem_empty lives in the leader; the epilogue warps of BOTH CTAs arrive on it (remote mbarrier.arrive)
+// Epilogue: the 16-warp quad-transposed form of conv_tcp.cu (whole 128-byte lines per quad of lanes).
+#include <cuda.h>
+
+#include "msb_internal.h"
+#include "msb_ptx.cuh"
+
+namespace msb {
+
+int make_tmap_rows64(CUtensorMap* m, const void* base, size_t rows, int box_rows);
+int make_tmap_split_plane(CUtensorMap* m, const void* base, int B, int H, int W, int C, int box_w, int box_h);
+size_t tcp_packed_weight_bytes(int C);
+
+namespace {
+
+constexpr int kEpiWarp0 = 4;
+constexpr int kEpiWarps = 16;
+constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;
+constexpr uint32_t kTmemCols = 512;
+constexpr int kMaxStages = 8;
+constexpr int kSmemBudget = 230400;
+constexpr int kStageBytesPerWarp = 4096;
+
+template <int C, int WIMG> struct Geom2 {
+    static constexpr int ROWS = 128 / WIMG;
+    static constexpr int PLANE_BYTES = (ROWS + 2) * WIMG * 128;
+    static constexpr int X_STAGE_BYTES = 2 * PLANE_BYTES;
+    static constexpr int ROW_BYTES = WIMG * 128;
+    static constexpr int WA_BYTES = C * 128;                          // this CTA's half of [W_hi ; W_lo]
+    static constexpr int WB_BYTES = (C / 2) * 128;                    // this CTA's half of W_hi
+    static constexpr int W_STAGE_BYTES = WA_BYTES + WB_BYTES;
+    static constexpr int X_STAGES = 2;
+    static constexpr int STAGE_BYTES = kEpiWarps * kStageBytesPerWarp;
+    static constexpr int RING = kSmemBudget - STAGE_BYTES - X_STAGES * X_STAGE_BYTES;
+    static constexpr int W_STAGES = RING / W_STAGE_BYTES > kMaxStages ? kMaxStages : RING / W_STAGE_BYTES;
+    static constexpr int ACC_COLS = 2 * C;
+    static constexpr int ACC_BUFS = (C == 64) ? 4 : 2;
+    static_assert(ACC_COLS * ACC_BUFS <= 512, "TMEM");
+    static_assert(W_STAGES >= 2, "weight ring");
+};
+
+struct __align__(8) Barriers2 {
+    uint64_t w_full[kMaxStages], w_empty[kMaxStages];
+    uint64_t x_full[kMaxStages], x_empty[kMaxStages];
+    uint64_t tmem_full[4], tmem_empty[4];
+    uint32_t tmem_base;
+};
+
+template <int C, int WIMG, int ACT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_w,
+                    const EpiParams epi, const int H, const int num_pairs, const int tiles_per_img) {
+    using G = Geom2<C, WIMG>;
+    constexpr int CHUNKS = C / 64;
+    constexpr int kWStages = G::W_STAGES, kXStages = G::X_STAGES, kAccBufs = G::ACC_BUFS;
+    constexpr int NG = C / 32, WPT = 4 * NG, TG = kEpiWarps / WPT;     // epilogue: channel groups, warps per tile, tile groups
+    static_assert(TG >= 1 && kEpiWarps % WPT == 0, "16 epilogue warps must split evenly");
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_x = smem;
+    uint8_t* smem_w = smem + kXStages * G::X_STAGE_BYTES;
+    uint8_t* smem_stage = smem_w + kWStages * G::W_STAGE_BYTES;
+    Barriers2* bars = reinterpret_cast<Barriers2*>(smem_stage + G::STAGE_BYTES);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmap_act);
+        ptx::prefetch_tmap(&tmap_w);
+        for (int i = 0; i < kWStages; ++i) { ptx::mbar_init(&bars->w_full[i], 1); ptx::mbar_init(&bars->w_empty[i], 1); }
+        for (int i = 0; i < kXStages; ++i) { ptx::mbar_init(&bars->x_full[i], 1); ptx::mbar_init(&bars->x_empty[i], 1); }
+        for (int i = 0; i < kAccBufs; ++i) { ptx::mbar_init(&bars->tmem_full[i], 1); ptx::mbar_init(&bars->tmem_empty[i], 2 * WPT); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc2(&bars->tmem_base, kTmemCols);
+        ptx::tmem_relinquish2();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();                      // the peer's barriers are initialised before anything signals them
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        // ===================== activation producer (both CTAs; own pixels) =====================
+        if (lane == 0) {
+            int st = 0; uint32_t ph = 0;
+            for (int pr = cluster_id; pr < num_pairs; pr += num_clusters) {
+                const int tile = 2 * pr + (int)rank;
+                const int n = tile / tiles_per_img;
+                const int h0 = (tile - n * tiles_per_img) * G::ROWS;
+                for (int chunk = 0; chunk < CHUNKS; ++chunk)
+                    for (int s = 0; s < 3; ++s) {
+                        ptx::mbar_wait(&bars->x_empty[st], ph ^ 1);
+                        const uint32_t full = ptx::mapa(ptx::smem_u32(&bars->x_full[st]), 0);
+                        if (leader) ptx::mbar_arrive_expect_tx(&bars->x_full[st], 2 * G::X_STAGE_BYTES);
+                        uint8_t* dst = smem_x + st * G::X_STAGE_BYTES;
+                        ptx::tma_load_5d_2sm(dst, &tmap_act, full, chunk * 64, s - 1, 0, h0 - 1, n);
+                        ptx::tma_load_5d_2sm(dst + G::PLANE_BYTES, &tmap_act, full, chunk * 64, s - 1, 1, h0 - 1, n);
+                        if (++st == kXStages) { st = 0; ph ^= 1; }
+                    }
+            }
+        }
+    } else if (warp == 3) {
+        // ===================== weight producer (both CTAs; own halves) =====================
+        if (lane == 0) {
+            int st = 0; uint32_t ph = 0;
+            for (int pr = cluster_id; pr < num_pairs; pr += num_clusters) {
+                for (int chunk = 0; chunk < CHUNKS; ++chunk)
+                    for (int s = 0; s < 3; ++s)
+                        for (int r = 0; r < 3; ++r) {
+                            const int wt = (r * 3 + s) * CHUNKS + chunk;
+                            ptx::mbar_wait(&bars->w_empty[st], ph ^ 1);
+                            const uint32_t full = ptx::mapa(ptx::smem_u32(&bars->w_full[st]), 0);
+                            if (leader) ptx::mbar_arrive_expect_tx(&bars->w_full[st], 2 * G::W_STAGE_BYTES);
+                            uint8_t* dst = smem_w + st * G::W_STAGE_BYTES;
+                            const int row0 = wt * 2 * C;                    // packed tile: rows [W_hi (C) ; W_lo (C)]
+                            // region A: rank 0 -> W_hi, rank 1 -> W_lo  (two boxes of C/2 rows)
+                            ptx::tma_load_2d_2sm(dst, &tmap_w, full, 0, row0 + (int)rank * C);
+                            ptx::tma_load_2d_2sm(dst + G::WB_BYTES, &tmap_w, full, 0, row0 + (int)rank * C + C / 2);
+                            // region B: rank r -> rows r*C/2 .. of W_hi
+                            ptx::tma_load_2d_2sm(dst + G::WA_BYTES, &tmap_w, full, 0, row0 + (int)rank * (C / 2));
+                            if (++st == kWStages) { st = 0; ph ^= 1; }
+                        }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread of the LEADER, for the pair) =====================
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc_full = ptx::make_idesc_bf16(256, 2 * C, 0, 0);   // X_hi * [W_hi ; W_lo]
+            constexpr uint32_t idesc_hi = ptx::make_idesc_bf16(256, C, 0, 0);         // X_lo * W_hi
+            int wst = 0, xst = 0; uint32_t wph = 0, xph = 0;
+            int acc = 0; uint32_t acc_ph = 0;
+            for (int pr = cluster_id; pr < num_pairs; pr += num_clusters) {
+                ptx::mbar_wait(&bars->tmem_empty[acc], acc_ph ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * G::ACC_COLS);
+                uint32_t accumulate = 0;
+                for (int chunk = 0; chunk < CHUNKS; ++chunk)
+                    for (int s = 0; s < 3; ++s) {
+                        ptx::mbar_wait(&bars->x_full[xst], xph);
+                        ptx::tc_fence_after();
+                        const uint32_t x_base = ptx::smem_u32(smem_x + xst * G::X_STAGE_BYTES);
+                        for (int r = 0; r < 3; ++r) {
+                            ptx::mbar_wait(&bars->w_full[wst], wph);
+                            ptx::tc_fence_after();
+                            const uint32_t w_base = ptx::smem_u32(smem_w + wst * G::W_STAGE_BYTES);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t wa = ptx::make_smem_desc_sw128(w_base + k * 32, 16, 1024);
+                                const uint64_t wb = ptx::make_smem_desc_sw128(w_base + G::WA_BYTES + k * 32, 16, 1024);
+                                const uint64_t xhi = ptx::make_smem_desc_sw128(x_base + r * G::ROW_BYTES + k * 32, 16, 1024);
+                                const uint64_t xlo =
+                                    ptx::make_smem_desc_sw128(x_base + G::PLANE_BYTES + r * G::ROW_BYTES + k * 32, 16, 1024);
+                                ptx::umma_bf16_2sm(d_tmem, xhi, wa, idesc_full, accumulate);
+                                ptx::umma_bf16_2sm(d_tmem, xlo, wb, idesc_hi, 1u);
+                                accumulate = 1;
+                            }
+                            ptx::umma_commit_2sm(&bars->w_empty[wst]);
+                            if (++wst == kWStages) { wst = 0; wph ^= 1; }
+                        }
+                        ptx::umma_commit_2sm(&bars->x_empty[xst]);
+                        if (++xst == kXStages) { xst = 0; xph ^= 1; }
+                    }
+                ptx::umma_commit_2sm(&bars->tmem_full[acc]);
+                if (++acc == kAccBufs) { acc = 0; acc_ph ^= 1; }
+            }
+        }
+    } else if (warp >= kEpiWarp0) {
+        // ===================== epilogue (both CTAs; see conv_tcp.cu, 16-warp form) =====================
+        const int we = warp - kEpiWarp0;
+        const int q = warp & 3;
+        uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        asm volatile("" : "+r"(lane_addr));
+        const size_t plane_stride = (size_t)WIMG * C;
+        const int tg = we / WPT, wi = we % WPT;
+        const int cb = (wi >> 2) * 32;
+        const uint32_t stage = ptx::smem_u32(smem_stage + we * kStageBytesPerWarp);
+        const int k4 = lane & 3, quad = lane >> 2;
+        auto owned = [&](size_t row0, int j, size_t& idx, size_t& sidx) {
+            const int pp = q * 32 + quad * 4 + j;
+            const int r2 = pp / WIMG, w2 = pp - r2 * WIMG;
+            idx = ((row0 + r2) * WIMG + w2) * C + cb + 8 * k4;
+            sidx = ((row0 + r2) * 2) * plane_stride + (size_t)w2 * C + cb + 8 * k4;
+        };
+        auto row0_of = [&](int pr) {
+            const int t = 2 * pr + (int)rank;
+            const int n = t / tiles_per_img;
+            return (size_t)n * H + (size_t)(t - n * tiles_per_img) * G::ROWS;
+        };
+        int it = tg;
+        int pr = cluster_id + tg * num_clusters;
+        EpiVec8 ops;
+        if (pr < num_pairs) { size_t i0, s0; owned(row0_of(pr), 0, i0, s0); epi_prefetch_vec8(epi, i0, ops); }
+        for (; pr < num_pairs; pr += TG * num_clusters, it += TG) {
+            const int acc = it % kAccBufs;
+            const uint32_t ph = (uint32_t)(it / kAccBufs) & 1u;
+            const EpiCoef coef = epi_coef(epi, (2 * pr + (int)rank) / tiles_per_img);
+            const size_t row0 = row0_of(pr);
+            ptx::mbar_wait(&bars->tmem_full[acc], ph);
+            ptx::tc_fence_after();
+            const uint32_t t_acc = tmem_base + (uint32_t)(acc * G::ACC_COLS) + lane_addr + (uint32_t)cb;
+            __syncwarp();
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+                float a[8], b[8];
+                ptx::tmem_ld<8>(t_acc + c8 * 8, a);
+                ptx::tmem_ld<8>(t_acc + C + c8 * 8, b);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const uint32_t addr = stage + lane * 128 + (((c8 * 2 + u) ^ (lane & 7)) << 4);
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a[4 * u] + b[4 * u]),
+                                 "f"(a[4 * u + 1] + b[4 * u + 1]), "f"(a[4 * u + 2] + b[4 * u + 2]),
+                                 "f"(a[4 * u + 3] + b[4 * u + 3]) : "memory");
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->tmem_empty[acc]), 0));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int row = quad * 4 + j;
+                float v[8];
+                {
+                    const uint32_t base = stage + row * 128;
+                    const uint32_t a0 = base + (((2 * k4) ^ (row & 7)) << 4), a1 = base + (((2 * k4 + 1) ^ (row & 7)) << 4);
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a0));
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(a1));
+                }
+                size_t idx, sidx;
+                owned(row0, j, idx, sidx);
+                epi_finish_vec8<ACT>(epi, coef, v, ops, idx, sidx, plane_stride);
+                if (j < 3) {
+                    owned(row0, j + 1, idx, sidx);
+                    epi_prefetch_vec8(epi, idx, ops);
+                } else {
+                    const int p2 = pr + TG * num_clusters;
+                    if (p2 < num_pairs) { owned(row0_of(p2), 0, idx, sidx); epi_prefetch_vec8(epi, idx, ops); }
+                }
+            }
+        }
+    }
+    // nobody leaves while the peer may still signal its barriers or the leader's MMAs write its TMEM
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc2(tmem_base, kTmemCols);
+    }
+}
+
+template <int C, int WIMG, int ACT>
+int launch_act(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, const EpiParams& epi, ConvShape s,
+               cudaStream_t st) {
+    using G = Geom2<C, WIMG>;
+    CUtensorMap tm_act, tm_w;
+    if (make_tmap_split_plane(&tm_act, split_in, s.B, s.H, s.W, s.C, WIMG, G::ROWS + 2)) return -1;
+    if (make_tmap_rows64(&tm_w, w_tiles, tcp_packed_weight_bytes(C) / 128, C / 2)) return -1;
+    constexpr size_t smem = (size_t)G::X_STAGES * G::X_STAGE_BYTES + (size_t)G::W_STAGES * G::W_STAGE_BYTES + G::STAGE_BYTES +
+                            sizeof(Barriers2) + 1024;
+    static_assert(smem <= 232448, "shared memory per CTA");
+    auto kern = conv3x3_tcp2_kernel<C, WIMG, ACT>;
+    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                   "cudaFuncSetAttribute(conv3x3_tcp2)"))
+        return -1;
+    const int tiles_per_img = s.H / G::ROWS;
+    const int num_pairs = s.B * tiles_per_img / 2;
+    const int clusters = std::min(num_pairs, num_sms() / 2);
+    kern<<<2 * clusters, kThreads, smem, st>>>(tm_act, tm_w, epi, s.H, num_pairs, tiles_per_img);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "conv3x3_tcp2 launch");
+}
+
+template <int C, int WIMG>
+int launch_impl(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, const EpiParams& epi, ConvShape s,
+                cudaStream_t st) {
+    const int act = (epi.out_split || epi.dact_out) ? epi.act : ACT_NONE;
+    if (act == ACT_GELU) return launch_act<C, WIMG, ACT_GELU>(split_in, w_tiles, epi, s, st);
+    if (act == ACT_RELU) return launch_act<C, WIMG, ACT_RELU>(split_in, w_tiles, epi, s, st);
+    return launch_act<C, WIMG, ACT_NONE>(split_in, w_tiles, epi, s, st);
+}
+
+}  // namespace
+
+// the pair form needs an even number of 128-pixel tiles (pairs never straddle... they may: a pair is two consecutive
+// tiles of the batch-major tile order, each CTA addresses its own tile independently)
+bool tcp2_shape_supported(int B, int C, int H, int W) {
+    if (!tc_shape_supported(C, H, W)) return false;
+    const int rows = 128 / W;
+    return ((B * (H / rows)) % 2) == 0;
+}
+
+int launch_conv3x3_tcp2(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, const EpiParams& epi, ConvShape s,
+                        cudaStream_t st) {
+    if (!tcp2_shape_supported(s.B, s.C, s.H, s.W)) {
+        set_error("tcgen05 pair conv: unsupported shape B=%d C=%d H=%d W=%d", s.B, s.C, s.H, s.W);
+        return -1;
+    }
+    if (epi.chan_bias || epi.pix_bias) { set_error("tcgen05 conv: bias terms are SIMT-engine only"); return -1; }
+    if (s.C == 64 && s.W == 32) return launch_impl<64, 32>(split_in, w_tiles, epi, s, st);
+    if (s.C == 64 && s.W == 16) return launch_impl<64, 16>(split_in, w_tiles, epi, s, st);
+    if (s.C == 128 && s.W == 32) return launch_impl<128, 32>(split_in, w_tiles, epi, s, st);
+    return launch_impl<128, 16>(split_in, w_tiles, epi, s, st);
+}
+
+}  // namespace msb

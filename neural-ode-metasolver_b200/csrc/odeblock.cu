@@ -40,7 +40,7 @@ static std::atomic<int> g_tune[TUNE_COUNT];
 static std::atomic<bool> g_tune_init{false};
 static const char* const kTuneNames[TUNE_COUNT] = {"epi_l2_prefetch", "tc_resident", "tcp_epi_warps", "tc_form_c64"};
 static const char* const kTuneEnv[TUNE_COUNT] = {"MSB_EPI_L2_PREFETCH", "MSB_TC_RESIDENT", "MSB_TCP_EPI_WARPS", "MSB_TC_FORM_C64"};
-static const int kTuneDefault[TUNE_COUNT] = {0, 0, 8, 0};
+static const int kTuneDefault[TUNE_COUNT] = {0, 0, 16, 1};
 static void tune_init() {
     if (g_tune_init.load(std::memory_order_acquire)) return;
     for (int i = 0; i < TUNE_COUNT; ++i) {
