@@ -200,6 +200,9 @@ uint64_t msb_launch_count(void);
  *   "tcp_epi_warps"    epilogue warps of the pixel-major convolution, 8 or 16      (env MSB_TCP_EPI_WARPS)
  *   "tc_form_c64"      tcgen05 convolution form for 64 channels: 0 = channel-major (4 hi/lo products),
  *                      1 = pixel-major (3 products)                      (env MSB_TC_FORM_C64)
+ *   "tc_pair"          pixel-major convolution on CTA pairs (tcgen05.mma.cta_group::2, M = 256, weights shared by
+ *                      the pair): 0 = off, 1 = every shape with an even tile count, 2 = only C >= 128 (default)
+ *                                                                        (env MSB_TC_PAIR)
  * Results do not depend on any option.  Returns 0, or -1 for an unknown name. */
 int msb_set_option(const char* name, int value);
 int msb_get_option(const char* name, int* value);

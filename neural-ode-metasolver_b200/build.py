@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libmetasolver_b200.so")
-SOURCES = ["odeblock.cu", "blocks.cu", "netlayers.cu", "elementwise.cu", "conv_simt.cu", "conv_tc.cu", "conv_tcp.cu", "wgrad_tc.cu",
+SOURCES = ["odeblock.cu", "blocks.cu", "netlayers.cu", "elementwise.cu", "conv_simt.cu", "conv_tc.cu", "conv_tcp.cu", "conv_tcp2.cu", "wgrad_tc.cu",
            "groupnorm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",

@@ -20,6 +20,7 @@ enum { TUNE_EPI_L2_PREFETCH = 0,   // conv epilogue operands: bulk L2 prefetch d
        TUNE_TC_RESIDENT = 1,       // channel-major C=64 conv: weights resident in shared memory
        TUNE_TCP_EPI_WARPS = 2,     // pixel-major conv: epilogue warps (8 or 16)
        TUNE_TC_FORM_C64 = 3,       // tcgen05 conv form for C = 64: 0 = channel-major, 1 = pixel-major
+       TUNE_TC_PAIR = 4,           // pixel-major conv on a CTA pair (cta_group::2, M = 256): 0 off, 1 on, 2 for C >= 128 (default)
        TUNE_COUNT };
 int tune_get(int which);
 
@@ -80,6 +81,10 @@ size_t tcp_packed_weight_bytes(int C);
 void launch_pack_w_tcp(const float* w, __nv_bfloat16* out, int C, int transpose, cudaStream_t st);
 int launch_conv3x3_tcp(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, const EpiParams& epi,
                        ConvShape s, cudaStream_t st);
+// the same on a CTA pair (conv_tcp2.cu): tcgen05.mma.cta_group::2, weights shared by the pair; same packed weights
+bool tcp2_shape_supported(int B, int C, int H, int W);
+int launch_conv3x3_tcp2(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, const EpiParams& epi,
+                        ConvShape s, cudaStream_t st);
 // which form MSB_ENGINE_TCGEN05 runs for C channels (odeblock.cu; env MSB_TC_CONV=cm|pm forces one)
 bool tc_pixel_major(int C);
 

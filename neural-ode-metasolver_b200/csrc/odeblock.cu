@@ -38,9 +38,10 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 // ---- tuning options (msb_set_option / environment MSB_<NAME>) ----
 static std::atomic<int> g_tune[TUNE_COUNT];
 static std::atomic<bool> g_tune_init{false};
-static const char* const kTuneNames[TUNE_COUNT] = {"epi_l2_prefetch", "tc_resident", "tcp_epi_warps", "tc_form_c64"};
-static const char* const kTuneEnv[TUNE_COUNT] = {"MSB_EPI_L2_PREFETCH", "MSB_TC_RESIDENT", "MSB_TCP_EPI_WARPS", "MSB_TC_FORM_C64"};
-static const int kTuneDefault[TUNE_COUNT] = {0, 0, 16, 1};
+static const char* const kTuneNames[TUNE_COUNT] = {"epi_l2_prefetch", "tc_resident", "tcp_epi_warps", "tc_form_c64", "tc_pair"};
+static const char* const kTuneEnv[TUNE_COUNT] = {"MSB_EPI_L2_PREFETCH", "MSB_TC_RESIDENT", "MSB_TCP_EPI_WARPS", "MSB_TC_FORM_C64",
+                                                 "MSB_TC_PAIR"};
+static const int kTuneDefault[TUNE_COUNT] = {0, 0, 16, 1, 2};
 static void tune_init() {
     if (g_tune_init.load(std::memory_order_acquire)) return;
     for (int i = 0; i < TUNE_COUNT; ++i) {
@@ -124,7 +125,10 @@ int run_conv(int engine, const __nv_bfloat16* in, const void* wpacked, const Epi
     int id = prof_begin(MSB_PROF_CONV, conv_flops(s), products, st);
     int rc;
     if (engine == MSB_ENGINE_TCGEN05)
-        rc = tc_pixel_major(s.C) ? launch_conv3x3_tcp(in, (const __nv_bfloat16*)wpacked, e, s, st)
+        rc = tc_pixel_major(s.C) ? (((tune_get(TUNE_TC_PAIR) == 1 || (tune_get(TUNE_TC_PAIR) == 2 && s.C >= 128)) &&
+                                     tcp2_shape_supported(s.B, s.C, s.H, s.W))
+                                        ? launch_conv3x3_tcp2(in, (const __nv_bfloat16*)wpacked, e, s, st)
+                                        : launch_conv3x3_tcp(in, (const __nv_bfloat16*)wpacked, e, s, st))
                               : launch_conv3x3_tc(in, (const __nv_bfloat16*)wpacked, e, s, st);
     else rc = launch_conv3x3_simt(in, (const float*)wpacked, e, s, st);
     prof_end(id, st);

@@ -220,3 +220,36 @@ def test_tuning_options_do_not_change_results(C, HW):
     finally:
         for k, v in defaults.items():
             metasolver_b200.set_option(k, v)
+
+
+@pytest.mark.parametrize("C,HW", [(64, 32), (128, 16)])
+def test_cta_pair_conv_matches_single_cta(C, HW):
+    """tc_pair=1 runs the pixel-major convolution on CTA pairs (tcgen05.mma.cta_group::2, M = 256, weights shared by
+    the pair): same operands, same products, same epilogue -- outputs and gradients must agree with the single-CTA
+    kernel to fp32 accumulation-order noise, and be reproducible."""
+    import metasolver_b200
+    blk, solver, opts = _block(C)
+    torch.manual_seed(5)
+    x0 = torch.randn(96, C, HW, HW, device="cuda").contiguous(memory_format=torch.channels_last)
+    r = torch.randn_like(x0)
+
+    def run():
+        x = x0.clone().requires_grad_(True)
+        for p in blk.parameters():
+            p.grad = None
+        y = blk(x, [solver], opts)
+        (y * r).sum().backward()
+        return [y.detach().clone(), x.grad.clone()] + [p.grad.clone() for p in blk.parameters()]
+
+    d = metasolver_b200.get_option("tc_pair")
+    try:
+        metasolver_b200.set_option("tc_pair", 0)
+        base = run()
+        metasolver_b200.set_option("tc_pair", 1)
+        pair = run()
+        pair2 = run()
+    finally:
+        metasolver_b200.set_option("tc_pair", d)
+    for a, b, c in zip(base, pair, pair2):
+        assert torch.equal(b, c)
+        assert max_rel(b.cpu().numpy(), a.cpu().numpy()) <= 2e-6
