@@ -332,7 +332,7 @@ class _StemFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             xc = x.detach().contiguous(memory_format=torch.channels_last)
             wc = w.detach().contiguous()
-            y = torch.empty((B, C, H, W), dtype=torch.float32, device=dev).contiguous(memory_format=torch.channels_last)
+            y = torch.empty((B, C, H, W), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
             dact = torch.empty_like(y) if need_grad else None
             _cabi.check(lib.msb_stem_forward(_ptr(xc), _ptr(wc), act, _ptr(y), _ptr(dact), B, H, W, C, _stream(dev)),
                         "stem forward")
@@ -400,8 +400,7 @@ class _DownBlockFn(torch.autograd.Function):
             if need_grad:
                 tape_bytes = lib.msb_downblock_tape_bytes(ctypes.byref(d))
                 tape = torch.empty(tape_bytes, dtype=torch.uint8, device=dev)
-            y = torch.empty((B, Co, H // 2, W // 2), dtype=torch.float32, device=dev).contiguous(
-                memory_format=torch.channels_last)
+            y = torch.empty((B, Co, H // 2, W // 2), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
             _cabi.check(lib.msb_downblock_forward(ctypes.byref(d), _ptr(xc), _ptr(ws_[0]), _ptr(ws_[1]), _ptr(ws_[2]),
                                                   _ptr(y), _ptr(ws), ws_bytes, _ptr(tape), tape_bytes, _stream(dev)),
                         "downblock forward")
@@ -423,7 +422,7 @@ class _DownBlockFn(torch.autograd.Function):
             ws_bytes = lib.msb_downblock_bwd_workspace_bytes(ctypes.byref(d))
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             B, Ci, H, W = ctx.shape
-            gx = torch.empty((B, Ci, H, W), dtype=torch.float32, device=dev).contiguous(memory_format=torch.channels_last)
+            gx = torch.empty((B, Ci, H, W), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
             gws = [torch.empty_like(w) if need_w else None for w in (w1, w2, wsc)]
             _cabi.check(lib.msb_downblock_backward(ctypes.byref(d), _ptr(gyc), _ptr(w1), _ptr(w2), _ptr(wsc), _ptr(ctx.tape),
                                                    ctx.tape_bytes, _ptr(gx), _ptr(gws[0]), _ptr(gws[1]), _ptr(gws[2]),
@@ -461,7 +460,7 @@ def conv3x3(split, w, transpose=False, engine="auto"):
     lib = _cabi.lib()
     B, H, _, W, C = split.shape
     dev = split.device
-    out = torch.empty((B, C, H, W), dtype=torch.float32, device=dev).contiguous(memory_format=torch.channels_last)
+    out = torch.empty((B, C, H, W), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
     ws_bytes = lib.msb_conv3x3_workspace_bytes(C)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):

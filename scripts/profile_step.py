@@ -35,3 +35,11 @@ e0.record()
 for _ in range(5): step()
 e1.record(); torch.cuda.synchronize()
 print("wall ms/step", e0.elapsed_time(e1) / 5)
+# which framework-side copies / elementwise ops are left (CPU-side op names with input shapes and their device time)
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=True) as prof2:
+    step()
+    torch.cuda.synchronize()
+print("-- aten ops with device time (one step), by input shape --")
+for e in sorted(prof2.key_averages(group_by_input_shape=True), key=lambda e: -e.self_device_time_total)[:40]:
+    if e.self_device_time_total > 5 and e.key.startswith("aten::"):
+        print("%-28s n=%3d %8.1f us  %s" % (e.key, e.count, e.self_device_time_total, str(e.input_shapes)[:110]))
