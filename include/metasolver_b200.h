@@ -192,6 +192,31 @@ size_t msb_wgrad3x3_workspace_bytes(int channels, int engine);
 /* Number of kernels this library has launched since load (bench.py's `gpu_launches`). */
 uint64_t msb_launch_count(void);
 
+/* ---- callers either side of the path -------------------------------------------
+ * Elementwise steps of the adversarial attacks as ONE kernel each, bit-identical to the reference's torch
+ * calls (MegaAdversarial/src/attacks/fgsm.py:27-40,93-105, pgd.py:28-53).  All tensors are fp32 images of
+ * n_elements = B*channels*hw values, NCHW-contiguous (channels_last = 0) or channels-last memory (1).
+ * chan_consts = 4 x channels floats [mean|lower][std|upper][eps][alpha] (per channel), may be NULL where unused.
+ *   UNNORMALIZE / NORMALIZE : out = (a - c0) / c1
+ *   FGSM_STEP   : out = clamp01(a + eps*sign(grad));                       normalize_out: (out - c0)/c1
+ *   PGD_STEP    : out = clamp01(clamp(a + step*sign(grad), ref-eps, ref+eps));   normalize_out as above
+ *   FGSMR_INIT  : out = clamp(c2 - (2 c2)*a, c0 - ref, c1 - ref)           (a = U[0,1) noise, ref = x)
+ *   FGSMR_STEP  : d = clamp(clamp(a + c3*sign(grad), -c2, c2), c0 - ref, c1 - ref);  out = normalize_out ? ref + d : d
+ */
+enum { MSB_ATTACK_UNNORMALIZE = 0, MSB_ATTACK_NORMALIZE = 1, MSB_ATTACK_FGSM_STEP = 2, MSB_ATTACK_PGD_STEP = 3,
+       MSB_ATTACK_FGSMR_INIT = 4, MSB_ATTACK_FGSMR_STEP = 5 };
+#define MSB_ATTACK_MAX_CHANNELS 4
+int msb_attack_step(int kind, const float* a, const float* grad, const float* ref, float* out, int64_t n_elements,
+                    int channels, int hw, int channels_last, float eps, float step, int normalize_out,
+                    const float* chan_consts /* host */, void* cuda_stream);
+
+/* SGD with momentum and weight decay (torch.optim.SGD semantics, no dampening / nesterov;
+ * examples/cifar10/train_and_attack.py:98-99,322) over ONE flat fp32 buffer:
+ *   g = grads*grad_scale + weight_decay*p;  buf = first_step ? g : momentum*buf + g;  p -= lr*buf
+ * grad_scale carries the 1/world average of the data-parallel all-reduce.  momentum_buf may be NULL if momentum == 0. */
+int msb_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t n, float lr, float momentum,
+                 float weight_decay, float grad_scale, int first_step, void* cuda_stream);
+
 /* Tuning options (process-wide; defaults are the measured best).  Names:
  *   "epi_l2_prefetch"  distance, in tiles, at which the tcgen05 convolutions bulk-prefetch their epilogue
  *                      operands (y, k_j, act') into L2; 0 = off          (env MSB_EPI_L2_PREFETCH)

@@ -14,7 +14,32 @@ Differences from the reference, none of which changes results:
 import torch
 import torch.nn as nn
 
+from .... import _cabi
 from ....ops import input_grad_only
+from ....train_ops import attack_step
+
+
+def _fusable(x):
+    """The elementwise attack steps run as one CUDA kernel each on CUDA fp32 image batches."""
+    return x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] <= _cabi.ATTACK_MAX_CHANNELS
+
+
+def _f32(vals):
+    """Python floats -> the fp32 values torch.as_tensor(..., dtype=float32) would hold."""
+    return torch.tensor([float(v) for v in vals], dtype=torch.float32).tolist()
+
+
+class _NormalizeFn(torch.autograd.Function):
+    """(x - mean) / std as one kernel, differentiable w.r.t. x (grad / std, as autograd derives for the reference)."""
+
+    @staticmethod
+    def forward(ctx, x, mean, std):
+        ctx.std = std
+        return attack_step(_cabi.ATTACK_NORMALIZE, x.detach(), chan_consts=[mean, std])
+
+    @staticmethod
+    def backward(ctx, g):
+        return g / _chan(ctx.std, g), None, None
 
 
 _CHAN_CACHE = {}
@@ -38,13 +63,20 @@ class _Normalizer:
         self.std = tuple(std) if std is not None else (1., 1., 1.)
 
     def normalize(self, x):
+        if _fusable(x):
+            return _NormalizeFn.apply(x, _f32(self.mean), _f32(self.std))
         return (x - _chan(self.mean, x)) / _chan(self.std, x)
 
     def unnormalize(self, x):
         # transforms.Normalize(mean=[-m/s], std=[1/s]) of fgsm.py:27 / pgd.py:28
         inv_mean = [-m / s for m, s in zip(self.mean, self.std)]
         inv_std = [1 / s for s in self.std]
+        if _fusable(x) and not x.requires_grad:
+            return attack_step(_cabi.ATTACK_UNNORMALIZE, x, chan_consts=[_f32(inv_mean), _f32(inv_std)])
         return (x - _chan(inv_mean, x)) / _chan(inv_std, x)
+
+    def consts(self):
+        return [_f32(self.mean), _f32(self.std)]
 
 
 class Attack(nn.Module):
@@ -105,7 +137,11 @@ class FGSM(Attack):
         xa = x01.clone().detach().requires_grad_(True)
         loss = self.loss_fn(self.model(self.norm.normalize(xa), **kwargs), y)
         grad = _input_gradient(loss, xa)
-        xa = self.norm.normalize(self._project(xa + self.eps * grad.sign())).detach()
+        if _fusable(xa):
+            xa = attack_step(_cabi.ATTACK_FGSM_STEP, xa.detach(), grad=grad, eps=self.eps, normalize_out=True,
+                             chan_consts=self.norm.consts())
+        else:
+            xa = self.norm.normalize(self._project(xa + self.eps * grad.sign())).detach()
         if was_training:
             self.model.train()
         return xa, y
@@ -136,18 +172,36 @@ class FGSMRandom(Attack):
 
     def forward(self, x, y, kwargs, noise=None):
         was_training = self._eval_mode([self.model])
-        lower, upper, epsilon, alpha = self._limits(x)
         u01 = torch.rand_like(x) if noise is None else noise.to(x)
-        delta = epsilon - (2 * epsilon) * u01                        # Uniform[-eps, eps]
-        delta = clamp(delta, lower - x, upper - x).detach().requires_grad_(True)
+        fused = _fusable(x) and not x.requires_grad
+        if fused:
+            consts = self._host_limits(x.shape[1])
+            delta = attack_step(_cabi.ATTACK_FGSMR_INIT, u01, ref=x, chan_consts=consts).requires_grad_(True)
+        else:
+            lower, upper, epsilon, alpha = self._limits(x)
+            delta = epsilon - (2 * epsilon) * u01                        # Uniform[-eps, eps]
+            delta = clamp(delta, lower - x, upper - x).detach().requires_grad_(True)
         loss = self.loss_fn(self.model(x + delta, **kwargs), y)
         loss.backward()                                              # parameter grads accumulate too
         grad = delta.grad.detach()
-        delta = clamp(delta.detach() + alpha * torch.sign(grad), -epsilon, epsilon)
-        delta = clamp(delta, lower - x, upper - x).detach()
+        if fused:
+            xa = attack_step(_cabi.ATTACK_FGSMR_STEP, delta.detach(), grad=grad, ref=x, normalize_out=True, chan_consts=consts)
+        else:
+            delta = clamp(delta.detach() + alpha * torch.sign(grad), -epsilon, epsilon)
+            delta = clamp(delta, lower - x, upper - x).detach()
+            xa = x + delta
         if was_training:
             self.model.train()
-        return x + delta, y
+        return xa, y
+
+    def _host_limits(self, C):
+        """[lower, upper, eps, alpha] per channel as the fp32 values `_limits` computes on the device."""
+        if self.scaled:
+            mu = torch.tensor(list(self.mu), dtype=torch.float32)
+            std = torch.tensor(list(self.std_), dtype=torch.float32)
+            return [((0. - mu) / std).tolist(), ((1. - mu) / std).tolist(), (self.epsilon_ / std).tolist(),
+                    (self.alpha_ / std).tolist()]
+        return [[0.] * C, [1.] * C, _f32([self.epsilon_]) * C, _f32([self.alpha_]) * C]
 
 
 class PGD(Attack):
@@ -171,6 +225,10 @@ class PGD(Attack):
             xa.requires_grad_(True)
             loss = self.loss_fn(self.model(self.norm.normalize(xa), **kwargs), y)
             grad = _input_gradient(loss, xa)
+            if _fusable(xa):
+                xa = attack_step(_cabi.ATTACK_PGD_STEP, xa.detach(), grad=grad, ref=x01, eps=self.eps, step=self.lr,
+                                 normalize_out=(i == self.n_iter - 1), chan_consts=self.norm.consts())
+                continue
             xa = self._project(self._clamp(xa + self.lr * grad.sign(), x01 - self.eps, x01 + self.eps))
             if i == self.n_iter - 1:
                 xa = self.norm.normalize(xa)
@@ -229,7 +287,11 @@ class FGSM2Ensemble(Attack2Ensemble):
         probs = probs / len(self.models)
         loss = self.loss_fn(torch.log(probs), y)
         grad = _input_gradient(loss, xa)
-        xa = self.norm.normalize(self._project(xa + self.eps * grad.sign())).detach()
+        if _fusable(xa):
+            xa = attack_step(_cabi.ATTACK_FGSM_STEP, xa.detach(), grad=grad, eps=self.eps, normalize_out=True,
+                             chan_consts=self.norm.consts())
+        else:
+            xa = self.norm.normalize(self._project(xa + self.eps * grad.sign())).detach()
         if was_training:
             for m in self.models:
                 m.train()

@@ -10,5 +10,6 @@ from . import _cabi  # noqa: F401
 from .ops import (ode_block_integrate, input_grad_only, set_default_engine, launch_count,  # noqa: F401
                   profile_enable, profile_read, profile_read_executed, set_option, get_option)
 from .graphs import GraphedStep  # noqa: F401
+from .train_ops import attack_step, FusedSGD  # noqa: F401
 
 __version__ = "0.1.0"

@@ -13,6 +13,9 @@ MSB_MAX_STAGES = 4
 ABI_VERSION = 2
 RHS_PREACT_NF, RHS_POSTACT_NF, RHS_MNIST_GN_T = 0, 1, 2
 ACT_NONE, ACT_GELU_ERF, ACT_RELU = 0, 1, 2
+(ATTACK_UNNORMALIZE, ATTACK_NORMALIZE, ATTACK_FGSM_STEP, ATTACK_PGD_STEP, ATTACK_FGSMR_INIT,
+ ATTACK_FGSMR_STEP) = range(6)
+ATTACK_MAX_CHANNELS = 4
 ENGINE_AUTO, ENGINE_TCGEN05, ENGINE_SIMT = 0, 1, 2
 ENGINES = {"auto": ENGINE_AUTO, "tcgen05": ENGINE_TCGEN05, "simt": ENGINE_SIMT}
 
@@ -24,7 +27,7 @@ EXPORTS = [
     "msb_downblock_workspace_bytes", "msb_downblock_tape_bytes", "msb_downblock_bwd_workspace_bytes",
     "msb_downblock_forward", "msb_downblock_backward",
     "msb_conv3x3_workspace_bytes", "msb_wgrad3x3", "msb_wgrad3x3_workspace_bytes", "msb_launch_count", "msb_profile_enable", "msb_profile_read", "msb_profile_read_executed",
-    "msb_set_option", "msb_get_option",
+    "msb_set_option", "msb_get_option", "msb_attack_step", "msb_sgd_step",
 ]
 
 
@@ -110,6 +113,9 @@ def _declare(lib):
     lib.msb_wgrad3x3_workspace_bytes.restype = sz
     lib.msb_set_option.argtypes = [ctypes.c_char_p, i32]
     lib.msb_get_option.argtypes = [ctypes.c_char_p, ctypes.POINTER(i32)]
+    f32, i64 = ctypes.c_float, ctypes.c_int64
+    lib.msb_attack_step.argtypes = [i32, vp, vp, vp, vp, i64, i32, i32, i32, f32, f32, i32, ctypes.POINTER(f32), vp]
+    lib.msb_sgd_step.argtypes = [vp, vp, vp, i64, f32, f32, f32, f32, i32, vp]
     lib.msb_profile_enable.argtypes = [i32]
     lib.msb_profile_read_executed.argtypes = [i32, ctypes.POINTER(ctypes.c_double)]
     lib.msb_profile_read.argtypes = [i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
