@@ -278,11 +278,12 @@ def run_ours(args):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["conv3x3_tc_bytes_per_launch"]
     except Exception:
         pass
-    roofline = dict(bound="tensor", kernel="conv3x3_tc / conv3x3_tcp (fwd + dgrad implicit GEMM, tcgen05)", achieved=ach,
+    roofline = dict(bound="tensor", kernel="conv3x3_tcp (C=64) / conv3x3_tcp2 (C=128, CTA pair): fwd + dgrad implicit GEMM, tcgen05", achieved=ach,
                     peak=peak, unit="TFLOP/s", frac=ach / peak, traffic=traffic, peak_source=peak_src,
                     note="achieved = algorithmic 2*M*N*K flops / CUDA-event duration per launch (timed region A: eager steps with "
-                         "events on the launch stream). The engine forms 4 (C=64) or 3 (C=128) bf16 hi/lo products per "
-                         "algorithmic MAC for fp32-grade accuracy: executed_* is the tensor-pipe figure. traffic = ncu "
+                         "events on the launch stream). The engine forms 3 bf16 hi/lo products per algorithmic MAC (pixel-major "
+                         "forms; 4 in the channel-major form) for fp32-grade accuracy: executed_* is the tensor-pipe figure. "
+                         "Kernels run at the board's software power cap (see clocks), as does the cuBLAS peak. traffic = ncu "
                          "dram__bytes_read+write per launch, mean over the launch mix (profiles/).",
                     executed_bf16_tflops=ex, executed_frac=ex / peak,
                     launches=conv_n, avg_launch_ms=conv_ms / max(conv_n, 1),
@@ -298,7 +299,7 @@ def run_ours(args):
                 data="synthetic",
                 config=dict(workload=WORKLOAD, batch_per_gpu=B, global_batch=B * world, parallelism="dp%d" % world,
                             l2="per-step working set (activation tape ~13 GB) >> 126 MB L2; no explicit flush needed",
-                            precision="bf16 hi/lo split operands, 3-4 tcgen05 products, fp32 accumulate (fp32-grade)",
+                            precision="bf16 hi/lo split operands, 3 tcgen05 products (4 in the weight gradient at C=64), fp32 accumulate (fp32-grade)",
                             launch=graph_note),
                 clocks=clocks,
                 e2e=dict(value=e2e_val, unit="images/s", h2d_bytes_per_step=x_host.numel() * 4 + y_host.numel() * 8,

@@ -76,7 +76,7 @@ out["C3_ensembles_B256"] = dict(solver_ensemble_4xRK2_stacked_ms=ms_st, four_sta
                                 images_per_s_solver_ensemble=256 / ms_st * 1e3, images_per_s_model_ensemble=256 / ms_me * 1e3)
 # ---- C4: FGSM-random training step, solver smoothing (u ~ N(0.5, 0.0125) redrawn per batch), SGD momentum
 model.train()
-opt = torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9, weight_decay=5e-4)
+opt = msb.FusedSGD(model.parameters(), lr=0.05, momentum=0.9, weight_decay=5e-4)     # flat buffers, one update kernel
 atk = FGSMRandom(model, alpha=10 / 255., epsilon=8 / 255., mu=MEAN, std=STD)
 base = create_solver("rk2", "u", 8, -1, 0.5, -1, torch.float32, dev); base.freeze_params()
 xt, yt = xin[:256], y[:256]
@@ -89,12 +89,12 @@ def train_step():
     xa, _ = atk(xt, yt, kws)
     loss = F.cross_entropy(model(xa, **kws), yt)
     loss.backward()
-    opt.step()
+    opt.step(grad_scale=opt.all_reduce())
 
 
 ms = timed(train_step, 5, 2)
 out["C4_fgsm_random_train_step_B256"] = dict(ms=ms, images_per_s=256 / ms * 1e3,
-                                             note="attack pass (fwd+bwd) + training pass (fwd+bwd) + SGD; u redrawn per batch")
+                                             note="attack pass (fwd+bwd) + training pass (fwd+bwd) + fused SGD; fused attack steps; u redrawn per batch")
 # ---- C5: PGD-7 evaluation
 model.eval()
 pgd = PGD(model, eps=8 / 255., lr=2 / 255., n_iter=7, mean=MEAN, std=STD)

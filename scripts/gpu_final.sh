@@ -10,7 +10,7 @@ python scripts/bench_configs.py > gpurun_out/configs_$TAG.json 2> gpurun_out/con
 grep -A3 "C5_" gpurun_out/configs_$TAG.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/ncu_bench_$TAG.log 2>&1
-for spec in "64 conv3x3_tc conv64" "128 conv3x3_tcp conv128" "64 wgrad3x3_tc wgrad64" "128 wgrad3x3_tc wgrad128"; do
+for spec in "64 conv3x3_tcp conv64" "128 conv3x3_tcp2 conv128" "64 wgrad3x3_tc wgrad64" "128 wgrad3x3_tc wgrad128"; do
   set -- $spec
   ncu --set full --clock-control none --import-source on -k regex:$2 -c 8 -o gpurun_out/full_$3_$TAG -f \
       python scripts/prof_odeblock.py $1 512 > gpurun_out/ncu_$3_$TAG.log 2>&1
