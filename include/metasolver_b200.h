@@ -228,6 +228,8 @@ int msb_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t
  *   "tc_pair"          pixel-major convolution on CTA pairs (tcgen05.mma.cta_group::2, M = 256, weights shared by
  *                      the pair): 0 = off, 1 = every shape with an even tile count, 2 = only C >= 128 (default)
  *                                                                        (env MSB_TC_PAIR)
+ *   "wait_backoff_ns"  first nanosleep step of waiting epilogue / TMA-producer warps (doubles up to 8x); 0 = tight
+ *                      mbarrier polling                                  (env MSB_WAIT_BACKOFF_NS)
  * Results do not depend on any option.  Returns 0, or -1 for an unknown name. */
 int msb_set_option(const char* name, int value);
 int msb_get_option(const char* name, int* value);

@@ -159,7 +159,7 @@ template <int C, int WIMG, int ACT, bool RES>
 __global__ void __launch_bounds__((TileGeom<C, WIMG, RES>::THREADS), 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_w,
                   const EpiParams epi, const int H, const int Wimg, const int num_tiles, const int tiles_per_img,
-                  const int l2pf_dist) {
+                  const int l2pf_dist, const uint32_t backoff_ns) {
     using G = TileGeom<C, WIMG, RES>;
     const int cols = Wimg / WIMG;                                  // tile columns per image
     // tile -> (image n, first row h0, first pixel column w_off); neighbouring tiles are neighbouring columns
@@ -349,7 +349,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
         for (; tile < num_tiles; tile += gridDim.x) {
             int n, h0, w_off;
             tile_coords(tile, n, h0, w_off);
-            ptx::mbar_wait(&bars->tmem_full[acc], acc_ph);
+            ptx::mbar_wait_backoff(&bars->tmem_full[acc], acc_ph, backoff_ns);
             ptx::tc_fence_after();
             const uint32_t t_acc = tmem_base + (uint32_t)acc * 256u + lane_addr;
             const EpiCoef coef = epi_coef(epi, n);          // one image per tile: the slice is tile-uniform
@@ -448,7 +448,7 @@ int launch_act(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, cons
     const int num_tiles = s.B * tiles_per_img;
     const int grid = std::min(num_tiles, num_sms());
     kern<<<grid, G::THREADS, smem, st>>>(tm_act, tm_w, epi, s.H, s.W, num_tiles, tiles_per_img,
-                                         tune_get(TUNE_EPI_L2_PREFETCH));
+                                         tune_get(TUNE_EPI_L2_PREFETCH), (uint32_t)tune_get(TUNE_WAIT_BACKOFF));
     count_launch();
     return check_cuda(cudaGetLastError(), "conv3x3_tc launch");
 }

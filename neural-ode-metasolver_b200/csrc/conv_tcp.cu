@@ -81,7 +81,8 @@ struct __align__(8) Barriers {
 template <int C, int WIMG, int ACT, int EW>
 __global__ void __launch_bounds__((kEpiWarp0 + EW) * 32, 1)
 conv3x3_tcp_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_w,
-                   const EpiParams epi, const int H, const int num_tiles, const int tiles_per_img, const int l2pf_dist) {
+                   const EpiParams epi, const int H, const int num_tiles, const int tiles_per_img, const int l2pf_dist,
+                   const uint32_t backoff_ns) {
     using G = Geom<C, WIMG, EW>;
     constexpr int CHUNKS = C / 64;
     constexpr int kWStages = G::W_STAGES, kXStages = G::X_STAGES, kAccBufs = G::ACC_BUFS;
@@ -277,7 +278,7 @@ conv3x3_tcp_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
                 const uint32_t ph16 = (uint32_t)(it / kAccBufs) & 1u;
                 const EpiCoef coef = epi_coef(epi, tile / tiles_per_img);
                 const size_t row0 = row0_of(tile);
-                ptx::mbar_wait(&bars->tmem_full[acc16], ph16);
+                ptx::mbar_wait_backoff(&bars->tmem_full[acc16], ph16, backoff_ns);
                 ptx::tc_fence_after();
                 if (MSB_DBG(1)) {
                     ptx::tc_fence_before();
@@ -336,7 +337,7 @@ conv3x3_tcp_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
             const size_t idx_t = pix * C + cbase;
             const size_t split_t = (((size_t)n * H + h) * 2) * plane_stride + (size_t)wq * C + cbase;
             const EpiCoef coef = epi_coef(epi, n);
-            ptx::mbar_wait(&bars->tmem_full[acc], acc_ph);
+            ptx::mbar_wait_backoff(&bars->tmem_full[acc], acc_ph, backoff_ns);
             ptx::tc_fence_after();
             const uint32_t t_acc = tmem_base + (uint32_t)(acc * G::ACC_COLS) + lane_addr + (uint32_t)cbase;
             if (MSB_DBG(1)) {
@@ -403,7 +404,8 @@ int launch_act_ew(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, c
     const int tiles_per_img = s.H / G::ROWS;
     const int num_tiles = s.B * tiles_per_img;
     const int grid = std::min(num_tiles, num_sms());
-    kern<<<grid, kThreads, smem, st>>>(tm_act, tm_w, epi, s.H, num_tiles, tiles_per_img, tune_get(TUNE_EPI_L2_PREFETCH));
+    kern<<<grid, kThreads, smem, st>>>(tm_act, tm_w, epi, s.H, num_tiles, tiles_per_img, tune_get(TUNE_EPI_L2_PREFETCH),
+                                       (uint32_t)tune_get(TUNE_WAIT_BACKOFF));
     count_launch();
     return check_cuda(cudaGetLastError(), "conv3x3_tcp launch");
 }

@@ -70,7 +70,8 @@ struct __align__(8) Barriers2 {
 template <int C, int WIMG, int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_w,
-                    const EpiParams epi, const int H, const int num_pairs, const int tiles_per_img) {
+                    const EpiParams epi, const int H, const int num_pairs, const int tiles_per_img,
+                    const uint32_t backoff_ns) {
     using G = Geom2<C, WIMG>;
     constexpr int CHUNKS = C / 64;
     constexpr int kWStages = G::W_STAGES, kXStages = G::X_STAGES, kAccBufs = G::ACC_BUFS;
@@ -223,7 +224,7 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
             const uint32_t ph = (uint32_t)(it / kAccBufs) & 1u;
             const EpiCoef coef = epi_coef(epi, (2 * pr + (int)rank) / tiles_per_img);
             const size_t row0 = row0_of(pr);
-            ptx::mbar_wait(&bars->tmem_full[acc], ph);
+            ptx::mbar_wait_backoff(&bars->tmem_full[acc], ph, backoff_ns);
             ptx::tc_fence_after();
             const uint32_t t_acc = tmem_base + (uint32_t)(acc * G::ACC_COLS) + lane_addr + (uint32_t)cb;
             __syncwarp();
@@ -294,7 +295,8 @@ int launch_act(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, cons
     const int tiles_per_img = s.H / G::ROWS;
     const int num_pairs = s.B * tiles_per_img / 2;
     const int clusters = std::min(num_pairs, num_sms() / 2);
-    kern<<<2 * clusters, kThreads, smem, st>>>(tm_act, tm_w, epi, s.H, num_pairs, tiles_per_img);
+    kern<<<2 * clusters, kThreads, smem, st>>>(tm_act, tm_w, epi, s.H, num_pairs, tiles_per_img,
+                                               (uint32_t)tune_get(TUNE_WAIT_BACKOFF));
     count_launch();
     return check_cuda(cudaGetLastError(), "conv3x3_tcp2 launch");
 }

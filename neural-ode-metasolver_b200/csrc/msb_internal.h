@@ -21,6 +21,7 @@ enum { TUNE_EPI_L2_PREFETCH = 0,   // conv epilogue operands: bulk L2 prefetch d
        TUNE_TCP_EPI_WARPS = 2,     // pixel-major conv: epilogue warps (8 or 16)
        TUNE_TC_FORM_C64 = 3,       // tcgen05 conv form for C = 64: 0 = channel-major, 1 = pixel-major
        TUNE_TC_PAIR = 4,           // pixel-major conv on a CTA pair (cta_group::2, M = 256): 0 off, 1 on, 2 for C >= 128 (default)
+       TUNE_WAIT_BACKOFF = 5,      // nanosleep back-off (ns, first step) of waiting epilogue / producer warps; 0 = tight poll
        TUNE_COUNT };
 int tune_get(int which);
 

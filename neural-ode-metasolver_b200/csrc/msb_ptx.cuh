@@ -55,6 +55,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Wait of a role that can afford a wake-up latency (epilogue warps waiting for the next accumulator, TMA producers
+// waiting for a free stage): optional back-off with nanosleep between polls.  ncu counts the try_wait loop of the 16
+// epilogue warps as 47 % of all executed warp instructions of the MMA-bound convolution, but an A/B on the device
+// (profiles/conv_backoff_ab_r1.txt: 0 / 16 / 32 / 64 / 128 ns) shows no gain from backing off -- try_wait with a
+// suspend-time hint already parks the warp -- so backoff_ns = 0 (tight loop) is the default.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t backoff_ns) {
+    uint32_t spins = 0, ns = backoff_ns;
+    while (!mbar_try_wait(bar, parity)) {
+        if (backoff_ns) {
+            asm volatile("nanosleep.u32 %0;" ::"r"(ns));
+            if (ns < 8 * backoff_ns) ns <<= 1;
+        }
+        if (++spins > (1u << 22)) __trap();
+    }
+}
+
 // ---- TMA ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

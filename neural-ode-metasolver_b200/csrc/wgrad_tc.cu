@@ -56,7 +56,7 @@ template <int C, int WIMG>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_go, const __grid_constant__ CUtensorMap tmap_in,
                    float* __restrict__ partial, const int num_tiles, const int tiles_per_img, const int nparts,
-                   const int accumulate_partial) {
+                   const int accumulate_partial, const uint32_t backoff_ns) {
     using G = WG<C, WIMG>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -136,7 +136,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_go, const __grid_con
     } else if (warp >= 4) {
         // final epilogue: D[lane = gout channel (or hi/lo half x channel)][col = r*64 + ci] -> partial
         const int q = warp & 3;
-        ptx::mbar_wait(&bars->done, 0);
+        ptx::mbar_wait_backoff(&bars->done, 0, backoff_ns ? 8 * backoff_ns : 0);     // waits for the whole kernel
         ptx::tc_fence_after();
         const int row = q * 32 + lane;                       // accumulator row
         int slice, co;
@@ -192,7 +192,8 @@ int launch_impl(const __nv_bfloat16* gout, const __nv_bfloat16* in, float* parti
     const int tiles_per_img = s.H / G::ROWS;
     const int num_tiles = s.B * tiles_per_img;
     const int np = nparts_impl<C, WIMG>(s);
-    kern<<<np * G::GROUPS, kThreads, smem, st>>>(tm_go, tm_in, partial, num_tiles, tiles_per_img, np, accumulate);
+    kern<<<np * G::GROUPS, kThreads, smem, st>>>(tm_go, tm_in, partial, num_tiles, tiles_per_img, np, accumulate,
+                                                        (uint32_t)tune_get(TUNE_WAIT_BACKOFF));
     count_launch();
     *nparts_out = np * G::HALVES;
     return check_cuda(cudaGetLastError(), "wgrad3x3_tc launch");
