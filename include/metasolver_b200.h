@@ -132,6 +132,16 @@ int msb_odeblock_backward(const MsbOdeDesc* d, const float* grad_y, const float*
 
 /* Same for MSB_RHS_MNIST_GN_T (tape recorded by msb_odeblock_forward with save_tape = 1).  `grads` NULL = input
  * gradient only.  Replaces torch.autograd through ODEfunc / ConcatConv2d / GroupNorm, mnist/layers.py:158-171, 250-253. */
+/* The same backward pass, additionally ACCUMULATING the gradient w.r.t. the Butcher coefficients into
+ * grad_tableau (device, MSB_MAX_STAGES + MSB_MAX_STAGES*MSB_MAX_STAGES doubles: dL/db_i, then dL/dw_ij row-major) --
+ * what autograd yields for solver.u / solver.v after unfreeze_params() (rk_parametric_order2stage2.py:104-109)
+ * once chained through the closed-form tableau on the host.  CIFAR right-hand sides (autonomous) only; one solver
+ * per call.  Needs msb_odeblock_bwd_workspace_bytes_tableau() bytes of workspace. */
+size_t msb_odeblock_bwd_workspace_bytes_tableau(const MsbOdeDesc* d);
+int msb_odeblock_backward_tableau(const MsbOdeDesc* d, const float* grad_y, const float* w1, const float* w2,
+                                  const void* tape, size_t tape_bytes, float* grad_x, float* grad_w1, float* grad_w2,
+                                  double* grad_tableau, void* workspace, size_t workspace_bytes, void* cuda_stream);
+
 int msb_odeblock_backward_mnist(const MsbOdeDesc* d, const float* grad_y, const MsbMnistParams* mnist, const void* tape,
                                 size_t tape_bytes, float* grad_x, const MsbMnistGrads* grads, void* workspace,
                                 size_t workspace_bytes, void* cuda_stream);

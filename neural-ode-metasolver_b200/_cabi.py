@@ -28,6 +28,7 @@ EXPORTS = [
     "msb_downblock_forward", "msb_downblock_backward",
     "msb_conv3x3_workspace_bytes", "msb_wgrad3x3", "msb_wgrad3x3_workspace_bytes", "msb_launch_count", "msb_profile_enable", "msb_profile_read", "msb_profile_read_executed",
     "msb_set_option", "msb_get_option", "msb_attack_step", "msb_sgd_step",
+    "msb_odeblock_bwd_workspace_bytes_tableau", "msb_odeblock_backward_tableau",
 ]
 
 
@@ -92,6 +93,9 @@ def _declare(lib):
         f.restype = sz
     lib.msb_odeblock_forward.argtypes = [dp, vp, vp, vp, ctypes.POINTER(MsbMnistParams), vp, vp, sz, vp, sz, vp]
     lib.msb_odeblock_backward.argtypes = [dp, vp, vp, vp, vp, sz, vp, vp, vp, vp, sz, vp]
+    lib.msb_odeblock_bwd_workspace_bytes_tableau.argtypes = [dp]
+    lib.msb_odeblock_bwd_workspace_bytes_tableau.restype = sz
+    lib.msb_odeblock_backward_tableau.argtypes = [dp, vp, vp, vp, vp, sz, vp, vp, vp, vp, vp, sz, vp]
     lib.msb_odeblock_backward_mnist.argtypes = [dp, vp, ctypes.POINTER(MsbMnistParams), vp, sz, vp,
                                                 ctypes.POINTER(MsbMnistGrads), vp, sz, vp]
     lib.msb_stem_forward.argtypes = [vp, vp, i32, vp, vp, i32, i32, i32, i32, vp]

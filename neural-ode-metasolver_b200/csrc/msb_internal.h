@@ -37,6 +37,10 @@ void launch_pack_w_tc(const float* w, __nv_bfloat16* out, int C, int transpose, 
 void launch_wgrad_reduce(const float* partial, int nparts, float* grad_w, int C, int accumulate, cudaStream_t st,
                          int cin_total = 0, int skip_in = 0);
 
+// ---- train_aux.cu: deterministic dot product (*out += scale * <a, b>) ----
+size_t dot_scratch_bytes();
+void launch_dot_accumulate(const float* a, const float* b, size_t n, double scale, double* out, double* scratch, cudaStream_t st);
+
 // ---- groupnorm.cu (MNIST right-hand side) ----
 int launch_groupnorm_epi(const float* x, const float* gamma, const float* beta, const EpiParams& epi, ConvShape s,
                          int groups, float eps, cudaStream_t st);

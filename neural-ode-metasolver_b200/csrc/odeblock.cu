@@ -375,6 +375,16 @@ size_t msb_odeblock_bwd_workspace_bytes(const MsbOdeDesc* d) {
     return n + 4096;
 }
 
+size_t msb_odeblock_bwd_workspace_bytes_tableau(const MsbOdeDesc* d) {
+    const size_t base = msb_odeblock_bwd_workspace_bytes(d);
+    if (base == 0) return 0;
+    if (d->rhs_kind == MSB_RHS_MNIST_GN_T) { set_error("tableau gradients: the MNIST right-hand side is time dependent (needs df/dt); not implemented"); return 0; }
+    int engine = resolve_engine(d);
+    // forward-packed conv2 weights, the recomputed stage derivatives k_1..k_S, the reduction scratch
+    return base + align_up(packed_w_bytes(engine, d->channels)) + (size_t)d->stages * align_up(state_elems(d) * 4) +
+           align_up(dot_scratch_bytes()) + 1024;
+}
+
 
 // ---------------------------------------------------------------------------------------------
 // MNIST right-hand side (forward):  f(t, x) = GN3(cconv2(t, relu(GN2(cconv1(t, relu(GN1(x)))))))
@@ -565,16 +575,25 @@ int msb_odeblock_forward(const MsbOdeDesc* d, const float* x, const float* w1, c
     return check_cuda(cudaGetLastError(), "odeblock forward");
 }
 
-int msb_odeblock_backward(const MsbOdeDesc* d, const float* grad_y, const float* w1, const float* w2,
-                          const void* tape, size_t tape_bytes, float* grad_x, float* grad_w1, float* grad_w2,
-                          void* workspace, size_t workspace_bytes, void* cuda_stream) {
+// grad_tab (optional, device): MSB_MAX_STAGES + MSB_MAX_STAGES^2 doubles, ACCUMULATED into:
+//   [i]                                   dL/db_i  = sum_n dt_n <gbar_{n+1}, k_i^n>
+//   [MSB_MAX_STAGES + i*MSB_MAX_STAGES+j] dL/dw_ij = sum_n dt_n <xbar_i^n, k_j^n>        (j < i)
+// from y1 = y + dt sum b_i k_i and x_i = y + dt sum_j w_ij k_j (rk_parametric_order2stage2.py:90-93 and analogues);
+// the c_i do not enter an autonomous right-hand side.  k_j is recomputed from the tape (one convolution per stage).
+static int odeblock_backward_impl(const MsbOdeDesc* d, const float* grad_y, const float* w1, const float* w2,
+                                  const void* tape, size_t tape_bytes, float* grad_x, float* grad_w1, float* grad_w2,
+                                  double* grad_tab, void* workspace, size_t workspace_bytes, void* cuda_stream) {
     if (validate(d)) return -1;
     if (d->rhs_kind == MSB_RHS_MNIST_GN_T) { set_error("use msb_odeblock_backward_mnist for the MNIST right-hand side"); return -1; }
     int engine = resolve_engine(d);
     if (engine < 0) return -1;
     if (!grad_y || !w1 || !w2 || !tape || !grad_x || !workspace) { set_error("null pointer argument"); return -1; }
     if (tape_bytes < msb_odeblock_tape_bytes(d)) { set_error("tape too small"); return -1; }
-    if (workspace_bytes < msb_odeblock_bwd_workspace_bytes(d)) { set_error("workspace too small"); return -1; }
+    if (workspace_bytes < (grad_tab ? msb_odeblock_bwd_workspace_bytes_tableau(d) : msb_odeblock_bwd_workspace_bytes(d))) {
+        set_error("workspace too small");
+        return -1;
+    }
+    if (grad_tab && d->n_solvers > 1) { set_error("tableau gradients are not implemented for a stacked solver axis"); return -1; }
     if ((grad_w1 == nullptr) != (grad_w2 == nullptr)) { set_error("grad_w1 and grad_w2 must both be given or both be NULL"); return -1; }
     const bool need_w = grad_w1 != nullptr;
     cudaStream_t st = (cudaStream_t)cuda_stream;
@@ -592,10 +611,19 @@ int msb_odeblock_backward(const MsbOdeDesc* d, const float* grad_y, const float*
     __nv_bfloat16* DP_full = cv.take<__nv_bfloat16>(E * 4);
     const size_t part_bytes = (size_t)wgrad_nparts(engine, ConvShape{d->batch, d->height, d->width, C}) * 9 * C * C * 4;
     WgradAcc acc1{cv.take<float>(part_bytes), grad_w1, 0, 0}, acc2{cv.take<float>(part_bytes), grad_w2, 0, 0};
+    void* wp2f = nullptr;                                      // tableau gradients: conv2 weights packed for the forward conv
+    float* kre[MSB_MAX_STAGES] = {nullptr, nullptr, nullptr, nullptr};
+    double* dot_scratch = nullptr;
+    if (grad_tab) {
+        wp2f = cv.take<char>(packed_w_bytes(engine, C));
+        for (int i = 0; i < S; ++i) kre[i] = cv.take<float>(E * 4);
+        dot_scratch = cv.take<double>(dot_scratch_bytes());
+    }
     if (!cv.ok()) { set_error("internal: workspace carve overflow"); return -1; }
 
     pack_w(engine, w1, wt1, C, 1, st);
     pack_w(engine, w2, wt2, C, 1, st);
+    if (grad_tab) pack_w(engine, w2, wp2f, C, 0, st);
     const Tabs tabs = make_tabs(d);
 
     auto dt_of = [&](int n) { return d->time_grid[n + 1] - d->time_grid[n]; };
@@ -620,6 +648,17 @@ int msb_odeblock_backward(const MsbOdeDesc* d, const float* grad_y, const float*
     for (int n = N - 1; n >= 0; --n) {
         const float dt = dt_of(n);
         float* g_next = ((n == 0) ? grad_x : gbuf[n & 1]) + off;
+        const size_t n_mb = (size_t)shp.B * img_elems;
+        if (grad_tab) {
+            // k_j = f(x_j) again (conv2 of the taped act(conv1(..))) and dL/db_j += dt <gbar, k_j>
+            for (int j = 0; j < S; ++j) {
+                EpiParams ek = epi_default();
+                ek.v_out = kre[j] + off;
+                if (post) ek.act_v = d->act;
+                if (run_conv(engine, slot(n, j).Hs, wp2f, ek, shp, st)) return -1;
+                launch_dot_accumulate(g_cur, kre[j] + off, n_mb, (double)dt, grad_tab + j, dot_scratch, st);
+            }
+        }
         for (int i = S - 1; i >= 0; --i) {
             TapeSlot cur = slot(n, i);
             // Kbar = split(kbar_i).   dW2 += kbar_i (x) Hs_i
@@ -664,12 +703,31 @@ int msb_odeblock_backward(const MsbOdeDesc* d, const float* grad_y, const float*
                 }
             }
             if (run_conv(engine, DP, wt1, e4, shp, st)) return -1;
+            if (grad_tab && i > 0)                     // dL/dw_ij += dt <xbar_i, k_j>, j < i
+                for (int j = 0; j < i; ++j)
+                    launch_dot_accumulate(xbar[i] + off, kre[j] + off, n_mb, (double)dt,
+                                          grad_tab + MSB_MAX_STAGES + i * MSB_MAX_STAGES + j, dot_scratch, st);
         }
         g_cur = g_next;
     }
     }   // micro-batches
     if (need_w && (wgrad_finish(engine, acc1, shp, st) || wgrad_finish(engine, acc2, shp, st))) return -1;
     return check_cuda(cudaGetLastError(), "odeblock backward");
+}
+
+int msb_odeblock_backward(const MsbOdeDesc* d, const float* grad_y, const float* w1, const float* w2,
+                          const void* tape, size_t tape_bytes, float* grad_x, float* grad_w1, float* grad_w2,
+                          void* workspace, size_t workspace_bytes, void* cuda_stream) {
+    return odeblock_backward_impl(d, grad_y, w1, w2, tape, tape_bytes, grad_x, grad_w1, grad_w2, nullptr, workspace,
+                                  workspace_bytes, cuda_stream);
+}
+
+int msb_odeblock_backward_tableau(const MsbOdeDesc* d, const float* grad_y, const float* w1, const float* w2,
+                                  const void* tape, size_t tape_bytes, float* grad_x, float* grad_w1, float* grad_w2,
+                                  double* grad_tableau, void* workspace, size_t workspace_bytes, void* cuda_stream) {
+    if (!grad_tableau) { set_error("msb_odeblock_backward_tableau: grad_tableau is NULL"); return -1; }
+    return odeblock_backward_impl(d, grad_y, w1, w2, tape, tape_bytes, grad_x, grad_w1, grad_w2, grad_tableau, workspace,
+                                  workspace_bytes, cuda_stream);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -89,6 +89,39 @@ __global__ void __launch_bounds__(256) sgd_step_kernel(float* __restrict__ p, co
     }
 }
 
+// <a, b> over n floats in two deterministic stages (fixed grid, fixed order; double accumulation):
+// the reductions behind the gradients w.r.t. the Butcher coefficients (odeblock.cu).
+constexpr int kDotBlocks = 592;      // 4 per SM
+__global__ void __launch_bounds__(256) dot_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n4,
+                                                          double* __restrict__ partial) {
+    double acc = 0.0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 x = reinterpret_cast<const float4*>(a)[i], y = reinterpret_cast<const float4*>(b)[i];
+        acc += (double)x.x * y.x + (double)x.y * y.y + (double)x.z * y.z + (double)x.w * y.w;
+    }
+    __shared__ double sh[256];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+__global__ void __launch_bounds__(256) dot_final_kernel(const double* __restrict__ partial, int nblocks, double scale,
+                                                        double* __restrict__ out) {
+    __shared__ double sh[256];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < nblocks; i += 256) acc += partial[i];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out += scale * sh[0];
+}
+
 int grid_for(size_t n) {
     size_t b = (n + 255) / 256;
     const size_t cap = (size_t)num_sms() * 8;
@@ -96,6 +129,15 @@ int grid_for(size_t n) {
 }
 
 }  // namespace
+
+size_t dot_scratch_bytes() { return kDotBlocks * sizeof(double); }
+// *out += scale * <a, b>   (n a multiple of 4; scratch = dot_scratch_bytes())
+void launch_dot_accumulate(const float* a, const float* b, size_t n, double scale, double* out, double* scratch, cudaStream_t st) {
+    dot_partial_kernel<<<kDotBlocks, 256, 0, st>>>(a, b, n / 4, scratch);
+    dot_final_kernel<<<1, 256, 0, st>>>(scratch, kDotBlocks, scale, out);
+    count_launch(2);
+}
+
 }  // namespace msb
 
 using namespace msb;

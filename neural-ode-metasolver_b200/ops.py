@@ -150,12 +150,18 @@ def _check_inputs(x, w1, w2):
 
 
 class _OdeBlockFn(torch.autograd.Function):
+    """coef (optional): a host float64 tensor [b_1..b_4, w_11..w_44] built DIFFERENTIABLY from solver.u / solver.v
+    (RKParametricSolver._tableau_torch).  Its values are not used -- the kernels take the bit-exact numpy tableau in
+    `prob` -- but when it requires grad the backward pass also reduces dL/db_i, dL/dw_ij on the device and returns
+    them as coef's gradient, which autograd chains to u and v (unfreeze_params())."""
+
     @staticmethod
-    def forward(ctx, x, w1, w2, prob):
+    def forward(ctx, x, w1, w2, prob, coef=None):
         _check_inputs(x, w1, w2)
         lib = _cabi.lib()
         dev = x.device
-        need_grad = any(ctx.needs_input_grad[:3])     # (grad mode is always off inside Function.forward)
+        need_grad = any(ctx.needs_input_grad[:3]) or (coef is not None and ctx.needs_input_grad[4])
+        ctx.coef_shape = None if coef is None else tuple(coef.shape)
         with torch.cuda.device(dev):
             xc = x.detach().contiguous(memory_format=torch.channels_last)
             w1c, w2c = w1.detach().contiguous(), w2.detach().contiguous()
@@ -188,31 +194,53 @@ class _OdeBlockFn(torch.autograd.Function):
             raise RuntimeError("metasolver_b200: backward called but no tape was recorded")
         dev = gy.device
         need_w = (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]) and not (_input_only_depth[0] > 0)
+        need_coef = ctx.coef_shape is not None and ctx.needs_input_grad[4]
+        gcoef = None
         with torch.cuda.device(dev):
             gyc = gy.contiguous(memory_format=torch.channels_last)
             d = ctx.prob.desc(ctx.shape, True)
-            ws_bytes = lib.msb_odeblock_bwd_workspace_bytes(ctypes.byref(d))
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             gx = torch.empty_like(gyc)
             gw1 = torch.empty_like(w1c) if need_w else None
             gw2 = torch.empty_like(w2c) if need_w else None
-            rc = lib.msb_odeblock_backward(ctypes.byref(d), _ptr(gyc), _ptr(w1c), _ptr(w2c), _ptr(ctx.tape),
-                                           ctx.tape_bytes, _ptr(gx), _ptr(gw1), _ptr(gw2), _ptr(ws), ws_bytes,
-                                           _stream(dev))
-            _cabi.check(rc, "odeblock backward")
+            if need_coef:
+                M = _cabi.MSB_MAX_STAGES
+                ws_bytes = lib.msb_odeblock_bwd_workspace_bytes_tableau(ctypes.byref(d))
+                if ws_bytes == 0:
+                    _cabi.check(-1, "odeblock tableau-gradient workspace query")
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                gtab = torch.zeros(M + M * M, dtype=torch.float64, device=dev)
+                rc = lib.msb_odeblock_backward_tableau(ctypes.byref(d), _ptr(gyc), _ptr(w1c), _ptr(w2c), _ptr(ctx.tape),
+                                                       ctx.tape_bytes, _ptr(gx), _ptr(gw1), _ptr(gw2), _ptr(gtab), _ptr(ws),
+                                                       ws_bytes, _stream(dev))
+                _cabi.check(rc, "odeblock backward (tableau gradients)")
+                gcoef = gtab.cpu().reshape(ctx.coef_shape)       # 20 doubles to the host (the solver scalars live there)
+            else:
+                ws_bytes = lib.msb_odeblock_bwd_workspace_bytes(ctypes.byref(d))
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                rc = lib.msb_odeblock_backward(ctypes.byref(d), _ptr(gyc), _ptr(w1c), _ptr(w2c), _ptr(ctx.tape),
+                                               ctx.tape_bytes, _ptr(gx), _ptr(gw1), _ptr(gw2), _ptr(ws), ws_bytes,
+                                               _stream(dev))
+                _cabi.check(rc, "odeblock backward")
         ctx.tape = None       # the tape is large; release it as soon as it has been consumed
-        return gx, gw1, gw2, None
+        return gx, gw1, gw2, None, gcoef
 
 
 def ode_block_integrate(x, w1, w2, tableau, time_grid, rhs_kind=_cabi.RHS_PREACT_NF, act=_cabi.ACT_GELU_ERF,
-                        engine=None):
+                        engine=None, tableau_coef=None):
     """y(t_end) of dy/dt = f(y) with f = conv2(act(conv1(act(y)))) integrated on `time_grid`
     by the explicit RK method `tableau`; differentiable w.r.t. x, w1, w2.
 
     `tableau` may be a list of K tableaus (same stage count): the batch is then K equal slices along
     dim 0 and slice s is integrated by solver s, all inside the same kernel launches (stacked solver axis)."""
     prob = OdeProblem(rhs_kind, act, tableau, time_grid, engine)
-    return _OdeBlockFn.apply(x, w1, w2, prob)
+    if tableau_coef is not None:
+        M = _cabi.MSB_MAX_STAGES
+        if len(prob.tableaus) != 1:
+            raise NotImplementedError("metasolver_b200: gradients w.r.t. solver parameters on a stacked solver axis")
+        if tableau_coef.dtype != torch.float64 or tableau_coef.is_cuda or tableau_coef.numel() != M + M * M:
+            raise ValueError("tableau_coef must be a host float64 tensor of %d elements" % (M + M * M))
+        return _OdeBlockFn.apply(x, w1, w2, prob, tableau_coef)
+    return _OdeBlockFn.apply(x, w1, w2, prob, None)
 
 
 def ode_block_integrate_stacked(x, w1, w2, tableaus, time_grid, rhs_kind=_cabi.RHS_PREACT_NF,

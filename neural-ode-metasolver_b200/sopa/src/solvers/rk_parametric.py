@@ -118,6 +118,26 @@ class RKParametricSolver(object, metaclass=abc.ABCMeta):
                 p.requires_grad = True
         self.build_ButcherTableau()
 
+    # ---- differentiable tableau (only evaluated when u / v require grad) ----
+    def _tableau_torch(self, u, v, eps):
+        """-> (b list, w lower-triangular rows) as float64 torch scalars, differentiable w.r.t. u, v: the same closed
+        forms (and the same clamps, hence the same zero gradient outside the valid range) as `_tableau_np`."""
+        raise NotImplementedError
+
+    def tableau_coef(self):
+        """Host float64 tensor [b_1..b_4 | w_11..w_44] (MSB_MAX_STAGES + MSB_MAX_STAGES^2) connected to self.u / self.v by
+        autograd -- the handle through which the fused backward returns dL/du, dL/dv (ops._OdeBlockFn)."""
+        M = _cabi.MSB_MAX_STAGES
+        u = self.u.to(torch.float64).reshape(()) if self.u is not None else None
+        v = self.v.to(torch.float64).reshape(()) if self.v is not None else None
+        b, w = self._tableau_torch(u, v, _clamp_eps(self.dtype))
+        zero = torch.zeros((), dtype=torch.float64)
+        flat = [b[i] if i < len(b) else zero for i in range(M)]
+        for i in range(M):
+            for j in range(M):
+                flat.append(w[i][j] if (i < len(w) and j < i) else zero)
+        return torch.stack([t.reshape(()).to(torch.float64) for t in flat])
+
     def _params_need_grad(self):
         return any(p is not None and torch.is_tensor(p) and p.requires_grad for p in (self.u, self.v))
 
@@ -145,8 +165,10 @@ class RKParametricSolver(object, metaclass=abc.ABCMeta):
             y = ode_block_integrate_mnist(x, spec["params"], self._host_tableau, grid.tolist(), spec["groups"],
                                           spec["eps"])
         else:
+            coef = self.tableau_coef() if (self._params_need_grad() and torch.is_grad_enabled()) else None
             y = ode_block_integrate(x, spec["w1"], spec["w2"], self._host_tableau, grid.tolist(),
-                                    rhs_kind=spec["rhs_kind"], act=spec["act"], engine=spec.get("engine"))
+                                    rhs_kind=spec["rhs_kind"], act=spec["act"], engine=spec.get("engine"),
+                                    tableau_coef=coef)
         rhs_func.nfe += self.n_stages * (len(grid) - 1)               # cifar10/layers.py:149
         return y
 
@@ -155,14 +177,16 @@ class RKParametricSolver(object, metaclass=abc.ABCMeta):
         if len(t) != 2:
             raise NotImplementedError("metasolver_b200: integrate() returns the solution at t[0] and t[-1] only "
                                       "(MetaODEBlock uses t=[0,1]); intermediate output times are not supported")
-        if self._params_need_grad() and torch.is_grad_enabled():
-            raise NotImplementedError("metasolver_b200: gradients w.r.t. the solver parameters u/v are not "
-                                      "implemented; call freeze_params() (as every reference script does)")
         spec = getattr(rhs_func, "fused_rhs_spec", None)
         if spec is None:
             raise NotImplementedError("metasolver_b200: %s is not a right-hand side the fused CUDA path knows; "
                                       "there is no unfused fallback" % type(rhs_func).__name__)
-        return spec(), self.host_time_grid(t)
+        spec = spec()
+        if self._params_need_grad() and torch.is_grad_enabled() and spec["rhs_kind"] == _cabi.RHS_MNIST_GN_T:
+            raise NotImplementedError("metasolver_b200: gradients w.r.t. the solver parameters u/v are implemented for the "
+                                      "autonomous (CIFAR) right-hand sides only -- the MNIST right-hand side depends on t, "
+                                      "its dL/dc_i term is not built; call freeze_params()")
+        return spec, self.host_time_grid(t)
 
     def print_is_requires_grad(self):
         print('\nIs requires grad? (RK solver)')
@@ -246,6 +270,9 @@ class Euler(RKParametricSolver):
         T = _np_dtype(self.dtype)
         return [T(0)], [T(1)], [[T(0)]], (None, None)
 
+    def _tableau_torch(self, u, v, eps):
+        return [torch.ones((), dtype=torch.float64)], [[]]
+
     def freeze_params(self):
         pass
 
@@ -276,6 +303,11 @@ class RKOrder2Stage2(RKParametricSolver):
         b1 = T(1.0) - b2
         return [T(0), u_], [b1, b2], [[T(0)], [u_, T(0)]], (u_, None)
 
+    def _tableau_torch(self, u, v, eps):
+        u_ = torch.clamp(u, eps, 1.)                                   # order2stage2.py:52-53
+        b2 = 1. / (2 * u_)
+        return [1. - b2, b2], [[], [u_]]
+
     @property
     def order(self):
         return 2
@@ -305,6 +337,20 @@ class RKOrder3Stage3(RKParametricSolver):
         w32 = v_ * (v_ - u_) / (u_ * (T(2.0) - T(3.0) * u_))
         w31 = v_ - w32
         return [T(0), u_, v_], [b1, b2, b3], [[T(0)], [u_, T(0)], [w31, w32, T(0)]], (u_, v_)
+
+    def _tableau_torch(self, u, v, eps):
+        u_, v_ = torch.clamp(u, eps, 1.), torch.clamp(v, eps, 1.)     # order3stage3.py:47-68
+        if float(u_.detach()) == float(v_.detach()):
+            if float(u_.detach()) < 1. - eps:
+                v_ = u_ + eps
+            else:
+                u_ = v_ - eps
+        d = v_ - u_
+        b2 = (2. - 3. * v_) / (6. * u_ * (-d))
+        b3 = (2. - 3. * u_) / (6. * v_ * d)
+        b1 = 1. - b2 - b3
+        w32 = v_ * (v_ - u_) / (u_ * (2. - 3. * u_))
+        return [b1, b2, b3], [[], [u_], [v_ - w32, w32]]
 
     @property
     def order(self):
@@ -368,6 +414,48 @@ class RKOrder4Stage4(RKParametricSolver):
         z = T(0)
         return ([z, c2, c3, c4], [b1, b2, b3, b4],
                 [[z], [c2, z], [w31, w32, z], [w41, w42, w43, z]], (u_, v_))
+
+    def _tableau_torch(self, u, v, eps):
+        kind = self.parameterization
+        T = lambda x: torch.tensor(float(x), dtype=torch.float64)
+        if v is not None:                                              # order4stage4.py:127-156
+            u_ = torch.clamp(u, eps, 0.5 - eps) if float(u.detach()) < 0.5 else torch.clamp(u, 0.5 + eps, 1. - eps)
+            v_ = torch.clamp(v, eps, 1. - eps)
+            if float(u_.detach()) == float(v_.detach()):
+                if float(u_.detach()) < 1. - eps:
+                    v_ = u_ + eps
+                else:
+                    u_ = v_ - eps
+        else:
+            u_, v_ = torch.clamp(u, eps, 1. - eps), None
+        one, half, sixth, two3 = T(1.), T(0.5), T(1 / 6.), T(2 / 3.)
+        if kind == 'u1':
+            c2, c3 = half, T(0.)
+            b1, b2, b3, b4 = sixth - u_, two3, u_, sixth
+        elif kind == 'u2':
+            c2, c3 = half, half
+            b1, b2, b3, b4 = sixth, two3 - u_, u_, sixth
+        elif kind == 'u3':
+            c2, c3 = one, half
+            b1, b2, b3, b4 = sixth, sixth - u_, two3, u_
+        else:
+            c2, c3 = u_, v_
+            su, sv, d = one - u_, one - v_, v_ - u_
+            b2 = (2. * v_ - one) / (12 * u_ * su * d)
+            b3 = (one - 2 * u_) / (12 * v_ * sv * d)
+            b4 = (6. * u_ * v_ + 3. - 4. * u_ - 4. * v_) / (12 * su * sv)
+            b1 = one - b2 - b3 - b4
+        c4 = one
+        w43 = b3 * (one - c3) / b4
+        a00, a01, a10, a11 = b3 * c3 * c2, b4 * c4 * c2, b3, b4
+        r0 = 0.125 - b4 * c4 * c3 * w43
+        r1 = b2 * (one - c2)
+        det = a00 * a11 - a01 * a10
+        w32 = (r0 * a11 - r1 * a01) / det
+        w42 = (a00 * r1 - a10 * r0) / det
+        w41 = c4 - (w42 + w43)
+        w31 = c3 - w32
+        return [b1, b2, b3, b4], [[], [c2], [w31, w32], [w41, w42, w43]]
 
     @property
     def order(self):

@@ -46,7 +46,8 @@ def make_time_grid(t, n_steps=None, step_size=None):
 def _rk_step(tab, rhs, x, t, dt):
     """One step; returns dy.  Scalars enter as 1-elem tensors exactly as in the reference."""
     s = tab["stages"]
-    sc = lambda v: torch.tensor((v,), dtype=x.dtype)
+    # python floats (frozen solver) or 1-elem tensors connected to u / v (tableau.butcher_tableau_tensors)
+    sc = lambda v: v if torch.is_tensor(v) else torch.tensor((v,), dtype=x.dtype)
     c, b, w = tab["c"], tab["b"], tab["w"]
     k = []
     for i in range(s):

@@ -136,6 +136,22 @@ def _rk4(param, u, v, dtype):
             [[z, z, z, z], [w21, z, z, z], [w31, w32, z, z], [w41, w42, w43, z]])
 
 
+def butcher_tableau_tensors(method, parameterization, u=None, v=None, dtype=torch.float32):
+    """-> dict(stages, c, b, w) of 1-element TENSORS still connected to `u`, `v` by autograd: what the reference's solver
+    holds after unfreeze_params() (order2stage2.py:104-109); used to restate the gradients w.r.t. u and v."""
+    if method == "euler":
+        c, b, w = [_t(0.0, dtype)], [_t(1.0, dtype)], [[_t(0.0, dtype)]]
+    elif method == "rk2":
+        c, b, w = _rk2(u, dtype)
+    elif method == "rk3":
+        c, b, w = _rk3(u, v, dtype)
+    elif method == "rk4":
+        c, b, w = _rk4(parameterization, u, v if parameterization == "uv" else None, dtype)
+    else:
+        raise ValueError("oracle tableau: unknown method %r" % (method,))
+    return dict(stages=len(c), c=c, b=b, w=w)
+
+
 def butcher_tableau(method, parameterization, u0=None, v0=None, dtype=torch.float32):
     """-> dict(stages, c, b, w) of python floats (exact images of the reference's tensors).
 

@@ -59,3 +59,17 @@ C3_RK2_SOLVERS = [("rk2", "u", 8, -1, 0.3, -1), ("rk2", "u", 8, -1, 0.5, -1), ("
                   ("rk2", "u", 8, -1, 1.0, -1)]
 C3_RK4_SOLVERS = [("rk4", "u2", 8, -1, 1 / 3., -1), ("rk4", "uv", 8, -1, 1 / 3., 2 / 3.)]
 C3_WEIGHTS = [0.4, 0.3, 0.2, 0.1]
+
+# gradients w.r.t. the solver parameters u (and v): name, C, H, W, B, rhs kind, solver tuple
+SOLVER_GRAD_CASES = [
+    ("sg_rk2_u05_n4", 64, 8, 32, 2, "preact", ("rk2", "u", 4, -1, 0.5, -1)),
+    ("sg_rk2_u03_n3", 64, 8, 32, 2, "preact", ("rk2", "u", 3, -1, 0.3, -1)),
+    ("sg_rk3_n2", 64, 8, 32, 2, "preact", ("rk3", "uv", 2, -1, 0.3, 0.7)),
+    ("sg_rk4u2_n2", 64, 8, 32, 2, "preact", ("rk4", "u2", 2, -1, 0.3, -1)),
+    ("sg_rk4uv_n1", 64, 8, 32, 2, "preact", ("rk4", "uv", 1, -1, 0.3, 0.7)),
+    ("sg_rk4u1_n1", 64, 4, 32, 1, "preact", ("rk4", "u1", 1, -1, 0.2, -1)),
+    ("sg_rk4u3_n1", 64, 4, 32, 1, "preact", ("rk4", "u3", 1, -1, 0.1, -1)),
+    ("sg_c128_rk2_n2", 128, 8, 16, 2, "preact", ("rk2", "u", 2, -1, 0.6, -1)),
+    ("sg_post_rk2_n2", 64, 8, 32, 2, "postact", ("rk2", "u", 2, -1, 0.5, -1)),
+    ("sg_rk2_clamped", 64, 4, 32, 1, "preact", ("rk2", "u", 2, -1, 1.5, -1)),   # u > 1 is clamped: zero gradient
+]

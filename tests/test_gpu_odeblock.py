@@ -86,9 +86,9 @@ def test_unsupported_configurations_raise():
     with pytest.raises(NotImplementedError):        # activation the fused epilogue does not know
         MetaODEBlock(PreBasicBlock2(64, norm_layer=Identity, act_layer=F.softsign)).cuda()(x, [solver], opts)
     blk = MetaODEBlock(PreBasicBlock2(64, norm_layer=Identity, act_layer=F.gelu)).cuda()
-    solver.unfreeze_params()
-    with pytest.raises(NotImplementedError):        # d/du is not implemented
-        blk(x, [solver], opts)
+    solver.unfreeze_params()                        # d/du IS implemented for the CIFAR right-hand sides
+    y = blk(x.clone().requires_grad_(True), [solver], opts)   # (tests/test_gpu_solver_grads.py)
+    assert y.requires_grad
     solver.freeze_params()
     with pytest.raises(NotImplementedError):        # intermediate output times
         solver.integrate(blk.rhs_func, x, torch.tensor([0., 0.5, 1.]))

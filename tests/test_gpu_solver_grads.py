@@ -1,0 +1,127 @@
+"""GPU: gradients w.r.t. the solver parameters u, v (unfreeze_params()).
+
+The device reduces dL/db_i = sum_n dt <gbar, k_i> and dL/dw_ij = sum_n dt <xbar_i, k_j>; the host chains them through the
+closed-form tableau.  Checks:
+  * the coefficient gradients against the fp64 oracle (differentiated through its own tableau tensors): <= 1e-4 of the
+    largest coefficient gradient (no cancellation in these);
+  * dL/du, dL/dv against the REAL reference's fp64 golden.  du = sum_i dL/dcoef_i * dcoef_i/du is a heavily cancelling
+    sum (changing u keeps the order of the method: the reference's own fp32 run is 0.2-20 % off its fp64 run), so the
+    tolerance is 1e-4 of the UN-cancelled magnitude sum_i |dL/dcoef_i * dcoef_i/du| plus the reference's own
+    fp32-vs-fp64 deviation;
+  * a clamped parameter (u > 1) gets exactly zero gradient; frozen solvers and weight / input gradients are unchanged.
+"""
+import os
+import sys
+from argparse import Namespace
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import golden, max_rel, ROOT
+
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import make_golden_cases as cases  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_coef_grads(case):
+    from oracle import integrate, rhs_preact, rhs_postact
+    from oracle.tableau import butcher_tableau_tensors
+    name, C, H, W, B, kind, sv = case
+    method, param, n_steps, step_size, u0, v0 = sv
+    dt = torch.float64
+    x, w1, w2, r = [torch.from_numpy(a).to(dt) for a in cases.ode_case_inputs(C, H, W, B)]
+    u = torch.tensor((u0,), dtype=dt, requires_grad=True)
+    v = torch.tensor((v0,), dtype=dt, requires_grad=True) if v0 != -1 else None
+    tab = butcher_tableau_tensors(method, param, u, v, dt)
+    S = tab["stages"]
+    # detach the coefficients from u, v so that each gets its own gradient
+    leaf = dict(stages=S, c=tab["c"], b=[t.detach().clone().requires_grad_(True) for t in tab["b"]],
+                w=[[t.detach().clone().requires_grad_(True) for t in row] for row in tab["w"]])
+    y = integrate(leaf, (rhs_preact if kind == "preact" else rhs_postact)(w1, w2), x, torch.tensor([0., 1.]), n_steps=n_steps)[-1]
+    (y * r).sum().backward()
+    gb = [float(t.grad) if t.grad is not None else 0.0 for t in leaf["b"]]
+    gw = [[float(leaf["w"][i][j].grad) if (j < i and leaf["w"][i][j].grad is not None) else 0.0 for j in range(S)] for i in range(S)]
+    return gb, gw
+
+
+@pytest.mark.parametrize("case", cases.SOLVER_GRAD_CASES, ids=[c[0] for c in cases.SOLVER_GRAD_CASES])
+def test_solver_parameter_gradients_vs_reference(case):
+    import metasolver_b200  # noqa: F401
+    from metasolver_b200 import _cabi
+    from metasolver_b200.sopa.src.solvers.utils import create_solver
+    from metasolver_b200.sopa.src.models.odenet_cifar10.layers import MetaODEBlock, PreBasicBlock2, BasicBlock2
+    from metasolver_b200.sopa.src.models.odenet_cifar10.utils import Identity
+    name, C, H, W, B, kind, sv = case
+    g = golden("solver_grads.npz")
+    x, w1, w2, r = [torch.from_numpy(a).cuda() for a in cases.ode_case_inputs(C, H, W, B)]
+    cls = PreBasicBlock2 if kind == "preact" else BasicBlock2
+    blk = MetaODEBlock(cls(C, norm_layer=Identity, act_layer=F.gelu)).cuda()
+    with torch.no_grad():
+        blk.rhs_func.conv1.weight.copy_(w1)
+        blk.rhs_func.conv2.weight.copy_(w2)
+    solver = create_solver(*sv, torch.float32, "cuda")
+    solver.unfreeze_params()
+    coefs = []
+    orig = solver.tableau_coef
+    solver.tableau_coef = lambda: (coefs.append(orig()), coefs[-1].retain_grad(), coefs[-1])[2]
+    x.requires_grad_(True)
+    y = blk(x, [solver], Namespace(solver_mode="standalone"))
+    (y * r).sum().backward()
+    torch.cuda.synchronize()
+    # forward / input gradient are the frozen-solver ones
+    assert max_rel(y.detach().cpu().numpy().reshape(-1)[::7], g["%s_f32_y" % name]) <= 1e-4
+    assert max_rel(x.grad.cpu().numpy().reshape(-1)[::7], g["%s_f32_gx" % name]) <= 1e-4
+    assert blk.rhs_func.conv1.weight.grad is not None
+    # coefficient gradients vs the fp64 oracle
+    M = _cabi.MSB_MAX_STAGES
+    gc = coefs[0].grad.numpy()
+    gb, gw = _oracle_coef_grads(case)
+    S = len(gb)
+    ref = np.zeros(M + M * M)
+    ref[:S] = gb
+    for i in range(S):
+        for j in range(i):
+            ref[M + i * M + j] = gw[i][j]
+    assert np.abs(gc - ref).max() <= 1e-4 * np.abs(ref).max(), (name, gc, ref)
+    # u, v vs the reference's fp64 golden, yardstick = the reference's own fp32 deviation
+    coef2 = orig()
+    for p, key in ((solver.u, "du"), (solver.v, "dv")):
+        if p is None:
+            continue
+        f64, f32 = float(g["%s_f64_%s" % (name, key)][0]), float(g["%s_f32_%s" % (name, key)][0])
+        got = float(p.grad.reshape(-1)[0])
+        jac = [torch.autograd.grad(coef2[i], p, retain_graph=True, allow_unused=True)[0] for i in range(coef2.numel())]
+        jac = np.array([0.0 if j is None else float(j.reshape(-1)[0]) for j in jac])
+        mag = float(np.abs(gc * jac).sum())
+        assert abs(float(np.dot(gc, jac)) - got) <= 1e-6 * mag + 1e-12                       # host chain rule (u.grad is fp32)
+        tol = 1e-4 * mag + 3.0 * abs(f32 - f64) + 1e-9
+        assert abs(got - f64) <= tol, (name, key, got, f64, f32, mag)
+        if name == "sg_rk2_clamped":
+            assert got == 0.0
+
+
+def test_frozen_solver_and_stacked_axis_behaviour():
+    import metasolver_b200  # noqa: F401
+    from metasolver_b200.sopa.src.solvers.utils import create_solver
+    from metasolver_b200.sopa.src.solvers.rk_parametric import integrate_stacked
+    from metasolver_b200.sopa.src.models.odenet_cifar10.layers import MetaODEBlock, PreBasicBlock2
+    from metasolver_b200.sopa.src.models.odenet_mnist.layers import MetaODEBlock as MnistBlock
+    from metasolver_b200.sopa.src.models.odenet_cifar10.utils import Identity
+    torch.manual_seed(0)
+    blk = MetaODEBlock(PreBasicBlock2(64, norm_layer=Identity, act_layer=F.gelu)).cuda()
+    x = torch.randn(2, 64, 8, 32, device="cuda", requires_grad=True)
+    s = create_solver("rk2", "u", 2, -1, 0.5, -1, torch.float32, "cuda")
+    s.freeze_params()
+    blk(x, [s], Namespace(solver_mode="standalone")).sum().backward()
+    assert s.u.grad is None                                    # frozen: no solver gradient is formed
+    s.unfreeze_params()
+    with torch.no_grad():                                      # unfrozen but no grad mode: plain forward
+        blk(x, [s], Namespace(solver_mode="standalone"))
+    # time-dependent MNIST right-hand side: dL/dc is not built -> loud failure, not a silently wrong gradient
+    mb = MnistBlock().cuda()
+    with pytest.raises(NotImplementedError):
+        mb(torch.randn(2, 64, 6, 6, device="cuda", requires_grad=True), [s], Namespace(solver_mode="standalone"))

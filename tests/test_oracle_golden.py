@@ -270,3 +270,30 @@ def test_non_ode_layer_gradients_bit_exact():
     for k in g.files:
         if k.startswith("g_"):
             assert np.array_equal(p[k[2:]].grad.numpy().reshape(-1)[::cases.WG_STRIDE], g[k]), k
+
+
+@pytest.mark.parametrize("case", cases.SOLVER_GRAD_CASES, ids=[c[0] for c in cases.SOLVER_GRAD_CASES])
+def test_solver_parameter_gradients(case):
+    """dL/du, dL/dv after unfreeze_params() (order2stage2.py:104-109): the oracle differentiates through the same
+    closed-form tableau; fp32 must reproduce the reference's fp32 run, fp64 its fp64 run."""
+    from oracle.tableau import butcher_tableau_tensors
+    name, C, H, W, B, kind, sv = case
+    method, param, n_steps, step_size, u0, v0 = sv
+    g = golden("solver_grads.npz")
+    for dt, tag, tol in ((torch.float32, "f32", 0.0), (torch.float64, "f64", 1e-9)):
+        x, w1, w2, r = [torch.from_numpy(a).to(dt) for a in cases.ode_case_inputs(C, H, W, B)]
+        u = torch.tensor((u0,), dtype=dt, requires_grad=True)
+        v = torch.tensor((v0,), dtype=dt, requires_grad=True) if v0 != -1 else None
+        tab = butcher_tableau_tensors(method, param, u, v, dt)
+        rhs = (rhs_preact if kind == "preact" else rhs_postact)(w1, w2)
+        y = integrate(tab, rhs, x, torch.tensor([0., 1.]), n_steps=n_steps)[-1]
+        (y * r).sum().backward()
+        for p, key in ((u, "du"), (v, "dv")):
+            if p is None:
+                continue
+            ref = g["%s_%s_%s" % (name, tag, key)]
+            got = p.grad.numpy()
+            if tol == 0.0:
+                assert np.array_equal(got, ref), (name, tag, key, got, ref)
+            else:
+                assert abs(float(got[0]) - float(ref[0])) <= tol * max(1.0, abs(float(ref[0]))), (name, tag, key, got, ref)
