@@ -154,13 +154,51 @@ class RKParametricSolver(object, metaclass=abc.ABCMeta):
         return grid.to(torch.float32)
 
     def integrate(self, rhs_func, x, t):
-        """-> Tensor[len(t), B, C, H, W]; differentiable w.r.t. x and rhs_func's conv weights."""
-        return torch.stack((x, self.integrate_end(rhs_func, x, t)))
+        """-> Tensor[len(t), B, C, H, W]; differentiable w.r.t. x, rhs_func's parameters (and u, v when unfrozen).
+
+        With more than two output times the solution at an interior t[j] is the linear interpolation between the two
+        grid points that bracket it (rk_parametric.py:108-123): the fused path integrates grid segment by grid segment
+        and interpolates with the reference's formula."""
+        if len(t) == 2:
+            return torch.stack((x, self.integrate_end(rhs_func, x, t)))
+        spec, grid = self._fused_args(rhs_func, t)
+        t_out = t.detach().to("cpu", torch.float32)
+        solution = [x]
+        j, start, y = 1, 0, x                                          # y = state at grid[start]
+        for i in range(len(grid) - 1):
+            t0, t1 = grid[i], grid[i + 1]
+            if j < len(t_out) and t1 >= t_out[j]:
+                if i > start:
+                    y = self._integrate_grid(rhs_func, spec, y, grid[start:i + 1])
+                y1 = self._integrate_grid(rhs_func, spec, y, grid[i:i + 2])
+                while j < len(t_out) and t1 >= t_out[j]:
+                    solution.append(self._linear_interp(t0, t1, y, y1, t_out[j]))
+                    j += 1
+                y, start = y1, i + 1
+        return torch.stack(solution)
+
+    @staticmethod
+    def _linear_interp(t0, t1, y0, y1, t):
+        # rk_parametric.py:116-123
+        if t == t0:
+            return y0
+        if t == t1:
+            return y1
+        t0, t1, t = t0.to(y0[0]), t1.to(y0[0]), t.to(y0[0])           # 0-dim tensors on y's device: true division
+        slope = (y1 - y0) / (t1 - t0)
+        return y0 + slope * (t - t0)
 
     def integrate_end(self, rhs_func, x, t):
         """The end state y(t[-1]) alone, (B, C, H, W): what MetaODEBlock keeps of integrate()'s result
         (`y[-1]`, cifar10/layers.py:207) -- without materialising the stacked [x, y] copy."""
+        if len(t) != 2:
+            raise NotImplementedError("metasolver_b200: integrate_end() takes t = [t0, t1]; use integrate() for "
+                                      "intermediate output times")
         spec, grid = self._fused_args(rhs_func, t)
+        return self._integrate_grid(rhs_func, spec, x, grid)
+
+    def _integrate_grid(self, rhs_func, spec, x, grid):
+        """One fused call over the (sub-)grid `grid` (host fp32 tensor of >= 2 points) -> state at grid[-1]."""
         if spec["rhs_kind"] == _cabi.RHS_MNIST_GN_T:
             y = ode_block_integrate_mnist(x, spec["params"], self._host_tableau, grid.tolist(), spec["groups"],
                                           spec["eps"])
@@ -174,9 +212,6 @@ class RKParametricSolver(object, metaclass=abc.ABCMeta):
 
     def _fused_args(self, rhs_func, t):
         """Checks shared by integrate() and integrate_stacked(); -> (rhs spec, host time grid)."""
-        if len(t) != 2:
-            raise NotImplementedError("metasolver_b200: integrate() returns the solution at t[0] and t[-1] only "
-                                      "(MetaODEBlock uses t=[0,1]); intermediate output times are not supported")
         spec = getattr(rhs_func, "fused_rhs_spec", None)
         if spec is None:
             raise NotImplementedError("metasolver_b200: %s is not a right-hand side the fused CUDA path knows; "

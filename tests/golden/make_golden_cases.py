@@ -73,3 +73,10 @@ SOLVER_GRAD_CASES = [
     ("sg_post_rk2_n2", 64, 8, 32, 2, "postact", ("rk2", "u", 2, -1, 0.5, -1)),
     ("sg_rk2_clamped", 64, 4, 32, 1, "preact", ("rk2", "u", 2, -1, 1.5, -1)),   # u > 1 is clamped: zero gradient
 ]
+
+# integrate() with interior output times: name, C, H, W, B, solver tuple, output times
+MULTITIME_CASES = [
+    ("mt_rk2_n4", 64, 8, 32, 2, ("rk2", "u", 4, -1, 0.5, -1), [0.0, 0.3, 0.55, 1.0]),
+    ("mt_rk4_n3_gridpoint", 64, 8, 32, 2, ("rk4", "u2", 3, -1, 1 / 3., -1), [0.0, 1 / 3., 0.9, 1.0]),
+    ("mt_rk2_two_in_one_step", 64, 4, 32, 1, ("rk2", "u", 2, -1, 0.7, -1), [0.0, 0.1, 0.4, 0.5, 1.0]),
+]

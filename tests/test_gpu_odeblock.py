@@ -90,8 +90,8 @@ def test_unsupported_configurations_raise():
     y = blk(x.clone().requires_grad_(True), [solver], opts)   # (tests/test_gpu_solver_grads.py)
     assert y.requires_grad
     solver.freeze_params()
-    with pytest.raises(NotImplementedError):        # intermediate output times
-        solver.integrate(blk.rhs_func, x, torch.tensor([0., 0.5, 1.]))
+    with pytest.raises(NotImplementedError):        # integrate_end keeps the two-point contract of MetaODEBlock
+        solver.integrate_end(blk.rhs_func, x, torch.tensor([0., 0.5, 1.]))
 
 
 @pytest.mark.parametrize("C,H,W,B", [(64, 32, 32, 3), (128, 16, 16, 5), (64, 12, 32, 2), (32, 6, 6, 4)])
@@ -267,3 +267,27 @@ def test_mnist_ode_block_trained_weights_vs_reference_golden():
     with torch.no_grad():
         out = model(torch.rand(4, 1, 28, 28, device="cuda"), [solver], Namespace(solver_mode="standalone"))
     assert out.shape == (4, 10)
+
+
+@pytest.mark.parametrize("case", cases.MULTITIME_CASES, ids=[c[0] for c in cases.MULTITIME_CASES])
+def test_integrate_with_interior_output_times(case):
+    """solver.integrate(rhs, x, t) with len(t) > 2 (rk_parametric.py:104-123): grid segments run through the fused path,
+    interior times are interpolated with the reference's formula; outputs, gradients and nfe vs the reference golden."""
+    msb, create_solver, MetaODEBlock, PreBasicBlock2, BasicBlock2, Identity = _mods()
+    name, C, H, W, B, sv, times = case
+    g = golden("multitime.npz")
+    x, w1, w2, r = [torch.from_numpy(a).cuda() for a in cases.ode_case_inputs(C, H, W, B)]
+    rhs = PreBasicBlock2(C, norm_layer=Identity, act_layer=F.gelu).cuda()
+    with torch.no_grad():
+        rhs.conv1.weight.copy_(w1)
+        rhs.conv2.weight.copy_(w2)
+    solver = create_solver(*sv, torch.float32, "cuda")
+    solver.freeze_params()
+    x.requires_grad_(True)
+    ys = solver.integrate(rhs, x, torch.tensor(times))
+    assert ys.shape[0] == len(times) and torch.equal(ys[0], x)
+    sum(((k + 1.0) * ys[k] * r).sum() for k in range(1, len(times))).backward()
+    assert rhs.nfe == int(g[name + "_nfe"])
+    assert max_rel(ys.detach().cpu().numpy()[1:, :, ::3], g[name + "_y"]) <= TOL
+    assert max_rel(x.grad.cpu().numpy(), g[name + "_gx"]) <= TOL
+    assert max_rel(rhs.conv1.weight.grad.cpu().numpy().reshape(-1)[::cases.WG_STRIDE], g[name + "_gw1"]) <= TOL

@@ -297,3 +297,20 @@ def test_solver_parameter_gradients(case):
                 assert np.array_equal(got, ref), (name, tag, key, got, ref)
             else:
                 assert abs(float(got[0]) - float(ref[0])) <= tol * max(1.0, abs(float(ref[0]))), (name, tag, key, got, ref)
+
+
+@pytest.mark.parametrize("case", cases.MULTITIME_CASES, ids=[c[0] for c in cases.MULTITIME_CASES])
+def test_integrate_with_interior_output_times_bit_exact(case):
+    """rk_parametric.py:104-123: solutions at interior times are linear interpolations between grid points."""
+    name, C, H, W, B, sv, times = case
+    g = golden("multitime.npz")
+    x, w1, w2, r = [torch.from_numpy(a) for a in cases.ode_case_inputs(C, H, W, B)]
+    x.requires_grad_(True); w1.requires_grad_(True); w2.requires_grad_(True)
+    cnt = RhsCounter()
+    tab = butcher_tableau(sv[0], sv[1], np.float32(sv[4]), None if sv[5] == -1 else np.float32(sv[5]))
+    ys = integrate(tab, rhs_preact(w1, w2, "gelu", cnt), x, torch.tensor(times), n_steps=sv[2])
+    sum(((k + 1.0) * ys[k] * r).sum() for k in range(1, len(times))).backward()
+    assert cnt.nfe == int(g[name + "_nfe"])
+    assert np.array_equal(ys.detach().numpy()[1:, :, ::3], g[name + "_y"])
+    assert np.array_equal(x.grad.numpy(), g[name + "_gx"])
+    assert np.array_equal(w1.grad.numpy().reshape(-1)[::cases.WG_STRIDE], g[name + "_gw1"])
