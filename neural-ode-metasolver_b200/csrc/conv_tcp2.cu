@@ -35,14 +35,14 @@ size_t tcp_packed_weight_bytes(int C);
 namespace {
 
 constexpr int kEpiWarp0 = 4;
-constexpr int kEpiWarps = 16;
-constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;
 constexpr uint32_t kTmemCols = 512;
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 230400;
 constexpr int kStageBytesPerWarp = 4096;
 
-template <int C, int WIMG> struct Geom2 {
+// EW = epilogue warps (16, or 8 for C = 64: one group of 8 warps on every tile frees 32 KB of staging for a third
+// activation stage -- with N = 128 / 64 MMAs a two-stage halo ring cannot hide the refill latency across the pair).
+template <int C, int WIMG, int EW> struct Geom2 {
     static constexpr int ROWS = 128 / WIMG;
     static constexpr int PLANE_BYTES = (ROWS + 2) * WIMG * 128;
     static constexpr int X_STAGE_BYTES = 2 * PLANE_BYTES;
@@ -50,8 +50,9 @@ template <int C, int WIMG> struct Geom2 {
     static constexpr int WA_BYTES = C * 128;                          // this CTA's half of [W_hi ; W_lo]
     static constexpr int WB_BYTES = (C / 2) * 128;                    // this CTA's half of W_hi
     static constexpr int W_STAGE_BYTES = WA_BYTES + WB_BYTES;
-    static constexpr int X_STAGES = 2;
-    static constexpr int STAGE_BYTES = kEpiWarps * kStageBytesPerWarp;
+    static constexpr int X_STAGES = (EW == 8) ? 3 : 2;
+    static constexpr int STAGE_BYTES = EW * kStageBytesPerWarp;
+    static constexpr int THREADS = (kEpiWarp0 + EW) * 32;
     static constexpr int RING = kSmemBudget - STAGE_BYTES - X_STAGES * X_STAGE_BYTES;
     static constexpr int W_STAGES = RING / W_STAGE_BYTES > kMaxStages ? kMaxStages : RING / W_STAGE_BYTES;
     static constexpr int ACC_COLS = 2 * C;
@@ -67,16 +68,16 @@ struct __align__(8) Barriers2 {
     uint32_t tmem_base;
 };
 
-template <int C, int WIMG, int ACT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+template <int C, int WIMG, int ACT, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((kEpiWarp0 + EW) * 32, 1)
 conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_w,
                     const EpiParams epi, const int H, const int num_pairs, const int tiles_per_img,
                     const uint32_t backoff_ns) {
-    using G = Geom2<C, WIMG>;
+    using G = Geom2<C, WIMG, EW>;
     constexpr int CHUNKS = C / 64;
     constexpr int kWStages = G::W_STAGES, kXStages = G::X_STAGES, kAccBufs = G::ACC_BUFS;
-    constexpr int NG = C / 32, WPT = 4 * NG, TG = kEpiWarps / WPT;     // epilogue: channel groups, warps per tile, tile groups
-    static_assert(TG >= 1 && kEpiWarps % WPT == 0, "16 epilogue warps must split evenly");
+    constexpr int NG = C / 32, WPT = 4 * NG, TG = EW / WPT;            // epilogue: channel groups, warps per tile, tile groups
+    static_assert(TG >= 1 && EW % WPT == 0, "the epilogue warps must split evenly over the channel groups");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_x = smem;
@@ -278,17 +279,18 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
     }
 }
 
-template <int C, int WIMG, int ACT>
-int launch_act(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, const EpiParams& epi, ConvShape s,
-               cudaStream_t st) {
-    using G = Geom2<C, WIMG>;
+template <int C, int WIMG, int ACT, int EW>
+int launch_act_ew(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, const EpiParams& epi, ConvShape s,
+                  cudaStream_t st) {
+    using G = Geom2<C, WIMG, EW>;
+    constexpr int kThreads = G::THREADS;
     CUtensorMap tm_act, tm_w;
     if (make_tmap_split_plane(&tm_act, split_in, s.B, s.H, s.W, s.C, WIMG, G::ROWS + 2)) return -1;
     if (make_tmap_rows64(&tm_w, w_tiles, tcp_packed_weight_bytes(C) / 128, C / 2)) return -1;
     constexpr size_t smem = (size_t)G::X_STAGES * G::X_STAGE_BYTES + (size_t)G::W_STAGES * G::W_STAGE_BYTES + G::STAGE_BYTES +
                             sizeof(Barriers2) + 1024;
     static_assert(smem <= 232448, "shared memory per CTA");
-    auto kern = conv3x3_tcp2_kernel<C, WIMG, ACT>;
+    auto kern = conv3x3_tcp2_kernel<C, WIMG, ACT, EW>;
     if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                    "cudaFuncSetAttribute(conv3x3_tcp2)"))
         return -1;
@@ -299,6 +301,15 @@ int launch_act(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, cons
                                                (uint32_t)tune_get(TUNE_WAIT_BACKOFF));
     count_launch();
     return check_cuda(cudaGetLastError(), "conv3x3_tcp2 launch");
+}
+
+template <int C, int WIMG, int ACT>
+int launch_act(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, const EpiParams& epi, ConvShape s,
+               cudaStream_t st) {
+    if constexpr (C == 64) {
+        if (tune_get(TUNE_TCP_EPI_WARPS) == 8) return launch_act_ew<C, WIMG, ACT, 8>(split_in, w_tiles, epi, s, st);
+    }
+    return launch_act_ew<C, WIMG, ACT, 16>(split_in, w_tiles, epi, s, st);
 }
 
 template <int C, int WIMG>

@@ -16,8 +16,8 @@ torch.manual_seed(0)
 OPTS = ("epi_l2_prefetch", "tc_resident", "tcp_epi_warps", "tc_form_c64", "tc_pair", "wait_backoff_ns")
 def S(pf=0, res=0, ew=16, pm64=1, pair=2, bo=0):
     return dict(epi_l2_prefetch=pf, tc_resident=res, tcp_epi_warps=ew, tc_form_c64=pm64, tc_pair=pair, wait_backoff_ns=bo)
-settings = {64: [S(bo=0), S(bo=16), S(bo=32), S(bo=64), S(bo=128)],
-            128: [S(bo=0), S(bo=16), S(bo=32), S(bo=64), S(bo=128)]}
+settings = {64: [S(), S(pair=1), S(pair=1, ew=8)],
+            128: [S()]}
 ROUNDS = 5
 for C, HW in ((64, 32), (128, 16)):
     blk = MetaODEBlock(PreBasicBlock2(C, norm_layer=Identity, act_layer=F.gelu)).cuda()
