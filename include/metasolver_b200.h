@@ -132,15 +132,20 @@ int msb_odeblock_backward(const MsbOdeDesc* d, const float* grad_y, const float*
 
 /* Same for MSB_RHS_MNIST_GN_T (tape recorded by msb_odeblock_forward with save_tape = 1).  `grads` NULL = input
  * gradient only.  Replaces torch.autograd through ODEfunc / ConcatConv2d / GroupNorm, mnist/layers.py:158-171, 250-253. */
-/* The same backward pass, additionally ACCUMULATING the gradient w.r.t. the Butcher coefficients into
- * grad_tableau (device, MSB_MAX_STAGES + MSB_MAX_STAGES*MSB_MAX_STAGES doubles: dL/db_i, then dL/dw_ij row-major) --
- * what autograd yields for solver.u / solver.v after unfreeze_params() (rk_parametric_order2stage2.py:104-109)
- * once chained through the closed-form tableau on the host.  CIFAR right-hand sides (autonomous) only; one solver
+/* The same backward passes, additionally ACCUMULATING the gradient w.r.t. the Butcher coefficients into
+ * grad_tableau (device, MSB_TABLEAU_GRAD_DOUBLES doubles: dL/db_i [M], dL/dw_ij row-major [M*M], dL/dc_i [M],
+ * M = MSB_MAX_STAGES) -- what autograd yields for solver.u / solver.v after unfreeze_params()
+ * (rk_parametric_order2stage2.py:104-109) once chained through the closed-form tableau on the host.  dL/dc_i is
+ * non-zero only for the time-dependent MNIST right-hand side (t_i = t_n + c_i dt, order2stage2.py:81-86).  One solver
  * per call.  Needs msb_odeblock_bwd_workspace_bytes_tableau() bytes of workspace. */
+#define MSB_TABLEAU_GRAD_DOUBLES (MSB_MAX_STAGES + MSB_MAX_STAGES * MSB_MAX_STAGES + MSB_MAX_STAGES)
 size_t msb_odeblock_bwd_workspace_bytes_tableau(const MsbOdeDesc* d);
 int msb_odeblock_backward_tableau(const MsbOdeDesc* d, const float* grad_y, const float* w1, const float* w2,
                                   const void* tape, size_t tape_bytes, float* grad_x, float* grad_w1, float* grad_w2,
                                   double* grad_tableau, void* workspace, size_t workspace_bytes, void* cuda_stream);
+int msb_odeblock_backward_mnist_tableau(const MsbOdeDesc* d, const float* grad_y, const MsbMnistParams* mnist,
+                                        const void* tape, size_t tape_bytes, float* grad_x, const MsbMnistGrads* grads,
+                                        double* grad_tableau, void* workspace, size_t workspace_bytes, void* cuda_stream);
 
 int msb_odeblock_backward_mnist(const MsbOdeDesc* d, const float* grad_y, const MsbMnistParams* mnist, const void* tape,
                                 size_t tape_bytes, float* grad_x, const MsbMnistGrads* grads, void* workspace,

@@ -258,6 +258,7 @@ def ensemble_logits(models, x, kwargs_arr):
             break
         solvers.append(sv[0])
     stackable = (same_model and solvers is not None and 2 <= K <= 8 and x.is_cuda
+                 and not (torch.is_grad_enabled() and any(s._params_need_grad() for s in solvers))
                  and all(s.n_stages == solvers[0].n_stages for s in solvers)
                  and all(torch.equal(s.host_time_grid(torch.tensor([0., 1.])), solvers[0].host_time_grid(torch.tensor([0., 1.])))
                          for s in solvers))

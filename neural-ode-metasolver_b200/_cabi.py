@@ -10,6 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmetasolver_b200.so")
 
 MSB_MAX_STAGES = 4
+TABLEAU_GRAD_DOUBLES = MSB_MAX_STAGES + MSB_MAX_STAGES * MSB_MAX_STAGES + MSB_MAX_STAGES   # [b | w | c]
 ABI_VERSION = 2
 RHS_PREACT_NF, RHS_POSTACT_NF, RHS_MNIST_GN_T = 0, 1, 2
 ACT_NONE, ACT_GELU_ERF, ACT_RELU = 0, 1, 2
@@ -28,7 +29,7 @@ EXPORTS = [
     "msb_downblock_forward", "msb_downblock_backward",
     "msb_conv3x3_workspace_bytes", "msb_wgrad3x3", "msb_wgrad3x3_workspace_bytes", "msb_launch_count", "msb_profile_enable", "msb_profile_read", "msb_profile_read_executed",
     "msb_set_option", "msb_get_option", "msb_attack_step", "msb_sgd_step",
-    "msb_odeblock_bwd_workspace_bytes_tableau", "msb_odeblock_backward_tableau",
+    "msb_odeblock_bwd_workspace_bytes_tableau", "msb_odeblock_backward_tableau", "msb_odeblock_backward_mnist_tableau",
 ]
 
 
@@ -96,6 +97,8 @@ def _declare(lib):
     lib.msb_odeblock_bwd_workspace_bytes_tableau.argtypes = [dp]
     lib.msb_odeblock_bwd_workspace_bytes_tableau.restype = sz
     lib.msb_odeblock_backward_tableau.argtypes = [dp, vp, vp, vp, vp, sz, vp, vp, vp, vp, vp, sz, vp]
+    lib.msb_odeblock_backward_mnist_tableau.argtypes = [dp, vp, ctypes.POINTER(MsbMnistParams), vp, sz, vp,
+                                                        ctypes.POINTER(MsbMnistGrads), vp, vp, sz, vp]
     lib.msb_odeblock_backward_mnist.argtypes = [dp, vp, ctypes.POINTER(MsbMnistParams), vp, sz, vp,
                                                 ctypes.POINTER(MsbMnistGrads), vp, sz, vp]
     lib.msb_stem_forward.argtypes = [vp, vp, i32, vp, vp, i32, i32, i32, i32, vp]

@@ -40,6 +40,8 @@ void launch_wgrad_reduce(const float* partial, int nparts, float* grad_w, int C,
 // ---- train_aux.cu: deterministic dot product (*out += scale * <a, b>) ----
 size_t dot_scratch_bytes();
 void launch_dot_accumulate(const float* a, const float* b, size_t n, double scale, double* out, double* scratch, cudaStream_t st);
+void launch_dot_bcast_accumulate(const float* a, const float* b, size_t n, size_t period, double scale, double* out,
+                                 double* scratch, cudaStream_t st);
 
 // ---- groupnorm.cu (MNIST right-hand side) ----
 int launch_groupnorm_epi(const float* x, const float* gamma, const float* beta, const EpiParams& epi, ConvShape s,

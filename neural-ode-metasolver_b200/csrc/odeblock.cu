@@ -378,7 +378,9 @@ size_t msb_odeblock_bwd_workspace_bytes(const MsbOdeDesc* d) {
 size_t msb_odeblock_bwd_workspace_bytes_tableau(const MsbOdeDesc* d) {
     const size_t base = msb_odeblock_bwd_workspace_bytes(d);
     if (base == 0) return 0;
-    if (d->rhs_kind == MSB_RHS_MNIST_GN_T) { set_error("tableau gradients: the MNIST right-hand side is time dependent (needs df/dt); not implemented"); return 0; }
+    if (d->rhs_kind == MSB_RHS_MNIST_GN_T)     // recomputed k_1..k_S, the two time-channel tap maps, the reduction scratch
+        return base + (size_t)d->stages * align_up(state_elems(d) * 4) +
+               2 * align_up((size_t)d->height * d->width * d->channels * 4) + align_up(dot_scratch_bytes()) + 1024;
     int engine = resolve_engine(d);
     // forward-packed conv2 weights, the recomputed stage derivatives k_1..k_S, the reduction scratch
     return base + align_up(packed_w_bytes(engine, d->channels)) + (size_t)d->stages * align_up(state_elems(d) * 4) +
@@ -575,11 +577,12 @@ int msb_odeblock_forward(const MsbOdeDesc* d, const float* x, const float* w1, c
     return check_cuda(cudaGetLastError(), "odeblock forward");
 }
 
-// grad_tab (optional, device): MSB_MAX_STAGES + MSB_MAX_STAGES^2 doubles, ACCUMULATED into:
-//   [i]                                   dL/db_i  = sum_n dt_n <gbar_{n+1}, k_i^n>
-//   [MSB_MAX_STAGES + i*MSB_MAX_STAGES+j] dL/dw_ij = sum_n dt_n <xbar_i^n, k_j^n>        (j < i)
-// from y1 = y + dt sum b_i k_i and x_i = y + dt sum_j w_ij k_j (rk_parametric_order2stage2.py:90-93 and analogues);
-// the c_i do not enter an autonomous right-hand side.  k_j is recomputed from the tape (one convolution per stage).
+// grad_tab (optional, device): MSB_TABLEAU_GRAD_DOUBLES doubles, ACCUMULATED into (M = MSB_MAX_STAGES):
+//   [i]             dL/db_i  = sum_n dt_n <gbar_{n+1}, k_i^n>
+//   [M + i*M + j]   dL/dw_ij = sum_n dt_n <xbar_i^n, k_j^n>        (j < i)
+//   [M + M*M + i]   dL/dc_i  = sum_n dt_n <kbar_i^n, df/dt(t_i, x_i)>   (time-dependent MNIST right-hand side only)
+// from y1 = y + dt sum b_i k_i, x_i = y + dt sum_j w_ij k_j, t_i = t_n + c_i dt (rk_parametric_order2stage2.py:81-93 and
+// analogues).  k_j is recomputed from the tape (one convolution / GroupNorm per stage).
 static int odeblock_backward_impl(const MsbOdeDesc* d, const float* grad_y, const float* w1, const float* w2,
                                   const void* tape, size_t tape_bytes, float* grad_x, float* grad_w1, float* grad_w2,
                                   double* grad_tab, void* workspace, size_t workspace_bytes, void* cuda_stream) {
@@ -736,16 +739,20 @@ int msb_odeblock_backward_tableau(const MsbOdeDesc* d, const float* grad_y, cons
 // with the Runge-Kutta adjoint combination as the epilogue of the GN1' launch, and the parameter gradients
 // (x-channel weights: wgrad GEMM; time channel + bias: concat_aux_grad; gamma / beta: per-sample partials).
 // ---------------------------------------------------------------------------------------------
-int msb_odeblock_backward_mnist(const MsbOdeDesc* d, const float* grad_y, const MsbMnistParams* mp, const void* tape,
-                                size_t tape_bytes, float* grad_x, const MsbMnistGrads* grads, void* workspace,
-                                size_t workspace_bytes, void* cuda_stream) {
+static int odeblock_backward_mnist_impl(const MsbOdeDesc* d, const float* grad_y, const MsbMnistParams* mp, const void* tape,
+                                        size_t tape_bytes, float* grad_x, const MsbMnistGrads* grads, double* grad_tab,
+                                        void* workspace, size_t workspace_bytes, void* cuda_stream) {
     if (validate(d)) return -1;
     if (d->rhs_kind != MSB_RHS_MNIST_GN_T) { set_error("msb_odeblock_backward_mnist: rhs_kind must be MSB_RHS_MNIST_GN_T"); return -1; }
+    if (grad_tab && d->n_solvers > 1) { set_error("tableau gradients are not implemented for a stacked solver axis"); return -1; }
     if (!grad_y || !mp || !tape || !grad_x || !workspace) { set_error("null pointer argument"); return -1; }
     for (int i = 0; i < 3; ++i) if (!mp->norm_w[i] || !mp->norm_b[i]) { set_error("MNIST params: null norm pointer"); return -1; }
     for (int i = 0; i < 2; ++i) if (!mp->conv_w[i] || !mp->conv_b[i]) { set_error("MNIST params: null conv pointer"); return -1; }
     if (tape_bytes < msb_odeblock_tape_bytes(d)) { set_error("tape too small"); return -1; }
-    if (workspace_bytes < msb_odeblock_bwd_workspace_bytes(d)) { set_error("workspace too small"); return -1; }
+    if (workspace_bytes < (grad_tab ? msb_odeblock_bwd_workspace_bytes_tableau(d) : msb_odeblock_bwd_workspace_bytes(d))) {
+        set_error("workspace too small");
+        return -1;
+    }
     const bool need_w = grads != nullptr;
     if (need_w) {
         for (int i = 0; i < 3; ++i) if (!grads->norm_w[i] || !grads->norm_b[i]) { set_error("MNIST grads: null norm pointer"); return -1; }
@@ -767,8 +774,19 @@ int msb_odeblock_backward_mnist(const MsbOdeDesc* d, const float* grad_y, const 
     float* wpart = cv.take<float>((size_t)wgrad_simt_nparts(shp) * 9 * C * C * 4);
     float* gnpart[6];
     for (int i = 0; i < 6; ++i) gnpart[i] = cv.take<float>((size_t)d->batch * C * 4);     // (dgamma_k, dbeta_k), k = 1..3
+    float* kre[MSB_MAX_STAGES] = {nullptr, nullptr, nullptr, nullptr};
+    float* tmap[2] = {nullptr, nullptr};
+    double* dot_scratch = nullptr;
+    const size_t map_elems = (size_t)d->height * d->width * C;
+    if (grad_tab) {
+        for (int i = 0; i < S; ++i) kre[i] = cv.take<float>(E * 4);
+        for (int k = 0; k < 2; ++k) tmap[k] = cv.take<float>(map_elems * 4);
+        dot_scratch = cv.take<double>(dot_scratch_bytes());
+    }
     if (!cv.ok()) { set_error("internal: workspace carve overflow"); return -1; }
     for (int k = 0; k < 2; ++k) launch_pack_w_simt(mp->conv_w[k], wt[k], C, C + 1, 1, 1, st);
+    if (grad_tab)     // dP/dt of a time-concatenated convolution = its per-pixel sum of in-bounds time-channel taps
+        for (int k = 0; k < 2; ++k) launch_time_tapmap(mp->conv_w[k], tmap[k], d->height, d->width, C, st);
 
     auto dt_of = [&](int n) { return d->time_grid[n + 1] - d->time_grid[n]; };
     int evals = 0;                                   // stage evaluations processed so far (first one overwrites the accumulators)
@@ -776,6 +794,17 @@ int msb_odeblock_backward_mnist(const MsbOdeDesc* d, const float* grad_y, const 
     for (int n = N - 1; n >= 0; --n) {
         const float dt = dt_of(n);
         float* g_next = (n == 0) ? grad_x : gbuf[n & 1];
+        if (grad_tab) {
+            // k_j = GN3(P2_j) again, and dL/db_j += dt <gbar, k_j>
+            for (int j = 0; j < S; ++j) {
+                const MnistSlot sj = mnist_slot(const_cast<void*>(tape), E, n * S + j);
+                EpiParams ek = epi_default();
+                ek.v_out = kre[j];
+                if (launch_groupnorm_epi(sj.P2, mp->norm_w[2], mp->norm_b[2], ek, shp, mp->groups, mp->eps, st)) return -1;
+                launch_dot_accumulate(g_cur, kre[j], E, (double)dt, grad_tab + j, dot_scratch, st);
+            }
+        }
+        double* const gc = grad_tab ? grad_tab + MSB_MAX_STAGES + MSB_MAX_STAGES * MSB_MAX_STAGES : nullptr;
         for (int i = S - 1; i >= 0; --i) {
             const MnistSlot sl = mnist_slot(const_cast<void*>(tape), E, n * S + i);
             const float ti = mnist_stage_time(d, n, i);
@@ -787,6 +816,8 @@ int msb_odeblock_backward_mnist(const MsbOdeDesc* d, const float* grad_y, const 
             e.out_f32 = dP; e.out_split = Dsplit;
             if (launch_groupnorm_bwd_epi(sl.P2, mp->norm_w[2], mp->norm_b[2], dy3, sc3, 0, e, need_w ? gnpart[4] : nullptr,
                                          need_w ? gnpart[5] : nullptr, acc, shp, mp->groups, mp->eps, st)) return -1;
+            if (gc && i > 0)      // t_i = t_n + c_i dt enters conv2 through its time channel: dL/dc_i += dt <dP2, dP2/dt>
+                launch_dot_bcast_accumulate(dP, tmap[1], E, map_elems, (double)dt, gc + i, dot_scratch, st);
             if (need_w) {
                 int np = 0;
                 if (launch_wgrad3x3_simt(Dsplit, sl.Hs, wpart, &np, shp, st)) return -1;
@@ -800,6 +831,8 @@ int msb_odeblock_backward_mnist(const MsbOdeDesc* d, const float* grad_y, const 
             e.out_f32 = dP; e.out_split = Dsplit;
             if (launch_groupnorm_bwd_epi(sl.P1, mp->norm_w[1], mp->norm_b[1], dH, 1.f, 1, e, need_w ? gnpart[2] : nullptr,
                                          need_w ? gnpart[3] : nullptr, acc, shp, mp->groups, mp->eps, st)) return -1;
+            if (gc && i > 0)      // ... and conv1 through its own
+                launch_dot_bcast_accumulate(dP, tmap[0], E, map_elems, (double)dt, gc + i, dot_scratch, st);
             if (need_w) {
                 int np = 0;
                 if (launch_wgrad3x3_simt(Dsplit, sl.A, wpart, &np, shp, st)) return -1;
@@ -830,6 +863,10 @@ int msb_odeblock_backward_mnist(const MsbOdeDesc* d, const float* grad_y, const 
             }
             if (launch_groupnorm_bwd_epi(sl.X, mp->norm_w[0], mp->norm_b[0], dH, 1.f, 1, e4, need_w ? gnpart[0] : nullptr,
                                          need_w ? gnpart[1] : nullptr, acc, shp, mp->groups, mp->eps, st)) return -1;
+            if (grad_tab && i > 0)                     // dL/dw_ij += dt <xbar_i, k_j>, j < i
+                for (int j = 0; j < i; ++j)
+                    launch_dot_accumulate(xbar[i], kre[j], E, (double)dt,
+                                          grad_tab + MSB_MAX_STAGES + i * MSB_MAX_STAGES + j, dot_scratch, st);
             ++evals;
         }
         g_cur = g_next;
@@ -840,6 +877,21 @@ int msb_odeblock_backward_mnist(const MsbOdeDesc* d, const float* grad_y, const 
             launch_sum_over_batch(gnpart[2 * k + 1], grads->norm_b[k], d->batch, C, st);
         }
     return check_cuda(cudaGetLastError(), "odeblock backward (mnist)");
+}
+
+int msb_odeblock_backward_mnist(const MsbOdeDesc* d, const float* grad_y, const MsbMnistParams* mp, const void* tape,
+                                size_t tape_bytes, float* grad_x, const MsbMnistGrads* grads, void* workspace,
+                                size_t workspace_bytes, void* cuda_stream) {
+    return odeblock_backward_mnist_impl(d, grad_y, mp, tape, tape_bytes, grad_x, grads, nullptr, workspace, workspace_bytes,
+                                        cuda_stream);
+}
+
+int msb_odeblock_backward_mnist_tableau(const MsbOdeDesc* d, const float* grad_y, const MsbMnistParams* mp, const void* tape,
+                                        size_t tape_bytes, float* grad_x, const MsbMnistGrads* grads, double* grad_tableau,
+                                        void* workspace, size_t workspace_bytes, void* cuda_stream) {
+    if (!grad_tableau) { set_error("msb_odeblock_backward_mnist_tableau: grad_tableau is NULL"); return -1; }
+    return odeblock_backward_mnist_impl(d, grad_y, mp, tape, tape_bytes, grad_x, grads, grad_tableau, workspace,
+                                        workspace_bytes, cuda_stream);
 }
 
 int msb_act_split(const float* x, int act, void* split_out, float* dact_out, int batch, int height, int width,

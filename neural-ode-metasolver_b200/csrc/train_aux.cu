@@ -108,6 +108,23 @@ __global__ void __launch_bounds__(256) dot_partial_kernel(const float* __restric
     }
     if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
 }
+// <a, b> with b of `period` elements repeated along a (a per-image map against a batch): n4, period4 in float4 units
+__global__ void __launch_bounds__(256) dot_bcast_partial_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                                size_t n4, size_t period4, double* __restrict__ partial) {
+    double acc = 0.0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 x = reinterpret_cast<const float4*>(a)[i], y = reinterpret_cast<const float4*>(b)[i % period4];
+        acc += (double)x.x * y.x + (double)x.y * y.y + (double)x.z * y.z + (double)x.w * y.w;
+    }
+    __shared__ double sh[256];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
 __global__ void __launch_bounds__(256) dot_final_kernel(const double* __restrict__ partial, int nblocks, double scale,
                                                         double* __restrict__ out) {
     __shared__ double sh[256];
@@ -134,6 +151,14 @@ size_t dot_scratch_bytes() { return kDotBlocks * sizeof(double); }
 // *out += scale * <a, b>   (n a multiple of 4; scratch = dot_scratch_bytes())
 void launch_dot_accumulate(const float* a, const float* b, size_t n, double scale, double* out, double* scratch, cudaStream_t st) {
     dot_partial_kernel<<<kDotBlocks, 256, 0, st>>>(a, b, n / 4, scratch);
+    dot_final_kernel<<<1, 256, 0, st>>>(scratch, kDotBlocks, scale, out);
+    count_launch(2);
+}
+
+// *out += scale * <a, tile(b)>   (b has `period` elements, n a multiple of period, both multiples of 4)
+void launch_dot_bcast_accumulate(const float* a, const float* b, size_t n, size_t period, double scale, double* out,
+                                 double* scratch, cudaStream_t st) {
+    dot_bcast_partial_kernel<<<kDotBlocks, 256, 0, st>>>(a, b, n / 4, period / 4, scratch);
     dot_final_kernel<<<1, 256, 0, st>>>(scratch, kDotBlocks, scale, out);
     count_launch(2);
 }

@@ -150,7 +150,7 @@ def _check_inputs(x, w1, w2):
 
 
 class _OdeBlockFn(torch.autograd.Function):
-    """coef (optional): a host float64 tensor [b_1..b_4, w_11..w_44] built DIFFERENTIABLY from solver.u / solver.v
+    """coef (optional): a host float64 tensor [b_1..b_4, w_11..w_44, c_1..c_4] built DIFFERENTIABLY from solver.u / solver.v
     (RKParametricSolver._tableau_torch).  Its values are not used -- the kernels take the bit-exact numpy tableau in
     `prob` -- but when it requires grad the backward pass also reduces dL/db_i, dL/dw_ij on the device and returns
     them as coef's gradient, which autograd chains to u and v (unfreeze_params())."""
@@ -203,12 +203,11 @@ class _OdeBlockFn(torch.autograd.Function):
             gw1 = torch.empty_like(w1c) if need_w else None
             gw2 = torch.empty_like(w2c) if need_w else None
             if need_coef:
-                M = _cabi.MSB_MAX_STAGES
                 ws_bytes = lib.msb_odeblock_bwd_workspace_bytes_tableau(ctypes.byref(d))
                 if ws_bytes == 0:
                     _cabi.check(-1, "odeblock tableau-gradient workspace query")
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-                gtab = torch.zeros(M + M * M, dtype=torch.float64, device=dev)
+                gtab = torch.zeros(_cabi.TABLEAU_GRAD_DOUBLES, dtype=torch.float64, device=dev)
                 rc = lib.msb_odeblock_backward_tableau(ctypes.byref(d), _ptr(gyc), _ptr(w1c), _ptr(w2c), _ptr(ctx.tape),
                                                        ctx.tape_bytes, _ptr(gx), _ptr(gw1), _ptr(gw2), _ptr(gtab), _ptr(ws),
                                                        ws_bytes, _stream(dev))
@@ -225,6 +224,13 @@ class _OdeBlockFn(torch.autograd.Function):
         return gx, gw1, gw2, None, gcoef
 
 
+def _check_coef(prob, coef):
+    if len(prob.tableaus) != 1:
+        raise NotImplementedError("metasolver_b200: gradients w.r.t. solver parameters on a stacked solver axis")
+    if coef.dtype != torch.float64 or coef.is_cuda or coef.numel() != _cabi.TABLEAU_GRAD_DOUBLES:
+        raise ValueError("tableau_coef must be a host float64 tensor of %d elements" % _cabi.TABLEAU_GRAD_DOUBLES)
+
+
 def ode_block_integrate(x, w1, w2, tableau, time_grid, rhs_kind=_cabi.RHS_PREACT_NF, act=_cabi.ACT_GELU_ERF,
                         engine=None, tableau_coef=None):
     """y(t_end) of dy/dt = f(y) with f = conv2(act(conv1(act(y)))) integrated on `time_grid`
@@ -234,11 +240,7 @@ def ode_block_integrate(x, w1, w2, tableau, time_grid, rhs_kind=_cabi.RHS_PREACT
     dim 0 and slice s is integrated by solver s, all inside the same kernel launches (stacked solver axis)."""
     prob = OdeProblem(rhs_kind, act, tableau, time_grid, engine)
     if tableau_coef is not None:
-        M = _cabi.MSB_MAX_STAGES
-        if len(prob.tableaus) != 1:
-            raise NotImplementedError("metasolver_b200: gradients w.r.t. solver parameters on a stacked solver axis")
-        if tableau_coef.dtype != torch.float64 or tableau_coef.is_cuda or tableau_coef.numel() != M + M * M:
-            raise ValueError("tableau_coef must be a host float64 tensor of %d elements" % (M + M * M))
+        _check_coef(prob, tableau_coef)
         return _OdeBlockFn.apply(x, w1, w2, prob, tableau_coef)
     return _OdeBlockFn.apply(x, w1, w2, prob, None)
 
@@ -274,10 +276,11 @@ class _MnistOdeBlockFn(torch.autograd.Function):
     (msb_odeblock_backward_mnist): gradients w.r.t. x and all ten RHS parameters."""
 
     @staticmethod
-    def forward(ctx, x, prob, groups, eps, *params):
+    def forward(ctx, x, prob, groups, eps, coef, *params):
         lib = _cabi.lib()
         dev = x.device
-        need_grad = ctx.needs_input_grad[0] or any(ctx.needs_input_grad[4:])
+        need_grad = ctx.needs_input_grad[0] or any(ctx.needs_input_grad[4:])      # x, coef or any parameter
+        ctx.coef_shape = None if coef is None else tuple(coef.shape)
         with torch.cuda.device(dev):
             xc = x.detach().contiguous(memory_format=torch.channels_last)
             keep = {k: v.detach().contiguous() for k, v in zip(_MNIST_KEYS, params)}
@@ -306,12 +309,17 @@ class _MnistOdeBlockFn(torch.autograd.Function):
             raise RuntimeError("metasolver_b200: backward called but no tape was recorded")
         keep = dict(zip(_MNIST_KEYS, ctx.saved_tensors))
         dev = gy.device
-        need_w = any(ctx.needs_input_grad[4:]) and not (_input_only_depth[0] > 0)
+        need_w = any(ctx.needs_input_grad[5:]) and not (_input_only_depth[0] > 0)
+        need_coef = ctx.coef_shape is not None and ctx.needs_input_grad[4]
+        gcoef = None
         with torch.cuda.device(dev):
             gyc = gy.contiguous(memory_format=torch.channels_last)
             mp = _mnist_params_struct(keep, ctx.groups, ctx.eps)
             d = ctx.prob.desc(ctx.shape, True)
-            ws_bytes = lib.msb_odeblock_bwd_workspace_bytes(ctypes.byref(d))
+            ws_bytes = (lib.msb_odeblock_bwd_workspace_bytes_tableau if need_coef else lib.msb_odeblock_bwd_workspace_bytes)(
+                ctypes.byref(d))
+            if ws_bytes == 0:
+                _cabi.check(-1, "odeblock backward workspace query (mnist)")
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             gx = torch.empty_like(gyc)
             grads, gstruct = None, None
@@ -324,22 +332,32 @@ class _MnistOdeBlockFn(torch.autograd.Function):
                 for i in range(2):
                     gstruct.conv_w[i] = grads["conv%d_w" % (i + 1)].data_ptr()
                     gstruct.conv_b[i] = grads["conv%d_b" % (i + 1)].data_ptr()
-            rc = lib.msb_odeblock_backward_mnist(ctypes.byref(d), _ptr(gyc), ctypes.byref(mp), _ptr(ctx.tape), ctx.tape_bytes,
-                                                 _ptr(gx), ctypes.byref(gstruct) if need_w else None, _ptr(ws), ws_bytes,
-                                                 _stream(dev))
-            _cabi.check(rc, "odeblock backward (mnist)")
+            if need_coef:
+                gtab = torch.zeros(_cabi.TABLEAU_GRAD_DOUBLES, dtype=torch.float64, device=dev)
+                rc = lib.msb_odeblock_backward_mnist_tableau(ctypes.byref(d), _ptr(gyc), ctypes.byref(mp), _ptr(ctx.tape),
+                                                             ctx.tape_bytes, _ptr(gx), ctypes.byref(gstruct) if need_w else None,
+                                                             _ptr(gtab), _ptr(ws), ws_bytes, _stream(dev))
+                _cabi.check(rc, "odeblock backward (mnist, tableau gradients)")
+                gcoef = gtab.cpu().reshape(ctx.coef_shape)
+            else:
+                rc = lib.msb_odeblock_backward_mnist(ctypes.byref(d), _ptr(gyc), ctypes.byref(mp), _ptr(ctx.tape), ctx.tape_bytes,
+                                                     _ptr(gx), ctypes.byref(gstruct) if need_w else None, _ptr(ws), ws_bytes,
+                                                     _stream(dev))
+                _cabi.check(rc, "odeblock backward (mnist)")
         ctx.tape = None
-        return (gx, None, None, None) + (tuple(grads[k] for k in _MNIST_KEYS) if need_w else (None,) * len(_MNIST_KEYS))
+        return (gx, None, None, None, gcoef) + (tuple(grads[k] for k in _MNIST_KEYS) if need_w else (None,) * len(_MNIST_KEYS))
 
 
-def ode_block_integrate_mnist(x, params, tableau, time_grid, groups, eps=1e-5):
+def ode_block_integrate_mnist(x, params, tableau, time_grid, groups, eps=1e-5, tableau_coef=None):
     """MNIST right-hand side (GroupNorm / ReLU / time-concatenated convs, mnist/layers.py:158-171).
     `params`: dict(norm{1,2,3}_{w,b}, conv{1,2}_{w,b}) of fp32 CUDA tensors.  Differentiable w.r.t. x and all params."""
     if not x.is_cuda:
         raise RuntimeError("metasolver_b200: the ODE-block path runs on CUDA only (got a %s tensor); "
                            "there is no CPU fallback" % x.device)
     prob = OdeProblem(_cabi.RHS_MNIST_GN_T, _cabi.ACT_RELU, tableau, time_grid, "simt")
-    return _MnistOdeBlockFn.apply(x, prob, groups, eps, *[params[k] for k in _MNIST_KEYS])
+    if tableau_coef is not None:
+        _check_coef(prob, tableau_coef)
+    return _MnistOdeBlockFn.apply(x, prob, groups, eps, tableau_coef, *[params[k] for k in _MNIST_KEYS])
 
 
 # --------------------------------------------------------------------------- non-ODE layers (SURVEY 8(f-1))

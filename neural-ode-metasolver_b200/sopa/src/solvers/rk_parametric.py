@@ -120,22 +120,24 @@ class RKParametricSolver(object, metaclass=abc.ABCMeta):
 
     # ---- differentiable tableau (only evaluated when u / v require grad) ----
     def _tableau_torch(self, u, v, eps):
-        """-> (b list, w lower-triangular rows) as float64 torch scalars, differentiable w.r.t. u, v: the same closed
-        forms (and the same clamps, hence the same zero gradient outside the valid range) as `_tableau_np`."""
+        """-> (b list, w lower-triangular rows, c list) as float64 torch scalars, differentiable w.r.t. u, v: the same
+        closed forms (and the same clamps, hence the same zero gradient outside the valid range) as `_tableau_np`."""
         raise NotImplementedError
 
     def tableau_coef(self):
-        """Host float64 tensor [b_1..b_4 | w_11..w_44] (MSB_MAX_STAGES + MSB_MAX_STAGES^2) connected to self.u / self.v by
-        autograd -- the handle through which the fused backward returns dL/du, dL/dv (ops._OdeBlockFn)."""
+        """Host float64 tensor [b_1..b_4 | w_11..w_44 | c_1..c_4] (_cabi.TABLEAU_GRAD_DOUBLES) connected to self.u /
+        self.v by autograd -- the handle through which the fused backward returns dL/du, dL/dv (ops._OdeBlockFn)."""
         M = _cabi.MSB_MAX_STAGES
         u = self.u.to(torch.float64).reshape(()) if self.u is not None else None
         v = self.v.to(torch.float64).reshape(()) if self.v is not None else None
-        b, w = self._tableau_torch(u, v, _clamp_eps(self.dtype))
+        b, w, c = self._tableau_torch(u, v, _clamp_eps(self.dtype))
         zero = torch.zeros((), dtype=torch.float64)
-        flat = [b[i] if i < len(b) else zero for i in range(M)]
+        as_t = lambda t: t if torch.is_tensor(t) else torch.tensor(float(t), dtype=torch.float64)
+        flat = [as_t(b[i]) if i < len(b) else zero for i in range(M)]
         for i in range(M):
             for j in range(M):
-                flat.append(w[i][j] if (i < len(w) and j < i) else zero)
+                flat.append(as_t(w[i][j]) if (i < len(w) and j < i) else zero)
+        flat += [as_t(c[i]) if i < len(c) else zero for i in range(M)]
         return torch.stack([t.reshape(()).to(torch.float64) for t in flat])
 
     def _params_need_grad(self):
@@ -199,11 +201,11 @@ class RKParametricSolver(object, metaclass=abc.ABCMeta):
 
     def _integrate_grid(self, rhs_func, spec, x, grid):
         """One fused call over the (sub-)grid `grid` (host fp32 tensor of >= 2 points) -> state at grid[-1]."""
+        coef = self.tableau_coef() if (self._params_need_grad() and torch.is_grad_enabled()) else None
         if spec["rhs_kind"] == _cabi.RHS_MNIST_GN_T:
             y = ode_block_integrate_mnist(x, spec["params"], self._host_tableau, grid.tolist(), spec["groups"],
-                                          spec["eps"])
+                                          spec["eps"], tableau_coef=coef)
         else:
-            coef = self.tableau_coef() if (self._params_need_grad() and torch.is_grad_enabled()) else None
             y = ode_block_integrate(x, spec["w1"], spec["w2"], self._host_tableau, grid.tolist(),
                                     rhs_kind=spec["rhs_kind"], act=spec["act"], engine=spec.get("engine"),
                                     tableau_coef=coef)
@@ -216,12 +218,7 @@ class RKParametricSolver(object, metaclass=abc.ABCMeta):
         if spec is None:
             raise NotImplementedError("metasolver_b200: %s is not a right-hand side the fused CUDA path knows; "
                                       "there is no unfused fallback" % type(rhs_func).__name__)
-        spec = spec()
-        if self._params_need_grad() and torch.is_grad_enabled() and spec["rhs_kind"] == _cabi.RHS_MNIST_GN_T:
-            raise NotImplementedError("metasolver_b200: gradients w.r.t. the solver parameters u/v are implemented for the "
-                                      "autonomous (CIFAR) right-hand sides only -- the MNIST right-hand side depends on t, "
-                                      "its dL/dc_i term is not built; call freeze_params()")
-        return spec, self.host_time_grid(t)
+        return spec(), self.host_time_grid(t)
 
     def print_is_requires_grad(self):
         print('\nIs requires grad? (RK solver)')
@@ -240,6 +237,8 @@ def can_stack(solvers, rhs_func, t):
         return False
     if any(s.n_stages != solvers[0].n_stages for s in solvers):
         return False
+    if torch.is_grad_enabled() and any(s._params_need_grad() for s in solvers):
+        return False                # gradients w.r.t. u / v are reduced per solver: integrate them one by one
     g0 = solvers[0].host_time_grid(t)
     return all(torch.equal(s.host_time_grid(t), g0) for s in solvers[1:])
 
@@ -306,7 +305,7 @@ class Euler(RKParametricSolver):
         return [T(0)], [T(1)], [[T(0)]], (None, None)
 
     def _tableau_torch(self, u, v, eps):
-        return [torch.ones((), dtype=torch.float64)], [[]]
+        return [torch.ones((), dtype=torch.float64)], [[]], [0.]
 
     def freeze_params(self):
         pass
@@ -341,7 +340,7 @@ class RKOrder2Stage2(RKParametricSolver):
     def _tableau_torch(self, u, v, eps):
         u_ = torch.clamp(u, eps, 1.)                                   # order2stage2.py:52-53
         b2 = 1. / (2 * u_)
-        return [1. - b2, b2], [[], [u_]]
+        return [1. - b2, b2], [[], [u_]], [0., u_]
 
     @property
     def order(self):
@@ -385,7 +384,7 @@ class RKOrder3Stage3(RKParametricSolver):
         b3 = (2. - 3. * u_) / (6. * v_ * d)
         b1 = 1. - b2 - b3
         w32 = v_ * (v_ - u_) / (u_ * (2. - 3. * u_))
-        return [b1, b2, b3], [[], [u_], [v_ - w32, w32]]
+        return [b1, b2, b3], [[], [u_], [v_ - w32, w32]], [0., u_, v_]
 
     @property
     def order(self):
@@ -490,7 +489,7 @@ class RKOrder4Stage4(RKParametricSolver):
         w42 = (a00 * r1 - a10 * r0) / det
         w41 = c4 - (w42 + w43)
         w31 = c3 - w32
-        return [b1, b2, b3, b4], [[], [c2], [w31, w32], [w41, w42, w43]]
+        return [b1, b2, b3, b4], [[], [c2], [w31, w32], [w41, w42, w43]], [0., c2, c3, c4]
 
     @property
     def order(self):

@@ -80,3 +80,12 @@ MULTITIME_CASES = [
     ("mt_rk4_n3_gridpoint", 64, 8, 32, 2, ("rk4", "u2", 3, -1, 1 / 3., -1), [0.0, 1 / 3., 0.9, 1.0]),
     ("mt_rk2_two_in_one_step", 64, 4, 32, 1, ("rk2", "u", 2, -1, 0.7, -1), [0.0, 0.1, 0.4, 0.5, 1.0]),
 ]
+
+# the same for the time-dependent MNIST right-hand side (trained weights): tag, solver tuple
+MNIST_SOLVER_GRAD_CASES = [
+    ("msg_rk2_u05_n4", ("rk2", "u", 4, -1, 0.5, -1)),
+    ("msg_rk2_u03_n2", ("rk2", "u", 2, -1, 0.3, -1)),
+    ("msg_rk3_n2", ("rk3", "uv", 2, -1, 0.3, 0.7)),
+    ("msg_rk4uv_n1", ("rk4", "uv", 1, -1, 0.3, 0.7)),
+    ("msg_rk4u3_n2", ("rk4", "u3", 2, -1, 0.1, -1)),
+]

@@ -81,7 +81,7 @@ def test_solver_parameter_gradients_vs_reference(case):
     gc = coefs[0].grad.numpy()
     gb, gw = _oracle_coef_grads(case)
     S = len(gb)
-    ref = np.zeros(M + M * M)
+    ref = np.zeros(_cabi.TABLEAU_GRAD_DOUBLES)               # [b | w | c]; c does not enter an autonomous right-hand side
     ref[:S] = gb
     for i in range(S):
         for j in range(i):
@@ -121,7 +121,48 @@ def test_frozen_solver_and_stacked_axis_behaviour():
     s.unfreeze_params()
     with torch.no_grad():                                      # unfrozen but no grad mode: plain forward
         blk(x, [s], Namespace(solver_mode="standalone"))
-    # time-dependent MNIST right-hand side: dL/dc is not built -> loud failure, not a silently wrong gradient
-    mb = MnistBlock().cuda()
-    with pytest.raises(NotImplementedError):
-        mb(torch.randn(2, 64, 6, 6, device="cuda", requires_grad=True), [s], Namespace(solver_mode="standalone"))
+    # unfrozen solvers are never folded onto a stacked solver axis (their gradients are reduced per solver)
+    from metasolver_b200.sopa.src.solvers.rk_parametric import can_stack
+    s2 = create_solver("rk2", "u", 2, -1, 0.7, -1, torch.float32, "cuda")
+    s2.freeze_params()
+    assert not can_stack([s, s2], blk.rhs_func, blk.integration_time)
+    s.freeze_params()
+    assert can_stack([s, s2], blk.rhs_func, blk.integration_time)
+
+
+@pytest.mark.parametrize("case", cases.MNIST_SOLVER_GRAD_CASES, ids=[c[0] for c in cases.MNIST_SOLVER_GRAD_CASES])
+def test_solver_parameter_gradients_mnist_vs_reference(case):
+    """Time-dependent MNIST right-hand side (trained weights): dL/du includes the node terms dL/dc_i = dt <dP, dP/dt>
+    (t_i = t_n + c_i dt enters both time-concatenated convolutions).  vs the REAL reference's fp64 golden."""
+    import metasolver_b200  # noqa: F401
+    from metasolver_b200.sopa.src.solvers.utils import create_solver
+    from metasolver_b200.sopa.src.models.odenet_mnist.layers import MetaODEBlock as MnistBlock
+    from oracle import det_normal
+    tag, sv = case
+    g = golden("solver_grads_mnist.npz")
+    w = golden("mnist_odeblock_weights.npz")
+    feat = golden("mnist_odeblock.npz")["feat"]
+    blk = MnistBlock().cuda()
+    rf = blk.rhs_func
+    with torch.no_grad():
+        for i in (1, 2, 3):
+            getattr(rf, "norm%d" % i).weight.copy_(torch.from_numpy(w["norm%d_w" % i]))
+            getattr(rf, "norm%d" % i).bias.copy_(torch.from_numpy(w["norm%d_b" % i]))
+        for i in (1, 2):
+            getattr(rf, "conv%d" % i)._layer.weight.copy_(torch.from_numpy(w["conv%d_w" % i]))
+            getattr(rf, "conv%d" % i)._layer.bias.copy_(torch.from_numpy(w["conv%d_b" % i]))
+    solver = create_solver(*sv, torch.float32, "cuda")
+    solver.unfreeze_params()
+    x = torch.from_numpy(feat).cuda().requires_grad_(True)
+    y = blk(x, [solver], Namespace(solver_mode="standalone"))
+    r = torch.from_numpy(det_normal(tuple(y.shape), 77)).cuda()
+    (y * r).sum().backward()
+    # ReLU masks can flip for pre-activations within rounding distance of zero (see test_gpu_odeblock.py): 2e-3 bound
+    assert max_rel(x.grad.cpu().numpy(), g[tag + "_f32_gx"]) <= 2e-3
+    assert rf.conv1._layer.weight.grad is not None
+    for p, key in ((solver.u, "du"), (solver.v, "dv")):
+        if p is None:
+            continue
+        f64, f32 = float(g["%s_f64_%s" % (tag, key)][0]), float(g["%s_f32_%s" % (tag, key)][0])
+        got = float(p.grad.reshape(-1)[0])
+        assert abs(got - f64) <= 2e-3 * abs(f64) + 3.0 * abs(f32 - f64), (tag, key, got, f64, f32)

@@ -314,3 +314,30 @@ def test_integrate_with_interior_output_times_bit_exact(case):
     assert np.array_equal(ys.detach().numpy()[1:, :, ::3], g[name + "_y"])
     assert np.array_equal(x.grad.numpy(), g[name + "_gx"])
     assert np.array_equal(w1.grad.numpy().reshape(-1)[::cases.WG_STRIDE], g[name + "_gw1"])
+
+
+@pytest.mark.parametrize("case", cases.MNIST_SOLVER_GRAD_CASES, ids=[c[0] for c in cases.MNIST_SOLVER_GRAD_CASES])
+def test_solver_parameter_gradients_mnist(case):
+    """Time-dependent right-hand side: dL/du also flows through the nodes c_i (t_i = t_n + c_i dt, order2stage2.py:81-86)."""
+    from oracle.tableau import butcher_tableau_tensors
+    tag, sv = case
+    method, param, n_steps, step_size, u0, v0 = sv
+    g = golden("solver_grads_mnist.npz")
+    w = golden("mnist_odeblock_weights.npz")
+    feat = golden("mnist_odeblock.npz")["feat"]
+    for dt, dn, tol in ((torch.float32, "f32", 2e-6), (torch.float64, "f64", 1e-10)):
+        po = {k: torch.from_numpy(w[k]).to(dt) for k in w.files}
+        x = torch.from_numpy(feat).to(dt).requires_grad_(True)
+        u = torch.tensor((u0,), dtype=dt, requires_grad=True)
+        v = torch.tensor((v0,), dtype=dt, requires_grad=True) if v0 != -1 else None
+        tab = butcher_tableau_tensors(method, param, u, v, dt)
+        y = integrate(tab, rhs_mnist(po), x, torch.tensor([0., 1.]), n_steps=n_steps)[-1]
+        r = torch.from_numpy(det_normal(tuple(y.shape), 77)).to(dt)
+        (y * r).sum().backward()
+        for p, key in ((u, "du"), (v, "dv")):
+            if p is None:
+                continue
+            ref, got = float(g["%s_%s_%s" % (tag, dn, key)][0]), float(p.grad[0])
+            assert abs(got - ref) <= tol * abs(ref), (tag, dn, key, got, ref)
+        if dn == "f32":
+            assert max_rel(x.grad.numpy(), g[tag + "_f32_gx"]) <= 1e-6
