@@ -68,6 +68,36 @@ class MetaODEBlock(_RegimeDispatch):
     def __init__(self, activation_type='relu'):
         super().__init__(ODEfunc(64, activation_type))
 
+    def ss_loss(self, y, solvers, solver_options):
+        """Steady-state regulariser (:53-93): integrate one more unit of time from the block output and penalise the
+        mean per-sample distance travelled.  The reference passes `partial(self.rhs_func, ss_loss=True).func` to the
+        solver -- `.func` is the un-wrapped module, so the `abs` branch of ODEfunc.forward (:168-169) is never taken:
+        the plain right-hand side is integrated over t in [1, 2].  Reproduced as is; runs on the fused path."""
+        z0 = y
+        t_ss = self.integration_time + 1
+        mode = solver_options.solver_mode
+        n = len(solvers)
+        if mode == 'standalone':
+            z = solvers[0].integrate(self.rhs_func, y, t_ss)
+        elif mode == 'switch':
+            z = solvers[solver_options.switch_solver_id].integrate(self.rhs_func, y, t_ss)
+        elif mode == 'ensemble':
+            if solver_options.ensemble_coin_flip:
+                weights = solver_options.ensemble_weights
+                if weights is None:
+                    weights = [1. / n for _ in range(n)]
+                z = None
+                for wi, solver in zip(weights, solvers):
+                    zi = wi * solver.integrate(self.rhs_func, y, t_ss)
+                    z = zi if z is None else z + zi
+            else:
+                z = solvers[0].integrate(self.rhs_func, y, t_ss)
+        else:
+            raise ValueError("unknown solver_mode %r" % (mode,))
+        z = z[-1] - z0
+        z = torch.norm(z.reshape((z.shape[0], -1)), dim=1)
+        return torch.mean(z)
+
 
 class ResBlock(nn.Module):
     expansion = 1
@@ -119,7 +149,12 @@ class MetaNODE(nn.Module):
         self.ss_loss = 0
         x = self.downsampling_layers(x)
         for block in self.blocks:
-            x = block(x, solvers, solver_options) if self.is_odenet else block(x)
+            if self.is_odenet:
+                x = block(x, solvers, solver_options)
+                if (loss_options is not None) and loss_options.ss_loss:          # :117-122
+                    self.ss_loss += block.ss_loss(x, solvers, solver_options)
+            else:
+                x = block(x)
         return self.fc_layers(x)
 
     def get_ss_loss(self):

@@ -166,3 +166,49 @@ def test_solver_parameter_gradients_mnist_vs_reference(case):
         f64, f32 = float(g["%s_f64_%s" % (tag, key)][0]), float(g["%s_f32_%s" % (tag, key)][0])
         got = float(p.grad.reshape(-1)[0])
         assert abs(got - f64) <= 2e-3 * abs(f64) + 3.0 * abs(f32 - f64), (tag, key, got, f64, f32)
+
+
+@pytest.mark.parametrize("tag,svs,opts", [
+    ("standalone_rk2", [("rk2", "u", 4, -1, 0.5, -1)], Namespace(solver_mode="standalone")),
+    ("ensemble_rk2x2", [("rk2", "u", 2, -1, 0.3, -1), ("rk2", "u", 2, -1, 1.0, -1)],
+     Namespace(solver_mode="ensemble", ensemble_prob=1.0, ensemble_weights=[0.25, 0.75]))])
+def test_mnist_steady_state_regulariser_vs_reference(tag, svs, opts):
+    """`loss_options.ss_loss` (odenet_mnist/layers.py:53-93,117-122): one more unit of time integrated from the block
+    output on the fused path; value, nfe and the gradients of (sum(y r) + 0.1 ss_loss) vs the REAL reference."""
+    import metasolver_b200  # noqa: F401
+    from metasolver_b200.sopa.src.solvers.utils import create_solver
+    from metasolver_b200.sopa.src.models.odenet_mnist.layers import MetaODEBlock as MnistBlock, MetaNODE
+    from oracle import det_normal
+    g = golden("ss_loss_mnist.npz")
+    w = golden("mnist_odeblock_weights.npz")
+    feat = golden("mnist_odeblock.npz")["feat"]
+    blk = MnistBlock().cuda()
+    rf = blk.rhs_func
+    with torch.no_grad():
+        for i in (1, 2, 3):
+            getattr(rf, "norm%d" % i).weight.copy_(torch.from_numpy(w["norm%d_w" % i]))
+            getattr(rf, "norm%d" % i).bias.copy_(torch.from_numpy(w["norm%d_b" % i]))
+        for i in (1, 2):
+            getattr(rf, "conv%d" % i)._layer.weight.copy_(torch.from_numpy(w["conv%d_w" % i]))
+            getattr(rf, "conv%d" % i)._layer.bias.copy_(torch.from_numpy(w["conv%d_b" % i]))
+    solvers = [create_solver(*s, torch.float32, "cuda") for s in svs]
+    for s in solvers:
+        s.freeze_params()
+    x = torch.from_numpy(feat).cuda().requires_grad_(True)
+    torch.manual_seed(0)
+    y = blk(x, solvers, opts)
+    ss = blk.ss_loss(y, solvers, opts)
+    r = torch.from_numpy(det_normal(tuple(y.shape), 77)).cuda()
+    ((y * r).sum() + 0.1 * ss).backward()
+    assert rf.nfe == int(g[tag + "_nfe"])
+    assert abs(float(ss) - float(g[tag + "_ss"])) <= 1e-4 * abs(float(g[tag + "_ss"]))
+    assert max_rel(y.detach().cpu().numpy(), g[tag + "_y"]) <= 1e-4
+    assert max_rel(x.grad.cpu().numpy(), g[tag + "_gx"]) <= 2e-3            # ReLU-mask flips, see test_gpu_odeblock.py
+    assert max_rel(rf.conv1._layer.weight.grad.cpu().numpy().reshape(-1)[::cases.WG_STRIDE], g[tag + "_gconv1_w"]) <= 5e-4
+    assert max_rel(rf.norm3.bias.grad.cpu().numpy(), g[tag + "_gnorm3_b"]) <= 5e-4
+    # whole-model wiring: MetaNODE accumulates the regulariser when loss_options.ss_loss is set
+    model = MetaNODE().cuda().eval()
+    out = model(torch.rand(4, 1, 28, 28, device="cuda"), solvers, opts, Namespace(ss_loss=True))
+    assert out.shape == (4, 10) and float(model.get_ss_loss()) > 0
+    model(torch.rand(4, 1, 28, 28, device="cuda"), solvers, opts, Namespace(ss_loss=False))
+    assert model.get_ss_loss() == 0
