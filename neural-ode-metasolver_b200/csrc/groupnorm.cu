@@ -54,8 +54,9 @@ int launch_groupnorm_epi(const float* x, const float* gamma, const float* beta, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// GroupNorm backward, fused with the ReLU mask of the forward output and with the generic epilogue:
-//   xhat = (x - mean) rstd,  y = xhat gamma + beta,  g = dy * dy_scale * (relu ? [y > 0] : 1)
+// GroupNorm backward, fused with the derivative of the activation that followed it in the forward pass (`relu` is an
+// activation code: 0 = none, ACT_GELU, ACT_RELU) and with the generic epilogue:
+//   xhat = (x - mean) rstd,  y = xhat gamma + beta,  g = dy * dy_scale * act'(y)
 //   dgamma_part[n][c] (+)= sum_p g xhat        dbeta_part[n][c] (+)= sum_p g          (per-sample partials:
 //                                               every (n, c) is owned by one warp -> deterministic)
 //   dx = rstd (g gamma - mean_grp(g gamma) - xhat mean_grp(g gamma xhat))  ->  epilogue_apply(dx)
@@ -98,7 +99,8 @@ __global__ void __launch_bounds__(128) groupnorm_bwd_epi_kernel(const float* __r
             const float xh = (x[idx] - mean) * rstd;
             const float y = (x[idx] - mean) * rstd * gm + bt;
             float gg = dy[idx] * dy_scale;
-            if (relu && !(y > 0.f)) gg = 0.f;
+            if (relu == ACT_RELU) { if (!(y > 0.f)) gg = 0.f; }
+            else if (relu != ACT_NONE) gg *= dact_f(relu, y);
             a += gg;
             b += gg * xh;
         }
@@ -124,7 +126,8 @@ __global__ void __launch_bounds__(128) groupnorm_bwd_epi_kernel(const float* __r
         const float xh = (x[idx] - mean) * rstd;
         const float y = (x[idx] - mean) * rstd * gm + beta[c];
         float gg = dy[idx] * dy_scale;
-        if (relu && !(y > 0.f)) gg = 0.f;
+        if (relu == ACT_RELU) { if (!(y > 0.f)) gg = 0.f; }
+        else if (relu != ACT_NONE) gg *= dact_f(relu, y);
         const float dx = rstd * (gg * gm - m1 - xh * m2);
         epilogue_apply(epi, dx, idx, n, h, w, c, H, W, C);
     }

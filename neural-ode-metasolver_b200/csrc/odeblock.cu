@@ -172,8 +172,9 @@ namespace {
 
 int validate(const MsbOdeDesc* d) {
     if (!d) { set_error("null descriptor"); return -1; }
-    if (d->rhs_kind != MSB_RHS_PREACT_NF && d->rhs_kind != MSB_RHS_POSTACT_NF && d->rhs_kind != MSB_RHS_MNIST_GN_T) {
-        set_error("rhs_kind %d is not implemented (supported: PREACT_NF, POSTACT_NF, MNIST_GN_T forward)", d->rhs_kind);
+    if (d->rhs_kind != MSB_RHS_PREACT_NF && d->rhs_kind != MSB_RHS_POSTACT_NF && d->rhs_kind != MSB_RHS_MNIST_GN_T &&
+        d->rhs_kind != MSB_RHS_PREACT_GN) {
+        set_error("rhs_kind %d is not implemented (supported: PREACT_NF, POSTACT_NF, MNIST_GN_T, PREACT_GN)", d->rhs_kind);
         return -1;
     }
     if (d->act != MSB_ACT_GELU_ERF && d->act != MSB_ACT_RELU && d->act != MSB_ACT_NONE) {
@@ -190,7 +191,10 @@ int validate(const MsbOdeDesc* d) {
     if (d->n_solvers > 1) {
         if (!d->solver_tableaus) { set_error("n_solvers = %d but solver_tableaus is NULL", d->n_solvers); return -1; }
         if (d->batch % d->n_solvers) { set_error("batch %d is not divisible into %d solver slices", d->batch, d->n_solvers); return -1; }
-        if (d->rhs_kind == MSB_RHS_MNIST_GN_T) { set_error("the stacked solver axis is not implemented for the MNIST right-hand side"); return -1; }
+        if (d->rhs_kind == MSB_RHS_MNIST_GN_T || d->rhs_kind == MSB_RHS_PREACT_GN) {
+            set_error("the stacked solver axis is not implemented for the GroupNorm right-hand sides");
+            return -1;
+        }
     }
     return 0;
 }
@@ -343,11 +347,12 @@ size_t msb_odeblock_workspace_bytes(const MsbOdeDesc* d) {
     n += 2 * align_up(E * 4);                                  // A / Hs split (inference)
     if (d->rhs_kind == MSB_RHS_MNIST_GN_T)                     // conv output, stage input, 2 tapmaps
         n += 2 * align_up(E * 4) + 2 * align_up((size_t)d->height * d->width * d->channels * 4);
+    if (d->rhs_kind == MSB_RHS_PREACT_GN) n += 2 * align_up(E * 4);     // conv1 output, stage input
     return n + 4096;
 }
 size_t msb_odeblock_tape_bytes(const MsbOdeDesc* d) {
     if (validate(d)) return 0;
-    const int per_slot = d->rhs_kind == MSB_RHS_MNIST_GN_T ? 5 : 4;      // MNIST: X, P1, P2, A, Hs
+    const int per_slot = d->rhs_kind == MSB_RHS_MNIST_GN_T ? 5 : 4;      // MNIST: X, P1, P2, A, Hs;  PREACT_GN: X, P1, A, Hs
     return (size_t)d->n_steps * d->stages * per_slot * align_up(state_elems(d) * 4);
 }
 size_t msb_odeblock_bwd_workspace_bytes(const MsbOdeDesc* d) {
@@ -372,6 +377,8 @@ size_t msb_odeblock_bwd_workspace_bytes(const MsbOdeDesc* d) {
     n += (size_t)(d->stages - 1) * align_up(E * 4);            // xbar_1 .. xbar_{s-1}
     n += 2 * align_up(E * 4);                                  // Kbar / DP split
     n += 2 * align_up((size_t)wgrad_nparts(engine, s) * 9 * d->channels * d->channels * 4);
+    if (d->rhs_kind == MSB_RHS_PREACT_GN)                      // dH (fp32) + per-sample dgamma / dbeta partials of 2 norms
+        n += align_up(E * 4) + 4 * align_up((size_t)d->batch * d->channels * 4);
     return n + 4096;
 }
 
@@ -483,12 +490,196 @@ static int mnist_forward(const MsbOdeDesc* d, const float* x, const MsbMnistPara
     return check_cuda(cudaGetLastError(), "odeblock forward (mnist)");
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// CIFAR pre-activation right-hand side WITH GroupNorm (the 'GN' / 'LN' / 'IN' normalisations of
+// sopa/src/models/odenet_cifar10/utils.py:26-36 inside PreBasicBlock2, layers.py:148-161):
+//     f(x) = conv2(act(GN2(conv1(act(GN1(x))))))
+// A normalisation needs whole-image statistics of a convolution OUTPUT, so it cannot ride in that convolution's tile
+// epilogue: each GroupNorm (+ activation + hi/lo split) is its own launch between the convolutions; the Runge-Kutta
+// stage combination stays fused in conv2's epilogue.  Tape per (step, stage): X (stage input), P1 (conv1 output),
+// A = split(act(GN1(X))), Hs = split(act(GN2(P1))).  Convolutions run on the engine of the shape (tcgen05 where tiled).
+// ---------------------------------------------------------------------------------------------
+struct GnSlot { float *X, *P1; __nv_bfloat16 *A, *Hs; };
+static GnSlot gn_slot(void* tape, size_t E, int slot) {
+    const size_t q = align_up(E * 4);
+    char* p = (char*)tape + (size_t)slot * 4 * q;
+    return GnSlot{(float*)p, (float*)(p + q), (__nv_bfloat16*)(p + 2 * q), (__nv_bfloat16*)(p + 3 * q)};
+}
+static int gn_check_params(const MsbMnistParams* mp) {
+    if (!mp) { set_error("MSB_RHS_PREACT_GN needs its parameters in MsbMnistParams"); return -1; }
+    for (int i = 0; i < 2; ++i)
+        if (!mp->norm_w[i] || !mp->norm_b[i] || !mp->conv_w[i]) { set_error("PREACT_GN params: null norm / conv pointer"); return -1; }
+    return 0;
+}
+
+static int gn_preact_forward(const MsbOdeDesc* d, const float* x, const MsbMnistParams* mp, float* y_out, void* workspace,
+                             size_t workspace_bytes, void* tape, size_t tape_bytes, cudaStream_t st) {
+    const bool save = d->save_tape != 0;
+    if (save && (!tape || tape_bytes < msb_odeblock_tape_bytes(d))) { set_error("tape missing or too small"); return -1; }
+    if (gn_check_params(mp)) return -1;
+    if (!x || !y_out || !workspace) { set_error("null pointer argument"); return -1; }
+    if (workspace_bytes < msb_odeblock_workspace_bytes(d)) { set_error("workspace too small"); return -1; }
+    const int engine = resolve_engine(d);
+    if (engine < 0) return -1;
+    const int S = d->stages, N = d->n_steps, C = d->channels;
+    const size_t E = state_elems(d);
+    ConvShape shp{d->batch, d->height, d->width, C};
+    Carver cv(workspace, workspace_bytes);
+    void* wp[2] = {cv.take<char>(packed_w_bytes(engine, C)), cv.take<char>(packed_w_bytes(engine, C))};
+    float* ybuf[2] = {cv.take<float>(E * 4), cv.take<float>(E * 4)};
+    float* kbuf[MSB_MAX_STAGES] = {nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < S - 1; ++i) kbuf[i] = cv.take<float>(E * 4);
+    __nv_bfloat16* A = cv.take<__nv_bfloat16>(E * 4);
+    __nv_bfloat16* Hs = cv.take<__nv_bfloat16>(E * 4);
+    float* P = cv.take<float>(E * 4);
+    float* xbuf = cv.take<float>(E * 4);
+    if (!cv.ok()) { set_error("internal: workspace carve overflow"); return -1; }
+    for (int k = 0; k < 2; ++k) pack_w(engine, mp->conv_w[k], wp[k], C, 0, st);
+    const float* y_cur = x;
+    if (save) {
+        GnSlot s0 = gn_slot(tape, E, 0);
+        if (check_cuda(cudaMemcpyAsync(s0.X, x, E * 4, cudaMemcpyDeviceToDevice, st), "copy x to tape")) return -1;
+        y_cur = s0.X;
+    }
+    for (int n = 0; n < N; ++n) {
+        const float dt = d->time_grid[n + 1] - d->time_grid[n];
+        float* y_next = (n == N - 1) ? y_out : (save ? gn_slot(tape, E, (n + 1) * S).X : ybuf[n & 1]);
+        for (int i = 0; i < S; ++i) {
+            GnSlot sl = save ? gn_slot(tape, E, n * S + i) : GnSlot{nullptr, P, A, Hs};
+            const float* xi = (i == 0) ? y_cur : (save ? sl.X : xbuf);
+            EpiParams g1 = epi_default();
+            g1.act = d->act; g1.out_split = sl.A;
+            if (launch_groupnorm_epi(xi, mp->norm_w[0], mp->norm_b[0], g1, shp, mp->groups, mp->eps, st)) return -1;
+            EpiParams c1 = epi_default();
+            c1.out_f32 = sl.P1;
+            if (run_conv(engine, sl.A, wp[0], c1, shp, st)) return -1;
+            EpiParams g2 = epi_default();
+            g2.act = d->act; g2.out_split = sl.Hs;
+            if (launch_groupnorm_epi(sl.P1, mp->norm_w[1], mp->norm_b[1], g2, shp, mp->groups, mp->eps, st)) return -1;
+            EpiParams e2 = epi_default();                       // k_i = conv2(.) and the RK combination
+            e2.base = y_cur; e2.k[0].dt = dt;
+            if (i < S - 1) {
+                e2.v_out = kbuf[i];
+                e2.nsrc = i;
+                for (int j = 0; j < i; ++j) { e2.src[j] = kbuf[j]; e2.k[0].coef[j] = d->w[(i + 1) * MSB_MAX_STAGES + j]; }
+                e2.k[0].coef_v = d->w[(i + 1) * MSB_MAX_STAGES + i];
+                e2.out_f32 = save ? gn_slot(tape, E, n * S + i + 1).X : xbuf;
+            } else {
+                e2.nsrc = S - 1;
+                for (int j = 0; j < S - 1; ++j) { e2.src[j] = kbuf[j]; e2.k[0].coef[j] = d->b[j]; }
+                e2.k[0].coef_v = d->b[S - 1];
+                e2.out_f32 = y_next;
+            }
+            if (run_conv(engine, sl.Hs, wp[1], e2, shp, st)) return -1;
+        }
+        y_cur = y_next;
+    }
+    return check_cuda(cudaGetLastError(), "odeblock forward (preact GN)");
+}
+
+//   kbar_i --conv2^T--> dH --act', GN2'--> dP1 --conv1^T--> dH --act', GN1'--> xbar_i  (+ the RK adjoint combination)
+static int gn_preact_backward(const MsbOdeDesc* d, const float* grad_y, const MsbMnistParams* mp, const void* tape,
+                              size_t tape_bytes, float* grad_x, const MsbMnistGrads* grads, void* workspace,
+                              size_t workspace_bytes, cudaStream_t st) {
+    if (gn_check_params(mp)) return -1;
+    if (!grad_y || !tape || !grad_x || !workspace) { set_error("null pointer argument"); return -1; }
+    if (tape_bytes < msb_odeblock_tape_bytes(d)) { set_error("tape too small"); return -1; }
+    if (workspace_bytes < msb_odeblock_bwd_workspace_bytes(d)) { set_error("workspace too small"); return -1; }
+    const bool need_w = grads != nullptr;
+    if (need_w)
+        for (int i = 0; i < 2; ++i)
+            if (!grads->norm_w[i] || !grads->norm_b[i] || !grads->conv_w[i]) { set_error("PREACT_GN grads: null pointer"); return -1; }
+    const int engine = resolve_engine(d);
+    if (engine < 0) return -1;
+    const int S = d->stages, N = d->n_steps, C = d->channels;
+    const size_t E = state_elems(d);
+    ConvShape shp{d->batch, d->height, d->width, C};
+    Carver cv(workspace, workspace_bytes);
+    void* wt[2] = {cv.take<char>(packed_w_bytes(engine, C)), cv.take<char>(packed_w_bytes(engine, C))};
+    float* gbuf[2] = {cv.take<float>(E * 4), cv.take<float>(E * 4)};
+    float* xbar[MSB_MAX_STAGES] = {nullptr, nullptr, nullptr, nullptr};
+    for (int i = 1; i < S; ++i) xbar[i] = cv.take<float>(E * 4);
+    __nv_bfloat16* Kbar = cv.take<__nv_bfloat16>(E * 4);
+    __nv_bfloat16* DP = cv.take<__nv_bfloat16>(E * 4);
+    const size_t part_bytes = (size_t)wgrad_nparts(engine, shp) * 9 * C * C * 4;
+    WgradAcc acc1{cv.take<float>(part_bytes), need_w ? grads->conv_w[0] : nullptr, 0, 0};
+    WgradAcc acc2{cv.take<float>(part_bytes), need_w ? grads->conv_w[1] : nullptr, 0, 0};
+    float* dH = cv.take<float>(E * 4);
+    float* gnpart[4];
+    for (int i = 0; i < 4; ++i) gnpart[i] = cv.take<float>((size_t)d->batch * C * 4);     // (dgamma_k, dbeta_k), k = 1, 2
+    if (!cv.ok()) { set_error("internal: workspace carve overflow"); return -1; }
+    for (int k = 0; k < 2; ++k) pack_w(engine, mp->conv_w[k], wt[k], C, 1, st);
+
+    auto dt_of = [&](int n) { return d->time_grid[n + 1] - d->time_grid[n]; };
+    launch_act_split(grad_y, nullptr, ACT_NONE, dt_of(N - 1) * d->b[S - 1], Kbar, nullptr, d->batch, d->height, d->width, C, st);
+    int evals = 0;
+    const float* g_cur = grad_y;
+    for (int n = N - 1; n >= 0; --n) {
+        const float dt = dt_of(n);
+        float* g_next = (n == 0) ? grad_x : gbuf[n & 1];
+        for (int i = S - 1; i >= 0; --i) {
+            const GnSlot sl = gn_slot(const_cast<void*>(tape), E, n * S + i);
+            const int acc = evals > 0;
+            // Kbar = split(kbar_i).   dW2 += kbar_i (x) Hs_i ;  dH = dgrad_W2(kbar_i)
+            if (need_w && run_wgrad(engine, Kbar, sl.Hs, acc2, shp, st)) return -1;
+            EpiParams e = epi_default();
+            e.out_f32 = dH;
+            if (run_conv(engine, Kbar, wt[1], e, shp, st)) return -1;
+            // dP1 = GN2'(act'(.) dH)
+            e = epi_default();
+            e.out_split = DP;
+            if (launch_groupnorm_bwd_epi(sl.P1, mp->norm_w[1], mp->norm_b[1], dH, 1.f, d->act, e, need_w ? gnpart[2] : nullptr,
+                                         need_w ? gnpart[3] : nullptr, acc, shp, mp->groups, mp->eps, st)) return -1;
+            // dW1 += dP1 (x) A_i ;  dH = dgrad_W1(dP1)
+            if (need_w && run_wgrad(engine, DP, sl.A, acc1, shp, st)) return -1;
+            e = epi_default();
+            e.out_f32 = dH;
+            if (run_conv(engine, DP, wt[0], e, shp, st)) return -1;
+            // xbar_i = GN1'(act'(.) dH), then the adjoint stage combination (as in the normalisation-free path)
+            EpiParams e4 = epi_default();
+            e4.base = g_cur;
+            if (i > 0) {
+                e4.v_out = xbar[i];
+                e4.base_is_one = 0;
+                e4.k[0].base_coef = dt * d->b[i - 1];
+                int ns = 0;
+                for (int j = S - 1; j > i; --j) { e4.src[ns] = xbar[j]; e4.k[0].coef[ns] = d->w[j * MSB_MAX_STAGES + (i - 1)]; ++ns; }
+                e4.nsrc = ns;
+                e4.k[0].coef_v = d->w[i * MSB_MAX_STAGES + (i - 1)];
+                e4.k[0].dt = dt;
+                e4.out_split = Kbar;                                  // = split(kbar_{i-1})
+            } else {
+                int ns = 0;
+                for (int j = S - 1; j > 0; --j) { e4.src[ns] = xbar[j]; e4.k[0].coef[ns] = 1.f; ++ns; }
+                e4.nsrc = ns;
+                e4.out_f32 = g_next;
+                if (n > 0) { e4.out_split = Kbar; e4.k[0].split_scale = dt_of(n - 1) * d->b[S - 1]; }
+            }
+            if (launch_groupnorm_bwd_epi(sl.X, mp->norm_w[0], mp->norm_b[0], dH, 1.f, d->act, e4, need_w ? gnpart[0] : nullptr,
+                                         need_w ? gnpart[1] : nullptr, acc, shp, mp->groups, mp->eps, st)) return -1;
+            ++evals;
+        }
+        g_cur = g_next;
+    }
+    if (need_w) {
+        if (wgrad_finish(engine, acc1, shp, st) || wgrad_finish(engine, acc2, shp, st)) return -1;
+        for (int k = 0; k < 2; ++k) {
+            launch_sum_over_batch(gnpart[2 * k], grads->norm_w[k], d->batch, C, st);
+            launch_sum_over_batch(gnpart[2 * k + 1], grads->norm_b[k], d->batch, C, st);
+        }
+    }
+    return check_cuda(cudaGetLastError(), "odeblock backward (preact GN)");
+}
+
 int msb_odeblock_forward(const MsbOdeDesc* d, const float* x, const float* w1, const float* w2,
                          const MsbMnistParams* mnist, float* y_out, void* workspace, size_t workspace_bytes,
                          void* tape, size_t tape_bytes, void* cuda_stream) {
     if (validate(d)) return -1;
     if (d->rhs_kind == MSB_RHS_MNIST_GN_T)
         return mnist_forward(d, x, mnist, y_out, workspace, workspace_bytes, tape, tape_bytes, (cudaStream_t)cuda_stream);
+    if (d->rhs_kind == MSB_RHS_PREACT_GN)
+        return gn_preact_forward(d, x, mnist, y_out, workspace, workspace_bytes, tape, tape_bytes, (cudaStream_t)cuda_stream);
     int engine = resolve_engine(d);
     if (engine < 0) return -1;
     if (!x || !w1 || !w2 || !y_out || !workspace) { set_error("null pointer argument"); return -1; }
@@ -587,7 +778,10 @@ static int odeblock_backward_impl(const MsbOdeDesc* d, const float* grad_y, cons
                                   const void* tape, size_t tape_bytes, float* grad_x, float* grad_w1, float* grad_w2,
                                   double* grad_tab, void* workspace, size_t workspace_bytes, void* cuda_stream) {
     if (validate(d)) return -1;
-    if (d->rhs_kind == MSB_RHS_MNIST_GN_T) { set_error("use msb_odeblock_backward_mnist for the MNIST right-hand side"); return -1; }
+    if (d->rhs_kind == MSB_RHS_MNIST_GN_T || d->rhs_kind == MSB_RHS_PREACT_GN) {
+        set_error("use msb_odeblock_backward_mnist for the GroupNorm right-hand sides");
+        return -1;
+    }
     int engine = resolve_engine(d);
     if (engine < 0) return -1;
     if (!grad_y || !w1 || !w2 || !tape || !grad_x || !workspace) { set_error("null pointer argument"); return -1; }
@@ -743,7 +937,12 @@ static int odeblock_backward_mnist_impl(const MsbOdeDesc* d, const float* grad_y
                                         size_t tape_bytes, float* grad_x, const MsbMnistGrads* grads, double* grad_tab,
                                         void* workspace, size_t workspace_bytes, void* cuda_stream) {
     if (validate(d)) return -1;
-    if (d->rhs_kind != MSB_RHS_MNIST_GN_T) { set_error("msb_odeblock_backward_mnist: rhs_kind must be MSB_RHS_MNIST_GN_T"); return -1; }
+    if (d->rhs_kind == MSB_RHS_PREACT_GN) {
+        if (grad_tab) { set_error("tableau gradients are not implemented for MSB_RHS_PREACT_GN"); return -1; }
+        return gn_preact_backward(d, grad_y, mp, tape, tape_bytes, grad_x, grads, workspace, workspace_bytes,
+                                  (cudaStream_t)cuda_stream);
+    }
+    if (d->rhs_kind != MSB_RHS_MNIST_GN_T) { set_error("msb_odeblock_backward_mnist: rhs_kind must be a GroupNorm right-hand side"); return -1; }
     if (grad_tab && d->n_solvers > 1) { set_error("tableau gradients are not implemented for a stacked solver axis"); return -1; }
     if (!grad_y || !mp || !tape || !grad_x || !workspace) { set_error("null pointer argument"); return -1; }
     for (int i = 0; i < 3; ++i) if (!mp->norm_w[i] || !mp->norm_b[i]) { set_error("MNIST params: null norm pointer"); return -1; }
@@ -829,7 +1028,7 @@ static int odeblock_backward_mnist_impl(const MsbOdeDesc* d, const float* grad_y
             if (run_conv(MSB_ENGINE_SIMT, Dsplit, wt[1], e, shp, st)) return -1;
             e = epi_default();
             e.out_f32 = dP; e.out_split = Dsplit;
-            if (launch_groupnorm_bwd_epi(sl.P1, mp->norm_w[1], mp->norm_b[1], dH, 1.f, 1, e, need_w ? gnpart[2] : nullptr,
+            if (launch_groupnorm_bwd_epi(sl.P1, mp->norm_w[1], mp->norm_b[1], dH, 1.f, ACT_RELU, e, need_w ? gnpart[2] : nullptr,
                                          need_w ? gnpart[3] : nullptr, acc, shp, mp->groups, mp->eps, st)) return -1;
             if (gc && i > 0)      // ... and conv1 through its own
                 launch_dot_bcast_accumulate(dP, tmap[0], E, map_elems, (double)dt, gc + i, dot_scratch, st);
@@ -861,7 +1060,7 @@ static int odeblock_backward_mnist_impl(const MsbOdeDesc* d, const float* grad_y
                 e4.nsrc = ns;
                 e4.out_f32 = g_next;
             }
-            if (launch_groupnorm_bwd_epi(sl.X, mp->norm_w[0], mp->norm_b[0], dH, 1.f, 1, e4, need_w ? gnpart[0] : nullptr,
+            if (launch_groupnorm_bwd_epi(sl.X, mp->norm_w[0], mp->norm_b[0], dH, 1.f, ACT_RELU, e4, need_w ? gnpart[0] : nullptr,
                                          need_w ? gnpart[1] : nullptr, acc, shp, mp->groups, mp->eps, st)) return -1;
             if (grad_tab && i > 0)                     // dL/dw_ij += dt <xbar_i, k_j>, j < i
                 for (int j = 0; j < i; ++j)

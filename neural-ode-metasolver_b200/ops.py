@@ -257,34 +257,40 @@ def ode_block_integrate_stacked(x, w1, w2, tableaus, time_grid, rhs_kind=_cabi.R
 
 
 _MNIST_KEYS = ("norm1_w", "norm1_b", "norm2_w", "norm2_b", "norm3_w", "norm3_b", "conv1_w", "conv1_b", "conv2_w", "conv2_b")
+_GN_KEYS = ("norm1_w", "norm1_b", "norm2_w", "norm2_b", "conv1_w", "conv2_w")      # MSB_RHS_PREACT_GN: no biases, two norms
 
 
-def _mnist_params_struct(keep, groups, eps):
-    mp = _cabi.MsbMnistParams()
+def _gn_params_struct(keep, groups, eps, cls=None):
+    """MsbMnistParams / MsbMnistGrads filled from the tensors present in `keep` (absent ones stay NULL)."""
+    mp = (cls or _cabi.MsbMnistParams)()
     for i in range(3):
-        mp.norm_w[i] = keep["norm%d_w" % (i + 1)].data_ptr()
-        mp.norm_b[i] = keep["norm%d_b" % (i + 1)].data_ptr()
+        for kind, arr in (("w", mp.norm_w), ("b", mp.norm_b)):
+            t = keep.get("norm%d_%s" % (i + 1, kind))
+            arr[i] = t.data_ptr() if t is not None else None
     for i in range(2):
-        mp.conv_w[i] = keep["conv%d_w" % (i + 1)].data_ptr()
-        mp.conv_b[i] = keep["conv%d_b" % (i + 1)].data_ptr()
-    mp.groups, mp.eps = groups, eps
+        for kind, arr in (("w", mp.conv_w), ("b", mp.conv_b)):
+            t = keep.get("conv%d_%s" % (i + 1, kind))
+            arr[i] = t.data_ptr() if t is not None else None
+    if cls is None:
+        mp.groups, mp.eps = groups, eps
     return mp
 
 
-class _MnistOdeBlockFn(torch.autograd.Function):
-    """ODE block with the MNIST right-hand side; backward = fused discretize-then-optimize pass
-    (msb_odeblock_backward_mnist): gradients w.r.t. x and all ten RHS parameters."""
+class _GnOdeBlockFn(torch.autograd.Function):
+    """ODE block with a GroupNorm right-hand side (MNIST: MSB_RHS_MNIST_GN_T; CIFAR 'GN'/'LN'/'IN': MSB_RHS_PREACT_GN);
+    backward = fused discretize-then-optimize pass: gradients w.r.t. x and every RHS parameter (and, for the MNIST
+    family, the Butcher coefficients through `coef`, see _OdeBlockFn)."""
 
     @staticmethod
-    def forward(ctx, x, prob, groups, eps, coef, *params):
+    def forward(ctx, x, prob, groups, eps, keys, coef, *params):
         lib = _cabi.lib()
         dev = x.device
-        need_grad = ctx.needs_input_grad[0] or any(ctx.needs_input_grad[4:])      # x, coef or any parameter
+        need_grad = ctx.needs_input_grad[0] or any(ctx.needs_input_grad[5:])      # x, coef or any parameter
         ctx.coef_shape = None if coef is None else tuple(coef.shape)
         with torch.cuda.device(dev):
             xc = x.detach().contiguous(memory_format=torch.channels_last)
-            keep = {k: v.detach().contiguous() for k, v in zip(_MNIST_KEYS, params)}
-            mp = _mnist_params_struct(keep, groups, eps)
+            keep = {k: v.detach().contiguous() for k, v in zip(keys, params)}
+            mp = _gn_params_struct(keep, groups, eps)
             d = prob.desc(tuple(x.shape), need_grad)
             ws_bytes = lib.msb_odeblock_workspace_bytes(ctypes.byref(d))
             if ws_bytes == 0:
@@ -297,9 +303,10 @@ class _MnistOdeBlockFn(torch.autograd.Function):
             y = torch.empty_like(xc)
             rc = lib.msb_odeblock_forward(ctypes.byref(d), _ptr(xc), None, None, ctypes.byref(mp), _ptr(y), _ptr(ws),
                                           ws_bytes, _ptr(tape), tape_bytes, _stream(dev))
-            _cabi.check(rc, "odeblock forward (mnist)")
+            _cabi.check(rc, "odeblock forward (GroupNorm right-hand side)")
         ctx.prob, ctx.groups, ctx.eps, ctx.tape, ctx.tape_bytes, ctx.shape = prob, groups, eps, tape, tape_bytes, tuple(x.shape)
-        ctx.save_for_backward(*[keep[k] for k in _MNIST_KEYS])
+        ctx.keys = tuple(keys)
+        ctx.save_for_backward(*[keep[k] for k in keys])
         return y
 
     @staticmethod
@@ -307,45 +314,40 @@ class _MnistOdeBlockFn(torch.autograd.Function):
         lib = _cabi.lib()
         if ctx.tape is None:
             raise RuntimeError("metasolver_b200: backward called but no tape was recorded")
-        keep = dict(zip(_MNIST_KEYS, ctx.saved_tensors))
+        keys = ctx.keys
+        keep = dict(zip(keys, ctx.saved_tensors))
         dev = gy.device
-        need_w = any(ctx.needs_input_grad[5:]) and not (_input_only_depth[0] > 0)
-        need_coef = ctx.coef_shape is not None and ctx.needs_input_grad[4]
+        need_w = any(ctx.needs_input_grad[6:]) and not (_input_only_depth[0] > 0)
+        need_coef = ctx.coef_shape is not None and ctx.needs_input_grad[5]
         gcoef = None
         with torch.cuda.device(dev):
             gyc = gy.contiguous(memory_format=torch.channels_last)
-            mp = _mnist_params_struct(keep, ctx.groups, ctx.eps)
+            mp = _gn_params_struct(keep, ctx.groups, ctx.eps)
             d = ctx.prob.desc(ctx.shape, True)
             ws_bytes = (lib.msb_odeblock_bwd_workspace_bytes_tableau if need_coef else lib.msb_odeblock_bwd_workspace_bytes)(
                 ctypes.byref(d))
             if ws_bytes == 0:
-                _cabi.check(-1, "odeblock backward workspace query (mnist)")
+                _cabi.check(-1, "odeblock backward workspace query (GroupNorm right-hand side)")
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             gx = torch.empty_like(gyc)
             grads, gstruct = None, None
             if need_w:
                 grads = {k: torch.zeros_like(v) for k, v in keep.items()}
-                gstruct = _cabi.MsbMnistGrads()
-                for i in range(3):
-                    gstruct.norm_w[i] = grads["norm%d_w" % (i + 1)].data_ptr()
-                    gstruct.norm_b[i] = grads["norm%d_b" % (i + 1)].data_ptr()
-                for i in range(2):
-                    gstruct.conv_w[i] = grads["conv%d_w" % (i + 1)].data_ptr()
-                    gstruct.conv_b[i] = grads["conv%d_b" % (i + 1)].data_ptr()
+                gstruct = _gn_params_struct(grads, None, None, cls=_cabi.MsbMnistGrads)
             if need_coef:
                 gtab = torch.zeros(_cabi.TABLEAU_GRAD_DOUBLES, dtype=torch.float64, device=dev)
                 rc = lib.msb_odeblock_backward_mnist_tableau(ctypes.byref(d), _ptr(gyc), ctypes.byref(mp), _ptr(ctx.tape),
                                                              ctx.tape_bytes, _ptr(gx), ctypes.byref(gstruct) if need_w else None,
                                                              _ptr(gtab), _ptr(ws), ws_bytes, _stream(dev))
-                _cabi.check(rc, "odeblock backward (mnist, tableau gradients)")
+                _cabi.check(rc, "odeblock backward (GroupNorm right-hand side, tableau gradients)")
                 gcoef = gtab.cpu().reshape(ctx.coef_shape)
             else:
                 rc = lib.msb_odeblock_backward_mnist(ctypes.byref(d), _ptr(gyc), ctypes.byref(mp), _ptr(ctx.tape), ctx.tape_bytes,
                                                      _ptr(gx), ctypes.byref(gstruct) if need_w else None, _ptr(ws), ws_bytes,
                                                      _stream(dev))
-                _cabi.check(rc, "odeblock backward (mnist)")
+                _cabi.check(rc, "odeblock backward (GroupNorm right-hand side)")
         ctx.tape = None
-        return (gx, None, None, None, gcoef) + (tuple(grads[k] for k in _MNIST_KEYS) if need_w else (None,) * len(_MNIST_KEYS))
+        return (gx, None, None, None, None, gcoef) + (tuple(grads[k] for k in keys) if need_w else (None,) * len(keys))
 
 
 def ode_block_integrate_mnist(x, params, tableau, time_grid, groups, eps=1e-5, tableau_coef=None):
@@ -357,7 +359,23 @@ def ode_block_integrate_mnist(x, params, tableau, time_grid, groups, eps=1e-5, t
     prob = OdeProblem(_cabi.RHS_MNIST_GN_T, _cabi.ACT_RELU, tableau, time_grid, "simt")
     if tableau_coef is not None:
         _check_coef(prob, tableau_coef)
-    return _MnistOdeBlockFn.apply(x, prob, groups, eps, tableau_coef, *[params[k] for k in _MNIST_KEYS])
+    return _GnOdeBlockFn.apply(x, prob, groups, eps, _MNIST_KEYS, tableau_coef, *[params[k] for k in _MNIST_KEYS])
+
+
+def ode_block_integrate_gn(x, params, tableau, time_grid, groups, eps=1e-5, act=_cabi.ACT_GELU_ERF, engine=None):
+    """CIFAR pre-activation right-hand side with GroupNorm, conv2(act(GN2(conv1(act(GN1(x)))))) (cifar10/layers.py:148-161
+    with the 'GN' / 'LN' / 'IN' normalisations of cifar10/utils.py:26-36).  `params`: dict(norm{1,2}_{w,b}, conv{1,2}_w)."""
+    if not x.is_cuda:
+        raise RuntimeError("metasolver_b200: the ODE-block path runs on CUDA only (got a %s tensor); "
+                           "there is no CPU fallback" % x.device)
+    C = x.shape[1]
+    for k in ("conv1_w", "conv2_w"):
+        if tuple(params[k].shape) != (C, C, 3, 3):
+            raise RuntimeError("metasolver_b200: conv weight must be (%d, %d, 3, 3), got %s" % (C, C, tuple(params[k].shape)))
+    if C % groups:
+        raise RuntimeError("metasolver_b200: %d channels are not divisible into %d groups" % (C, groups))
+    prob = OdeProblem(_cabi.RHS_PREACT_GN, act, tableau, time_grid, engine)
+    return _GnOdeBlockFn.apply(x, prob, groups, eps, _GN_KEYS, None, *[params[k] for k in _GN_KEYS])
 
 
 # --------------------------------------------------------------------------- non-ODE layers (SURVEY 8(f-1))

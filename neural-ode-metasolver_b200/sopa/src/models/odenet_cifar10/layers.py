@@ -136,16 +136,37 @@ class _FusedRhs(nn.Module):
         self.act = act_layer
         self.shortcut = nn.Sequential()
 
+    def _group_norm_params(self, bn, tag):
+        """(weight, bias, groups, eps) of a per-sample normalisation: nn.GroupNorm ('GN', 'LN' = one group) or a plain
+        nn.InstanceNorm2d ('IN' = one group per channel, no affine parameters); None for anything else."""
+        if isinstance(bn, nn.GroupNorm) and bn.affine:
+            return bn.weight, bn.bias, bn.num_groups, bn.eps
+        if isinstance(bn, nn.InstanceNorm2d) and not bn.affine and not bn.track_running_stats:
+            ones = getattr(self, "_in_ones_" + tag, None)
+            if ones is None or ones.device != self.conv1.weight.device:
+                ones = torch.ones(bn.num_features, device=self.conv1.weight.device)
+                setattr(self, "_in_ones_" + tag, ones)
+            return ones, torch.zeros_like(ones), bn.num_features, bn.eps
+        return None
+
     def fused_rhs_spec(self):
-        for bn in (self.bn1, self.bn2):
-            if not isinstance(bn, Identity):
-                raise NotImplementedError("metasolver_b200: ODE-block normalisation %s is not implemented on the "
-                                          "fused path (published config is 'NF')" % type(bn).__name__)
         for conv in (self.conv1, self.conv2):
             if type(conv) is not nn.Conv2d or hasattr(conv, "weight_orig") or hasattr(conv, "weight_g"):
                 raise NotImplementedError("metasolver_b200: weight-normalised ODE-block convolutions are not "
                                           "implemented on the fused path (published config is 'PNF')")
-        return dict(rhs_kind=self.rhs_kind, act=_act_code(self.act), w1=self.conv1.weight, w2=self.conv2.weight)
+        if isinstance(self.bn1, Identity) and isinstance(self.bn2, Identity):
+            return dict(rhs_kind=self.rhs_kind, act=_act_code(self.act), w1=self.conv1.weight, w2=self.conv2.weight)
+        n1, n2 = self._group_norm_params(self.bn1, "1"), self._group_norm_params(self.bn2, "2")
+        if n1 is None or n2 is None or n1[2:] != n2[2:]:
+            raise NotImplementedError("metasolver_b200: ODE-block normalisation %s / %s is not implemented on the fused "
+                                      "path (implemented: 'NF', and the per-sample 'GN' / 'LN' / 'IN'; batch statistics "
+                                      "would couple the samples of a batch)" % (type(self.bn1).__name__, type(self.bn2).__name__))
+        if self.rhs_kind != _cabi.RHS_PREACT_NF:
+            raise NotImplementedError("metasolver_b200: GroupNorm inside the post-activation right-hand side (BasicBlock2) "
+                                      "is not implemented; the pre-activation one (PreBasicBlock2) is")
+        return dict(rhs_kind=_cabi.RHS_PREACT_GN, act=_act_code(self.act), groups=n1[2], eps=n1[3],
+                    params=dict(norm1_w=n1[0], norm1_b=n1[1], norm2_w=n2[0], norm2_b=n2[1],
+                                conv1_w=self.conv1.weight, conv2_w=self.conv2.weight))
 
     def forward(self, t, x, ss_loss=False):
         raise RuntimeError("metasolver_b200: ODE right-hand sides are evaluated inside the fused CUDA kernels; "

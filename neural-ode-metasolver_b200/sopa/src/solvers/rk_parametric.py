@@ -14,7 +14,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from ....ops import ode_block_integrate, ode_block_integrate_mnist, ode_block_integrate_stacked
+from ....ops import ode_block_integrate, ode_block_integrate_gn, ode_block_integrate_mnist, ode_block_integrate_stacked
 from .... import _cabi
 
 
@@ -205,6 +205,12 @@ class RKParametricSolver(object, metaclass=abc.ABCMeta):
         if spec["rhs_kind"] == _cabi.RHS_MNIST_GN_T:
             y = ode_block_integrate_mnist(x, spec["params"], self._host_tableau, grid.tolist(), spec["groups"],
                                           spec["eps"], tableau_coef=coef)
+        elif spec["rhs_kind"] == _cabi.RHS_PREACT_GN:
+            if coef is not None:
+                raise NotImplementedError("metasolver_b200: gradients w.r.t. the solver parameters are not implemented for "
+                                          "the GroupNorm CIFAR right-hand side; call freeze_params()")
+            y = ode_block_integrate_gn(x, spec["params"], self._host_tableau, grid.tolist(), spec["groups"], spec["eps"],
+                                       act=spec["act"], engine=spec.get("engine"))
         else:
             y = ode_block_integrate(x, spec["w1"], spec["w2"], self._host_tableau, grid.tolist(),
                                     rhs_kind=spec["rhs_kind"], act=spec["act"], engine=spec.get("engine"),
@@ -233,7 +239,7 @@ def can_stack(solvers, rhs_func, t):
     if not (2 <= len(solvers) <= _cabi.MSB_MAX_SOLVERS):
         return False
     spec = getattr(rhs_func, "fused_rhs_spec", None)
-    if spec is None or spec()["rhs_kind"] == _cabi.RHS_MNIST_GN_T:
+    if spec is None or spec()["rhs_kind"] in (_cabi.RHS_MNIST_GN_T, _cabi.RHS_PREACT_GN):
         return False
     if any(s.n_stages != solvers[0].n_stages for s in solvers):
         return False

@@ -121,6 +121,28 @@ def rhs_preact(w1, w2, act="gelu", counter=None):
     return f
 
 
+def rhs_preact_gn(p, groups, eps=1e-5, act="gelu", counter=None, instance_norm=False):
+    """PreBasicBlock2 with a per-sample normalisation ('GN' / 'LN' / 'IN' of cifar10/utils.py:26-36, all group norms):
+    conv2(act(GN2(conv1(act(GN1(x)))))); cifar10/layers.py:148-161.  p: dict(norm{1,2}_{w,b}, conv{1,2}_w).
+    instance_norm: 'IN' is nn.InstanceNorm2d (no affine parameters) -- mathematically one group per channel, but torch
+    evaluates it with a different kernel, so the bit-exact restatement calls F.instance_norm."""
+    a = _act(act)
+    if instance_norm:
+        norm = lambda z, k: F.instance_norm(z, eps=eps)
+    else:
+        norm = lambda z, k: F.group_norm(z, groups, p["norm%d_w" % k], p["norm%d_b" % k], eps)
+
+    def f(t, x):
+        if counter is not None:
+            counter.nfe += 1
+        out = a(norm(x, 1))
+        out = F.conv2d(out, p["conv1_w"], None, 1, 1)
+        out = a(norm(out, 2))
+        out = F.conv2d(out, p["conv2_w"], None, 1, 1)
+        return out
+    return f
+
+
 def rhs_postact(w1, w2, act="gelu", counter=None):
     """BasicBlock2 with NF norm: act(conv2(act(conv1(x)))); cifar10/layers.py:108-121."""
     a = _act(act)

@@ -89,3 +89,18 @@ MNIST_SOLVER_GRAD_CASES = [
     ("msg_rk4uv_n1", ("rk4", "uv", 1, -1, 0.3, 0.7)),
     ("msg_rk4u3_n2", ("rk4", "u3", 2, -1, 0.1, -1)),
 ]
+
+# CIFAR pre-activation right-hand side with a per-sample normalisation inside the ODE block:
+# name, C, H, W, B, normalisation key (cifar10/utils.py:26-36), num_groups, solver tuple
+GN_CASES = [
+    ("gn_c64_rk2_n3", 64, 8, 32, 2, "GN", 32, ("rk2", "u", 3, -1, 0.5, -1)),
+    ("gn_c128_rk2_n2", 128, 16, 16, 2, "GN", 32, ("rk2", "u", 2, -1, 0.3, -1)),
+    ("ln_c64_rk4_n1", 64, 8, 32, 2, "LN", 32, ("rk4", "u2", 1, -1, 1 / 3., -1)),
+    ("in_c64_euler_n2", 64, 8, 32, 2, "IN", 32, ("euler", None, 2, -1, -1, -1)),
+    ("gn_c16_odd_rk2_n2", 16, 5, 7, 3, "GN", 4, ("rk2", "u", 2, -1, 0.5, -1)),
+]
+
+
+def gn_affine(C, k):
+    """deterministic, non-trivial GroupNorm weight / bias of norm layer k"""
+    return det_uniform((C,), 61 + k, 0.5, 1.5), det_uniform((C,), 71 + k, -0.3, 0.3)
