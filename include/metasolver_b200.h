@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define MSB_ABI_VERSION 2
+#define MSB_ABI_VERSION 3   /* v3: + tuning options, attack / SGD steps, tableau gradients, MSB_RHS_PREACT_GN (structs unchanged) */
 #define MSB_MAX_STAGES 4
 
 /* right-hand-side families */

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(HERE, "libmetasolver_b200.so")
 
 MSB_MAX_STAGES = 4
 TABLEAU_GRAD_DOUBLES = MSB_MAX_STAGES + MSB_MAX_STAGES * MSB_MAX_STAGES + MSB_MAX_STAGES   # [b | w | c]
-ABI_VERSION = 2
+ABI_VERSION = 3
 RHS_PREACT_NF, RHS_POSTACT_NF, RHS_MNIST_GN_T, RHS_PREACT_GN = 0, 1, 2, 3
 ACT_NONE, ACT_GELU_ERF, ACT_RELU = 0, 1, 2
 (ATTACK_UNNORMALIZE, ATTACK_NORMALIZE, ATTACK_FGSM_STEP, ATTACK_PGD_STEP, ATTACK_FGSMR_INIT,
