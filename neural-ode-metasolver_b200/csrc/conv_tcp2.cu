@@ -40,9 +40,17 @@ constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 230400;
 constexpr int kStageBytesPerWarp = 4096;
 
-// EW = epilogue warps (16, or 8 for C = 64: one group of 8 warps on every tile frees 32 KB of staging for a third
-// activation stage -- with N = 128 / 64 MMAs a two-stage halo ring cannot hide the refill latency across the pair).
+// EW = epilogue warps: 16 = weight ring (any C); 8 = RESIDENT WEIGHTS (C = 64 only).  With N = 128 / 64 MMAs a weight
+// stage is ~0.3 us of MMA work, shorter than the cross-CTA round trip its ring needs (commit -> multicast -> peer
+// producer -> TMA -> remote complete_tx; profiles/conv_pair64_ab_r1.txt).  A CTA of a pair holds only HALF of every
+// weight tile, so for C = 64 all nine taps (9 x 12 KB) fit next to the two activation stages: they are loaded once per
+// kernel and the weight ring, its barriers and ~600 MB of L2 -> SM weight traffic per launch disappear.  The price is
+// the shared memory of the epilogue stage: 8 warps with 2 KB each, transposing 16 pixels at a time.  Measured: 185 us per
+// launch vs 197 us for the ring pair and 171 us for the single-CTA kernel (profiles/conv_pair64_resident_ab_r1.txt), so
+// it is an option (tcp_epi_warps = 8 with tc_pair = 1), not the default.
 template <int C, int WIMG, int EW> struct Geom2 {
+    static constexpr bool RES = (EW == 8);
+    static_assert(!RES || C == 64, "resident weights: C = 64 only");
     static constexpr int ROWS = 128 / WIMG;
     static constexpr int PLANE_BYTES = (ROWS + 2) * WIMG * 128;
     static constexpr int X_STAGE_BYTES = 2 * PLANE_BYTES;
@@ -50,11 +58,12 @@ template <int C, int WIMG, int EW> struct Geom2 {
     static constexpr int WA_BYTES = C * 128;                          // this CTA's half of [W_hi ; W_lo]
     static constexpr int WB_BYTES = (C / 2) * 128;                    // this CTA's half of W_hi
     static constexpr int W_STAGE_BYTES = WA_BYTES + WB_BYTES;
-    static constexpr int X_STAGES = (EW == 8) ? 3 : 2;
-    static constexpr int STAGE_BYTES = EW * kStageBytesPerWarp;
+    static constexpr int X_STAGES = 2;
+    static constexpr int STAGE_BYTES = RES ? EW * (kStageBytesPerWarp / 2) : EW * kStageBytesPerWarp;
     static constexpr int THREADS = (kEpiWarp0 + EW) * 32;
     static constexpr int RING = kSmemBudget - STAGE_BYTES - X_STAGES * X_STAGE_BYTES;
-    static constexpr int W_STAGES = RING / W_STAGE_BYTES > kMaxStages ? kMaxStages : RING / W_STAGE_BYTES;
+    static constexpr int W_STAGES = RES ? 9 * (C / 64) : (RING / W_STAGE_BYTES > kMaxStages ? kMaxStages : RING / W_STAGE_BYTES);
+    static_assert(!RES || 9 * W_STAGE_BYTES <= RING, "resident weights do not fit");
     static constexpr int ACC_COLS = 2 * C;
     static constexpr int ACC_BUFS = (C == 64) ? 4 : 2;
     static_assert(ACC_COLS * ACC_BUFS <= 512, "TMEM");
@@ -94,7 +103,7 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmap_act);
         ptx::prefetch_tmap(&tmap_w);
-        for (int i = 0; i < kWStages; ++i) { ptx::mbar_init(&bars->w_full[i], 1); ptx::mbar_init(&bars->w_empty[i], 1); }
+        for (int i = 0; i < (G::RES ? 1 : kWStages); ++i) { ptx::mbar_init(&bars->w_full[i], 1); ptx::mbar_init(&bars->w_empty[i], 1); }
         for (int i = 0; i < kXStages; ++i) { ptx::mbar_init(&bars->x_full[i], 1); ptx::mbar_init(&bars->x_empty[i], 1); }
         for (int i = 0; i < kAccBufs; ++i) { ptx::mbar_init(&bars->tmem_full[i], 1); ptx::mbar_init(&bars->tmem_empty[i], 2 * WPT); }
         ptx::fence_barrier_init();
@@ -131,7 +140,18 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
         }
     } else if (warp == 3) {
         // ===================== weight producer (both CTAs; own halves) =====================
-        if (lane == 0) {
+        if (lane == 0 && G::RES) {
+            // resident: every tap once, this CTA's halves, all bytes of both CTAs counted on the leader's w_full[0]
+            const uint32_t full = ptx::mapa(ptx::smem_u32(&bars->w_full[0]), 0);
+            if (leader) ptx::mbar_arrive_expect_tx(&bars->w_full[0], 2 * 9 * G::W_STAGE_BYTES);
+            for (int tap = 0; tap < 9; ++tap) {
+                uint8_t* dst = smem_w + tap * G::W_STAGE_BYTES;
+                const int row0 = tap * 2 * C;
+                ptx::tma_load_2d_2sm(dst, &tmap_w, full, 0, row0 + (int)rank * C);
+                ptx::tma_load_2d_2sm(dst + G::WB_BYTES, &tmap_w, full, 0, row0 + (int)rank * C + C / 2);
+                ptx::tma_load_2d_2sm(dst + G::WA_BYTES, &tmap_w, full, 0, row0 + (int)rank * (C / 2));
+            }
+        } else if (lane == 0) {
             int st = 0; uint32_t ph = 0;
             for (int pr = cluster_id; pr < num_pairs; pr += num_clusters) {
                 for (int chunk = 0; chunk < CHUNKS; ++chunk)
@@ -159,6 +179,7 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
             constexpr uint32_t idesc_hi = ptx::make_idesc_bf16(256, C, 0, 0);         // X_lo * W_hi
             int wst = 0, xst = 0; uint32_t wph = 0, xph = 0;
             int acc = 0; uint32_t acc_ph = 0;
+            if (G::RES) { ptx::mbar_wait(&bars->w_full[0], 0); ptx::tc_fence_after(); }
             for (int pr = cluster_id; pr < num_pairs; pr += num_clusters) {
                 ptx::mbar_wait(&bars->tmem_empty[acc], acc_ph ^ 1);
                 ptx::tc_fence_after();
@@ -170,8 +191,8 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
                         ptx::tc_fence_after();
                         const uint32_t x_base = ptx::smem_u32(smem_x + xst * G::X_STAGE_BYTES);
                         for (int r = 0; r < 3; ++r) {
-                            ptx::mbar_wait(&bars->w_full[wst], wph);
-                            ptx::tc_fence_after();
+                            if (G::RES) wst = r * 3 + s;
+                            else { ptx::mbar_wait(&bars->w_full[wst], wph); ptx::tc_fence_after(); }
                             const uint32_t w_base = ptx::smem_u32(smem_w + wst * G::W_STAGE_BYTES);
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
@@ -184,8 +205,10 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
                                 ptx::umma_bf16_2sm(d_tmem, xlo, wb, idesc_hi, 1u);
                                 accumulate = 1;
                             }
-                            ptx::umma_commit_2sm(&bars->w_empty[wst]);
-                            if (++wst == kWStages) { wst = 0; wph ^= 1; }
+                            if (!G::RES) {
+                                ptx::umma_commit_2sm(&bars->w_empty[wst]);
+                                if (++wst == kWStages) { wst = 0; wph ^= 1; }
+                            }
                         }
                         ptx::umma_commit_2sm(&bars->x_empty[xst]);
                         if (++xst == kXStages) { xst = 0; xph ^= 1; }
@@ -203,6 +226,89 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
         const size_t plane_stride = (size_t)WIMG * C;
         const int tg = we / WPT, wi = we % WPT;
         const int cb = (wi >> 2) * 32;
+        auto row0_of = [&](int pr) {
+            const int t = 2 * pr + (int)rank;
+            const int n = t / tiles_per_img;
+            return (size_t)n * H + (size_t)(t - n * tiles_per_img) * G::ROWS;
+        };
+        if constexpr (G::RES) {
+            // ---- resident-weight variant: 8 warps, 2 KB stage per warp, 16 pixels transposed at a time ----
+            // lane pair (2m, 2m+1) owns pixel m of the current half: 64 B (16 channels) each, i.e. the pair covers the
+            // pixel's whole 128-byte line; block b = 2*pass + qq is pixel 16*pass + (lane >> 1), channels 16*(lane & 1) + 8*qq
+            const int cb = ((we % WPT) >> 2) * 32;
+            const uint32_t stage = ptx::smem_u32(smem_stage + we * (kStageBytesPerWarp / 2));
+            const int rl2 = lane >> 1, half = lane & 1;
+            auto owned = [&](size_t row0, int b, size_t& idx, size_t& sidx) {
+                const int pp = q * 32 + 16 * (b >> 1) + rl2;
+                const int r2 = pp / WIMG, w2 = pp - r2 * WIMG;
+                const int ch = cb + 16 * half + 8 * (b & 1);
+                idx = ((row0 + r2) * WIMG + w2) * C + ch;
+                sidx = ((row0 + r2) * 2) * plane_stride + (size_t)w2 * C + ch;
+            };
+            int it = 0;
+            int pr = cluster_id;
+            EpiVec8 ops;
+            if (pr < num_pairs) { size_t i0, s0; owned(row0_of(pr), 0, i0, s0); epi_prefetch_vec8(epi, i0, ops); }
+            for (; pr < num_pairs; pr += num_clusters, ++it) {
+                const int acc = it % kAccBufs;
+                const uint32_t ph = (uint32_t)(it / kAccBufs) & 1u;
+                const EpiCoef coef = epi_coef(epi, (2 * pr + (int)rank) / tiles_per_img);
+                const size_t row0 = row0_of(pr);
+                ptx::mbar_wait_backoff(&bars->tmem_full[acc], ph, backoff_ns);
+                ptx::tc_fence_after();
+                const uint32_t t_acc = tmem_base + (uint32_t)(acc * G::ACC_COLS) + lane_addr + (uint32_t)cb;
+                float vv[4][8];
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    float a[8], b[8];
+                    ptx::tmem_ld<8>(t_acc + c8 * 8, a);
+                    ptx::tmem_ld<8>(t_acc + C + c8 * 8, b);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) vv[c8][j] = a[j] + b[j];
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->tmem_empty[acc]), 0));
+#pragma unroll
+                for (int pass = 0; pass < 2; ++pass) {
+                    __syncwarp();                                  // the previous half has been read by every lane
+                    if ((lane >> 4) == pass) {
+                        const int rl = lane & 15;
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const uint32_t addr = stage + rl * 128 + ((u ^ (rl & 7)) << 4);
+                            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(vv[u >> 1][4 * (u & 1)]),
+                                         "f"(vv[u >> 1][4 * (u & 1) + 1]), "f"(vv[u >> 1][4 * (u & 1) + 2]),
+                                         "f"(vv[u >> 1][4 * (u & 1) + 3]) : "memory");
+                        }
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int qq = 0; qq < 2; ++qq) {
+                        const int b = 2 * pass + qq;
+                        float v[8];
+                        {
+                            const uint32_t base = stage + rl2 * 128;
+                            const int u0 = 4 * half + 2 * qq;
+                            const uint32_t a0 = base + ((u0 ^ (rl2 & 7)) << 4), a1 = base + (((u0 + 1) ^ (rl2 & 7)) << 4);
+                            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a0));
+                            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(a1));
+                        }
+                        size_t idx, sidx;
+                        owned(row0, b, idx, sidx);
+                        epi_finish_vec8<ACT>(epi, coef, v, ops, idx, sidx, plane_stride);
+                        if (b < 3) {
+                            owned(row0, b + 1, idx, sidx);
+                            epi_prefetch_vec8(epi, idx, ops);
+                        } else {
+                            const int p2 = pr + num_clusters;
+                            if (p2 < num_pairs) { owned(row0_of(p2), 0, idx, sidx); epi_prefetch_vec8(epi, idx, ops); }
+                        }
+                    }
+                }
+            }
+        } else {
         const uint32_t stage = ptx::smem_u32(smem_stage + we * kStageBytesPerWarp);
         const int k4 = lane & 3, quad = lane >> 2;
         auto owned = [&](size_t row0, int j, size_t& idx, size_t& sidx) {
@@ -210,11 +316,6 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
             const int r2 = pp / WIMG, w2 = pp - r2 * WIMG;
             idx = ((row0 + r2) * WIMG + w2) * C + cb + 8 * k4;
             sidx = ((row0 + r2) * 2) * plane_stride + (size_t)w2 * C + cb + 8 * k4;
-        };
-        auto row0_of = [&](int pr) {
-            const int t = 2 * pr + (int)rank;
-            const int n = t / tiles_per_img;
-            return (size_t)n * H + (size_t)(t - n * tiles_per_img) * G::ROWS;
         };
         int it = tg;
         int pr = cluster_id + tg * num_clusters;
@@ -267,6 +368,7 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
                     if (p2 < num_pairs) { owned(row0_of(p2), 0, idx, sidx); epi_prefetch_vec8(epi, idx, ops); }
                 }
             }
+        }
         }
     }
     // nobody leaves while the peer may still signal its barriers or the leader's MMAs write its TMEM

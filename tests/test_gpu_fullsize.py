@@ -241,15 +241,19 @@ def test_cta_pair_conv_matches_single_cta(C, HW):
         (y * r).sum().backward()
         return [y.detach().clone(), x.grad.clone()] + [p.grad.clone() for p in blk.parameters()]
 
-    d = metasolver_b200.get_option("tc_pair")
+    d, dw = metasolver_b200.get_option("tc_pair"), metasolver_b200.get_option("tcp_epi_warps")
     try:
         metasolver_b200.set_option("tc_pair", 0)
         base = run()
         metasolver_b200.set_option("tc_pair", 1)
         pair = run()
         pair2 = run()
+        metasolver_b200.set_option("tcp_epi_warps", 8)      # C = 64: the resident-weight variant of the pair kernel
+        res = run()
     finally:
         metasolver_b200.set_option("tc_pair", d)
-    for a, b, c in zip(base, pair, pair2):
+        metasolver_b200.set_option("tcp_epi_warps", dw)
+    for a, b, c, e in zip(base, pair, pair2, res):
         assert torch.equal(b, c)
         assert max_rel(b.cpu().numpy(), a.cpu().numpy()) <= 2e-6
+        assert max_rel(e.cpu().numpy(), a.cpu().numpy()) <= 2e-6
