@@ -257,3 +257,32 @@ def test_cta_pair_conv_matches_single_cta(C, HW):
         assert torch.equal(b, c)
         assert max_rel(b.cpu().numpy(), a.cpu().numpy()) <= 2e-6
         assert max_rel(e.cpu().numpy(), a.cpu().numpy()) <= 2e-6
+
+
+@pytest.mark.parametrize("C,H,W,B", [(128, 8, 32, 4), (64, 16, 16, 4), (128, 16, 16, 3), (64, 4, 32, 1), (128, 8, 16, 1)])
+def test_every_tcgen05_tile_geometry_agrees_with_simt_engine(C, H, W, B):
+    """All (C, W) instantiations of the tcgen05 convolutions -- single-CTA and CTA-pair (even tile counts), full-width and
+    16-pixel-wide tiles, odd tile counts that fall back to the single-CTA kernel -- against the independent fp32 SIMT
+    engine on the same operands: forward and every gradient."""
+    import metasolver_b200
+    from metasolver_b200 import _cabi
+    assert _cabi.lib().msb_shape_supports_tcgen05(C, H, W)
+    blk, solver, opts = _block(C)
+    torch.manual_seed(11)
+    x0 = torch.randn(B, C, H, W, device="cuda").contiguous(memory_format=torch.channels_last)
+    r = torch.randn_like(x0)
+
+    def run(engine):
+        metasolver_b200.set_default_engine(engine)
+        try:
+            x = x0.clone().requires_grad_(True)
+            for p in blk.parameters():
+                p.grad = None
+            y = blk(x, [solver], opts)
+            (y * r).sum().backward()
+            return [y.detach().clone(), x.grad.clone()] + [p.grad.clone() for p in blk.parameters()]
+        finally:
+            metasolver_b200.set_default_engine("auto")
+
+    for a, b in zip(run("tcgen05"), run("simt")):
+        assert max_rel(a.cpu().numpy(), b.cpu().numpy()) <= 2e-5
