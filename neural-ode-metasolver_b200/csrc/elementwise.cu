@@ -143,13 +143,19 @@ void launch_pack_w_tc(const float* w, __nv_bfloat16* out, int C, int transpose, 
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nparts, float* __restrict__ grad_w,
                                     int C, int accumulate, int cin_total, int skip_in) {
     int total = 9 * C * C;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        // i indexes OIHW of the C x C x 3 x 3 GEMM result
-        int s = i % 3, r = (i / 3) % 3;
-        int ci = (i / 9) % C, co = i / (9 * C);
-        size_t src = ((size_t)(r * 3 + s) * C + ci) * C + co;
+    // thread = one element of the partial layout [tap][ci][co] (co fastest): the nparts reads of a warp are coalesced;
+    // the sum runs over the parts in ascending order (fixed order: bitwise reproducible), four loads in flight
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gridDim.x * blockDim.x) {
+        const int co = j % C, ci = (j / C) % C, tap = j / (C * C);
+        const int r = tap / 3, s = tap - 3 * r;
         float acc = 0.f;
-        for (int p = 0; p < nparts; ++p) acc += partial[(size_t)p * total + src];
+        int p = 0;
+        for (; p + 4 <= nparts; p += 4) {
+            const float a0 = partial[(size_t)p * total + j], a1 = partial[(size_t)(p + 1) * total + j];
+            const float a2 = partial[(size_t)(p + 2) * total + j], a3 = partial[(size_t)(p + 3) * total + j];
+            acc += a0; acc += a1; acc += a2; acc += a3;
+        }
+        for (; p < nparts; ++p) acc += partial[(size_t)p * total + j];
         float* q = grad_w + (((size_t)co * cin_total + ci + skip_in) * 3 + r) * 3 + s;
         *q = accumulate ? *q + acc : acc;
     }

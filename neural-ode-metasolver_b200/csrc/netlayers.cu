@@ -107,7 +107,7 @@ int launch_stem_fwd(const float* x, const float* w, int act, float* y, float* da
 // pixels; the four pixel quarters are summed through shared memory in a fixed order.  Deterministic: fixed
 // pixel order per block + fixed-order reduction over blocks.
 // ---------------------------------------------------------------------------------------------
-constexpr int kStemPix = 32;   // pixels staged per iteration
+constexpr int kStemPix = 64;   // pixels staged per iteration (45 KB of static shared memory)
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ gy, const float* __restrict__ dact,
                                                          const float* __restrict__ x, float* __restrict__ partial, int B,
                                                          int H, int W, int C, long long pix_per_block) {
@@ -144,10 +144,11 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
                 float v = 0.f;
                 if (pix < p_end && (slot & 7) < 7 && k < 27) {
                     const int ci = k / 9, r = (k % 9) / 3, s = k % 3;
-                    const int wq = (int)(pix % W);
-                    const long long rest = pix / W;
-                    const int h = (int)(rest % H);
-                    const long long n = rest / H;
+                    const unsigned upix = (unsigned)pix;                 // B*H*W < 2^31 (checked by the launcher): 32-bit divides
+                    const int wq = (int)(upix % (unsigned)W);
+                    const unsigned rest = upix / (unsigned)W;
+                    const int h = (int)(rest % (unsigned)H);
+                    const long long n = rest / (unsigned)H;
                     const int ih = h + r - 1, iw = wq + s - 1;
                     if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = x[(((size_t)n * H + ih) * W + iw) * 3 + ci];
                 }
@@ -206,6 +207,7 @@ int stem_wgrad_blocks() { return num_sms() * 2; }
 int launch_stem_wgrad(const float* gy, const float* dact, const float* x, float* partial, float* gw, int B, int H, int W,
                       int C, cudaStream_t st) {
     if (C % 64) { set_error("stem wgrad: output channels must be a multiple of 64 (got %d)", C); return -1; }
+    if ((long long)B * H * W >= (1LL << 31)) { set_error("stem wgrad: more than 2^31 pixels"); return -1; }
     const int nb = stem_wgrad_blocks();
     const long long P = (long long)B * H * W;
     long long per = (P + nb - 1) / nb;
