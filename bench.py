@@ -104,13 +104,45 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region: NVML in-process every 10 ms (the recipe's nvidia-smi clocks
+    line needs ~0.2 s per sample, too coarse for a 0.3 s region); nvidia-smi is the fallback when NVML is unavailable."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
         self.index, self.rows, self.stop_flag, self.th = index, [], False, None
+        self.nvml, self.handle = None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:          # the CUDA device -> its NVML handle by PCI address (CUDA_VISIBLE_DEVICES may renumber / use UUIDs)
+                import torch
+                pr = torch.cuda.get_device_properties(index)
+                bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+                self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _run_nvml(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.rows.append([str(mhz), str(self.max_mhz)] + ["Active" if mask & b else "Not Active" for _, b in
+                                                                   (self.BITS[0], self.BITS[1], self.BITS[2], self.BITS[3])])
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def _run(self):
+        if self.nvml is not None:
+            return self._run_nvml()
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
@@ -133,7 +165,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == "active"})
         return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=reasons, samples=len(sm))
+                    reasons=reasons, samples=len(sm), source="nvml" if self.nvml is not None else "nvidia-smi")
 
 
 # ------------------------------------------------------------------------------------ GPU arm
