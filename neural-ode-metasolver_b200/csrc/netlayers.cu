@@ -124,8 +124,15 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 7; ++j) acc[i][j] = 0.f;
-        for (long long p0 = p_beg; p0 < p_end; p0 += kStemPix) {
-            for (int i = threadIdx.x; i < kStemPix * 16; i += 256) {          // gpre: 32 pixels x 16 float4
+        // global loads of chunk i+1 are issued before the FMAs of chunk i (register prefetch): the staging loop was
+        // latency-bound (load -> shared -> barrier -> compute -> barrier, nothing in flight during the compute)
+        constexpr int NG4 = kStemPix * 16 / 256, NX = kStemPix * 32 / 256;
+        float4 rg[NG4];
+        float rx[NX];
+        auto load_chunk = [&](long long p0) {
+#pragma unroll
+            for (int t = 0; t < NG4; ++t) {                                    // gpre: kStemPix pixels x 16 float4
+                const int i = threadIdx.x + t * 256;
                 const int pl = i >> 4, c4 = i & 15;
                 const long long pix = p0 + pl;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -135,9 +142,11 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
                     const float4 d = *reinterpret_cast<const float4*>(dact + idx);
                     v = make_float4(g.x * d.x, g.y * d.y, g.z * d.z, g.w * d.w);
                 }
-                *reinterpret_cast<float4*>(&sg[pl][c4 * 4]) = v;
+                rg[t] = v;
             }
-            for (int i = threadIdx.x; i < kStemPix * 32; i += 256) {          // input patches
+#pragma unroll
+            for (int t = 0; t < NX; ++t) {                                     // input patches
+                const int i = threadIdx.x + t * 256;
                 const int pl = i >> 5, slot = i & 31;
                 const int k = (slot >> 3) * 7 + (slot & 7);
                 const long long pix = p0 + pl;
@@ -152,8 +161,22 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
                     const int ih = h + r - 1, iw = wq + s - 1;
                     if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = x[(((size_t)n * H + ih) * W + iw) * 3 + ci];
                 }
-                sx[pl][slot] = v;
+                rx[t] = v;
             }
+        };
+        if (p_beg < p_end) load_chunk(p_beg);
+        for (long long p0 = p_beg; p0 < p_end; p0 += kStemPix) {
+#pragma unroll
+            for (int t = 0; t < NG4; ++t) {
+                const int i = threadIdx.x + t * 256;
+                *reinterpret_cast<float4*>(&sg[i >> 4][(i & 15) * 4]) = rg[t];
+            }
+#pragma unroll
+            for (int t = 0; t < NX; ++t) {
+                const int i = threadIdx.x + t * 256;
+                sx[i >> 5][i & 31] = rx[t];
+            }
+            if (p0 + kStemPix < p_end) load_chunk(p0 + kStemPix);
             __syncthreads();
 #pragma unroll
             for (int q = 0; q < kStemPix / 4; ++q) {
