@@ -249,6 +249,9 @@ int msb_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t
  *                                                                        (env MSB_TC_PAIR)
  *   "wait_backoff_ns"  first nanosleep step of waiting epilogue / TMA-producer warps (doubles up to 8x); 0 = tight
  *                      mbarrier polling                                  (env MSB_WAIT_BACKOFF_NS)
+ *   "pdl"              1 (default) = the tcgen05 kernels are launched with programmatic stream serialization: their
+ *                      prologue (barrier init, TMEM allocation, tensor-map prefetch) overlaps the predecessor's tail,
+ *                      griddepcontrol.wait orders every access to the predecessor's outputs   (env MSB_PDL)
  * Results do not depend on any option.  Returns 0, or -1 for an unknown name. */
 int msb_set_option(const char* name, int value);
 int msb_get_option(const char* name, int* value);

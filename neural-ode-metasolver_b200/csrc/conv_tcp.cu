@@ -113,6 +113,8 @@ conv3x3_tcp_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    ptx::pdl_launch_dependents();       // the next kernel may set itself up while this one runs ...
+    ptx::pdl_wait();                    // ... and this one touches its inputs only after its predecessor has finished
 
     if (warp == 0) {
         // ===================== activation producer =====================
@@ -404,10 +406,10 @@ int launch_act_ew(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, c
     const int tiles_per_img = s.H / G::ROWS;
     const int num_tiles = s.B * tiles_per_img;
     const int grid = std::min(num_tiles, num_sms());
-    kern<<<grid, kThreads, smem, st>>>(tm_act, tm_w, epi, s.H, num_tiles, tiles_per_img, tune_get(TUNE_EPI_L2_PREFETCH),
-                                       (uint32_t)tune_get(TUNE_WAIT_BACKOFF));
+    const cudaError_t le = launch_maybe_pdl(kern, grid, kThreads, smem, st, tm_act, tm_w, epi, s.H, num_tiles, tiles_per_img,
+                                            tune_get(TUNE_EPI_L2_PREFETCH), (uint32_t)tune_get(TUNE_WAIT_BACKOFF));
     count_launch();
-    return check_cuda(cudaGetLastError(), "conv3x3_tcp launch");
+    return check_cuda(le != cudaSuccess ? le : cudaGetLastError(), "conv3x3_tcp launch");
 }
 
 template <int C, int WIMG, int ACT>

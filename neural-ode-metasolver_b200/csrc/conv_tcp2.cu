@@ -117,6 +117,8 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
     ptx::cluster_sync();                      // the peer's barriers are initialised before anything signals them
     ptx::tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    ptx::pdl_launch_dependents();
+    ptx::pdl_wait();                          // inputs are read (TMA, epilogue loads) only after the predecessor has finished
 
     if (warp == 0) {
         // ===================== activation producer (both CTAs; own pixels) =====================
@@ -399,10 +401,10 @@ int launch_act_ew(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, c
     const int tiles_per_img = s.H / G::ROWS;
     const int num_pairs = s.B * tiles_per_img / 2;
     const int clusters = std::min(num_pairs, num_sms() / 2);
-    kern<<<2 * clusters, kThreads, smem, st>>>(tm_act, tm_w, epi, s.H, num_pairs, tiles_per_img,
-                                               (uint32_t)tune_get(TUNE_WAIT_BACKOFF));
+    const cudaError_t le = launch_maybe_pdl(kern, 2 * clusters, kThreads, smem, st, tm_act, tm_w, epi, s.H, num_pairs,
+                                            tiles_per_img, (uint32_t)tune_get(TUNE_WAIT_BACKOFF));
     count_launch();
-    return check_cuda(cudaGetLastError(), "conv3x3_tcp2 launch");
+    return check_cuda(le != cudaSuccess ? le : cudaGetLastError(), "conv3x3_tcp2 launch");
 }
 
 template <int C, int WIMG, int ACT>

@@ -22,10 +22,25 @@ enum { TUNE_EPI_L2_PREFETCH = 0,   // conv epilogue operands: bulk L2 prefetch d
        TUNE_TC_FORM_C64 = 3,       // tcgen05 conv form for C = 64: 0 = channel-major, 1 = pixel-major
        TUNE_TC_PAIR = 4,           // pixel-major conv on a CTA pair (cta_group::2, M = 256): 0 off, 1 on, 2 for C >= 128 (default)
        TUNE_WAIT_BACKOFF = 5,      // nanosleep back-off (ns, first step) of waiting epilogue / producer warps; 0 = tight poll
+       TUNE_PDL = 6,               // programmatic dependent launch of the tcgen05 kernels (prologue overlaps the predecessor's tail)
        TUNE_COUNT };
 int tune_get(int which);
 
 struct ConvShape { int B, H, W, C; };
+
+// Launch `kern` with the programmatic-stream-serialization attribute when the "pdl" option is on (the kernel must call
+// ptx::pdl_wait() before it touches anything its predecessor wrote), plainly otherwise.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_maybe_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = tune_get(TUNE_PDL) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // ---- elementwise.cu ----
 void launch_act_split(const float* x, const float* mul, int act, float scale, __nv_bfloat16* split, float* dact,

@@ -160,6 +160,14 @@ template <int N> __device__ __forceinline__ void tmem_ld(uint32_t taddr, float* 
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- programmatic dependent launch ------------------------------------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the
+// stream is still running (its CTAs are scheduled as the predecessor's exit): everything up to pdl_wait() -- barrier
+// init, TMEM allocation, tensor-map prefetch -- overlaps the predecessor's tail; pdl_wait() returns once the predecessor
+// grid has completed and its memory is visible.  pdl_launch_dependents() lets the NEXT kernel do the same with us.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- CTA pair (cta_group::2) ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;

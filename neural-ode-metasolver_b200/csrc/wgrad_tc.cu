@@ -84,6 +84,8 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_go, const __grid_con
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    ptx::pdl_launch_dependents();
+    ptx::pdl_wait();                    // operands (and the partial slots accumulated in place) are the predecessors' outputs
 
     if (warp == 0) {
         if (lane == 0) {
@@ -192,11 +194,11 @@ int launch_impl(const __nv_bfloat16* gout, const __nv_bfloat16* in, float* parti
     const int tiles_per_img = s.H / G::ROWS;
     const int num_tiles = s.B * tiles_per_img;
     const int np = nparts_impl<C, WIMG>(s);
-    kern<<<np * G::GROUPS, kThreads, smem, st>>>(tm_go, tm_in, partial, num_tiles, tiles_per_img, np, accumulate,
-                                                        (uint32_t)tune_get(TUNE_WAIT_BACKOFF));
+    const cudaError_t le = launch_maybe_pdl(kern, np * G::GROUPS, kThreads, smem, st, tm_go, tm_in, partial, num_tiles,
+                                            tiles_per_img, np, accumulate, (uint32_t)tune_get(TUNE_WAIT_BACKOFF));
     count_launch();
     *nparts_out = np * G::HALVES;
-    return check_cuda(cudaGetLastError(), "wgrad3x3_tc launch");
+    return check_cuda(le != cudaSuccess ? le : cudaGetLastError(), "wgrad3x3_tc launch");
 }
 
 }  // namespace
