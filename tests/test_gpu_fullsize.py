@@ -202,15 +202,15 @@ def test_tuning_options_do_not_change_results(C, HW):
         (y * r).sum().backward()
         return [y.detach().clone(), x.grad.clone()] + [p.grad.clone() for p in blk.parameters()]
 
-    names = ("epi_l2_prefetch", "tc_resident", "tcp_epi_warps")
+    names = ("epi_l2_prefetch", "tc_resident", "tcp_epi_warps", "pdl", "wait_backoff_ns")
     defaults = {k: metasolver_b200.get_option(k) for k in names + ("tc_form_c64",)}
     try:
         for form in (0, 1):           # the two conv forms differ in the products they form: compare within a form
             metasolver_b200.set_option("tc_form_c64", form)
-            for k, v in zip(names, (0, 0, 8)):
+            for k, v in zip(names, (0, 0, 8, 0, 0)):
                 metasolver_b200.set_option(k, v)
             base = run()
-            for vals in ((1, 0, 8), (2, 0, 16), (3, 1, 16), (0, 1, 8), (0, 0, 16)):
+            for vals in ((1, 0, 8, 1, 0), (2, 0, 16, 0, 64), (3, 1, 16, 1, 0), (0, 1, 8, 0, 0), (0, 0, 16, 1, 32)):
                 for k, v in zip(names, vals):
                     metasolver_b200.set_option(k, v)
                 for a, b in zip(base, run()):
