@@ -252,6 +252,8 @@ int msb_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t
  *   "pdl"              1 (default) = the tcgen05 kernels are launched with programmatic stream serialization: their
  *                      prologue (barrier init, TMEM allocation, tensor-map prefetch) overlaps the predecessor's tail,
  *                      griddepcontrol.wait orders every access to the predecessor's outputs   (env MSB_PDL)
+ *   "wgrad_multicast"  1 = weight-gradient GEMM as clusters of the tap groups with the shared gout box loaded once by
+ *                      TMA multicast (measured slower with the current two-stage ring; default 0)  (env MSB_WGRAD_MULTICAST)
  * Results do not depend on any option.  Returns 0, or -1 for an unknown name. */
 int msb_set_option(const char* name, int value);
 int msb_get_option(const char* name, int* value);

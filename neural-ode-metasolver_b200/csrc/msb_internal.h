@@ -23,6 +23,7 @@ enum { TUNE_EPI_L2_PREFETCH = 0,   // conv epilogue operands: bulk L2 prefetch d
        TUNE_TC_PAIR = 4,           // pixel-major conv on a CTA pair (cta_group::2, M = 256): 0 off, 1 on, 2 for C >= 128 (default)
        TUNE_WAIT_BACKOFF = 5,      // nanosleep back-off (ns, first step) of waiting epilogue / producer warps; 0 = tight poll
        TUNE_PDL = 6,               // programmatic dependent launch of the tcgen05 kernels (prologue overlaps the predecessor's tail)
+       TUNE_WGRAD_MULTICAST = 7,   // weight-gradient GEMM: cluster of the tap groups, gout box multicast (one L2 read per cluster)
        TUNE_COUNT };
 int tune_get(int which);
 

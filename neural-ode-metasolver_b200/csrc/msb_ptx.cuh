@@ -229,6 +229,24 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
                  ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 
+// ---- cluster multicast (cta_group::1 kernels in a cluster) --------------------------------------------------
+// One TMA load whose box lands at the same shared-memory offset in every CTA of `cta_mask`, each CTA's mbarrier (same
+// offset) receiving the bytes: the L2 is read once for the whole cluster.
+__device__ __forceinline__ void tma_load_5d_multicast(void* smem_dst, const CUtensorMap* m, uint64_t* bar, uint16_t cta_mask,
+                                                      int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3), "r"(c4), "h"(cta_mask)
+        : "memory");
+}
+// arrive (once all MMAs issued so far by this thread have completed) on the barrier at this offset in every CTA of the mask
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+
 // ---- descriptors --------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [49,52) base offset | [61,64) layout (2 = SW128)

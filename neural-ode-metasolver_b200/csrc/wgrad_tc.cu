@@ -48,11 +48,16 @@ template <int C, int WIMG> struct WG {
 
 struct __align__(8) WBarriers {
     uint64_t full[kStages], empty[kStages];
+    uint64_t gempty[kStages];          // cluster form, rank 0: every CTA of the cluster has released the stage
     uint64_t done;
     uint32_t tmem_base;
 };
 
-template <int C, int WIMG>
+// MC: the GROUPS CTAs that share a pixel slice -- (horizontal tap, c_in chunk) pairs -- form one thread-block cluster and
+// the gout box, identical for all of them, is loaded ONCE by rank 0 and multicast into every CTA's stage.  ncu had the
+// kernel at 91 % of the L2 slice throughput cap (983 MB of L2 -> SM traffic per C = 64 launch, 9.4 TB/s): it was
+// L2-bound, and a third (C = 64) / half (C = 128) of that traffic was the same gout tile fetched by each group's CTA.
+template <int C, int WIMG, bool MC>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_go, const __grid_constant__ CUtensorMap tmap_in,
                    float* __restrict__ partial, const int num_tiles, const int tiles_per_img, const int nparts,
@@ -64,15 +69,19 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_go, const __grid_con
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int group = blockIdx.x / nparts;
-    const int part = blockIdx.x - group * nparts;
+    // plain launch: blocks [group][part]; cluster launch: blocks [part][group] so that a cluster = the groups of one part
+    const int group = MC ? (int)(blockIdx.x % G::GROUPS) : (int)(blockIdx.x / nparts);
+    const int part = MC ? (int)(blockIdx.x / G::GROUPS) : (int)(blockIdx.x - group * nparts);
+    constexpr uint16_t kAllCtas = (uint16_t)((1u << G::GROUPS) - 1);
     const int s = group % 3;
     const int ci_chunk = group / 3;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmap_go);
         ptx::prefetch_tmap(&tmap_in);
-        for (int i = 0; i < kStages; ++i) { ptx::mbar_init(&bars->full[i], 1); ptx::mbar_init(&bars->empty[i], 1); }
+        for (int i = 0; i < kStages; ++i) {
+            ptx::mbar_init(&bars->full[i], 1); ptx::mbar_init(&bars->empty[i], 1); ptx::mbar_init(&bars->gempty[i], G::GROUPS);
+        }
         ptx::mbar_init(&bars->done, 1);
         ptx::fence_barrier_init();
     }
@@ -82,6 +91,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_go, const __grid_con
     }
     ptx::tc_fence_before();
     __syncthreads();
+    if (MC) ptx::cluster_sync();         // every CTA's barriers exist before rank 0 multicasts into them
     ptx::tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
     ptx::pdl_launch_dependents();
@@ -96,6 +106,14 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_go, const __grid_con
                 uint8_t* stage = smem + st * G::STAGE_BYTES;
                 ptx::mbar_wait(&bars->empty[st], ph ^ 1);
                 ptx::mbar_arrive_expect_tx(&bars->full[st], G::STAGE_BYTES);
+                if (MC) {
+                    if (group == 0) {            // (group == cluster rank) one gout load for the whole cluster
+                        ptx::mbar_wait(&bars->gempty[st], ph ^ 1);
+                        for (int cc = 0; cc < G::CO_CHUNKS; ++cc)
+                            ptx::tma_load_5d_multicast(stage + cc * G::GO_CHUNK_BYTES, &tmap_go, &bars->full[st], kAllCtas,
+                                                       cc * 64, 0, 0, h0, n);
+                    }
+                } else
                 for (int cc = 0; cc < G::CO_CHUNKS; ++cc)
                     ptx::tma_load_5d(stage + cc * G::GO_CHUNK_BYTES, &tmap_go, &bars->full[st], cc * 64, 0, 0, h0, n);
                 ptx::tma_load_5d(stage + G::GO_BYTES, &tmap_in, &bars->full[st], ci_chunk * 64, s - 1, 0, h0 - 1, n);
@@ -131,6 +149,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_go, const __grid_con
                         }
                     }
                 ptx::umma_commit(&bars->empty[st]);
+                if (MC) ptx::umma_commit_multicast(&bars->gempty[st], (uint16_t)1);      // -> rank 0
                 if (++st == kStages) { st = 0; ph ^= 1; }
             }
             ptx::umma_commit(&bars->done);
@@ -163,6 +182,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_go, const __grid_con
     }
     ptx::tc_fence_before();
     __syncthreads();
+    if (MC) ptx::cluster_sync();         // nobody leaves while a peer may still multicast into / signal this CTA
     if (warp == 2) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, kTmemCols);
@@ -187,15 +207,31 @@ int launch_impl(const __nv_bfloat16* gout, const __nv_bfloat16* in, float* parti
     if (make_tmap_split5d(&tm_go, gout, s.B, s.H, s.W, s.C, WIMG, G::ROWS)) return -1;
     if (make_tmap_split5d(&tm_in, in, s.B, s.H, s.W, s.C, WIMG, G::ROWS + 2)) return -1;
     const size_t smem = (size_t)kStages * G::STAGE_BYTES + sizeof(WBarriers) + 1024;
-    auto kern = wgrad3x3_tc_kernel<C, WIMG>;
+    const bool mc = tune_get(TUNE_WGRAD_MULTICAST) != 0;
+    auto kern = mc ? wgrad3x3_tc_kernel<C, WIMG, true> : wgrad3x3_tc_kernel<C, WIMG, false>;
     if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                    "cudaFuncSetAttribute(wgrad3x3_tc)"))
         return -1;
     const int tiles_per_img = s.H / G::ROWS;
     const int num_tiles = s.B * tiles_per_img;
     const int np = nparts_impl<C, WIMG>(s);
-    const cudaError_t le = launch_maybe_pdl(kern, np * G::GROUPS, kThreads, smem, st, tm_go, tm_in, partial, num_tiles,
-                                            tiles_per_img, np, accumulate, (uint32_t)tune_get(TUNE_WAIT_BACKOFF));
+    cudaError_t le;
+    if (mc) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(np * G::GROUPS)); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = G::GROUPS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = tune_get(TUNE_PDL) ? 2 : 1;
+        le = cudaLaunchKernelEx(&cfg, kern, tm_go, tm_in, partial, num_tiles, tiles_per_img, np, accumulate,
+                                (uint32_t)tune_get(TUNE_WAIT_BACKOFF));
+    } else {
+        le = launch_maybe_pdl(kern, np * G::GROUPS, kThreads, smem, st, tm_go, tm_in, partial, num_tiles, tiles_per_img, np,
+                              accumulate, (uint32_t)tune_get(TUNE_WAIT_BACKOFF));
+    }
     count_launch();
     *nparts_out = np * G::HALVES;
     return check_cuda(le != cudaSuccess ? le : cudaGetLastError(), "wgrad3x3_tc launch");
