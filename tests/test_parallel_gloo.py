@@ -22,6 +22,7 @@ def _free_port():
 
 def _worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""          # this is the CPU / gloo test, also when run on a GPU box
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
                       MASTER_PORT=str(port))
     import metasolver_b200  # noqa: F401
