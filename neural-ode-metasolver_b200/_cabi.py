@@ -7,7 +7,8 @@ import os
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmetasolver_b200.so")
+# MSB_LIB_PATH: a differently built copy of the library (the -DMSB_CONV_DEBUG instrumented build of scripts/)
+LIB_PATH = os.environ.get("MSB_LIB_PATH") or os.path.join(HERE, "libmetasolver_b200.so")
 
 MSB_MAX_STAGES = 4
 TABLEAU_GRAD_DOUBLES = MSB_MAX_STAGES + MSB_MAX_STAGES * MSB_MAX_STAGES + MSB_MAX_STAGES   # [b | w | c]

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libmetasolver_b200.so")
-SOURCES = ["odeblock.cu", "blocks.cu", "netlayers.cu", "elementwise.cu", "conv_simt.cu", "conv_tc.cu", "conv_tcp.cu", "conv_tcp2.cu", "wgrad_tc.cu",
+SOURCES = ["odeblock.cu", "blocks.cu", "netlayers.cu", "elementwise.cu", "conv_simt.cu", "conv_tc.cu", "conv_tcp.cu", "conv_tcp2.cu", "conv_tct.cu", "wgrad_tc.cu",
            "groupnorm.cu", "train_aux.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",
@@ -36,15 +36,23 @@ def _digest():
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, debug=False):
+    """debug=True: the instrumented variant (-DMSB_CONV_DEBUG: bottleneck-decomposition switches, bounded waits that
+    report instead of trapping) as libmetasolver_b200_dbg.so; select it with MSB_LIB_PATH."""
+    if debug:
+        return _build(LIB.replace(".so", "_dbg.so"), NVCC_FLAGS + ["-DMSB_CONV_DEBUG"], "_dbg.o", force, verbose)
+    return _build(LIB, NVCC_FLAGS, ".o", force, verbose)
+
+
+def _build(LIB, NVCC_FLAGS, osuffix, force, verbose):
     stamp = LIB + ".stamp"
-    dig = _digest()
+    dig = _digest() + "".join(NVCC_FLAGS[-1:])
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
         return LIB
     objs = []
     procs = []
     for s in SOURCES:
-        o = os.path.join(CSRC, s.replace(".cu", ".o"))
+        o = os.path.join(CSRC, s.replace(".cu", osuffix))
         objs.append(o)
         cmd = [_nvcc()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, s), "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -66,4 +74,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, debug="--debug" in sys.argv))

@@ -125,8 +125,8 @@ int msb_downblock_forward(const MsbDownDesc* d, const float* x, const float* w1,
     if (!cv.ok()) { set_error("internal: workspace carve overflow"); return -1; }
     const size_t per = (size_t)g.Co * g.Co * 9;
     launch_down_weights_build(w1, wsc, Wd, g.Ci, g.Co, st);
-    for (int i = 0; i < 3; ++i) pack_w(g.engine, Wd + i * per, wp[i], g.Co, 0, st);
-    pack_w(g.engine, w2, wp[3], g.Co, 0, st);
+    for (int i = 0; i < 3; ++i) pack_w(g.engine, Wd + i * per, wp[i], g.Co, 0, st, g.shp.H, g.shp.W);
+    pack_w(g.engine, w2, wp[3], g.Co, 0, st, g.shp.H, g.shp.W);
     launch_s2d_act_split(x, d->act, t.T0, t.T1, t.Tsc, t.G0, g.B, g.H, g.W, g.Ci, st);
     // shortcut: SC = conv1x1_s2(x)
     EpiParams e = epi_default();
@@ -172,8 +172,8 @@ int msb_downblock_backward(const MsbDownDesc* d, const float* grad_y, const floa
     if (!cv.ok()) { set_error("internal: workspace carve overflow"); return -1; }
     const size_t per = (size_t)g.Co * g.Co * 9;
     launch_down_weights_build(w1, wsc, Wd, g.Ci, g.Co, st);
-    for (int i = 0; i < 3; ++i) pack_w(g.engine, Wd + i * per, wt[i], g.Co, 1, st);
-    pack_w(g.engine, w2, wt[3], g.Co, 1, st);
+    for (int i = 0; i < 3; ++i) pack_w(g.engine, Wd + i * per, wt[i], g.Co, 1, st, g.shp.H, g.shp.W);
+    pack_w(g.engine, w2, wt[3], g.Co, 1, st, g.shp.H, g.shp.W);
 
     launch_act_split(grad_y, nullptr, ACT_NONE, 1.f, Kbar, nullptr, g.B, g.Ho, g.Wo, g.Co, st);
     auto wgrad_once = [&](const __nv_bfloat16* go, const __nv_bfloat16* in, float* out) {

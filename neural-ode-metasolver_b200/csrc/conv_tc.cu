@@ -98,13 +98,14 @@ int make_tmap_rows64(CUtensorMap* m, const void* base, size_t rows, int box_rows
 
 #ifdef MSB_CONV_DEBUG
 int tcp_debug_set(int flags);
+int tct_debug_set(int flags);
 int tcp_debug_hint(unsigned ns);
 extern "C" int msb_debug_suspend_hint(unsigned ns) {
     if (tcp_debug_hint(ns)) return -1;
     return cudaMemcpyToSymbol(ptx::g_suspend_hint, &ns, sizeof(ns)) == cudaSuccess ? 0 : -1;
 }
 extern "C" int msb_debug_conv_flags(int flags) {
-    if (tcp_debug_set(flags)) return -1;
+    if (tcp_debug_set(flags) || tct_debug_set(flags)) return -1;
     return cudaMemcpyToSymbol(g_conv_debug, &flags, sizeof(int)) == cudaSuccess ? 0 : -1;
 }
 #endif

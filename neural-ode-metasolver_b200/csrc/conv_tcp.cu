@@ -319,7 +319,7 @@ conv3x3_tcp_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
                     }
                     size_t idx, sidx;
                     owned(row0, j, idx, sidx);
-                    epi_finish_vec8<ACT>(epi, coef, v, ops, idx, sidx, plane_stride);
+                    epi_finish_v8<ACT>(epi, coef, v, ops, idx, sidx, plane_stride);
                     if (j < 3) {
                         owned(row0, j + 1, idx, sidx);
                         epi_prefetch_vec8(epi, idx, ops);
@@ -368,7 +368,7 @@ conv3x3_tcp_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
                 } else {
                     epi_prefetch_vec8(epi, idx_t + (ch + 1) * 8, nxt);
                 }
-                epi_finish_vec8<ACT>(epi, coef, v, cur, idx_t + ch * 8, split_t + ch * 8, plane_stride);
+                epi_finish_v8<ACT>(epi, coef, v, cur, idx_t + ch * 8, split_t + ch * 8, plane_stride);
             };
 #pragma unroll
             for (int ch = 0; ch < NCHUNK; ch += 2) {

@@ -299,7 +299,7 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
                         }
                         size_t idx, sidx;
                         owned(row0, b, idx, sidx);
-                        epi_finish_vec8<ACT>(epi, coef, v, ops, idx, sidx, plane_stride);
+                        epi_finish_v8<ACT>(epi, coef, v, ops, idx, sidx, plane_stride);
                         if (b < 3) {
                             owned(row0, b + 1, idx, sidx);
                             epi_prefetch_vec8(epi, idx, ops);
@@ -361,7 +361,7 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
                 }
                 size_t idx, sidx;
                 owned(row0, j, idx, sidx);
-                epi_finish_vec8<ACT>(epi, coef, v, ops, idx, sidx, plane_stride);
+                epi_finish_v8<ACT>(epi, coef, v, ops, idx, sidx, plane_stride);
                 if (j < 3) {
                     owned(row0, j + 1, idx, sidx);
                     epi_prefetch_vec8(epi, idx, ops);

@@ -377,12 +377,19 @@ __device__ __forceinline__ void epi_finish(const EpiParams& e_in, const EpiCoef&
 // Arithmetic and evaluation order are those of epilogue_apply() / epi_finish().
 namespace msb {
 
-struct EpiVec8 {
+// MAXSRC / SMUL: how many src[] arrays and whether split_mul can occur (compile-time bounds on the run-time
+// e.nsrc / e.split_mul: a kernel instantiated for the common RK2 / Euler launches holds 24 operand registers instead
+// of 48 -- the callers pick the instantiation from the EpiParams they launch with, see epi_is_lean()).
+template <int MAXSRC_, bool SMUL_> struct EpiVec8T {
+    static constexpr int MAXSRC = MAXSRC_;
+    static constexpr bool SMUL = SMUL_;
     float mul[8];
     float base[8];
-    float src[3][8];
-    float smul[8];
+    float src[MAXSRC_ > 0 ? MAXSRC_ : 1][8];
+    float smul[SMUL_ ? 8 : 1];
 };
+typedef EpiVec8T<3, true> EpiVec8;
+__host__ inline bool epi_is_lean(const EpiParams& e) { return e.nsrc <= 1 && e.split_mul == nullptr; }
 
 __device__ __forceinline__ void ldg256_stream(const float* p, float* v) {
 #ifdef MSB_CONV_DEBUG
@@ -405,14 +412,168 @@ __device__ __forceinline__ void stg256(float* p, const float* v) {
                  : "memory");
 }
 
-__device__ __forceinline__ void epi_prefetch_vec8(const EpiParams& e, size_t idx0_in, EpiVec8& r) {
+template <class OPS>
+__device__ __forceinline__ void epi_prefetch_vec8(const EpiParams& e, size_t idx0_in, OPS& r) {
     const size_t idx0 = MSB_DBG_LD(idx0_in);
     if (e.mul) ldg256_stream(e.mul + idx0, r.mul);
     if (e.base) ldg256_stream(e.base + idx0, r.base);
-    if (e.nsrc > 0) ldg256_stream(e.src[0] + idx0, r.src[0]);
-    if (e.nsrc > 1) ldg256_stream(e.src[1] + idx0, r.src[1]);
-    if (e.nsrc > 2) ldg256_stream(e.src[2] + idx0, r.src[2]);
-    if (e.split_mul) ldg256_stream(e.split_mul + idx0, r.smul);
+    if (OPS::MAXSRC > 0 && e.nsrc > 0) ldg256_stream(e.src[0] + idx0, r.src[0]);
+    if (OPS::MAXSRC > 1 && e.nsrc > 1) ldg256_stream(e.src[1] + idx0, r.src[1]);
+    if (OPS::MAXSRC > 2 && e.nsrc > 2) ldg256_stream(e.src[2] + idx0, r.src[2]);
+    if (OPS::SMUL && e.split_mul) ldg256_stream(e.split_mul + idx0, r.smul);
+}
+
+// ---- packed fp32 arithmetic (sm_100: mul / add / sub / fma .f32x2, two IEEE operations per issued instruction) ----
+// The vector epilogue is issue-bound (ncu: the epilogue warps keep the schedulers ~55 % busy and 36 % of their
+// instructions are FMUL / FFMA / FADD), so the same round-to-nearest operations are issued on PAIRS of adjacent
+// channels.  Every lane of a packed operation is the IEEE operation of the scalar code (explicit .rn, no contraction):
+// results are bit-identical to epilogue_apply() / epi_finish().
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pk2(float lo, float hi) { f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(f32x2_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) { f32x2_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) { f32x2_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2_t sub2(f32x2_t a, f32x2_t b) { f32x2_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) { f32x2_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2_t bc2(float c) { return pk2(c, c); }
+
+// gelu_both() on a pair (same operations in the same order, lane by lane)
+__device__ __forceinline__ void gelu_both2(f32x2_t x, f32x2_t& a, f32x2_t& d) {
+    float x0, x1;
+    upk2(x, x0, x1);
+    const f32x2_t ax = x & 0x7fffffff7fffffffull;
+    float e0, e1;
+    upk2(mul2(mul2(x, x), bc2(-0.72134752044448170368f)), e0, e1);
+    const f32x2_t E = pk2(ex2_approx(e0), ex2_approx(e1));
+    float t0, t1;
+    upk2(fma2(ax, bc2(0.31819805153394638f), bc2(1.0f)), t0, t1);
+    const f32x2_t t = pk2(rcp_approx(t0), rcp_approx(t1));
+    f32x2_t q = bc2(0.04628484081253973f);
+    q = fma2(q, t, bc2(-0.2470522577736345f));
+    q = fma2(q, t, bc2(0.4285840718840338f));
+    q = fma2(q, t, bc2(-0.18790157886011314f));
+    q = fma2(q, t, bc2(0.23008541295425833f));
+    q = fma2(q, t, bc2(0.1005046642482306f));
+    q = fma2(q, t, bc2(0.12949484725821528f));
+    const f32x2_t h = mul2(mul2(q, t), E);
+    const f32x2_t omh = sub2(bc2(1.0f), h);
+    float h0, h1, m0, m1;
+    upk2(h, h0, h1);
+    upk2(omh, m0, m1);
+    const f32x2_t cdf = pk2(x0 >= 0.f ? m0 : h0, x1 >= 0.f ? m1 : h1);
+    a = mul2(x, cdf);
+    d = fma2(x, mul2(E, bc2(0.39894228040143267794f)), cdf);
+}
+template <int ACT>
+__device__ __forceinline__ void act_both2_t(f32x2_t x, f32x2_t& a, f32x2_t& d) {
+    if (ACT == 1) {
+        gelu_both2(x, a, d);
+    } else if (ACT == 2) {
+        float x0, x1;
+        upk2(x, x0, x1);
+        a = pk2(x0 > 0.f ? x0 : 0.f, x1 > 0.f ? x1 : 0.f);
+        d = pk2(x0 > 0.f ? 1.f : 0.f, x1 > 0.f ? 1.f : 0.f);
+    } else {
+        a = x; d = bc2(1.f);
+    }
+}
+__device__ __forceinline__ void stg256_2(float* p, const f32x2_t* v) {
+#ifdef MSB_CONV_DEBUG
+    if ((g_conv_debug & 16) && v[0] != 0x12345678ull) return;
+#endif
+    asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(v[0]), "l"(v[1]), "l"(v[2]), "l"(v[3]) : "memory");
+}
+
+// The packed form of epi_finish_vec8 (below): same contract, same bits.
+template <int ACT, class OPS>
+__device__ __forceinline__ void epi_finish_vec8_x2(const EpiParams& e, const EpiCoef& k, const float* acc, const OPS& r,
+                                                   size_t idx0_in, size_t split_idx0_in, size_t plane_stride) {
+    constexpr int P = 4;
+    const size_t idx0 = MSB_DBG_ST(idx0_in), split_idx0 = MSB_DBG_ST(split_idx0_in);
+    f32x2_t v[P], o[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) v[j] = pk2(acc[2 * j], acc[2 * j + 1]);
+    if (e.act_v != ACT_NONE) {            // post-activation RHS only (rare): generic scalar path
+        float av[8], d[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) act_both(e.act_v, acc[j], av[j], d[j]);
+#pragma unroll
+        for (int j = 0; j < P; ++j) v[j] = pk2(av[2 * j], av[2 * j + 1]);
+        if (e.dact_v_out) stg256(e.dact_v_out + idx0, d);
+    }
+    if (e.mul) {
+#pragma unroll
+        for (int j = 0; j < P; ++j) v[j] = mul2(v[j], pk2(r.mul[2 * j], r.mul[2 * j + 1]));
+    }
+    if (e.v_out) stg256_2(e.v_out + idx0, v);
+    const f32x2_t cv = bc2(k.coef_v);
+    if (e.nsrc == 0) {
+#pragma unroll
+        for (int j = 0; j < P; ++j) o[j] = mul2(v[j], cv);
+    } else {
+        const f32x2_t c0 = bc2(k.coef[0]);
+#pragma unroll
+        for (int j = 0; j < P; ++j) o[j] = mul2(pk2(r.src[0][2 * j], r.src[0][2 * j + 1]), c0);
+        if (OPS::MAXSRC > 1 && e.nsrc > 1) {
+            const f32x2_t c1 = bc2(k.coef[1]);
+#pragma unroll
+            for (int j = 0; j < P; ++j) o[j] = add2(o[j], mul2(pk2(r.src[OPS::MAXSRC > 1 ? 1 : 0][2 * j], r.src[OPS::MAXSRC > 1 ? 1 : 0][2 * j + 1]), c1));
+        }
+        if (OPS::MAXSRC > 2 && e.nsrc > 2) {
+            const f32x2_t c2 = bc2(k.coef[2]);
+#pragma unroll
+            for (int j = 0; j < P; ++j) o[j] = add2(o[j], mul2(pk2(r.src[OPS::MAXSRC > 2 ? 2 : 0][2 * j], r.src[OPS::MAXSRC > 2 ? 2 : 0][2 * j + 1]), c2));
+        }
+#pragma unroll
+        for (int j = 0; j < P; ++j) o[j] = add2(o[j], mul2(v[j], cv));
+    }
+    const f32x2_t dt2 = bc2(k.dt);
+#pragma unroll
+    for (int j = 0; j < P; ++j) o[j] = mul2(o[j], dt2);
+    if (e.base) {
+        if (e.base_is_one) {
+#pragma unroll
+            for (int j = 0; j < P; ++j) o[j] = add2(pk2(r.base[2 * j], r.base[2 * j + 1]), o[j]);
+        } else {
+            const f32x2_t bcf = bc2(k.base_coef);
+#pragma unroll
+            for (int j = 0; j < P; ++j) o[j] = add2(mul2(pk2(r.base[2 * j], r.base[2 * j + 1]), bcf), o[j]);
+        }
+    }
+    if (e.out_f32) stg256_2(e.out_f32 + idx0, o);
+    if (e.out_split || e.dact_out) {
+        f32x2_t a[P], d[P];
+#pragma unroll
+        for (int j = 0; j < P; ++j) act_both2_t<ACT>(o[j], a[j], d[j]);
+        if (e.dact_out) stg256_2(e.dact_out + idx0, d);
+        if (e.out_split) {
+            if (OPS::SMUL && e.split_mul) {
+#pragma unroll
+                for (int j = 0; j < P; ++j) a[j] = mul2(a[j], pk2(r.smul[OPS::SMUL ? 2 * j : 0], r.smul[OPS::SMUL ? 2 * j + 1 : 0]));
+            }
+            const f32x2_t ss = bc2(k.split_scale);
+            uint32_t hi[P], lo[P];
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const f32x2_t x = mul2(a[j], ss);
+                float x0, x1;
+                upk2(x, x0, x1);
+                uint32_t h;
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));     // element 2j in the low half
+                const f32x2_t hf = pk2(__uint_as_float(h << 16), __uint_as_float(h & 0xffff0000u));
+                float l0, l1;
+                upk2(sub2(x, hf), l0, l1);
+                uint32_t l;
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(l1), "f"(l0));
+                hi[j] = h; lo[j] = l;
+            }
+#ifdef MSB_CONV_DEBUG
+            if ((g_conv_debug & 16) && hi[0] != 0x12345678u) return;
+#endif
+            *reinterpret_cast<uint4*>(e.out_split + split_idx0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(e.out_split + split_idx0 + plane_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+    }
 }
 
 // split_idx0 = index of element 0 in the hi plane of out_split; the lo plane is plane_stride further.
@@ -497,6 +658,21 @@ __device__ __forceinline__ void epi_finish_vec8(const EpiParams& e, const EpiCoe
             *reinterpret_cast<uint4*>(e.out_split + split_idx0 + plane_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
     }
+}
+
+// which implementation the tensor-core engines call (MSB_EPI_X2=0 builds the scalar one for A/B runs)
+#ifndef MSB_EPI_X2
+#define MSB_EPI_X2 1
+#endif
+template <int ACT, class OPS>
+__device__ __forceinline__ void epi_finish_v8(const EpiParams& e, const EpiCoef& k, const float* acc, const OPS& r,
+                                              size_t idx0, size_t split_idx0, size_t plane_stride) {
+#if MSB_EPI_X2
+    epi_finish_vec8_x2<ACT, OPS>(e, k, acc, r, idx0, split_idx0, plane_stride);
+#else
+    static_assert(OPS::MAXSRC == 3 && OPS::SMUL, "the scalar A/B build has no lean instantiation");
+    epi_finish_vec8<ACT>(e, k, acc, r, idx0, split_idx0, plane_stride);
+#endif
 }
 
 }  // namespace msb

@@ -23,7 +23,8 @@ int resolve_engine_shape(int engine, int C, int H, int W);     // MSB_ENGINE_AUT
 double conv_flops(ConvShape s);
 // one convolution launch on `engine` (records profile events when profiling is on)
 int run_conv(int engine, const __nv_bfloat16* in, const void* wpacked, const EpiParams& e, ConvShape s, cudaStream_t st);
-void pack_w(int engine, const float* w, void* out, int C, int transpose, cudaStream_t st);
+// (H, W) = the images the packed weights will be used on: the tcgen05 conv form, hence the packing, depends on them
+void pack_w(int engine, const float* w, void* out, int C, int transpose, cudaStream_t st, int H, int W);
 int wgrad_nparts(int engine, ConvShape s);
 // Weight-gradient accumulation over the launches of one backward pass (see odeblock.cu).
 struct WgradAcc { float* partial; float* grad_w; int launches; int nparts; };

@@ -19,11 +19,14 @@ int check_cuda(cudaError_t e, const char* what);   // 0 if ok, else sets error a
 enum { TUNE_EPI_L2_PREFETCH = 0,   // conv epilogue operands: bulk L2 prefetch distance in tiles (0 = off)
        TUNE_TC_RESIDENT = 1,       // channel-major C=64 conv: weights resident in shared memory
        TUNE_TCP_EPI_WARPS = 2,     // pixel-major conv: epilogue warps (8 or 16)
-       TUNE_TC_FORM_C64 = 3,       // tcgen05 conv form for C = 64: 0 = channel-major, 1 = pixel-major
+       TUNE_TC_FORM_C64 = 3,       // tcgen05 conv form for C = 64: 0 = channel-major, 1 = pixel-major, 2 = weights resident in
+                                   // TMEM (conv_tct.cu; 32-pixel-wide images, else pixel-major)
        TUNE_TC_PAIR = 4,           // pixel-major conv on a CTA pair (cta_group::2, M = 256): 0 off, 1 on, 2 for C >= 128 (default)
        TUNE_WAIT_BACKOFF = 5,      // nanosleep back-off (ns, first step) of waiting epilogue / producer warps; 0 = tight poll
        TUNE_PDL = 6,               // programmatic dependent launch of the tcgen05 kernels (prologue overlaps the predecessor's tail)
        TUNE_WGRAD_MULTICAST = 7,   // weight-gradient GEMM: cluster of the tap groups, gout box multicast (one L2 read per cluster)
+       TUNE_TCT_BAND = 8,          // TMEM-resident-weight conv: image rows per work item (0 = 16 / 8 / 4 by image height)
+       TUNE_TCT_DEBUG = 9,         // TMEM-resident-weight conv: decomposition switches (timing experiments only; results are garbage)
        TUNE_COUNT };
 int tune_get(int which);
 
@@ -108,8 +111,15 @@ int launch_conv3x3_tcp(const __nv_bfloat16* split_in, const __nv_bfloat16* w_til
 bool tcp2_shape_supported(int B, int C, int H, int W);
 int launch_conv3x3_tcp2(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, const EpiParams& epi,
                         ConvShape s, cudaStream_t st);
-// which form MSB_ENGINE_TCGEN05 runs for C channels (odeblock.cu; env MSB_TC_CONV=cm|pm forces one)
-bool tc_pixel_major(int C);
+// which form MSB_ENGINE_TCGEN05 runs for a shape: 0 = channel-major (conv_tc.cu), 1 = pixel-major (conv_tcp.cu / conv_tcp2.cu),
+// 2 = weights resident in TMEM (conv_tct.cu)   (odeblock.cu; env MSB_TC_CONV=cm|pm forces one of the first two)
+int tc_form(int C, int H, int W);
+
+// ---- conv_tct.cu : C = 64, weights resident in tensor memory as the A operand, activations on N from a row ring ----
+bool tct_shape_supported(int C, int H, int W);
+size_t tct_packed_weight_bytes();
+void launch_pack_w_tct(const float* w, void* out, int transpose, cudaStream_t st);
+int launch_conv3x3_tct(const __nv_bfloat16* split_in, const void* wpacked, const EpiParams& epi, ConvShape s, cudaStream_t st);
 
 // ---- wgrad_tc.cu ----
 bool wgrad_tc_supported(ConvShape s);

@@ -39,10 +39,10 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 static std::atomic<int> g_tune[TUNE_COUNT];
 static std::atomic<bool> g_tune_init{false};
 static const char* const kTuneNames[TUNE_COUNT] = {"epi_l2_prefetch", "tc_resident", "tcp_epi_warps", "tc_form_c64", "tc_pair",
-                                                   "wait_backoff_ns", "pdl", "wgrad_multicast"};
+                                                   "wait_backoff_ns", "pdl", "wgrad_multicast", "tct_band", "tct_debug"};
 static const char* const kTuneEnv[TUNE_COUNT] = {"MSB_EPI_L2_PREFETCH", "MSB_TC_RESIDENT", "MSB_TCP_EPI_WARPS", "MSB_TC_FORM_C64",
-                                                 "MSB_TC_PAIR", "MSB_WAIT_BACKOFF_NS", "MSB_PDL", "MSB_WGRAD_MULTICAST"};
-static const int kTuneDefault[TUNE_COUNT] = {0, 0, 16, 1, 2, 0, 1, 0};
+                                                 "MSB_TC_PAIR", "MSB_WAIT_BACKOFF_NS", "MSB_PDL", "MSB_WGRAD_MULTICAST", "MSB_TCT_BAND", "MSB_TCT_DEBUG"};
+static const int kTuneDefault[TUNE_COUNT] = {0, 0, 16, 2, 2, 0, 1, 0, 0, 0};
 static void tune_init() {
     if (g_tune_init.load(std::memory_order_acquire)) return;
     for (int i = 0; i < TUNE_COUNT; ++i) {
@@ -92,22 +92,28 @@ static void prof_end(int id, cudaStream_t st) {
 }
 
 // ---- host helpers shared with blocks.cu (declared in msb_host.h) ----
-// Which form of the tcgen05 convolution runs for C channels.  Measured on B200 (profiles/conv_forms_r1.txt):
-// the pixel-major form (3 hi/lo products) wins for C = 128, where the channel-major form is MMA-bound; for
-// C = 64 its N = 128 / N = 64 MMAs are shared-memory-operand-bound and the channel-major form (N = 256) wins.
-// MSB_TC_CONV=cm|pm forces one form for every shape (A/B runs).
-bool tc_pixel_major(int C) {
+// Which form of the tcgen05 convolution runs for a shape.  Measured on B200 (profiles/): the pixel-major form (3 hi/lo
+// products, CTA pair) wins for C = 128; for C = 64 its N = 128 / N = 64 MMAs are shared-memory-operand-bound, and the form
+// with the weights resident in tensor memory (conv_tct.cu: A from TMEM, only the activations read from shared memory)
+// is the default wherever it tiles (32-pixel-wide images), the pixel-major form elsewhere.
+// MSB_TC_CONV=cm|pm forces one of the older forms for every shape (A/B runs).
+int tc_form(int C, int H, int W) {
     static int forced = -2;
     if (forced == -2) {
         const char* e = getenv("MSB_TC_CONV");
         forced = !e ? -1 : (strcmp(e, "cm") == 0 ? 0 : (strcmp(e, "pm") == 0 ? 1 : -1));
     }
-    if (forced >= 0) return forced == 1;
-    return C >= 128 || tune_get(TUNE_TC_FORM_C64) == 1;
+    if (forced >= 0) return forced;
+    if (C >= 128) return 1;
+    const int v = tune_get(TUNE_TC_FORM_C64);
+    if (v == 2) return tct_shape_supported(C, H, W) ? 2 : 1;
+    return v == 0 ? 0 : 1;
 }
 size_t packed_w_bytes(int engine, int C) {
     if (engine != MSB_ENGINE_TCGEN05) return (size_t)9 * C * C * sizeof(float);
-    return tc_pixel_major(C) ? tcp_packed_weight_bytes(C) : tc_packed_weight_bytes(C);
+    size_t n = std::max(tcp_packed_weight_bytes(C), tc_packed_weight_bytes(C));     // any form
+    if (C == 64) n = std::max(n, tct_packed_weight_bytes());
+    return n;
 }
 int resolve_engine_shape(int engine, int C, int H, int W) {
     const bool tc_ok = tc_shape_supported(C, H, W);
@@ -122,22 +128,25 @@ int resolve_engine_shape(int engine, int C, int H, int W) {
 }
 double conv_flops(ConvShape s) { return 2.0 * s.B * s.H * s.W * (double)s.C * 9.0 * s.C; }
 int run_conv(int engine, const __nv_bfloat16* in, const void* wpacked, const EpiParams& e, ConvShape s, cudaStream_t st) {
-    const double products = engine != MSB_ENGINE_TCGEN05 ? 1.0 : (tc_pixel_major(s.C) ? 3.0 : 4.0);
+    const int form = engine == MSB_ENGINE_TCGEN05 ? tc_form(s.C, s.H, s.W) : -1;
+    const double products = form < 0 ? 1.0 : (form == 1 ? 3.0 : 4.0);
     int id = prof_begin(MSB_PROF_CONV, conv_flops(s), products, st);
     int rc;
-    if (engine == MSB_ENGINE_TCGEN05)
-        rc = tc_pixel_major(s.C) ? (((tune_get(TUNE_TC_PAIR) == 1 || (tune_get(TUNE_TC_PAIR) == 2 && s.C >= 128)) &&
-                                     tcp2_shape_supported(s.B, s.C, s.H, s.W))
-                                        ? launch_conv3x3_tcp2(in, (const __nv_bfloat16*)wpacked, e, s, st)
-                                        : launch_conv3x3_tcp(in, (const __nv_bfloat16*)wpacked, e, s, st))
-                              : launch_conv3x3_tc(in, (const __nv_bfloat16*)wpacked, e, s, st);
+    if (form == 2) rc = launch_conv3x3_tct(in, wpacked, e, s, st);
+    else if (form == 1)
+        rc = ((tune_get(TUNE_TC_PAIR) == 1 || (tune_get(TUNE_TC_PAIR) == 2 && s.C >= 128)) && tcp2_shape_supported(s.B, s.C, s.H, s.W))
+                 ? launch_conv3x3_tcp2(in, (const __nv_bfloat16*)wpacked, e, s, st)
+                 : launch_conv3x3_tcp(in, (const __nv_bfloat16*)wpacked, e, s, st);
+    else if (form == 0) rc = launch_conv3x3_tc(in, (const __nv_bfloat16*)wpacked, e, s, st);
     else rc = launch_conv3x3_simt(in, (const float*)wpacked, e, s, st);
     prof_end(id, st);
     return rc;
 }
-void pack_w(int engine, const float* w, void* out, int C, int transpose, cudaStream_t st) {
+void pack_w(int engine, const float* w, void* out, int C, int transpose, cudaStream_t st, int H, int W) {
     if (engine == MSB_ENGINE_TCGEN05) {
-        if (tc_pixel_major(C)) launch_pack_w_tcp(w, (__nv_bfloat16*)out, C, transpose, st);
+        const int form = tc_form(C, H, W);
+        if (form == 2) launch_pack_w_tct(w, out, transpose, st);
+        else if (form == 1) launch_pack_w_tcp(w, (__nv_bfloat16*)out, C, transpose, st);
         else launch_pack_w_tc(w, (__nv_bfloat16*)out, C, transpose, st);
     } else launch_pack_w_simt(w, (float*)out, C, C, 0, transpose, st);
 }
@@ -535,7 +544,7 @@ static int gn_preact_forward(const MsbOdeDesc* d, const float* x, const MsbMnist
     float* P = cv.take<float>(E * 4);
     float* xbuf = cv.take<float>(E * 4);
     if (!cv.ok()) { set_error("internal: workspace carve overflow"); return -1; }
-    for (int k = 0; k < 2; ++k) pack_w(engine, mp->conv_w[k], wp[k], C, 0, st);
+    for (int k = 0; k < 2; ++k) pack_w(engine, mp->conv_w[k], wp[k], C, 0, st, d->height, d->width);
     const float* y_cur = x;
     if (save) {
         GnSlot s0 = gn_slot(tape, E, 0);
@@ -609,7 +618,7 @@ static int gn_preact_backward(const MsbOdeDesc* d, const float* grad_y, const Ms
     float* gnpart[4];
     for (int i = 0; i < 4; ++i) gnpart[i] = cv.take<float>((size_t)d->batch * C * 4);     // (dgamma_k, dbeta_k), k = 1, 2
     if (!cv.ok()) { set_error("internal: workspace carve overflow"); return -1; }
-    for (int k = 0; k < 2; ++k) pack_w(engine, mp->conv_w[k], wt[k], C, 1, st);
+    for (int k = 0; k < 2; ++k) pack_w(engine, mp->conv_w[k], wt[k], C, 1, st, d->height, d->width);
 
     auto dt_of = [&](int n) { return d->time_grid[n + 1] - d->time_grid[n]; };
     launch_act_split(grad_y, nullptr, ACT_NONE, dt_of(N - 1) * d->b[S - 1], Kbar, nullptr, d->batch, d->height, d->width, C, st);
@@ -700,8 +709,8 @@ int msb_odeblock_forward(const MsbOdeDesc* d, const float* x, const float* w1, c
     __nv_bfloat16* Hs_inf = cv.take<__nv_bfloat16>(E * 4);
     if (!cv.ok()) { set_error("internal: workspace carve overflow"); return -1; }
 
-    pack_w(engine, w1, wp1, C, 0, st);
-    pack_w(engine, w2, wp2, C, 0, st);
+    pack_w(engine, w1, wp1, C, 0, st, d->height, d->width);
+    pack_w(engine, w2, wp2, C, 0, st, d->height, d->width);
     const Tabs tabs = make_tabs(d);
 
     auto slot_full = [&](int n, int i) {
@@ -818,9 +827,9 @@ static int odeblock_backward_impl(const MsbOdeDesc* d, const float* grad_y, cons
     }
     if (!cv.ok()) { set_error("internal: workspace carve overflow"); return -1; }
 
-    pack_w(engine, w1, wt1, C, 1, st);
-    pack_w(engine, w2, wt2, C, 1, st);
-    if (grad_tab) pack_w(engine, w2, wp2f, C, 0, st);
+    pack_w(engine, w1, wt1, C, 1, st, d->height, d->width);
+    pack_w(engine, w2, wt2, C, 1, st, d->height, d->width);
+    if (grad_tab) pack_w(engine, w2, wp2f, C, 0, st, d->height, d->width);
     const Tabs tabs = make_tabs(d);
 
     auto dt_of = [&](int n) { return d->time_grid[n + 1] - d->time_grid[n]; };
@@ -1101,7 +1110,7 @@ int msb_act_split(const float* x, int act, void* split_out, float* dact_out, int
 }
 
 size_t msb_conv3x3_workspace_bytes(int channels) {
-    size_t a = std::max(tc_packed_weight_bytes(channels), tcp_packed_weight_bytes(channels)), b = (size_t)9 * channels * channels * 4;
+    size_t a = packed_w_bytes(MSB_ENGINE_TCGEN05, channels), b = (size_t)9 * channels * channels * 4;
     return align_up(a > b ? a : b) + 1024;
 }
 
@@ -1119,7 +1128,7 @@ int msb_conv3x3(const void* split_in, const float* w_oihw, float* out, int trans
         set_error("msb_conv3x3: bad arguments / workspace too small"); return -1;
     }
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    pack_w(eng, w_oihw, workspace, channels, transpose, st);
+    pack_w(eng, w_oihw, workspace, channels, transpose, st, height, width);
     EpiParams e = epi_default();
     e.out_f32 = out;
     return run_conv(eng, (const __nv_bfloat16*)split_in, workspace, e, ConvShape{batch, height, width, channels}, st);

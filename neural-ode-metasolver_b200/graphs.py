@@ -11,6 +11,13 @@ parameters are fixed can be captured ONCE and replayed with no host work:
 Re-capture when u / v change (solver smoothing draws new values per batch: capture one graph per drawn value,
 or run those steps eagerly).  Gradients produced inside the step live in the graph's memory pool and are
 overwritten by the next replay.
+
+Everything the HOST decides during the step is frozen into the graph, not only u / v:
+  * the solver id drawn by the 'switch' regime (numpy RNG) and the coin flip of 'ensemble' with ensemble_prob < 1
+    (CPU torch.bernoulli) -- a replay repeats the captured draw;
+  * `FusedSGD.step()`'s lr, grad_scale and first-step flag (it refuses to be captured; keep the optimizer step, and a
+    CyclicLR schedule, outside the graph);
+  * the tableau-gradient backward (unfrozen solvers) copies 20 doubles to the host and cannot be captured at all.
 """
 import torch
 

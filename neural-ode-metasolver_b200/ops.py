@@ -135,6 +135,13 @@ def _stream(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def _wants_tape(*tensors):
+    """Record a tape only when a backward pass can follow.  Decided by the CALLER of Function.apply: inside
+    Function.forward grad mode is always off and ctx.needs_input_grad stays True for trainable parameters even under
+    torch.no_grad(), so an evaluation forward of a trainable model would otherwise allocate and write the whole tape."""
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
 def _check_inputs(x, w1, w2):
     if not x.is_cuda:
         raise RuntimeError("metasolver_b200: the ODE-block path runs on CUDA only (got a %s tensor); "
@@ -156,11 +163,11 @@ class _OdeBlockFn(torch.autograd.Function):
     them as coef's gradient, which autograd chains to u and v (unfreeze_params())."""
 
     @staticmethod
-    def forward(ctx, x, w1, w2, prob, coef=None):
+    def forward(ctx, x, w1, w2, prob, coef=None, save=True):
         _check_inputs(x, w1, w2)
         lib = _cabi.lib()
         dev = x.device
-        need_grad = any(ctx.needs_input_grad[:3]) or (coef is not None and ctx.needs_input_grad[4])
+        need_grad = bool(save)
         ctx.coef_shape = None if coef is None else tuple(coef.shape)
         with torch.cuda.device(dev):
             xc = x.detach().contiguous(memory_format=torch.channels_last)
@@ -221,7 +228,7 @@ class _OdeBlockFn(torch.autograd.Function):
                                                _stream(dev))
                 _cabi.check(rc, "odeblock backward")
         ctx.tape = None       # the tape is large; release it as soon as it has been consumed
-        return gx, gw1, gw2, None, gcoef
+        return gx, gw1, gw2, None, gcoef, None
 
 
 def _check_coef(prob, coef):
@@ -241,8 +248,7 @@ def ode_block_integrate(x, w1, w2, tableau, time_grid, rhs_kind=_cabi.RHS_PREACT
     prob = OdeProblem(rhs_kind, act, tableau, time_grid, engine)
     if tableau_coef is not None:
         _check_coef(prob, tableau_coef)
-        return _OdeBlockFn.apply(x, w1, w2, prob, tableau_coef)
-    return _OdeBlockFn.apply(x, w1, w2, prob, None)
+    return _OdeBlockFn.apply(x, w1, w2, prob, tableau_coef, _wants_tape(x, w1, w2, tableau_coef))
 
 
 def ode_block_integrate_stacked(x, w1, w2, tableaus, time_grid, rhs_kind=_cabi.RHS_PREACT_NF,
@@ -282,10 +288,10 @@ class _GnOdeBlockFn(torch.autograd.Function):
     family, the Butcher coefficients through `coef`, see _OdeBlockFn)."""
 
     @staticmethod
-    def forward(ctx, x, prob, groups, eps, keys, coef, *params):
+    def forward(ctx, x, prob, groups, eps, keys, coef, save, *params):
         lib = _cabi.lib()
         dev = x.device
-        need_grad = ctx.needs_input_grad[0] or any(ctx.needs_input_grad[5:])      # x, coef or any parameter
+        need_grad = bool(save)                                                    # x, coef or any parameter (see _wants_tape)
         ctx.coef_shape = None if coef is None else tuple(coef.shape)
         with torch.cuda.device(dev):
             xc = x.detach().contiguous(memory_format=torch.channels_last)
@@ -317,7 +323,7 @@ class _GnOdeBlockFn(torch.autograd.Function):
         keys = ctx.keys
         keep = dict(zip(keys, ctx.saved_tensors))
         dev = gy.device
-        need_w = any(ctx.needs_input_grad[6:]) and not (_input_only_depth[0] > 0)
+        need_w = any(ctx.needs_input_grad[7:]) and not (_input_only_depth[0] > 0)
         need_coef = ctx.coef_shape is not None and ctx.needs_input_grad[5]
         gcoef = None
         with torch.cuda.device(dev):
@@ -347,7 +353,7 @@ class _GnOdeBlockFn(torch.autograd.Function):
                                                      _stream(dev))
                 _cabi.check(rc, "odeblock backward (GroupNorm right-hand side)")
         ctx.tape = None
-        return (gx, None, None, None, None, gcoef) + (tuple(grads[k] for k in keys) if need_w else (None,) * len(keys))
+        return (gx, None, None, None, None, gcoef, None) + (tuple(grads[k] for k in keys) if need_w else (None,) * len(keys))
 
 
 def ode_block_integrate_mnist(x, params, tableau, time_grid, groups, eps=1e-5, tableau_coef=None):
@@ -359,7 +365,8 @@ def ode_block_integrate_mnist(x, params, tableau, time_grid, groups, eps=1e-5, t
     prob = OdeProblem(_cabi.RHS_MNIST_GN_T, _cabi.ACT_RELU, tableau, time_grid, "simt")
     if tableau_coef is not None:
         _check_coef(prob, tableau_coef)
-    return _GnOdeBlockFn.apply(x, prob, groups, eps, _MNIST_KEYS, tableau_coef, *[params[k] for k in _MNIST_KEYS])
+    ps = [params[k] for k in _MNIST_KEYS]
+    return _GnOdeBlockFn.apply(x, prob, groups, eps, _MNIST_KEYS, tableau_coef, _wants_tape(x, tableau_coef, *ps), *ps)
 
 
 def ode_block_integrate_gn(x, params, tableau, time_grid, groups, eps=1e-5, act=_cabi.ACT_GELU_ERF, engine=None):
@@ -375,7 +382,8 @@ def ode_block_integrate_gn(x, params, tableau, time_grid, groups, eps=1e-5, act=
     if C % groups:
         raise RuntimeError("metasolver_b200: %d channels are not divisible into %d groups" % (C, groups))
     prob = OdeProblem(_cabi.RHS_PREACT_GN, act, tableau, time_grid, engine)
-    return _GnOdeBlockFn.apply(x, prob, groups, eps, _GN_KEYS, None, *[params[k] for k in _GN_KEYS])
+    ps = [params[k] for k in _GN_KEYS]
+    return _GnOdeBlockFn.apply(x, prob, groups, eps, _GN_KEYS, None, _wants_tape(x, *ps), *ps)
 
 
 # --------------------------------------------------------------------------- non-ODE layers
@@ -387,10 +395,10 @@ class _StemFn(torch.autograd.Function):
     """y = act(conv3x3(x, w)), 3 -> C channels (MetaNODE stem, cifar10/layers.py:411-413)."""
 
     @staticmethod
-    def forward(ctx, x, w, act):
+    def forward(ctx, x, w, act, save=True):
         lib = _cabi.lib()
         dev = x.device
-        need_grad = any(ctx.needs_input_grad[:2])
+        need_grad = bool(save)
         B, _, H, W = x.shape
         C = w.shape[0]
         with torch.cuda.device(dev):
@@ -420,7 +428,7 @@ class _StemFn(torch.autograd.Function):
             gx = torch.empty_like(xc) if need_x else None
             _cabi.check(lib.msb_stem_backward(_ptr(gyc), _ptr(dact), _ptr(xc), _ptr(wc), _ptr(gw), _ptr(gx), B, H, W, C,
                                               _ptr(ws), ws_bytes, _stream(dev)), "stem backward")
-        return gx, gw, None
+        return gx, gw, None, None
 
 
 def stem_conv_act(x, w, act=_cabi.ACT_GELU_ERF):
@@ -430,7 +438,7 @@ def stem_conv_act(x, w, act=_cabi.ACT_GELU_ERF):
     if x.dtype != torch.float32 or w.dtype != torch.float32 or x.dim() != 4 or x.shape[1] != 3 \
             or tuple(w.shape[1:]) != (3, 3, 3):
         raise RuntimeError("metasolver_b200: stem expects fp32 (B,3,H,W) input and (C,3,3,3) weight")
-    return _StemFn.apply(x, w, act)
+    return _StemFn.apply(x, w, act, _wants_tape(x, w))
 
 
 class _DownBlockFn(torch.autograd.Function):
@@ -446,10 +454,10 @@ class _DownBlockFn(torch.autograd.Function):
         return d
 
     @staticmethod
-    def forward(ctx, x, w1, w2, wsc, act, engine):
+    def forward(ctx, x, w1, w2, wsc, act, engine, save=True):
         lib = _cabi.lib()
         dev = x.device
-        need_grad = any(ctx.needs_input_grad[:4])
+        need_grad = bool(save)
         B, Ci, H, W = x.shape
         Co = w1.shape[0]
         with torch.cuda.device(dev):
@@ -492,7 +500,7 @@ class _DownBlockFn(torch.autograd.Function):
                                                    ctx.tape_bytes, _ptr(gx), _ptr(gws[0]), _ptr(gws[1]), _ptr(gws[2]),
                                                    _ptr(ws), ws_bytes, _stream(dev)), "downblock backward")
         ctx.tape = None
-        return gx, gws[0], gws[1], gws[2], None, None
+        return gx, gws[0], gws[1], gws[2], None, None, None
 
 
 def resblock_down(x, w1, w2, wsc, act=_cabi.ACT_GELU_ERF, engine=None):
@@ -502,7 +510,7 @@ def resblock_down(x, w1, w2, wsc, act=_cabi.ACT_GELU_ERF, engine=None):
     C = x.shape[1]
     if tuple(w1.shape) != (2 * C, C, 3, 3) or tuple(w2.shape) != (2 * C, 2 * C, 3, 3) or tuple(wsc.shape) != (2 * C, C, 1, 1):
         raise RuntimeError("metasolver_b200: strided block weight shapes do not match a %d -> %d block" % (C, 2 * C))
-    return _DownBlockFn.apply(x, w1, w2, wsc, act, _cabi.ENGINES[engine or _default_engine[0]])
+    return _DownBlockFn.apply(x, w1, w2, wsc, act, _cabi.ENGINES[engine or _default_engine[0]], _wants_tape(x, w1, w2, wsc))
 
 
 # --------------------------------------------------------------------------- single-kernel entry points

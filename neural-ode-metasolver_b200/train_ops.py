@@ -91,7 +91,7 @@ class FusedSGD:
         self.flat_param = torch.empty(n, dtype=torch.float32, device=dev)
         self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
         self.momentum_buf = torch.zeros(n, dtype=torch.float32, device=dev) if self.momentum != 0.0 else None
-        self._first = True
+        self._seen = [False] * len(self.params)      # torch.optim.SGD creates a momentum buffer at a parameter's first update
         off = 0
         with torch.no_grad():
             for p in self.params:
@@ -111,19 +111,68 @@ class FusedSGD:
                 p.grad = self.flat_grad[off:off + k].view(p.shape)
             off += k
 
+    def _gather_grads(self):
+        """Make the flat gradient buffer hold what the parameters' `.grad`s hold.
+
+        `model.zero_grad()` / `zero_grad(set_to_none=True)` (the torch >= 2.0 default) detach `.grad` from the flat buffer:
+        the next backward then writes fresh tensors the flat buffer never sees.  Stray gradients are copied in and
+        re-attached; a parameter whose grad is None gets a zero slice (for the all-reduce sum) and is reported so that
+        step() can skip it like torch.optim.SGD does.  Returns the list of booleans "has a gradient" per parameter."""
+        has = []
+        off = 0
+        base = self.flat_grad.data_ptr()
+        with torch.no_grad():
+            for p in self.params:
+                k = p.numel()
+                view = self.flat_grad[off:off + k].view(p.shape)
+                if p.grad is None:
+                    view.zero_()
+                    has.append(False)
+                else:
+                    if p.grad.data_ptr() != base + 4 * off:
+                        if p.grad.shape != p.shape or p.grad.dtype != torch.float32 or p.grad.device != self.flat_grad.device:
+                            raise RuntimeError("metasolver_b200.FusedSGD: gradient of shape %s / %s on %s does not match its "
+                                               "parameter" % (tuple(p.grad.shape), p.grad.dtype, p.grad.device))
+                        view.copy_(p.grad)
+                        p.grad = view
+                    has.append(True)
+                off += k
+        return has
+
     def all_reduce(self):
         """Sum the flat gradient over the ranks; returns the scale (1/world) that step() must apply."""
+        self._gather_grads()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)
             return 1.0 / dist.get_world_size()
         return 1.0
 
     def step(self, grad_scale=1.0):
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("metasolver_b200.FusedSGD.step() passes lr / grad_scale / the first-step flag by value: a "
+                               "captured step would replay a frozen learning rate.  Call it outside the CUDA graph.")
+        has = self._gather_grads()
         self.lr = float(self.param_groups[0]["lr"])
         dev = self.flat_param.device
+        # contiguous runs of parameters that have a gradient and share the "first update" state: ONE run (one kernel)
+        # in the normal case; parameters without a gradient are skipped entirely (no weight decay, no momentum
+        # update), exactly like torch.optim.SGD
+        runs = []
+        off = 0
+        for i, p in enumerate(self.params):
+            k = p.numel()
+            if has[i]:
+                first = not self._seen[i]
+                if runs and runs[-1][0] + runs[-1][1] == off and runs[-1][2] == first:
+                    runs[-1][1] += k
+                else:
+                    runs.append([off, k, first])
+                self._seen[i] = True
+            off += k
         with torch.cuda.device(dev):
-            _cabi.check(_cabi.lib().msb_sgd_step(_ptr(self.flat_param), _ptr(self.flat_grad), _ptr(self.momentum_buf),
-                                                 self.flat_param.numel(), self.lr, self.momentum, self.weight_decay,
-                                                 float(grad_scale), 1 if self._first else 0,
-                                                 ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "sgd_step")
-        self._first = False
+            st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            for off, k, first in runs:
+                mom = self.momentum_buf[off:off + k] if self.momentum_buf is not None else None
+                _cabi.check(_cabi.lib().msb_sgd_step(_ptr(self.flat_param[off:off + k]), _ptr(self.flat_grad[off:off + k]),
+                                                     _ptr(mom), k, self.lr, self.momentum, self.weight_decay,
+                                                     float(grad_scale), 1 if first else 0, st), "sgd_step")

@@ -205,7 +205,7 @@ def test_tuning_options_do_not_change_results(C, HW):
     names = ("epi_l2_prefetch", "tc_resident", "tcp_epi_warps", "pdl", "wait_backoff_ns")
     defaults = {k: metasolver_b200.get_option(k) for k in names + ("tc_form_c64",)}
     try:
-        for form in (0, 1):           # the two conv forms differ in the products they form: compare within a form
+        for form in ((0, 1, 2) if C == 64 else (1,)):   # the conv forms differ in the products they form: compare within a form
             metasolver_b200.set_option("tc_form_c64", form)
             for k, v in zip(names, (0, 0, 8, 0, 0)):
                 metasolver_b200.set_option(k, v)
@@ -215,6 +215,12 @@ def test_tuning_options_do_not_change_results(C, HW):
                     metasolver_b200.set_option(k, v)
                 for a, b in zip(base, run()):
                     assert torch.equal(a, b), (form, vals)
+            if form == 2:             # band height of the TMEM-resident-weight form: same sums, same order
+                for band in (4, 8, 32):
+                    metasolver_b200.set_option("tct_band", band)
+                    for a, b in zip(base, run()):
+                        assert torch.equal(a, b), (form, "tct_band", band)
+                metasolver_b200.set_option("tct_band", 0)
         with pytest.raises(RuntimeError):
             metasolver_b200.set_option("no_such_option", 1)
     finally:
@@ -259,7 +265,8 @@ def test_cta_pair_conv_matches_single_cta(C, HW):
         assert max_rel(e.cpu().numpy(), a.cpu().numpy()) <= 2e-6
 
 
-@pytest.mark.parametrize("C,H,W,B", [(128, 8, 32, 4), (64, 16, 16, 4), (128, 16, 16, 3), (64, 4, 32, 1), (128, 8, 16, 1)])
+@pytest.mark.parametrize("C,H,W,B", [(128, 8, 32, 4), (64, 16, 16, 4), (128, 16, 16, 3), (64, 4, 32, 1), (128, 8, 16, 1),
+                                     (64, 32, 32, 5), (64, 12, 32, 2), (64, 16, 32, 3), (64, 8, 32, 37)])
 def test_every_tcgen05_tile_geometry_agrees_with_simt_engine(C, H, W, B):
     """All (C, W) instantiations of the tcgen05 convolutions -- single-CTA and CTA-pair (even tile counts), full-width and
     16-pixel-wide tiles, odd tile counts that fall back to the single-CTA kernel -- against the independent fp32 SIMT
@@ -286,3 +293,37 @@ def test_every_tcgen05_tile_geometry_agrees_with_simt_engine(C, H, W, B):
 
     for a, b in zip(run("tcgen05"), run("simt")):
         assert max_rel(a.cpu().numpy(), b.cpu().numpy()) <= 2e-5
+
+
+@pytest.mark.parametrize("B", [3, 160])
+def test_tmem_resident_weight_conv_matches_pixel_major_form(B):
+    """tc_form_c64 = 2 (conv_tct.cu: weights resident in tensor memory as the A operand, activations from a ring of image
+    rows, all four hi/lo products) against the pixel-major form (three products): outputs and every gradient agree to
+    the dropped lo*lo term / accumulation order, and the new form is bitwise reproducible.  B = 160 gives every CTA more
+    than one work item (ring wrap-around, accumulator phases)."""
+    import metasolver_b200
+    blk, solver, opts = _block(64)
+    torch.manual_seed(7)
+    x0 = torch.randn(B, 64, 32, 32, device="cuda").contiguous(memory_format=torch.channels_last)
+    r = torch.randn_like(x0)
+
+    def run():
+        x = x0.clone().requires_grad_(True)
+        for p in blk.parameters():
+            p.grad = None
+        y = blk(x, [solver], opts)
+        (y * r).sum().backward()
+        return [y.detach().clone(), x.grad.clone()] + [p.grad.clone() for p in blk.parameters()]
+
+    d = metasolver_b200.get_option("tc_form_c64")
+    try:
+        metasolver_b200.set_option("tc_form_c64", 1)
+        pm = run()
+        metasolver_b200.set_option("tc_form_c64", 2)
+        t1 = run()
+        t2 = run()
+    finally:
+        metasolver_b200.set_option("tc_form_c64", d)
+    for a, b, c in zip(pm, t1, t2):
+        assert torch.equal(b, c)
+        assert max_rel(b.cpu().numpy(), a.cpu().numpy()) <= 1e-5
