@@ -86,10 +86,24 @@ constexpr int kRowBytes = 2 * 32 * 128;                    // one image row, bot
 constexpr int kSlotBytes = 3 * kRowBytes;                  // ... for the three horizontal taps
 constexpr int kSlots = 8;                                  // image rows in the ring
 constexpr int kStageBytes = 32 * 64 * 4;                   // one output row, fp32, per epilogue group
-constexpr int kAccBufs = 3;
+constexpr int kMaxAccBufs = 6;
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kAccCols = 64;
-constexpr uint32_t kWCol0 = kAccBufs * kAccCols;           // weights: columns 192 .. 479
+constexpr uint32_t kWCol0 = 192;                           // accumulators: columns 0 .. 191, weights: columns 192 .. 479
+// P3 (three hi/lo products, option tct_products = 3): per k-step  D[:, 32 px] (+)= [W_hi ; W_lo] * X_hi   (M = 128, N = 32)
+//                                                     D[hi rows, 32 px] += W_hi * X_lo          (M = 64,  N = 32)
+// An M = 64 MMA reads its A rows from / adds its D rows into lanes 0-15 of each 32-lane TMEM quadrant (measured,
+// scripts/probes/mma_m64_probe.cu) -- exactly where the interleaved row order keeps the W_hi rows, so both MMAs name
+// the same A slab and the same accumulator.  Same tensor-pipe time as the four-product form (an M = 64 MMA is not
+// faster than an M = 128 one) but a quarter fewer MACs, which is what counts under the board power cap; the
+// accumulator of an output row shrinks to 32 columns (the two activation planes are summed by the tensor core),
+// so six rows are in flight instead of three.  Measured (profiles/conv_forms_r2.txt): 148 vs 121 us per launch -- 72 MMAs
+// of 16 clocks per row are bound by the issue rate of the pipe, not by power -- so it is an option, not the default.
+// !P3 (four products, the default): one M = 128, N = 64 MMA per k-step on [X_hi ; X_lo], 64-column accumulators, three in
+// flight.
+template <bool P3> struct AccGeom {
+    static constexpr int BUFS = P3 ? 6 : 3;
+    static constexpr uint32_t COLS = P3 ? 32 : 64;
+};
 constexpr int kWChunks = 18;                               // 288 columns in chunks of 16
 
 // An mbarrier wait names a phase by its PARITY, so a waiter must see every phase of a barrier (it may lag by at most
@@ -100,7 +114,7 @@ constexpr int kWChunks = 18;                               // 288 columns in chu
 constexpr int kFullBars = 12;
 struct __align__(8) Barriers {
     uint64_t full[kSlots], empty[kSlots];
-    uint64_t tmem_full[kFullBars], tmem_empty[kAccBufs];
+    uint64_t tmem_full[kFullBars], tmem_empty[kMaxAccBufs];
     uint32_t tmem_base;
 };
 
@@ -139,12 +153,14 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int ACT, bool LEAN>
+template <int ACT, bool LEAN, bool P3>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tct_kernel(const __grid_constant__ CUtensorMap tmap_act, const uint4* __restrict__ wpacked, const EpiParams epi,
                    const int H, const int num_items, const int bands_per_img, const int BH, const int l2pf,
                    const uint32_t backoff_ns, const int dbg) {
     constexpr int C = 64, W = 32;
+    constexpr int kAccBufs = AccGeom<P3>::BUFS;
+    constexpr uint32_t kAccCols = AccGeom<P3>::COLS;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_rows = smem;                                       // kSlots x kSlotBytes
@@ -158,7 +174,7 @@ conv3x3_tct_kernel(const __grid_constant__ CUtensorMap tmap_act, const uint4* __
         ptx::prefetch_tmap(&tmap_act);
         for (int i = 0; i < kSlots; ++i) { ptx::mbar_init(&bars->full[i], 1); ptx::mbar_init(&bars->empty[i], 1); }
         for (int i = 0; i < kFullBars; ++i) ptx::mbar_init(&bars->tmem_full[i], 1);
-        for (int i = 0; i < kAccBufs; ++i) ptx::mbar_init(&bars->tmem_empty[i], 4);
+        for (int i = 0; i < kMaxAccBufs; ++i) ptx::mbar_init(&bars->tmem_empty[i], 4);
         ptx::fence_barrier_init();
     }
     if (warp == kAllocWarp) {
@@ -221,7 +237,8 @@ conv3x3_tct_kernel(const __grid_constant__ CUtensorMap tmap_act, const uint4* __
         named_bar_sync(5, (kEpiWarps + 2) * 32);       // the weights are in TMEM (written by the epilogue warps below)
         ptx::tc_fence_after();
         {
-            constexpr uint32_t idesc = ptx::make_idesc_bf16(128, 64, 0, 0);
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(128, P3 ? 32 : 64, 0, 0);
+            constexpr uint32_t idesc_hi = ptx::make_idesc_bf16(64, 32, 0, 0);       // P3: the W_hi rows only
             const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
             const uint32_t w_tmem = tb + kWCol0;
             const uint32_t rows_u32 = ptx::smem_u32(smem_rows);
@@ -257,9 +274,15 @@ conv3x3_tct_kernel(const __grid_constant__ CUtensorMap tmap_act, const uint4* __
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 const uint64_t bdesc = ptx::make_smem_desc_sw128(b_base[r] + s * kRowBytes + k * 32, 16, 1024);
-                                if (!(dbg & 2))
-                                    umma_bf16_ts(d_tmem, w_tmem + (uint32_t)((r * 3 + s) * 32 + k * 8), bdesc, idesc,
-                                                 (r | s | k) ? 1u : 0u);
+                                const uint32_t a_tmem = w_tmem + (uint32_t)((r * 3 + s) * 32 + k * 8);
+                                if (!(dbg & 2)) {
+                                    umma_bf16_ts(d_tmem, a_tmem, bdesc, idesc, (r | s | k) ? 1u : 0u);
+                                    if (P3) {       // the lo plane of the activations starts 32 rows (4 KB) further
+                                        const uint64_t bdesc_lo =
+                                            ptx::make_smem_desc_sw128(b_base[r] + s * kRowBytes + kRowBytes / 2 + k * 32, 16, 1024);
+                                        umma_bf16_ts(d_tmem, a_tmem, bdesc_lo, idesc_hi, 1u);
+                                    }
+                                }
                             }
                         }
                     }
@@ -367,7 +390,11 @@ conv3x3_tct_kernel(const __grid_constant__ CUtensorMap tmap_act, const uint4* __
             {
                 const uint32_t t_acc = tmem_base + (uint32_t)acc * kAccCols + lane_addr;
                 float s0[16], s1[16];
-                {
+                if (P3) {                     // the tensor core has already summed the two activation planes
+                    ptx::tmem_ld16(t_acc + 0, s0);
+                    ptx::tmem_ld16(t_acc + 16, s1);
+                    ptx::tmem_ld_wait();
+                } else {
                     float a[16], b[16];
                     ptx::tmem_ld16(t_acc + 0, a);
                     ptx::tmem_ld16(t_acc + 32, b);
@@ -428,13 +455,13 @@ conv3x3_tct_kernel(const __grid_constant__ CUtensorMap tmap_act, const uint4* __
     }
 }
 
-template <int ACT, bool LEAN>
+template <int ACT, bool LEAN, bool P3>
 int launch_act(const __nv_bfloat16* split_in, const void* wpacked, const EpiParams& epi, ConvShape s, cudaStream_t st) {
     CUtensorMap tm_act;
     if (make_tmap_split5d(&tm_act, split_in, s.B, s.H, s.W, s.C, 32, 1)) return -1;
     constexpr size_t smem = (size_t)kSlots * kSlotBytes + 4 * kStageBytes + sizeof(Barriers) + 1024;
     static_assert(smem <= 232448, "shared memory per CTA");
-    auto kern = conv3x3_tct_kernel<ACT, LEAN>;
+    auto kern = conv3x3_tct_kernel<ACT, LEAN, P3>;
     if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                    "cudaFuncSetAttribute(conv3x3_tct)"))
         return -1;
@@ -461,10 +488,16 @@ int launch_conv3x3_tct(const __nv_bfloat16* split_in, const void* wpacked, const
     const int act = (epi.out_split || epi.dact_out) ? epi.act : ACT_NONE;
     // lean instantiation: at most one src[] operand and no split_mul (every RK2 / Euler launch of the pre-activation RHS)
     const bool lean = epi_is_lean(epi);
-    if (act == ACT_GELU) return lean ? launch_act<ACT_GELU, true>(split_in, wpacked, epi, s, st) : launch_act<ACT_GELU, false>(split_in, wpacked, epi, s, st);
-    if (act == ACT_RELU) return lean ? launch_act<ACT_RELU, true>(split_in, wpacked, epi, s, st) : launch_act<ACT_RELU, false>(split_in, wpacked, epi, s, st);
-    return lean ? launch_act<ACT_NONE, true>(split_in, wpacked, epi, s, st) : launch_act<ACT_NONE, false>(split_in, wpacked, epi, s, st);
+    const bool p3 = tune_get(TUNE_TCT_PRODUCTS) == 3;
+#define MSB_TCT_GO(A) (lean ? (p3 ? launch_act<A, true, true>(split_in, wpacked, epi, s, st) : launch_act<A, true, false>(split_in, wpacked, epi, s, st)) \
+                            : (p3 ? launch_act<A, false, true>(split_in, wpacked, epi, s, st) : launch_act<A, false, false>(split_in, wpacked, epi, s, st)))
+    if (act == ACT_GELU) return MSB_TCT_GO(ACT_GELU);
+    if (act == ACT_RELU) return MSB_TCT_GO(ACT_RELU);
+    return MSB_TCT_GO(ACT_NONE);
+#undef MSB_TCT_GO
 }
+
+int tct_products() { return tune_get(TUNE_TCT_PRODUCTS) == 3 ? 3 : 4; }
 
 // ---------------------------------------------------------------------------------------------
 // weight pack for this form: OIHW fp32 -> the TMEM image of A = [W_hi ; W_lo], as 32-bit words

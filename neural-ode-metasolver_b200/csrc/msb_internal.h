@@ -27,6 +27,7 @@ enum { TUNE_EPI_L2_PREFETCH = 0,   // conv epilogue operands: bulk L2 prefetch d
        TUNE_WGRAD_MULTICAST = 7,   // weight-gradient GEMM: cluster of the tap groups, gout box multicast (one L2 read per cluster)
        TUNE_TCT_BAND = 8,          // TMEM-resident-weight conv: image rows per work item (0 = 16 / 8 / 4 by image height)
        TUNE_TCT_DEBUG = 9,         // TMEM-resident-weight conv: decomposition switches (timing experiments only; results are garbage)
+       TUNE_TCT_PRODUCTS = 10,     // TMEM-resident-weight conv: hi/lo products formed, 3 (default) or 4
        TUNE_COUNT };
 int tune_get(int which);
 
@@ -120,6 +121,7 @@ bool tct_shape_supported(int C, int H, int W);
 size_t tct_packed_weight_bytes();
 void launch_pack_w_tct(const float* w, void* out, int transpose, cudaStream_t st);
 int launch_conv3x3_tct(const __nv_bfloat16* split_in, const void* wpacked, const EpiParams& epi, ConvShape s, cudaStream_t st);
+int tct_products();
 
 // ---- wgrad_tc.cu ----
 bool wgrad_tc_supported(ConvShape s);

@@ -13,9 +13,9 @@ from metasolver_b200.sopa.src.models.odenet_cifar10.utils import Identity
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 REPS, ROUNDS = 3, 4
 torch.manual_seed(0)
-def S(form=2, pf=0, band=0, pdl=1):
-    return dict(tc_form_c64=form, epi_l2_prefetch=pf, tct_band=band, pdl=pdl)
-sets = [S(1), S(2), S(2, pf=1), S(2, band=8), S(2, band=32), S(2, pdl=0), S(0)]
+def S(form=2, pf=0, band=0, pdl=1, prod=3):
+    return dict(tc_form_c64=form, epi_l2_prefetch=pf, tct_band=band, pdl=pdl, tct_products=prod)
+sets = [S(1), S(2), S(2, prod=4), S(2, band=8), S(2, pf=1)]
 C, HW = 64, 32
 blk = MetaODEBlock(PreBasicBlock2(C, norm_layer=Identity, act_layer=F.gelu)).cuda()
 solver = create_solver("rk2", "u", 8, -1, 0.5, -1, torch.float32, "cuda"); solver.freeze_params()

@@ -315,15 +315,20 @@ def test_tmem_resident_weight_conv_matches_pixel_major_form(B):
         (y * r).sum().backward()
         return [y.detach().clone(), x.grad.clone()] + [p.grad.clone() for p in blk.parameters()]
 
-    d = metasolver_b200.get_option("tc_form_c64")
+    d, dp = metasolver_b200.get_option("tc_form_c64"), metasolver_b200.get_option("tct_products")
     try:
         metasolver_b200.set_option("tc_form_c64", 1)
         pm = run()
         metasolver_b200.set_option("tc_form_c64", 2)
+        metasolver_b200.set_option("tct_products", 3)     # M = 128 MMA on the hi plane + M = 64 MMA on the lo plane
         t1 = run()
         t2 = run()
+        metasolver_b200.set_option("tct_products", 4)     # one M = 128 MMA on both planes
+        t4 = run()
     finally:
         metasolver_b200.set_option("tc_form_c64", d)
-    for a, b, c in zip(pm, t1, t2):
+        metasolver_b200.set_option("tct_products", dp)
+    for a, b, c, e in zip(pm, t1, t2, t4):
         assert torch.equal(b, c)
         assert max_rel(b.cpu().numpy(), a.cpu().numpy()) <= 1e-5
+        assert max_rel(e.cpu().numpy(), a.cpu().numpy()) <= 1e-5
