@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define MSB_ABI_VERSION 3   /* v3: + tuning options, attack / SGD steps, tableau gradients, MSB_RHS_PREACT_GN (structs unchanged) */
+#define MSB_ABI_VERSION 4   /* v3: + tuning options, attack / SGD steps, tableau gradients, MSB_RHS_PREACT_GN; v4: + network head (pool + FC, cross-entropy) (structs unchanged) */
 #define MSB_MAX_STAGES 4
 
 /* right-hand-side families */
@@ -236,6 +236,24 @@ int msb_attack_step(int kind, const float* a, const float* grad, const float* re
 int msb_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t n, float lr, float momentum,
                  float weight_decay, float grad_scale, int first_step, void* cuda_stream);
 
+/* Network head of MetaNODE: AdaptiveAvgPool2d((1,1)) + Flatten + Linear (sopa/src/models/odenet_cifar10/layers.py:390-392,425)
+ * on an NHWC fp32 map, and its gradient.  pooled[batch][channels] is an output of the forward (saved for the backward).
+ *   logits[n][k] = bias[k] + sum_c W[k][c] * mean_p x[n][p][c]
+ * backward: dx[n][p][c] = (sum_k dlogits[n][k] W[k][c]) / hw   (dx may be NULL),
+ *           dw[k][c] = sum_n dlogits[n][k] pooled[n][c], dbias[k] = sum_n dlogits[n][k]   (dw NULL = no parameter gradients;
+ *           fixed summation order: bitwise reproducible).  channels must be a multiple of 4. */
+int msb_pool_fc_forward(const float* x_nhwc, const float* w, const float* bias, float* pooled, float* logits, int batch,
+                        int hw, int channels, int classes, void* cuda_stream);
+int msb_pool_fc_backward(const float* dlogits, const float* w, const float* pooled, float* dx_nhwc, float* dw, float* dbias,
+                         int batch, int hw, int channels, int classes, void* cuda_stream);
+/* Mean cross-entropy over the batch (nn.CrossEntropyLoss / F.cross_entropy with default reduction;
+ * examples/cifar10/train_and_attack.py:303-311, fgsm.py:33, pgd.py:43): loss[0] = mean_n (logsumexp(z_n) - z_n[y_n]);
+ * lse[batch] is saved for the backward: dlogits = (softmax(z) - onehot(y)) * grad_loss[0] / batch.  labels are int64. */
+int msb_cross_entropy_forward(const float* logits, const int64_t* labels, float* loss, float* lse, int batch, int classes,
+                              void* cuda_stream);
+int msb_cross_entropy_backward(const float* logits, const int64_t* labels, const float* lse, const float* grad_loss,
+                               float* dlogits, int batch, int classes, void* cuda_stream);
+
 /* Tuning options (process-wide; defaults are the measured best).  Names:
  *   "epi_l2_prefetch"  distance, in tiles, at which the tcgen05 convolutions bulk-prefetch their epilogue
  *                      operands (y, k_j, act') into L2; 0 = off          (env MSB_EPI_L2_PREFETCH)
@@ -243,7 +261,13 @@ int msb_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t
  *                                                                        (env MSB_TC_RESIDENT)
  *   "tcp_epi_warps"    epilogue warps of the pixel-major convolution, 8 or 16      (env MSB_TCP_EPI_WARPS)
  *   "tc_form_c64"      tcgen05 convolution form for 64 channels: 0 = channel-major (4 hi/lo products),
- *                      1 = pixel-major (3 products)                      (env MSB_TC_FORM_C64)
+ *                      1 = pixel-major (3 products), 2 (default) = weights resident in tensor memory as the A operand,
+ *                      activations from a ring of image rows (32-pixel-wide images; pixel-major elsewhere)
+ *                                                                        (env MSB_TC_FORM_C64)
+ *   "tct_band"         image rows per work item of form 2 (0 = 16 / 8 / 4 by image height)   (env MSB_TCT_BAND)
+ *   "tct_products"     hi/lo products of form 2: 4 (default) or 3 (an M = 64 MMA for the lo plane)  (env MSB_TCT_PRODUCTS)
+ *   "tct_debug"        decomposition switches of form 2 for timing experiments (results are garbage; 0 = off)
+ *   "mma_warp_high"    1 = pixel-major convolutions place their TMA / MMA warps on the highest warp ids (env MSB_MMA_WARP_HIGH)
  *   "tc_pair"          pixel-major convolution on CTA pairs (tcgen05.mma.cta_group::2, M = 256, weights shared by
  *                      the pair): 0 = off, 1 = every shape with an even tile count, 2 = only C >= 128 (default)
  *                                                                        (env MSB_TC_PAIR)
@@ -254,7 +278,8 @@ int msb_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t
  *                      griddepcontrol.wait orders every access to the predecessor's outputs   (env MSB_PDL)
  *   "wgrad_multicast"  1 = weight-gradient GEMM as clusters of the tap groups with the shared gout box loaded once by
  *                      TMA multicast (measured slower with the current two-stage ring; default 0)  (env MSB_WGRAD_MULTICAST)
- * Results do not depend on any option.  Returns 0, or -1 for an unknown name. */
+ * Results do not depend on any option except the products formed (tc_form_c64, tct_products: last-bit differences) and
+ * tct_debug.  Returns 0, or -1 for an unknown name. */
 int msb_set_option(const char* name, int value);
 int msb_get_option(const char* name, int* value);
 

@@ -8,7 +8,8 @@ include/metasolver_b200.h (ctypes binding: _cabi.py).  There is no cuDNN, Triton
 """
 from . import _cabi  # noqa: F401
 from .ops import (ode_block_integrate, input_grad_only, set_default_engine, launch_count,  # noqa: F401
-                  profile_enable, profile_read, profile_read_executed, set_option, get_option)
+                  profile_enable, profile_read, profile_read_executed, set_option, get_option, pool_fc, cross_entropy,
+                  set_library_fallback, library_fallback_allowed)
 from .graphs import GraphedStep  # noqa: F401
 from .train_ops import attack_step, FusedSGD  # noqa: F401
 

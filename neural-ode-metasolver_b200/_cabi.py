@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("MSB_LIB_PATH") or os.path.join(HERE, "libmetasolver_b
 
 MSB_MAX_STAGES = 4
 TABLEAU_GRAD_DOUBLES = MSB_MAX_STAGES + MSB_MAX_STAGES * MSB_MAX_STAGES + MSB_MAX_STAGES   # [b | w | c]
-ABI_VERSION = 3
+ABI_VERSION = 4
 RHS_PREACT_NF, RHS_POSTACT_NF, RHS_MNIST_GN_T, RHS_PREACT_GN = 0, 1, 2, 3
 ACT_NONE, ACT_GELU_ERF, ACT_RELU = 0, 1, 2
 (ATTACK_UNNORMALIZE, ATTACK_NORMALIZE, ATTACK_FGSM_STEP, ATTACK_PGD_STEP, ATTACK_FGSMR_INIT,
@@ -31,6 +31,7 @@ EXPORTS = [
     "msb_conv3x3_workspace_bytes", "msb_wgrad3x3", "msb_wgrad3x3_workspace_bytes", "msb_launch_count", "msb_profile_enable", "msb_profile_read", "msb_profile_read_executed",
     "msb_set_option", "msb_get_option", "msb_attack_step", "msb_sgd_step",
     "msb_odeblock_bwd_workspace_bytes_tableau", "msb_odeblock_backward_tableau", "msb_odeblock_backward_mnist_tableau",
+    "msb_pool_fc_forward", "msb_pool_fc_backward", "msb_cross_entropy_forward", "msb_cross_entropy_backward",
 ]
 
 
@@ -124,6 +125,10 @@ def _declare(lib):
     f32, i64 = ctypes.c_float, ctypes.c_int64
     lib.msb_attack_step.argtypes = [i32, vp, vp, vp, vp, i64, i32, i32, i32, f32, f32, i32, ctypes.POINTER(f32), vp]
     lib.msb_sgd_step.argtypes = [vp, vp, vp, i64, f32, f32, f32, f32, i32, vp]
+    lib.msb_pool_fc_forward.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.msb_pool_fc_backward.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.msb_cross_entropy_forward.argtypes = [vp, vp, vp, vp, i32, i32, vp]
+    lib.msb_cross_entropy_backward.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp]
     lib.msb_profile_enable.argtypes = [i32]
     lib.msb_profile_read_executed.argtypes = [i32, ctypes.POINTER(ctypes.c_double)]
     lib.msb_profile_read.argtypes = [i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),

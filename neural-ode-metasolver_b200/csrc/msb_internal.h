@@ -28,6 +28,7 @@ enum { TUNE_EPI_L2_PREFETCH = 0,   // conv epilogue operands: bulk L2 prefetch d
        TUNE_TCT_BAND = 8,          // TMEM-resident-weight conv: image rows per work item (0 = 16 / 8 / 4 by image height)
        TUNE_TCT_DEBUG = 9,         // TMEM-resident-weight conv: decomposition switches (timing experiments only; results are garbage)
        TUNE_TCT_PRODUCTS = 10,     // TMEM-resident-weight conv: hi/lo products formed, 3 (default) or 4
+       TUNE_MMA_WARP_HIGH = 11,    // pixel-major convs: TMA / MMA roles on the highest physical warps (scheduler priority)
        TUNE_COUNT };
 int tune_get(int which);
 

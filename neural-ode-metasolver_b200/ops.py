@@ -19,6 +19,28 @@ from . import _cabi
 # thread, where a thread-local set by the caller of autograd.grad() would not be visible.
 _input_only_depth = [0]
 _default_engine = ["auto"]
+_library_fallback = [False]
+
+
+def set_library_fallback(allow):
+    """Layers of the model zoo AROUND the ODE blocks (stem, residual blocks, head) run on this library's kernels for
+    the published configurations.  For anything else (BatchNorm residual blocks, the post-activation `BasicBlock`,
+    weight-normed convolutions, CPU tensors ...) they raise, like the ODE blocks do -- unless the caller explicitly opts
+    in to PyTorch's own (cuDNN / ATen) kernels for those layers with `set_library_fallback(True)`.  The ODE blocks
+    themselves never fall back."""
+    _library_fallback[0] = bool(allow)
+
+
+def library_fallback_allowed():
+    return _library_fallback[0]
+
+
+def require_fallback(what, why):
+    if not _library_fallback[0]:
+        raise NotImplementedError(
+            "metasolver_b200: %s is not implemented on the library's kernels (%s).  There is no silent cuDNN / CPU "
+            "fallback; call metasolver_b200.set_library_fallback(True) to run this layer with PyTorch's own kernels."
+            % (what, why))
 
 
 def set_default_engine(name):
@@ -511,6 +533,94 @@ def resblock_down(x, w1, w2, wsc, act=_cabi.ACT_GELU_ERF, engine=None):
     if tuple(w1.shape) != (2 * C, C, 3, 3) or tuple(w2.shape) != (2 * C, 2 * C, 3, 3) or tuple(wsc.shape) != (2 * C, C, 1, 1):
         raise RuntimeError("metasolver_b200: strided block weight shapes do not match a %d -> %d block" % (C, 2 * C))
     return _DownBlockFn.apply(x, w1, w2, wsc, act, _cabi.ENGINES[engine or _default_engine[0]], _wants_tape(x, w1, w2, wsc))
+
+
+class _PoolFcFn(torch.autograd.Function):
+    """logits = Linear(mean over pixels(x)): the head of MetaNODE (cifar10/layers.py:390-392, 425) as one kernel."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        lib = _cabi.lib()
+        dev = x.device
+        B, C, H, W = x.shape
+        K = w.shape[0]
+        with torch.cuda.device(dev):
+            xc = x.detach().contiguous(memory_format=torch.channels_last)
+            wc = w.detach().contiguous()
+            bc = b.detach().contiguous() if b is not None else None
+            pooled = torch.empty((B, C), dtype=torch.float32, device=dev)
+            logits = torch.empty((B, K), dtype=torch.float32, device=dev)
+            _cabi.check(lib.msb_pool_fc_forward(_ptr(xc), _ptr(wc), _ptr(bc), _ptr(pooled), _ptr(logits), B, H * W, C, K,
+                                                _stream(dev)), "pool_fc forward")
+        ctx.save_for_backward(wc, pooled)
+        ctx.geom = (B, C, H, W, K, b is not None)
+        return logits
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _cabi.lib()
+        wc, pooled = ctx.saved_tensors
+        B, C, H, W, K, has_b = ctx.geom
+        dev = g.device
+        need_x = ctx.needs_input_grad[0]
+        need_w = (ctx.needs_input_grad[1] or (has_b and ctx.needs_input_grad[2])) and not _input_only()
+        with torch.cuda.device(dev):
+            gc = g.contiguous()
+            dx = torch.empty((B, C, H, W), dtype=torch.float32, device=dev, memory_format=torch.channels_last) if need_x else None
+            dw = torch.empty_like(wc) if need_w else None
+            db = torch.empty(K, dtype=torch.float32, device=dev) if (need_w and has_b) else None
+            _cabi.check(lib.msb_pool_fc_backward(_ptr(gc), _ptr(wc), _ptr(pooled), _ptr(dx), _ptr(dw), _ptr(db), B, H * W, C, K,
+                                                 _stream(dev)), "pool_fc backward")
+        return dx, dw, db
+
+
+def pool_fc(x, w, b=None):
+    """AdaptiveAvgPool2d((1,1)) + Flatten + Linear on a (B,C,H,W) CUDA fp32 map; differentiable w.r.t. x, w, b."""
+    if not x.is_cuda:
+        raise RuntimeError("metasolver_b200: CUDA tensors required (got %s)" % x.device)
+    if x.dtype != torch.float32 or x.dim() != 4 or w.dim() != 2 or w.shape[1] != x.shape[1] or x.shape[1] % 4:
+        raise RuntimeError("metasolver_b200: pool_fc expects an fp32 (B,C,H,W) map with C %% 4 == 0 and a (K,C) weight")
+    return _PoolFcFn.apply(x, w, b)
+
+
+class _CrossEntropyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels):
+        lib = _cabi.lib()
+        dev = logits.device
+        B, K = logits.shape
+        with torch.cuda.device(dev):
+            z = logits.detach().contiguous()
+            y = labels.contiguous()
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            lse = torch.empty(B, dtype=torch.float32, device=dev)
+            _cabi.check(lib.msb_cross_entropy_forward(_ptr(z), _ptr(y), _ptr(loss), _ptr(lse), B, K, _stream(dev)),
+                        "cross_entropy forward")
+        ctx.save_for_backward(z, y, lse)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _cabi.lib()
+        z, y, lse = ctx.saved_tensors
+        dev = z.device
+        B, K = z.shape
+        with torch.cuda.device(dev):
+            gc = g.reshape(1).to(torch.float32).contiguous()
+            dz = torch.empty_like(z)
+            _cabi.check(lib.msb_cross_entropy_backward(_ptr(z), _ptr(y), _ptr(lse), _ptr(gc), _ptr(dz), B, K, _stream(dev)),
+                        "cross_entropy backward")
+        return dz, None
+
+
+def cross_entropy(logits, labels):
+    """F.cross_entropy(logits, labels) (mean reduction) for CUDA fp32 (B,K) logits and int64 (B,) labels, as one kernel
+    each way (the loss of examples/cifar10/train_and_attack.py:303-311 and of the attacks, fgsm.py:33 / pgd.py:43)."""
+    if not logits.is_cuda or logits.dtype != torch.float32 or logits.dim() != 2:
+        raise RuntimeError("metasolver_b200: cross_entropy expects CUDA fp32 (B,K) logits")
+    if labels.dtype != torch.int64 or labels.shape != (logits.shape[0],) or labels.device != logits.device:
+        raise RuntimeError("metasolver_b200: cross_entropy expects int64 (B,) labels on the logits' device")
+    return _CrossEntropyFn.apply(logits, labels)
 
 
 # --------------------------------------------------------------------------- single-kernel entry points

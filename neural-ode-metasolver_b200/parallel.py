@@ -84,9 +84,9 @@ def sync_solver_params(solvers, src=0):
     i = 0
     for s in solvers:
         if s.u is not None:
-            s.u = torch.tensor((vals[i],), dtype=s.dtype)
+            s.u = torch.tensor((vals[i],), dtype=s.u.dtype)      # keep the dtype the draw had (float32 after noise_params)
         if s.v is not None:
-            s.v = torch.tensor((vals[i + 1],), dtype=s.dtype)
+            s.v = torch.tensor((vals[i + 1],), dtype=s.v.dtype)
         i += 2
         s.build_ButcherTableau()
 

@@ -3,8 +3,12 @@ blocks routed to the fused B200 kernels.
 
 Hot path (ours): MetaODEBlock + the RHS modules PreBasicBlock2 / BasicBlock2 -- their forward is
 never run op-by-op; `solver.integrate` asks the RHS module for its weights (`fused_rhs_spec`) and
-launches the fused steps x stages kernels.  Everything else (stem, residual blocks, pooling, FC:
-5 % of the flops) stays ordinary PyTorch around the custom op.
+launches the fused steps x stages kernels.  The rest of the published pre-activation networks
+(stem conv + activation, identity-shortcut residual block = one Euler step of the ODE
+kernels, strided residual block via space-to-depth, average pool + FC head) runs on this library's
+own kernels too; configurations those kernels do not cover (BatchNorm residual blocks, the
+post-activation `BasicBlock`, weight-normed convolutions, CPU tensors) RAISE unless the caller opts
+in to PyTorch's kernels with `metasolver_b200.set_library_fallback(True)`.
 Module / parameter names equal the reference's so its checkpoints load unchanged.
 """
 import numpy as np
@@ -14,7 +18,7 @@ import torch.nn.functional as F
 
 from .utils import Identity
 from ..... import _cabi
-from .....ops import ode_block_integrate, resblock_down, stem_conv_act
+from .....ops import ode_block_integrate, resblock_down, stem_conv_act, pool_fc, require_fallback
 from ...solvers.rk_parametric import can_stack, integrate_stacked
 
 _EULER_STEP = dict(stages=1, c=[0.0], b=[1.0], w=[[0.0]])
@@ -43,7 +47,8 @@ class Flatten(nn.Module):
 
 
 class BasicBlock(nn.Module):
-    """Residual block, post-activation order (layers.py:22-51). Plain PyTorch (not on the hot path)."""
+    """Residual block, post-activation order (layers.py:22-51): act(x + conv2(act(conv1(x)))) is not a step of either fused
+    right-hand side, so this block has no kernel of ours: it needs metasolver_b200.set_library_fallback(True)."""
     expansion = 1
 
     def __init__(self, in_planes, planes, stride=1, norm_layer=None, act_layer=None, param_norm=lambda x: x):
@@ -60,13 +65,15 @@ class BasicBlock(nn.Module):
                 norm_layer(self.expansion * planes))
 
     def forward(self, x):
+        require_fallback("the post-activation residual block (BasicBlock)", "only the pre-activation blocks are fused")
         out = self.act(self.bn1(self.conv1(x)))
         out = self.bn2(self.conv2(out))
         return self.act(out + self.shortcut(x))
 
 
 class PreBasicBlock(nn.Module):
-    """Residual block, pre-activation order (layers.py:54-81). Plain PyTorch (not on the hot path)."""
+    """Residual block, pre-activation order (layers.py:54-81): one Euler step of the fused ODE kernels (identity
+    shortcut) or the space-to-depth strided block (stride 2, 1x1 shortcut); other configurations raise."""
     expansion = 1
 
     def __init__(self, in_planes, planes, stride=1, norm_layer=None, act_layer=None, param_norm=lambda x: x):
@@ -119,6 +126,8 @@ class PreBasicBlock(nn.Module):
         if self._fusable_down(x):
             return resblock_down(x, self.conv1.weight, self.conv2.weight, self.shortcut[0].weight,
                                  act=_act_code(self.act))
+        require_fallback("this pre-activation residual block (%s)" % (tuple(x.shape),),
+                         "fused: CUDA fp32, Identity norm, gelu / relu, plain nn.Conv2d, tcgen05-tiled shape or stride-2 C -> 2C")
         out = self.conv1(self.act(self.bn1(x)))
         out = self.conv2(self.act(self.bn2(out)))
         return out + self.shortcut(x)
@@ -339,6 +348,8 @@ class MetaNODE(nn.Module):
         if self._fusable_stem(x):
             out = stem_conv_act(x, self.conv1.weight, _act_code(self.act))
         else:
+            require_fallback("this stem (conv1 + norm + activation)", "fused: CUDA fp32 3-channel input, Identity norm, gelu / relu, "
+                             "plain nn.Conv2d with 64 / 128 / 192 / 256 output channels")
             out = self.conv1(x)
             if not self.is_preactivation:
                 out = self.act(self.bn1(out))
@@ -347,6 +358,16 @@ class MetaNODE(nn.Module):
             self.ss_loss += layer.ss_loss
         if self.is_preactivation:
             out = self.act(self.bn1(out))
+        return self._head(out)
+
+    def _head(self, out):
+        """AdaptiveAvgPool2d((1,1)) + Flatten + Linear (layers.py:390-392, 425) as one kernel of ours each way."""
+        fc = self.fc_layers
+        if (out.is_cuda and out.dtype == torch.float32 and out.dim() == 4 and out.shape[1] % 4 == 0 and len(fc) == 3
+                and isinstance(fc[0], nn.AdaptiveAvgPool2d) and fc[0].output_size in ((1, 1), 1) and isinstance(fc[1], Flatten)
+                and type(fc[2]) is nn.Linear and fc[2].in_features == out.shape[1]):
+            return pool_fc(out, fc[2].weight, fc[2].bias)
+        require_fallback("this network head", "fused: CUDA fp32 map, AdaptiveAvgPool2d((1,1)) + Flatten + nn.Linear")
         return self.fc_layers(out)
 
 

@@ -70,9 +70,19 @@ class RKParametricSolver(object, metaclass=abc.ABCMeta):
         return make
 
     # ---- parameters -> tableau ----
+    def _work_dtype(self):
+        """The reference computes the tableau -- and picks the clamp epsilon -- in the dtype of the CURRENT `u` tensor
+        (`_make_params_valid` tests `self.u.dtype`, rk_parametric_order2stage2.py:56-60), not in the dtype the solver was
+        created with: after `noise_params` / `sample_solver_by_noising_params` (solvers/utils.py:60-105) u is a float32
+        tensor even on a float64 solver."""
+        u = getattr(self, "u", None)
+        if isinstance(u, torch.Tensor) and u.dtype in (torch.float32, torch.float64):
+            return u.dtype
+        return self.dtype
+
     def _param_np(self, p):
         """current value of u / v as a numpy scalar of the solver dtype"""
-        return _np_dtype(self.dtype)(p.detach().cpu().reshape(-1)[0].item())
+        return _np_dtype(self._work_dtype())(p.detach().cpu().reshape(-1)[0].item())
 
     @abc.abstractmethod
     def _tableau_np(self):
@@ -80,7 +90,7 @@ class RKParametricSolver(object, metaclass=abc.ABCMeta):
 
     def build_ButcherTableau(self, return_tableau=False):
         c, b, w, (u_, v_) = self._tableau_np()
-        mk = lambda val: torch.tensor((float(val),), dtype=self.dtype)
+        mk = lambda val: torch.tensor((float(val),), dtype=self._work_dtype())
         self.u_ = None if u_ is None else mk(u_)
         self.v_ = None if v_ is None else mk(v_)
         s = len(c)
@@ -97,9 +107,10 @@ class RKParametricSolver(object, metaclass=abc.ABCMeta):
     def _collect_ButcherTableau(self):
         t = self._host_tableau
         s = t["stages"]
-        c = torch.tensor(t["c"])
-        w = [torch.tensor(t["w"][i][:i + 1]) for i in range(s)]
-        b = torch.tensor(t["b"])
+        dt = self._work_dtype()      # torch.tensor([self.c1, self.c2]) of the reference inherits the scalars' dtype
+        c = torch.tensor(t["c"], dtype=dt)
+        w = [torch.tensor(t["w"][i][:i + 1], dtype=dt) for i in range(s)]
+        b = torch.tensor(t["b"], dtype=dt)
         return c, w, b
 
     def host_tableau(self):
@@ -130,7 +141,7 @@ class RKParametricSolver(object, metaclass=abc.ABCMeta):
         M = _cabi.MSB_MAX_STAGES
         u = self.u.to(torch.float64).reshape(()) if self.u is not None else None
         v = self.v.to(torch.float64).reshape(()) if self.v is not None else None
-        b, w, c = self._tableau_torch(u, v, _clamp_eps(self.dtype))
+        b, w, c = self._tableau_torch(u, v, _clamp_eps(self._work_dtype()))
         zero = torch.zeros((), dtype=torch.float64)
         as_t = lambda t: t if torch.is_tensor(t) else torch.tensor(float(t), dtype=torch.float64)
         flat = [as_t(b[i]) if i < len(b) else zero for i in range(M)]
@@ -307,7 +318,7 @@ class Euler(RKParametricSolver):
         self.build_ButcherTableau()
 
     def _tableau_np(self):
-        T = _np_dtype(self.dtype)
+        T = _np_dtype(self._work_dtype())
         return [T(0)], [T(1)], [[T(0)]], (None, None)
 
     def _tableau_torch(self, u, v, eps):
@@ -336,8 +347,8 @@ class RKOrder2Stage2(RKParametricSolver):
         self.build_ButcherTableau()
 
     def _tableau_np(self):
-        T = _np_dtype(self.dtype)
-        eps = _clamp_eps(self.dtype)
+        T = _np_dtype(self._work_dtype())
+        eps = _clamp_eps(self._work_dtype())
         u_ = min(max(self._param_np(self.u), T(eps)), T(1.0))
         b2 = T(1.0) / (T(2) * u_)
         b1 = T(1.0) - b2
@@ -365,8 +376,8 @@ class RKOrder3Stage3(RKParametricSolver):
         self.build_ButcherTableau()
 
     def _tableau_np(self):
-        T = _np_dtype(self.dtype)
-        eps = _clamp_eps(self.dtype)
+        T = _np_dtype(self._work_dtype())
+        eps = _clamp_eps(self._work_dtype())
         u_ = min(max(self._param_np(self.u), T(eps)), T(1.0))
         v_ = min(max(self._param_np(self.v), T(eps)), T(1.0))
         u_, v_ = _separate(u_, v_, eps, T)
@@ -409,8 +420,8 @@ class RKOrder4Stage4(RKParametricSolver):
         self.build_ButcherTableau()
 
     def _tableau_np(self):
-        T = _np_dtype(self.dtype)
-        eps = _clamp_eps(self.dtype)
+        T = _np_dtype(self._work_dtype())
+        eps = _clamp_eps(self._work_dtype())
         u = self._param_np(self.u)
         kind = self.parameterization
         one, half = T(1.0), T(0.5)

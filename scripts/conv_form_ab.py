@@ -15,8 +15,13 @@ REPS, ROUNDS = 3, 4
 torch.manual_seed(0)
 def S(form=2, pf=0, band=0, pdl=1, prod=3):
     return dict(tc_form_c64=form, epi_l2_prefetch=pf, tct_band=band, pdl=pdl, tct_products=prod)
-sets = [S(1), S(2), S(2, prod=4), S(2, band=8), S(2, pf=1)]
+sets = [S(1), S(2), S(2, prod=3), S(2, band=8), S(2, pf=1)]
 C, HW = 64, 32
+if os.environ.get("CONV_AB_C") == "128":          # CTA-pair kernel: role placement A/B
+    C, HW = 128, 16
+    sets = [dict(mma_warp_high=0), dict(mma_warp_high=1)]
+elif os.environ.get("CONV_AB_C") == "64pm":
+    sets = [dict(tc_form_c64=1, mma_warp_high=0), dict(tc_form_c64=1, mma_warp_high=1), dict(tc_form_c64=2)]
 blk = MetaODEBlock(PreBasicBlock2(C, norm_layer=Identity, act_layer=F.gelu)).cuda()
 solver = create_solver("rk2", "u", 8, -1, 0.5, -1, torch.float32, "cuda"); solver.freeze_params()
 x = torch.randn(B, C, HW, HW, device="cuda").contiguous(memory_format=torch.channels_last)

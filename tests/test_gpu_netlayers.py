@@ -88,8 +88,10 @@ def test_strided_residual_block_vs_cpu(B, H, W, Ci, engine):
 
 
 def test_whole_model_runs_without_library_convolutions_and_matches_reference_gradients():
-    """premetanode10 forward+backward: every convolution is one of this library's kernels (torch only sees the
-    pooling / FC head); gradients of ALL layers against the real reference."""
+    """premetanode10 forward + loss + backward: EVERY compute kernel is one of this library's (stem, residual blocks, ODE
+    blocks, pool + FC head, cross-entropy): no cuDNN / cuBLAS / ATen GEMM, convolution, reduction or loss kernel;
+    gradients of ALL layers against the real reference."""
+    import metasolver_b200
     from torch.profiler import profile, ProfilerActivity
     from metasolver_b200.sopa.src.solvers.utils import create_solver
     from metasolver_b200.sopa.src.models.odenet_cifar10.layers import premetanode10
@@ -109,12 +111,18 @@ def test_whole_model_runs_without_library_convolutions_and_matches_reference_gra
     model.layer2.blocks_res.register_forward_hook(lambda m, i, o: taps.__setitem__("l2", o.detach().cpu().numpy()))
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         logits = model(x, [solver], Namespace(solver_mode="standalone"))
-        F.cross_entropy(logits, torch.tensor([3, 1, 4, 1]).cuda()).backward()
+        metasolver_b200.cross_entropy(logits, torch.tensor([3, 1, 4, 1]).cuda()).backward()
         torch.cuda.synchronize()
     names = [e.key for e in prof.key_averages() if e.device_type == torch.autograd.DeviceType.CUDA]
-    foreign = [n for n in names if any(t in n.lower() for t in ("cudnn", "convolve", "wgrad_alg", "dgrad_engine", "fft", "cgemm",
-                                                                 "implicit_gemm", "conv2d"))]
+    foreign = [n for n in names if "msb::" not in n and
+               any(t in n.lower() for t in ("cudnn", "convolve", "wgrad_alg", "dgrad_engine", "fft", "cgemm", "implicit_gemm",
+                                            "conv2d", "gemm", "gemv", "cublas", "cutlass", "softmax", "nll_loss",
+                                            "reduce_kernel", "mean"))]
     assert not foreign, foreign
+    # what is left of ATen are layout copies / fills of the autograd glue (no arithmetic on activations)
+    ours = [n for n in names if "msb::" in n]
+    assert len(ours) >= 10, names
+    print("non-msb kernels in a training step:", sorted(n for n in names if "msb::" not in n))
     assert max_rel(logits.detach().cpu().numpy(), g["logits"]) <= TOL
     assert max_rel(taps["l2"], g2["layer2_res_out"]) <= TOL
     assert max_rel(x.grad.cpu().numpy(), g["gx"]) <= TOL
@@ -124,3 +132,50 @@ def test_whole_model_runs_without_library_convolutions_and_matches_reference_gra
             if k.startswith("g_"):
                 got = params[k[2:]].grad.cpu().numpy().reshape(-1)[::cases.WG_STRIDE]
                 assert max_rel(got, gold[k]) <= TOL, (k, max_rel(got, gold[k]))
+
+
+def test_pool_fc_head_and_cross_entropy_match_torch():
+    """msb_pool_fc_forward / backward and msb_cross_entropy_* against AdaptiveAvgPool2d + Linear + F.cross_entropy
+    (cifar10/layers.py:390-392, 425; train_and_attack.py:303-311): values and every gradient."""
+    import metasolver_b200
+    torch.manual_seed(0)
+    for (B, C, HW, K) in ((37, 128, 16, 10), (4, 64, 32, 10), (512, 128, 16, 10)):
+        x = torch.randn(B, C, HW, HW, device="cuda").contiguous(memory_format=torch.channels_last)
+        w = (torch.randn(K, C, device="cuda") / C ** 0.5)
+        b = torch.randn(K, device="cuda") * 0.1
+        y = torch.randint(0, K, (B,), device="cuda")
+        xa, wa, ba = (t.clone().requires_grad_(True) for t in (x, w, b))
+        la = metasolver_b200.cross_entropy(metasolver_b200.pool_fc(xa, wa, ba), y)
+        la.backward()
+        xb, wb, bb = (t.clone().double().requires_grad_(True) for t in (x, w, b))
+        lb = F.cross_entropy(F.linear(F.adaptive_avg_pool2d(xb, (1, 1)).flatten(1), wb, bb), y)
+        lb.backward()
+        assert abs(float(la) - float(lb)) <= 1e-6 * abs(float(lb)) + 1e-7
+        for got, ref in ((xa.grad, xb.grad), (wa.grad, wb.grad), (ba.grad, bb.grad)):
+            assert max_rel(got.cpu().numpy(), ref.cpu().numpy()) <= 1e-5
+        # deterministic
+        xa2, wa2, ba2 = (t.clone().requires_grad_(True) for t in (x, w, b))
+        metasolver_b200.cross_entropy(metasolver_b200.pool_fc(xa2, wa2, ba2), y).backward()
+        assert torch.equal(wa.grad, wa2.grad) and torch.equal(xa.grad, xa2.grad) and torch.equal(ba.grad, ba2.grad)
+
+
+def test_layers_outside_the_fused_configurations_raise_unless_opted_in():
+    """No silent cuDNN fallback: a BatchNorm residual block / stem, the post-activation BasicBlock and CPU tensors raise;
+    metasolver_b200.set_library_fallback(True) is the explicit opt-in to PyTorch's kernels for those layers."""
+    import torch.nn as nn
+    import metasolver_b200
+    from metasolver_b200.sopa.src.models.odenet_cifar10.layers import PreBasicBlock, BasicBlock, premetanode10
+    from metasolver_b200.sopa.src.models.odenet_cifar10.utils import Identity
+    x = torch.randn(2, 64, 32, 32, device="cuda")
+    bn_block = PreBasicBlock(64, 64, norm_layer=nn.BatchNorm2d, act_layer=F.gelu).cuda()
+    post = BasicBlock(64, 64, norm_layer=Identity, act_layer=F.gelu).cuda()
+    model = premetanode10((nn.BatchNorm2d,) * 3, (lambda m: m,) * 3, (F.gelu,) * 3, in_planes=64, is_odenet=True).cuda()
+    for fn in (lambda: bn_block(x), lambda: post(x), lambda: model.conv1 and model(torch.randn(2, 3, 32, 32, device="cuda"), [], None)):
+        with pytest.raises(NotImplementedError, match="set_library_fallback"):
+            fn()
+    metasolver_b200.set_library_fallback(True)
+    try:
+        assert bn_block(x).shape == x.shape and post(x).shape == x.shape
+    finally:
+        metasolver_b200.set_library_fallback(False)
+    assert not metasolver_b200.library_fallback_allowed()

@@ -291,3 +291,37 @@ def test_integrate_with_interior_output_times(case):
     assert max_rel(ys.detach().cpu().numpy()[1:, :, ::3], g[name + "_y"]) <= TOL
     assert max_rel(x.grad.cpu().numpy(), g[name + "_gx"]) <= TOL
     assert max_rel(rhs.conv1.weight.grad.cpu().numpy().reshape(-1)[::cases.WG_STRIDE], g[name + "_gw1"]) <= TOL
+
+
+def test_forward_under_no_grad_records_no_tape():
+    """An evaluation forward of a TRAINABLE model under torch.no_grad() must not allocate the backward tape
+    (n_steps * stages * 16 B per state element): the decision is taken by the caller of Function.apply, where grad
+    mode is visible (ctx.needs_input_grad stays True for parameters under no_grad)."""
+    from argparse import Namespace
+    import torch.nn.functional as F
+    import metasolver_b200  # noqa: F401
+    from metasolver_b200.sopa.src.solvers.utils import create_solver
+    from metasolver_b200.sopa.src.models.odenet_cifar10.layers import MetaODEBlock, PreBasicBlock2
+    from metasolver_b200.sopa.src.models.odenet_cifar10.utils import Identity
+    blk = MetaODEBlock(PreBasicBlock2(64, norm_layer=Identity, act_layer=F.gelu)).cuda()
+    assert all(p.requires_grad for p in blk.parameters())
+    solver = create_solver("rk2", "u", 8, -1, 0.5, -1, torch.float32, "cuda")
+    solver.freeze_params()
+    x = torch.randn(32, 64, 32, 32, device="cuda").contiguous(memory_format=torch.channels_last)
+    state = x.numel() * 4
+    tape = 8 * 2 * 4 * state                                   # what a training forward records
+    opts = Namespace(solver_mode="standalone")
+
+    def peak(fn):
+        torch.cuda.synchronize(); torch.cuda.empty_cache(); torch.cuda.reset_peak_memory_stats()
+        base = torch.cuda.memory_allocated()
+        fn()
+        torch.cuda.synchronize()
+        return torch.cuda.max_memory_allocated() - base
+    with torch.no_grad():
+        p_eval = peak(lambda: blk(x, [solver], opts))
+    p_train = peak(lambda: blk(x, [solver], opts))
+    assert p_train >= tape and p_eval < tape // 4, (p_eval, p_train, tape)
+    with torch.no_grad():
+        y_eval = blk(x, [solver], opts)
+    assert torch.equal(y_eval, blk(x, [solver], opts).detach())   # same kernels, same numbers

@@ -120,3 +120,29 @@ def test_fused_sgd_follows_torch_sgd():
             torch.testing.assert_close(b.detach(), a.detach(), rtol=2e-6, atol=1e-7)
     with pytest.raises(RuntimeError):
         metasolver_b200.FusedSGD([torch.zeros(3, requires_grad=True)], lr=0.1)
+
+
+def test_fused_sgd_sees_gradients_detached_by_zero_grad_set_to_none():
+    """model.zero_grad(set_to_none=True) (the torch >= 2.0 default) detaches `.grad` from FusedSGD's flat buffer; step() /
+    all_reduce() must gather the fresh gradients instead of applying stale zeros, and a parameter whose grad is None is
+    skipped entirely (no weight decay, no momentum update) like torch.optim.SGD does."""
+    import copy
+    import torch.nn as nn
+    from metasolver_b200 import FusedSGD
+    torch.manual_seed(0)
+    net = nn.Sequential(nn.Linear(16, 32), nn.Linear(32, 8), nn.Linear(8, 4)).cuda()
+    ref = copy.deepcopy(net)
+    opt = FusedSGD(net.parameters(), lr=0.1, momentum=0.9, weight_decay=5e-4)
+    ropt = torch.optim.SGD(ref.parameters(), lr=0.1, momentum=0.9, weight_decay=5e-4)
+    x = torch.randn(64, 16, device="cuda")
+    for it in range(4):
+        for m, o in ((net, opt), (ref, ropt)):
+            m.zero_grad(set_to_none=True)                      # NOT FusedSGD.zero_grad: grads get detached from the flat buffer
+            h = m[1](m[0](x))
+            out = h.square().mean() if it == 2 else m[2](h).square().mean()      # iteration 2: the last layer gets no gradient
+            out.backward()
+            if o is opt:
+                assert opt.all_reduce() == 1.0
+            o.step()
+        for a, b in zip(net.parameters(), ref.parameters()):
+            assert torch.allclose(a, b, rtol=1e-6, atol=1e-7), it

@@ -95,7 +95,7 @@ def test_cabi_library_exports_header_symbols():
     lib = _cabi.lib()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.msb_abi_version() == _cabi.ABI_VERSION == 3
+    assert lib.msb_abi_version() == _cabi.ABI_VERSION == 4
     assert lib.msb_shape_supports_tcgen05(64, 32, 32) in (0, 1)
     # descriptor validation is host-only: bad stage count must be refused with a message
     d = _cabi.MsbOdeDesc()
@@ -137,3 +137,72 @@ def test_descriptor_validation_is_host_side_and_loud():
     o.rhs_kind = 0
     assert mn * 4 == lib.msb_odeblock_tape_bytes(ctypes.byref(o)) * 5
     assert lib.msb_stem_backward_workspace_bytes(64) > 0
+
+
+def test_package_detrand_equals_the_oracle_generator_and_shards():
+    """metasolver_b200.detrand (synthetic evaluation sets of scripts/eval_pgd_sweep.py, product side) generates the same
+    tensors as oracle.detrand (test side), any slice of a tensor can be generated on its own, and the deterministic
+    premetanode10 weights equal the oracle's recipe."""
+    import torch.nn.functional as F
+    from metasolver_b200 import detrand
+    from metasolver_b200.sopa.src.models.odenet_cifar10.layers import premetanode10
+    from metasolver_b200.sopa.src.models.odenet_cifar10.utils import Identity
+    from metasolver_b200.sopa.src.models.odenet_cifar10.data import CIFAR_MEAN, CIFAR_STD, augment_batch
+    import oracle
+    from oracle.models import det_premetanode10_params
+    a = detrand.uniform((7, 3, 4, 5), 9100, 0.0, 1.0)
+    assert np.array_equal(a, oracle.det_uniform((7, 3, 4, 5), 9100, 0.0, 1.0))
+    per = 3 * 4 * 5
+    assert np.array_equal(a[2:5], detrand.uniform((3, 3, 4, 5), 9100, 0.0, 1.0, offset=2 * per))
+    model = premetanode10((Identity,) * 3, (lambda x: x,) * 3, (F.gelu,) * 3, in_planes=64, is_odenet=True)
+    sd, ref = detrand.premetanode10_state_dict(model), det_premetanode10_params()
+    assert list(sd) == list(ref)
+    for k in sd:
+        assert torch.equal(sd[k], ref[k]), k
+    assert (CIFAR_MEAN, CIFAR_STD) == (oracle.models.CIFAR_MEAN, oracle.models.CIFAR_STD)
+    # batched RandomCrop(32, padding=4) + RandomHorizontalFlip (data.py:41-43): every output is a shifted / mirrored window
+    g = torch.Generator().manual_seed(3)
+    img = torch.rand(16, 3, 32, 32)
+    out = augment_batch(img, generator=g)
+    assert out.shape == img.shape
+    pad = torch.nn.functional.pad(img, (4, 4, 4, 4))
+    for n in range(16):
+        wins = [pad[n, :, dy:dy + 32, dx:dx + 32] for dy in range(9) for dx in range(9)]
+        assert any(torch.equal(out[n], w) or torch.equal(out[n], w.flip(-1)) for w in wins), n
+
+
+def test_noise_samplers_match_reference_golden():
+    """noise_params / sample_solver_by_noising_params / create_solver_ensemble_by_noising_params make the
+    same torch CPU RNG calls as the reference (solvers/utils.py:60-117): same drawn u / v and bit-identical rebuilt
+    tableaus under the same seed, for float32 and float64 solvers (tests/golden/make_golden_noise.py)."""
+    import contextlib
+    import io
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden_noise as mg          # case table only; its reference imports are not needed here
+    from metasolver_b200.sopa.src.solvers.utils import (sample_solver_by_noising_params,
+                                                        create_solver_ensemble_by_noising_params)
+    g = golden("noise_samplers.npz")
+
+    def tab(s):
+        c, w, b = s.build_ButcherTableau(return_tableau=True)
+        flat = [float(x) for x in c] + [float(x) for x in b]
+        for row in w:
+            flat += [float(x) for x in np.atleast_1d(row.detach().numpy())]
+        return np.asarray(flat, dtype=np.float64)
+    for name, args, kw, seed in mg.CASES:
+        for dt, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+            solver = create_solver(*args, dt, "cpu")
+            solver.freeze_params()
+            torch.manual_seed(seed)
+            with contextlib.redirect_stdout(io.StringIO()):
+                for i in range(mg.N_DRAWS):
+                    s2 = sample_solver_by_noising_params(solver, **kw)
+                    key = "%s_%s" % (name, tag)
+                    assert float(s2.u) == g[key + "_u"][i], (key, i)
+                    if s2.v is not None:
+                        assert float(s2.v) == g[key + "_v"][i], (key, i)
+                    assert str(s2.u.dtype) == str(g[key + "_udtype"][0]), key
+                    assert np.array_equal(tab(s2), g[key + "_tab"][i]), (key, i)
+                ens = create_solver_ensemble_by_noising_params(solver, ensemble_size=4, kwargs_noise=kw)
+            assert np.array_equal(np.asarray([float(e.u) for e in ens]), g[key + "_ens_u"]), key
+            assert np.array_equal(np.stack([tab(e) for e in ens]), g[key + "_ens_tab"]), key

@@ -56,6 +56,9 @@ def _worker(rank, world, port, q):
     lo, hi = parallel.shard_range(11, rank, world)
     out["shard"] = (lo, hi)
     out["count"] = parallel.allreduce_sum_int(hi - lo, dev)
+    # 4. a sharded synthetic evaluation set (scripts/eval_pgd_sweep.py): every rank generates only its slice
+    from metasolver_b200 import detrand
+    out["shard_data"] = detrand.uniform((hi - lo, 3, 4, 4), 9100, 0.0, 1.0, offset=lo * 48).tolist()
     q.put((rank, out))
     dist.barrier()
     dist.destroy_process_group()
@@ -77,6 +80,11 @@ def test_data_parallel_host_logic_world2():
         assert g0 == g1
         assert torch.allclose(torch.tensor(g0), (torch.tensor(l0) + torch.tensor(l1)) / 2, rtol=0, atol=1e-6)
     assert a["nbytes"] == 4 * (5 * 4 + 4 + 4 * 3 + 3)
+    import numpy as np
+    from metasolver_b200 import detrand
+    full = detrand.uniform((11, 3, 4, 4), 9100, 0.0, 1.0)
+    assert np.array_equal(np.concatenate([np.asarray(a["shard_data"], dtype=np.float32),
+                                          np.asarray(b["shard_data"], dtype=np.float32)]), full)
     assert a["u_before"] != b["u_before"]
     assert a["u_after"] == b["u_after"] == pytest.approx(a["u_before"], abs=1e-7)
     assert a["tab"] == b["tab"]
