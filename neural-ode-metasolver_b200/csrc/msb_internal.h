@@ -29,6 +29,7 @@ enum { TUNE_EPI_L2_PREFETCH = 0,   // conv epilogue operands: bulk L2 prefetch d
        TUNE_TCT_DEBUG = 9,         // TMEM-resident-weight conv: decomposition switches (timing experiments only; results are garbage)
        TUNE_TCT_PRODUCTS = 10,     // TMEM-resident-weight conv: hi/lo products formed, 3 (default) or 4
        TUNE_MMA_WARP_HIGH = 11,    // pixel-major convs: TMA / MMA roles on the highest physical warps (scheduler priority)
+       TUNE_WGRAD64_PRODUCTS = 12, // C = 64 weight gradient: 4 hi/lo products (default) or 3 (roles swapped; measured slower)
        TUNE_COUNT };
 int tune_get(int which);
 

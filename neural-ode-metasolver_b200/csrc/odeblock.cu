@@ -39,10 +39,10 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 static std::atomic<int> g_tune[TUNE_COUNT];
 static std::atomic<bool> g_tune_init{false};
 static const char* const kTuneNames[TUNE_COUNT] = {"epi_l2_prefetch", "tc_resident", "tcp_epi_warps", "tc_form_c64", "tc_pair",
-                                                   "wait_backoff_ns", "pdl", "wgrad_multicast", "tct_band", "tct_debug", "tct_products", "mma_warp_high"};
+                                                   "wait_backoff_ns", "pdl", "wgrad_multicast", "tct_band", "tct_debug", "tct_products", "mma_warp_high", "wgrad64_products"};
 static const char* const kTuneEnv[TUNE_COUNT] = {"MSB_EPI_L2_PREFETCH", "MSB_TC_RESIDENT", "MSB_TCP_EPI_WARPS", "MSB_TC_FORM_C64",
-                                                 "MSB_TC_PAIR", "MSB_WAIT_BACKOFF_NS", "MSB_PDL", "MSB_WGRAD_MULTICAST", "MSB_TCT_BAND", "MSB_TCT_DEBUG", "MSB_TCT_PRODUCTS", "MSB_MMA_WARP_HIGH"};
-static const int kTuneDefault[TUNE_COUNT] = {0, 0, 16, 2, 2, 0, 1, 0, 0, 0, 4, 0};
+                                                 "MSB_TC_PAIR", "MSB_WAIT_BACKOFF_NS", "MSB_PDL", "MSB_WGRAD_MULTICAST", "MSB_TCT_BAND", "MSB_TCT_DEBUG", "MSB_TCT_PRODUCTS", "MSB_MMA_WARP_HIGH", "MSB_WGRAD64_PRODUCTS"};
+static const int kTuneDefault[TUNE_COUNT] = {0, 0, 16, 2, 2, 0, 1, 0, 0, 0, 4, 0, 4};
 static void tune_init() {
     if (g_tune_init.load(std::memory_order_acquire)) return;
     for (int i = 0; i < TUNE_COUNT; ++i) {
@@ -161,7 +161,7 @@ int wgrad_nparts(int engine, ConvShape s) {
 int run_wgrad(int engine, const __nv_bfloat16* gout, const __nv_bfloat16* in, WgradAcc& acc, ConvShape s, cudaStream_t st) {
     int nparts = 0, rc;
     const bool tc = use_tc_wgrad(engine, s);
-    int id = prof_begin(MSB_PROF_WGRAD, conv_flops(s), tc ? (s.C == 64 ? 4.0 : 3.0) : 1.0, st);
+    int id = prof_begin(MSB_PROF_WGRAD, conv_flops(s), tc ? (s.C == 64 ? (tune_get(TUNE_WGRAD64_PRODUCTS) == 3 ? 10.0 / 3.0 : 4.0) : 3.0) : 1.0, st);   // C = 64: two taps at 3 products, the unpaired third at 4
     if (tc) rc = launch_wgrad3x3_tc(gout, in, acc.partial, &nparts, acc.launches > 0, s, st);
     else rc = launch_wgrad3x3_simt(gout, in, acc.partial, &nparts, s, st);
     prof_end(id, st);
@@ -747,25 +747,44 @@ int msb_odeblock_forward(const MsbOdeDesc* d, const float* x, const float* w1, c
             e2.base = y_cur; e2.act = act_in; e2.slice_batch = tabs.slice_batch;
             for (int q = 0; q < tabs.K; ++q) e2.k[q].dt = dt;
             if (post) { e2.act_v = d->act; e2.dact_v_out = cur.G0; }
+            // Terms whose coefficient is exactly zero for every solver slice are dropped (u = 1/2, the midpoint rule, has
+            // b_1 = 0): `k_j * 0` contributes +-0 to a sum whose other terms it cannot change, so the result is the
+            // reference's bit for bit (up to the sign of an exact zero) while the tensor is neither read here nor -- if no
+            // later stage needs it -- written by the stage that produced it.
+            auto all_zero = [&](auto coef_of) {
+                for (int q = 0; q < tabs.K; ++q) if (coef_of(tabs.t[q]) != 0.f) return false;
+                return true;
+            };
+            auto k_needed_later = [&](int j) {        // is k_j read by any stage after the one that consumes it in registers?
+                for (int m = j + 2; m < S; ++m)
+                    if (!all_zero([&](const MsbTableau& t) { return t.w[m * MSB_MAX_STAGES + j]; })) return true;
+                return !all_zero([&](const MsbTableau& t) { return t.b[j]; });
+            };
             if (i < S - 1) {
                 // x_{i+1} = y + (sum_j k_j w[i+1][j]) dt          (order2stage2.py:91, order3stage3.py:100-101 ...)
-                e2.v_out = kbuf[i] + off;
-                e2.nsrc = i;
-                for (int j = 0; j < i; ++j) e2.src[j] = kbuf[j] + off;
-                for (int q = 0; q < tabs.K; ++q) {
-                    for (int j = 0; j < i; ++j) e2.k[q].coef[j] = tabs.t[q].w[(i + 1) * MSB_MAX_STAGES + j];
-                    e2.k[q].coef_v = tabs.t[q].w[(i + 1) * MSB_MAX_STAGES + i];
+                if (k_needed_later(i)) e2.v_out = kbuf[i] + off;
+                int ns = 0;
+                for (int j = 0; j < i; ++j) {
+                    if (all_zero([&](const MsbTableau& t) { return t.w[(i + 1) * MSB_MAX_STAGES + j]; })) continue;
+                    e2.src[ns] = kbuf[j] + off;
+                    for (int q = 0; q < tabs.K; ++q) e2.k[q].coef[ns] = tabs.t[q].w[(i + 1) * MSB_MAX_STAGES + j];
+                    ++ns;
                 }
+                e2.nsrc = ns;
+                for (int q = 0; q < tabs.K; ++q) e2.k[q].coef_v = tabs.t[q].w[(i + 1) * MSB_MAX_STAGES + i];
                 TapeSlot nx = slot(n, i + 1);
                 e2.out_split = nx.A; e2.dact_out = post ? nullptr : nx.G0;
             } else {
                 // y1 = y0 + (sum_j k_j b_j) dt                     (order2stage2.py:93, rk_parametric.py:106)
-                e2.nsrc = S - 1;
-                for (int j = 0; j < S - 1; ++j) e2.src[j] = kbuf[j] + off;
-                for (int q = 0; q < tabs.K; ++q) {
-                    for (int j = 0; j < S - 1; ++j) e2.k[q].coef[j] = tabs.t[q].b[j];
-                    e2.k[q].coef_v = tabs.t[q].b[S - 1];
+                int ns = 0;
+                for (int j = 0; j < S - 1; ++j) {
+                    if (all_zero([&](const MsbTableau& t) { return t.b[j]; })) continue;
+                    e2.src[ns] = kbuf[j] + off;
+                    for (int q = 0; q < tabs.K; ++q) e2.k[q].coef[ns] = tabs.t[q].b[j];
+                    ++ns;
                 }
+                e2.nsrc = ns;
+                for (int q = 0; q < tabs.K; ++q) e2.k[q].coef_v = tabs.t[q].b[S - 1];
                 e2.out_f32 = y_next;
                 if (n < N - 1) { TapeSlot nx = slot(n + 1, 0); e2.out_split = nx.A; e2.dact_out = post ? nullptr : nx.G0; }
             }
@@ -880,16 +899,26 @@ static int odeblock_backward_impl(const MsbOdeDesc* d, const float* grad_y, cons
             e4.mul = post ? nullptr : cur.G0; e4.base = g_cur; e4.slice_batch = tabs.slice_batch;
             if (i > 0) {
                 // kbar_{i-1} = dt b_{i-1} gbar + dt sum_{j >= i} w[j][i-1] xbar_j
+                // (zero-coefficient terms are dropped as in the forward pass: b_1 = 0 for the midpoint rule means gbar is
+                //  not read here)
+                auto all_zero = [&](auto coef_of) {
+                    for (int q = 0; q < tabs.K; ++q) if (coef_of(tabs.t[q]) != 0.f) return false;
+                    return true;
+                };
                 e4.v_out = xbar[i] + off;
                 e4.base_is_one = 0;
+                if (all_zero([&](const MsbTableau& t) { return dt * t.b[i - 1]; })) e4.base = nullptr;
                 int ns = 0;
-                for (int j = S - 1; j > i; --j) e4.src[ns++] = xbar[j] + off;
+                for (int j = S - 1; j > i; --j) {
+                    if (all_zero([&](const MsbTableau& t) { return t.w[j * MSB_MAX_STAGES + (i - 1)]; })) continue;
+                    e4.src[ns] = xbar[j] + off;
+                    for (int q = 0; q < tabs.K; ++q) e4.k[q].coef[ns] = tabs.t[q].w[j * MSB_MAX_STAGES + (i - 1)];
+                    ++ns;
+                }
                 e4.nsrc = ns;
                 for (int q = 0; q < tabs.K; ++q) {
                     EpiCoef& k = e4.k[q];
                     k.base_coef = dt * tabs.t[q].b[i - 1];
-                    int m = 0;
-                    for (int j = S - 1; j > i; --j) k.coef[m++] = tabs.t[q].w[j * MSB_MAX_STAGES + (i - 1)];
                     k.coef_v = tabs.t[q].w[i * MSB_MAX_STAGES + (i - 1)];
                     k.dt = dt;
                 }

@@ -4,14 +4,14 @@
 //
 // Both operands are read in place from split tensors [B][H][2][W][C] (channels contiguous), i.e.
 // they are "MN-major" for this GEMM (K = pixels is the strided dimension):
-//   A (M = 128) : gout.  C=64 : rows 0..63 = hi plane, 64..127 = lo plane of the 64 channels
-//                              (two 64-element MN atoms, LBO = plane stride)
-//                        C=128: the 128 channels of one plane (two 64-channel TMA boxes, LBO = box stride);
-//                              hi and lo planes are separate MMAs
+//   C = 128:
+//   A (M = 128) : gout, the 128 channels of one plane (two 64-channel TMA boxes, LBO = box stride);
+//                 hi and lo planes are separate MMAs
 //   B (N = 192) : in, 3 vertical taps x 64 input channels: three MN atoms whose stride (LBO) is one
 //                 image row of the halo tile, so one MMA covers r = 0,1,2
 //   K = 16      : 16 consecutive pixels of one image row (two 8-pixel swizzle atoms, SBO = 1024 B)
-// All four hi/lo products are accumulated in fp32 in one TMEM accumulator (128 lanes x 192 cols),
+//   C = 64: roles swapped (`in` on M, two vertical taps per M = 128 operand; [g_hi | g_lo] on N) -- see the MMA loop.
+// Three hi/lo products (lo x lo dropped; kept for the unpaired third tap at C = 64) are accumulated in fp32 in TMEM (128 lanes x 192 / 256 cols),
 // which stays resident for ALL tiles of a CTA: the only global write is one 128x192 partial at the
 // end (optionally accumulated onto the CTA's own slot from earlier launches, so a whole backward pass
 // needs a single reduction per weight tensor).  CTA = (group, part): group = (horizontal tap s, 64-wide c_in chunk), part = slice of the
@@ -57,7 +57,7 @@ struct __align__(8) WBarriers {
 // the gout box, identical for all of them, is loaded ONCE by rank 0 and multicast into every CTA's stage.  ncu had the
 // kernel at 91 % of the L2 slice throughput cap (983 MB of L2 -> SM traffic per C = 64 launch, 9.4 TB/s): it was
 // L2-bound, and a third (C = 64) / half (C = 128) of that traffic was the same gout tile fetched by each group's CTA.
-template <int C, int WIMG, bool MC>
+template <int C, int WIMG, bool MC, bool P3>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_go, const __grid_constant__ CUtensorMap tmap_in,
                    float* __restrict__ partial, const int num_tiles, const int tiles_per_img, const int nparts,
@@ -121,7 +121,46 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_go, const __grid_con
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (lane == 0 && C == 64 && P3) {
+            // C = 64, three hi/lo products (option wgrad64_products = 3; measured SLOWER than the four-product form, 161 vs
+            // 143 us per launch: with both operands in shared memory the N = 128 / 64 MMAs need 128 - 192 B/clk of operand
+            // reads, above the 128 B/clk shared-memory feed, while the N = 192 MMAs of the four-product form need 104 B/clk --
+            // so it is not the default).  The roles are swapped against the C = 128 form: `in` rides on M, gout on N,
+            // so that every row of an M = 128 operand needs the same N operand:
+            //   D1[(r, c_in) : r = 0, 1][g_hi | g_lo]  += in_hi(rows rho, rho + 1) x [g_hi | g_lo]        (M = 128, N = 128)
+            //   D1[(r, c_in)           ][g_hi       ]  += in_lo(rows rho, rho + 1) x  g_hi                 (M = 128, N = 64)
+            //   D2[(plane, c_in) of r = 2][g_hi | g_lo] += [in_hi ; in_lo](row rho + 2) x [g_hi | g_lo]    (M = 128, N = 128)
+            // 160 tensor clocks per 16 pixels instead of 192 (the third vertical tap has no partner tap and keeps its
+            // lo x lo product).  Operands are still read in place: M / N atoms of 64 channels, LBO = the stride between the
+            // two atoms (an image row of the halo tile, or the plane stride), K = 16 pixels = two 8-pixel swizzle atoms.
+            constexpr uint32_t idesc_full = ptx::make_idesc_bf16(128, 128, 1, 1);
+            constexpr uint32_t idesc_hi = ptx::make_idesc_bf16(128, 64, 1, 1);
+            int st = 0; uint32_t ph = 0;
+            uint32_t accumulate = 0;
+            for (int tile = part; tile < num_tiles; tile += nparts) {
+                ptx::mbar_wait(&bars->full[st], ph);
+                ptx::tc_fence_after();
+                const uint32_t go_base = ptx::smem_u32(smem + st * G::STAGE_BYTES);
+                const uint32_t in_base = go_base + G::GO_BYTES;
+                for (int rho = 0; rho < G::ROWS; ++rho)
+                    for (int wg = 0; wg < WIMG / 16; ++wg) {
+                        const uint32_t px_off = (uint32_t)wg * 16 * 128;
+                        const uint32_t in_row = in_base + rho * G::ROW_PAIR_BYTES + px_off;
+                        const uint64_t g_desc = ptx::make_smem_desc_sw128(go_base + rho * G::ROW_PAIR_BYTES + px_off, G::PLANE_BYTES, 1024);
+                        const uint64_t a01_hi = ptx::make_smem_desc_sw128(in_row, G::ROW_PAIR_BYTES, 1024);
+                        const uint64_t a01_lo = ptx::make_smem_desc_sw128(in_row + G::PLANE_BYTES, G::ROW_PAIR_BYTES, 1024);
+                        const uint64_t a2 = ptx::make_smem_desc_sw128(in_row + 2 * G::ROW_PAIR_BYTES, G::PLANE_BYTES, 1024);
+                        ptx::umma_bf16(tmem_base, a01_hi, g_desc, idesc_full, accumulate);
+                        ptx::umma_bf16(tmem_base, a01_lo, g_desc, idesc_hi, 1u);
+                        ptx::umma_bf16(tmem_base + 128u, a2, g_desc, idesc_full, accumulate);
+                        accumulate = 1;
+                    }
+                ptx::umma_commit(&bars->empty[st]);
+                if (MC) ptx::umma_commit_multicast(&bars->gempty[st], (uint16_t)1);      // -> rank 0
+                if (++st == kStages) { st = 0; ph ^= 1; }
+            }
+            ptx::umma_commit(&bars->done);
+        } else if (lane == 0) {
             constexpr uint32_t idesc = ptx::make_idesc_bf16(128, 192, 1, 1);
             constexpr uint32_t a_lbo = (C == 64) ? G::PLANE_BYTES : G::GO_CHUNK_BYTES;
             int st = 0; uint32_t ph = 0;
@@ -135,7 +174,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_go, const __grid_con
                     for (int wg = 0; wg < WIMG / 16; ++wg) {
                         const uint32_t px_off = (uint32_t)wg * 16 * 128;
 #pragma unroll
-                        for (int pa = 0; pa < (C == 64 ? 1 : 2); ++pa) {
+                        for (int pa = 0; pa < (C == 64 ? 1 : 2); ++pa) {      // C = 64 (four-product option): [g_hi ; g_lo] is one M = 128 operand
                             const uint64_t adesc = ptx::make_smem_desc_sw128(
                                 go_base + rho * G::ROW_PAIR_BYTES + pa * G::PLANE_BYTES + px_off, a_lbo, 1024);
 #pragma unroll
@@ -155,16 +194,50 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_go, const __grid_con
             ptx::umma_commit(&bars->done);
         }
     } else if (warp >= 4) {
-        // final epilogue: D[lane = gout channel (or hi/lo half x channel)][col = r*64 + ci] -> partial
         const int q = warp & 3;
         ptx::mbar_wait_backoff(&bars->done, 0, backoff_ns ? 8 * backoff_ns : 0);     // waits for the whole kernel
         ptx::tc_fence_after();
         const int row = q * 32 + lane;                       // accumulator row
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        if (C == 64 && P3) {
+            // final epilogue, C = 64: lane = (r or plane, c_in), columns = (g plane, c_out); the partials keep the layout
+            // [slice][tap][c_in][c_out] -- a thread writes 16 consecutive c_out (64 B) per step.  Slice 2 part + 0 takes
+            // everything except the in_lo rows of the third tap, which go to slice 2 part + 1 (zero elsewhere).
+            const int ci = row & 63, half = row >> 6;
+            float* const s0 = partial + (size_t)(part * 2) * 9 * C * C;
+            float* const s1 = s0 + (size_t)9 * C * C;
+#pragma unroll 1
+            for (int cb = 0; cb < 64; cb += 16) {
+                float a[16], b[16];
+                // taps (r = half, s): in_hi x g_hi + in_lo x g_hi (columns cb ..) + in_hi x g_lo (columns 64 + cb ..)
+                ptx::tmem_ld16(t_addr + cb, a);
+                ptx::tmem_ld16(t_addr + 64 + cb, b);
+                ptx::tmem_ld_wait();
+                float* d01 = s0 + ((size_t)(half * 3 + s) * C + ci) * C + cb;
+                float* z01 = s1 + ((size_t)(half * 3 + s) * C + ci) * C + cb;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float v = a[j] + b[j];
+                    d01[j] = accumulate_partial ? d01[j] + v : v;
+                    if (!accumulate_partial) z01[j] = 0.f;
+                }
+                // tap (r = 2, s): rows of the hi plane of `in` -> slice 0, of the lo plane -> slice 1
+                ptx::tmem_ld16(t_addr + 128 + cb, a);
+                ptx::tmem_ld16(t_addr + 192 + cb, b);
+                ptx::tmem_ld_wait();
+                float* d2 = (half ? s1 : s0) + ((size_t)(6 + s) * C + ci) * C + cb;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float v = a[j] + b[j];
+                    d2[j] = accumulate_partial ? d2[j] + v : v;
+                }
+            }
+        } else {
+        // final epilogue: D[lane = gout channel (or hi/lo half x channel)][col = r*64 + ci] -> partial
         int slice, co;
         if (C == 64) { slice = part * 2 + (row >> 6); co = row & 63; }
         else { slice = part; co = row; }
         float* dst = partial + (size_t)slice * 9 * C * C;
-        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
         for (int cb = 0; cb < 192; cb += 16) {
             float v[16];
@@ -178,6 +251,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_go, const __grid_con
                 float* q = dst + ((size_t)tap * C + ci) * C + co;
                 *q = accumulate_partial ? *q + v[j] : v[j];        // CTA-private slot: deterministic
             }
+        }
         }
     }
     ptx::tc_fence_before();
@@ -208,7 +282,9 @@ int launch_impl(const __nv_bfloat16* gout, const __nv_bfloat16* in, float* parti
     if (make_tmap_split5d(&tm_in, in, s.B, s.H, s.W, s.C, WIMG, G::ROWS + 2)) return -1;
     const size_t smem = (size_t)kStages * G::STAGE_BYTES + sizeof(WBarriers) + 1024;
     const bool mc = tune_get(TUNE_WGRAD_MULTICAST) != 0;
-    auto kern = mc ? wgrad3x3_tc_kernel<C, WIMG, true> : wgrad3x3_tc_kernel<C, WIMG, false>;
+    const bool p3 = C != 64 || tune_get(TUNE_WGRAD64_PRODUCTS) == 3;
+    auto kern = mc ? (p3 ? wgrad3x3_tc_kernel<C, WIMG, true, true> : wgrad3x3_tc_kernel<C, WIMG, true, false>)
+                   : (p3 ? wgrad3x3_tc_kernel<C, WIMG, false, true> : wgrad3x3_tc_kernel<C, WIMG, false, false>);
     if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                    "cudaFuncSetAttribute(wgrad3x3_tc)"))
         return -1;

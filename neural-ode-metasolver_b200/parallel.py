@@ -33,13 +33,23 @@ def shard_range(n_items, rank, world):
 
 
 class GradAllReducer:
-    """One all-reduce per step over a single flat fp32 buffer holding every parameter gradient."""
+    """One all-reduce per step over a single flat fp32 buffer holding every parameter gradient.
+
+    The gradients are gathered into the flat buffer by ONE concatenation kernel, the buffer is reduced (NCCL: averaging
+    inside the collective), and every `p.grad` is then re-pointed at its slice of the buffer (host-side view
+    assignments: no unpack copies).  Round 1 issued ~36 pack copies, the all-reduce, a scale and ~36 unpack copies."""
 
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device if self.params else torch.device("cpu")
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.views = []
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            self.views.append(self.flat[off:off + k].view(p.shape))
+            off += k
 
     @property
     def nbytes(self):
@@ -48,24 +58,24 @@ class GradAllReducer:
     def __call__(self, average=True):
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
             return
-        off = 0
-        for p in self.params:
-            n = p.numel()
+        pieces = []
+        for p, v in zip(self.params, self.views):
             if p.grad is None:
-                self.flat[off:off + n].zero_()
+                v.zero_()
+                pieces.append(v.reshape(-1))
             else:
-                self.flat[off:off + n].copy_(p.grad.reshape(-1))
-            off += n
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-        if average:
-            self.flat.mul_(1.0 / dist.get_world_size())
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            if p.grad is None:
-                p.grad = torch.empty_like(p)
-            p.grad.copy_(self.flat[off:off + n].view_as(p))
-            off += n
+                pieces.append(p.grad.reshape(-1))
+        if any(g.data_ptr() != v.data_ptr() for g, v in zip(pieces, self.views)):
+            with torch.no_grad():
+                torch.cat(pieces, out=self.flat)                  # one gather kernel (no-op when grads already live in `flat`)
+        if average and dist.get_backend() == "nccl":
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
+        else:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            if average:
+                self.flat.mul_(1.0 / dist.get_world_size())
+        for p, v in zip(self.params, self.views):
+            p.grad = v
 
 
 def sync_solver_params(solvers, src=0):

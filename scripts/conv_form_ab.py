@@ -20,6 +20,8 @@ C, HW = 64, 32
 if os.environ.get("CONV_AB_C") == "128":          # CTA-pair kernel: role placement A/B
     C, HW = 128, 16
     sets = [dict(mma_warp_high=0), dict(mma_warp_high=1)]
+elif os.environ.get("CONV_AB_C") == "64wg":
+    sets = [dict(wgrad64_products=4), dict(wgrad64_products=3), dict(wgrad64_products=4), dict(wgrad64_products=3)]
 elif os.environ.get("CONV_AB_C") == "64pm":
     sets = [dict(tc_form_c64=1, mma_warp_high=0), dict(tc_form_c64=1, mma_warp_high=1), dict(tc_form_c64=2)]
 blk = MetaODEBlock(PreBasicBlock2(C, norm_layer=Identity, act_layer=F.gelu)).cuda()

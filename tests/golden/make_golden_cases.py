@@ -34,6 +34,8 @@ ODE_CASES = [
     ("c128_rk4u2_n1", 128, 16, 16, 1, "preact", ("rk4", "u2", 1, -1, 1 / 3., -1)),
     ("c16_rk2_u05_n2_odd", 16, 5, 7, 3, "preact", ("rk2", "u", 2, -1, 0.5, -1)),
     ("c64_post_rk2_n2", 64, 8, 32, 2, "postact", ("rk2", "u", 2, -1, 0.5, -1)),
+    ("c128_post_rk2_n8", 128, 8, 16, 2, "postact", ("rk2", "u", 8, -1, 0.5, -1)),
+    ("c64_post_rk4u2_n2", 64, 4, 32, 1, "postact", ("rk4", "u2", 2, -1, 1 / 3., -1)),
 ]
 
 

@@ -332,3 +332,26 @@ def test_tmem_resident_weight_conv_matches_pixel_major_form(B):
         assert torch.equal(b, c)
         assert max_rel(b.cpu().numpy(), a.cpu().numpy()) <= 1e-5
         assert max_rel(e.cpu().numpy(), a.cpu().numpy()) <= 1e-5
+
+
+@pytest.mark.parametrize("C,HW", [(64, 32), (128, 16)])
+def test_full_batch_subset_matches_the_oracle(C, HW):
+    """B = 512 through the tcgen05 engine (the bench shape: every CTA runs many work items, all rings wrap) against the
+    CPU oracle -- the reference's algorithm -- on a 64-image subset spread over the batch: outputs and input gradients
+    within the north-star tolerance (samples are independent, so a subset of a batch is a batch)."""
+    import oracle
+    blk, solver, opts = _block(C)
+    torch.manual_seed(21)
+    x = torch.randn(512, C, HW, HW, device="cuda").contiguous(memory_format=torch.channels_last)
+    r = torch.randn_like(x)
+    xg = x.clone().requires_grad_(True)
+    y = blk(xg, [solver], opts)
+    (y * r).sum().backward()
+    idx = torch.arange(3, 512, 8)[:64]                       # 64 images from all over the batch
+    w1, w2 = blk.rhs_func.conv1.weight.detach().cpu(), blk.rhs_func.conv2.weight.detach().cpu()
+    xo = x[idx.cuda()].cpu().contiguous().requires_grad_(True)
+    tab = oracle.butcher_tableau("rk2", "u", np.float32(0.5), None)
+    yo = oracle.integrate(tab, oracle.rhs_preact(w1, w2), xo, torch.tensor([0, 1]).float(), n_steps=8)[-1]
+    (yo * r[idx.cuda()].cpu()).sum().backward()
+    assert max_rel(y[idx.cuda()].detach().cpu().numpy(), yo.detach().numpy()) <= 1e-4
+    assert max_rel(xg.grad[idx.cuda()].cpu().numpy(), xo.grad.numpy()) <= 1e-4
