@@ -507,7 +507,7 @@ int tct_products() { return tune_get(TUNE_TCT_PRODUCTS) == 3 ? 3 : 4; }
 //   (the two rows of one channel sit 16 lanes apart inside a quadrant: one shuffle adds them in the epilogue).
 // transpose = the input-gradient convolution (W^T, rotated 180 degrees).
 // ---------------------------------------------------------------------------------------------
-__global__ void pack_w_tct_kernel(const float* __restrict__ w, uint32_t* __restrict__ out, int transpose) {
+__global__ void pack_w_tct_kernel(const float* __restrict__ w, uint32_t* __restrict__ out, int transpose, int cin_total, int skip_in) {
     constexpr int C = 64;
     const int total = 128 * 288;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -522,8 +522,8 @@ __global__ void pack_w_tct_kernel(const float* __restrict__ w, uint32_t* __restr
         float v[2];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            if (!transpose) v[e] = w[(((size_t)co * C + (ci + e)) * 3 + r) * 3 + s];
-            else v[e] = w[(((size_t)(ci + e) * C + co) * 3 + (2 - r)) * 3 + (2 - s)];
+            if (!transpose) v[e] = w[(((size_t)co * cin_total + (ci + e) + skip_in) * 3 + r) * 3 + s];
+            else v[e] = w[(((size_t)(ci + e) * cin_total + co + skip_in) * 3 + (2 - r)) * 3 + (2 - s)];
         }
         __nv_bfloat16 hi0, lo0, hi1, lo1;
         split_bf16(v[0], hi0, lo0);
@@ -533,10 +533,12 @@ __global__ void pack_w_tct_kernel(const float* __restrict__ w, uint32_t* __restr
     }
 }
 
-void launch_pack_w_tct(const float* w, void* out, int transpose, cudaStream_t st) {
+// cin_total / skip_in: see pack_w_tc_kernel (MNIST ConcatConv2d weights carry the time channel first)
+void launch_pack_w_tct_ex(const float* w, void* out, int transpose, int cin_total, int skip_in, cudaStream_t st) {
     const int total = 128 * 288;
-    pack_w_tct_kernel<<<(total + 255) / 256, 256, 0, st>>>(w, (uint32_t*)out, transpose);
+    pack_w_tct_kernel<<<(total + 255) / 256, 256, 0, st>>>(w, (uint32_t*)out, transpose, cin_total, skip_in);
     count_launch();
 }
+void launch_pack_w_tct(const float* w, void* out, int transpose, cudaStream_t st) { launch_pack_w_tct_ex(w, out, transpose, 64, 0, st); }
 
 }  // namespace msb

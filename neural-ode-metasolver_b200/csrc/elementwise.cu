@@ -96,7 +96,8 @@ void launch_pack_w_simt(const float* w, float* out, int C, int Cin_total, int sk
 //             chunk = 64-wide slice of c_in.
 // Element (row, k) of a tile = W[co][chunk*64 + k][r][s] (or the transposed/rotated weight).
 // ---------------------------------------------------------------------------------------------
-__global__ void pack_w_tc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int C, int transpose) {
+__global__ void pack_w_tc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int C, int transpose,
+                                 int cin_total, int skip_in) {
     int chunks = C / 64;
     int tiles = (C == 64) ? 9 : 9 * chunks * 2;
     int total = tiles * 128 * 64;
@@ -119,19 +120,24 @@ __global__ void pack_w_tc_kernel(const float* __restrict__ w, __nv_bfloat16* __r
         int ci = chunk * 64 + k;
         int r = tap / 3, s = tap % 3;
         float v;
-        if (!transpose) v = w[(((size_t)co * C + ci) * 3 + r) * 3 + s];
-        else v = w[(((size_t)ci * C + co) * 3 + (2 - r)) * 3 + (2 - s)];
+        // cin_total / skip_in: the weight tensor has cin_total input channels of which the first skip_in are not part of
+        // this GEMM (ConcatConv2d: channel 0 is the time channel)
+        if (!transpose) v = w[(((size_t)co * cin_total + ci + skip_in) * 3 + r) * 3 + s];
+        else v = w[(((size_t)ci * cin_total + co + skip_in) * 3 + (2 - r)) * 3 + (2 - s)];
         __nv_bfloat16 hi, lo;
         split_bf16(v, hi, lo);
         out[i] = part ? lo : hi;
     }
 }
 
-void launch_pack_w_tc(const float* w, __nv_bfloat16* out, int C, int transpose, cudaStream_t st) {
+void launch_pack_w_tc_ex(const float* w, __nv_bfloat16* out, int C, int transpose, int cin_total, int skip_in, cudaStream_t st) {
     int tiles = (C == 64) ? 9 : 9 * (C / 64) * 2;
     int total = tiles * 128 * 64;
-    pack_w_tc_kernel<<<(total + 255) / 256, 256, 0, st>>>(w, out, C, transpose);
+    pack_w_tc_kernel<<<(total + 255) / 256, 256, 0, st>>>(w, out, C, transpose, cin_total, skip_in);
     count_launch();
+}
+void launch_pack_w_tc(const float* w, __nv_bfloat16* out, int C, int transpose, cudaStream_t st) {
+    launch_pack_w_tc_ex(w, out, C, transpose, C, 0, st);
 }
 
 // ---------------------------------------------------------------------------------------------

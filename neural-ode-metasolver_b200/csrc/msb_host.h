@@ -1,5 +1,6 @@
 // Host-side helpers of libmetasolver_b200.so shared by odeblock.cu and blocks.cu (not part of the ABI).
 #pragma once
+#include "metasolver_b200.h"
 #include "msb_internal.h"
 
 namespace msb {
@@ -30,5 +31,11 @@ int wgrad_nparts(int engine, ConvShape s);
 struct WgradAcc { float* partial; float* grad_w; int launches; int nparts; };
 int run_wgrad(int engine, const __nv_bfloat16* gout, const __nv_bfloat16* in, WgradAcc& acc, ConvShape s, cudaStream_t st);
 int wgrad_finish(int engine, WgradAcc& acc, ConvShape s, cudaStream_t st);
+
+// ---- mnist_fused.cu: MNIST ODE block forward as one persistent launch ----
+bool mnist_fused_supported(const MsbOdeDesc* d, const MsbMnistParams* mp);
+size_t mnist_fused_workspace_bytes();
+int launch_mnist_fused_forward(const MsbOdeDesc* d, const float* x, const MsbMnistParams* mp, float* y_out, void* workspace,
+                               void* tape, size_t slot_stride, cudaStream_t st);
 
 }  // namespace msb

@@ -30,6 +30,7 @@ enum { TUNE_EPI_L2_PREFETCH = 0,   // conv epilogue operands: bulk L2 prefetch d
        TUNE_TCT_PRODUCTS = 10,     // TMEM-resident-weight conv: hi/lo products formed, 3 (default) or 4
        TUNE_MMA_WARP_HIGH = 11,    // pixel-major convs: TMA / MMA roles on the highest physical warps (scheduler priority)
        TUNE_WGRAD64_PRODUCTS = 12, // C = 64 weight gradient: 4 hi/lo products (default) or 3 (roles swapped; measured slower)
+       TUNE_MNIST_FUSED = 13,      // MNIST right-hand side forward: whole solve in one persistent tcgen05 launch (1, default) or the SIMT multi-launch path
        TUNE_COUNT };
 int tune_get(int which);
 

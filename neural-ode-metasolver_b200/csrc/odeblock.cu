@@ -39,10 +39,10 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 static std::atomic<int> g_tune[TUNE_COUNT];
 static std::atomic<bool> g_tune_init{false};
 static const char* const kTuneNames[TUNE_COUNT] = {"epi_l2_prefetch", "tc_resident", "tcp_epi_warps", "tc_form_c64", "tc_pair",
-                                                   "wait_backoff_ns", "pdl", "wgrad_multicast", "tct_band", "tct_debug", "tct_products", "mma_warp_high", "wgrad64_products"};
+                                                   "wait_backoff_ns", "pdl", "wgrad_multicast", "tct_band", "tct_debug", "tct_products", "mma_warp_high", "wgrad64_products", "mnist_fused"};
 static const char* const kTuneEnv[TUNE_COUNT] = {"MSB_EPI_L2_PREFETCH", "MSB_TC_RESIDENT", "MSB_TCP_EPI_WARPS", "MSB_TC_FORM_C64",
-                                                 "MSB_TC_PAIR", "MSB_WAIT_BACKOFF_NS", "MSB_PDL", "MSB_WGRAD_MULTICAST", "MSB_TCT_BAND", "MSB_TCT_DEBUG", "MSB_TCT_PRODUCTS", "MSB_MMA_WARP_HIGH", "MSB_WGRAD64_PRODUCTS"};
-static const int kTuneDefault[TUNE_COUNT] = {0, 0, 16, 2, 2, 0, 1, 0, 0, 0, 4, 0, 4};
+                                                 "MSB_TC_PAIR", "MSB_WAIT_BACKOFF_NS", "MSB_PDL", "MSB_WGRAD_MULTICAST", "MSB_TCT_BAND", "MSB_TCT_DEBUG", "MSB_TCT_PRODUCTS", "MSB_MMA_WARP_HIGH", "MSB_WGRAD64_PRODUCTS", "MSB_MNIST_FUSED"};
+static const int kTuneDefault[TUNE_COUNT] = {0, 0, 16, 2, 2, 0, 1, 0, 0, 0, 4, 0, 4, 1};
 static void tune_init() {
     if (g_tune_init.load(std::memory_order_acquire)) return;
     for (int i = 0; i < TUNE_COUNT; ++i) {
@@ -354,8 +354,8 @@ size_t msb_odeblock_workspace_bytes(const MsbOdeDesc* d) {
     n += 2 * align_up(E * 4);                                  // y ping-pong
     n += (size_t)(d->stages - 1) * align_up(E * 4);            // k_1 .. k_{s-1}
     n += 2 * align_up(E * 4);                                  // A / Hs split (inference)
-    if (d->rhs_kind == MSB_RHS_MNIST_GN_T)                     // conv output, stage input, 2 tapmaps
-        n += 2 * align_up(E * 4) + 2 * align_up((size_t)d->height * d->width * d->channels * 4);
+    if (d->rhs_kind == MSB_RHS_MNIST_GN_T)                     // conv output, stage input, 2 tapmaps; fused path: packed weights + maps
+        n += 2 * align_up(E * 4) + 2 * align_up((size_t)d->height * d->width * d->channels * 4) + mnist_fused_workspace_bytes() + 1024;
     if (d->rhs_kind == MSB_RHS_PREACT_GN) n += 2 * align_up(E * 4);     // conv1 output, stage input
     return n + 4096;
 }
@@ -434,6 +434,8 @@ static int mnist_forward(const MsbOdeDesc* d, const float* x, const MsbMnistPara
     if (workspace_bytes < msb_odeblock_workspace_bytes(d)) { set_error("workspace too small"); return -1; }
     const int S = d->stages, N = d->n_steps, C = d->channels;
     const size_t E = state_elems(d);
+    if (mnist_fused_supported(d, mp))       // the whole solve in ONE persistent tcgen05 launch (mnist_fused.cu)
+        return launch_mnist_fused_forward(d, x, mp, y_out, workspace, save ? tape : nullptr, align_up(E * 4), st);
     ConvShape shp{d->batch, d->height, d->width, C};
     Carver cv(workspace, workspace_bytes);
     float* wp[2] = {cv.take<float>((size_t)9 * C * C * 4), cv.take<float>((size_t)9 * C * C * 4)};

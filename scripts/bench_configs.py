@@ -44,8 +44,12 @@ with torch.no_grad():
     ms = timed(lambda: blk(x, [s05], opts), 20)
     gs = msb.GraphedStep(lambda xx: blk(xx, [s05], opts), (x,))
     ms_g = timed(lambda: gs(x), 20)
-out["C1_mnist_odeblock_fwd_B128"] = dict(ms=ms, ms_cuda_graph=ms_g, images_per_s=128 / ms_g * 1e3,
-                                         note="reference: 46 ms on 8 CPU cores (SURVEY 8a9)")
+msb.set_option("mnist_fused", 0)
+with torch.no_grad():
+    ms_unfused = timed(lambda: blk(x, [s05], opts), 20)
+msb.set_option("mnist_fused", 1)
+out["C1_mnist_odeblock_fwd_B128"] = dict(ms=ms, ms_cuda_graph=ms_g, images_per_s=128 / ms_g * 1e3, ms_multi_launch_simt_path=ms_unfused,
+                                         note="one persistent tcgen05 launch for the whole solve (mnist_fused.cu); reference: 46 ms on 8 CPU cores (SURVEY 8a9)")
 # ---- C2..C5 model
 model = premetanode10((Identity,) * 3, (lambda t: t,) * 3, (F.gelu,) * 3, in_planes=64, is_odenet=True).to(dev)
 model = model.to(memory_format=torch.channels_last).eval()
