@@ -81,7 +81,7 @@ template <int C, int WIMG, int ACT, int EW>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((kEpiWarp0 + EW) * 32, 1)
 conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_w,
                     const EpiParams epi, const int H, const int num_pairs, const int tiles_per_img,
-                    const uint32_t backoff_ns, const int role_shift) {
+                    const uint32_t backoff_ns, const int role_shift, const int uniform_issue) {
     using G = Geom2<C, WIMG, EW>;
     constexpr int CHUNKS = C / 64;
     constexpr int kWStages = G::W_STAGES, kXStages = G::X_STAGES, kAccBufs = G::ACC_BUFS;
@@ -180,47 +180,62 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread of the LEADER, for the pair) =====================
-        if (lane == 0 && leader) {
+        // uniform_issue (default): the whole warp runs the loop -- waits, ring bookkeeping and descriptor arithmetic are
+        // warp-uniform and live in uniform registers -- and one elected lane issues the MMAs / commits.  The round-1 style
+        // (`if (lane == 0)` around everything) makes every operand of every MMA go through a ~15-instruction R2UR election
+        // loop, which at 64 - 128 clocks per MMA and a pipe that queues only ~4 of them is close to the issue limit.
+        auto issue_loop = [&](const bool el) {
             constexpr uint32_t idesc_full = ptx::make_idesc_bf16(256, 2 * C, 0, 0);   // X_hi * [W_hi ; W_lo]
             constexpr uint32_t idesc_hi = ptx::make_idesc_bf16(256, C, 0, 0);         // X_lo * W_hi
+            const uint32_t tb = __shfl_sync(__activemask(), tmem_base, 0);
+            const uint32_t xs_u32 = ptx::smem_u32(smem_x), ws_u32 = ptx::smem_u32(smem_w);
             int wst = 0, xst = 0; uint32_t wph = 0, xph = 0;
             int acc = 0; uint32_t acc_ph = 0;
             if (G::RES) { ptx::mbar_wait(&bars->w_full[0], 0); ptx::tc_fence_after(); }
             for (int pr = cluster_id; pr < num_pairs; pr += num_clusters) {
                 ptx::mbar_wait(&bars->tmem_empty[acc], acc_ph ^ 1);
                 ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * G::ACC_COLS);
+                const uint32_t d_tmem = tb + (uint32_t)(acc * G::ACC_COLS);
                 uint32_t accumulate = 0;
                 for (int chunk = 0; chunk < CHUNKS; ++chunk)
                     for (int s = 0; s < 3; ++s) {
                         ptx::mbar_wait(&bars->x_full[xst], xph);
                         ptx::tc_fence_after();
-                        const uint32_t x_base = ptx::smem_u32(smem_x + xst * G::X_STAGE_BYTES);
+                        const uint32_t x_base = xs_u32 + (uint32_t)(xst * G::X_STAGE_BYTES);
                         for (int r = 0; r < 3; ++r) {
                             if (G::RES) wst = r * 3 + s;
                             else { ptx::mbar_wait(&bars->w_full[wst], wph); ptx::tc_fence_after(); }
-                            const uint32_t w_base = ptx::smem_u32(smem_w + wst * G::W_STAGE_BYTES);
+                            const uint32_t w_base = ws_u32 + (uint32_t)(wst * G::W_STAGE_BYTES);
+                            if (el) {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const uint64_t wa = ptx::make_smem_desc_sw128(w_base + k * 32, 16, 1024);
-                                const uint64_t wb = ptx::make_smem_desc_sw128(w_base + G::WA_BYTES + k * 32, 16, 1024);
-                                const uint64_t xhi = ptx::make_smem_desc_sw128(x_base + r * G::ROW_BYTES + k * 32, 16, 1024);
-                                const uint64_t xlo =
-                                    ptx::make_smem_desc_sw128(x_base + G::PLANE_BYTES + r * G::ROW_BYTES + k * 32, 16, 1024);
-                                ptx::umma_bf16_2sm(d_tmem, xhi, wa, idesc_full, accumulate);
-                                ptx::umma_bf16_2sm(d_tmem, xlo, wb, idesc_hi, 1u);
-                                accumulate = 1;
+                                for (int k = 0; k < 4; ++k) {
+                                    const uint64_t wa = ptx::make_smem_desc_sw128(w_base + k * 32, 16, 1024);
+                                    const uint64_t wb = ptx::make_smem_desc_sw128(w_base + G::WA_BYTES + k * 32, 16, 1024);
+                                    const uint64_t xhi = ptx::make_smem_desc_sw128(x_base + r * G::ROW_BYTES + k * 32, 16, 1024);
+                                    const uint64_t xlo =
+                                        ptx::make_smem_desc_sw128(x_base + G::PLANE_BYTES + r * G::ROW_BYTES + k * 32, 16, 1024);
+                                    ptx::umma_bf16_2sm(d_tmem, xhi, wa, idesc_full, (k == 0) ? accumulate : 1u);
+                                    ptx::umma_bf16_2sm(d_tmem, xlo, wb, idesc_hi, 1u);
+                                }
+                                if (!G::RES) ptx::umma_commit_2sm(&bars->w_empty[wst]);
                             }
-                            if (!G::RES) {
-                                ptx::umma_commit_2sm(&bars->w_empty[wst]);
-                                if (++wst == kWStages) { wst = 0; wph ^= 1; }
-                            }
+                            accumulate = 1;
+                            if (!G::RES) { if (++wst == kWStages) { wst = 0; wph ^= 1; } }
                         }
-                        ptx::umma_commit_2sm(&bars->x_empty[xst]);
+                        if (el) ptx::umma_commit_2sm(&bars->x_empty[xst]);
                         if (++xst == kXStages) { xst = 0; xph ^= 1; }
                     }
-                ptx::umma_commit_2sm(&bars->tmem_full[acc]);
+                if (el) ptx::umma_commit_2sm(&bars->tmem_full[acc]);
                 if (++acc == kAccBufs) { acc = 0; acc_ph ^= 1; }
+            }
+        };
+        if (leader) {
+            if (uniform_issue) {
+                uint32_t e;
+                asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(e));
+                issue_loop(e != 0);
+            } else if (lane == 0) {
+                issue_loop(true);
             }
         }
     } else if (warp >= kEpiWarp0) {
@@ -406,7 +421,8 @@ int launch_act_ew(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, c
     const int num_pairs = s.B * tiles_per_img / 2;
     const int clusters = std::min(num_pairs, num_sms() / 2);
     const cudaError_t le = launch_maybe_pdl(kern, 2 * clusters, kThreads, smem, st, tm_act, tm_w, epi, s.H, num_pairs,
-                                            tiles_per_img, (uint32_t)tune_get(TUNE_WAIT_BACKOFF), tune_get(TUNE_MMA_WARP_HIGH) ? kEpiWarp0 : 0);
+                                            tiles_per_img, (uint32_t)tune_get(TUNE_WAIT_BACKOFF), tune_get(TUNE_MMA_WARP_HIGH) ? kEpiWarp0 : 0,
+                                            tune_get(TUNE_UNIFORM_ISSUE) & 1);
     count_launch();
     return check_cuda(le != cudaSuccess ? le : cudaGetLastError(), "conv3x3_tcp2 launch");
 }

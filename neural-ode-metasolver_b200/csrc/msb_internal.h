@@ -31,6 +31,8 @@ enum { TUNE_EPI_L2_PREFETCH = 0,   // conv epilogue operands: bulk L2 prefetch d
        TUNE_MMA_WARP_HIGH = 11,    // pixel-major convs: TMA / MMA roles on the highest physical warps (scheduler priority)
        TUNE_WGRAD64_PRODUCTS = 12, // C = 64 weight gradient: 4 hi/lo products (default) or 3 (roles swapped; measured slower)
        TUNE_MNIST_FUSED = 13,      // MNIST right-hand side forward: whole solve in one persistent tcgen05 launch (1, default) or the SIMT multi-launch path
+       TUNE_UNIFORM_ISSUE = 14,    // warp-uniform MMA issue loop instead of the one-lane loop of round 1: bit 0 = CTA-pair conv (default on: -2..3 %),
+                                   // bit 1 = weight gradient (default off: no gain measured)
        TUNE_COUNT };
 int tune_get(int which);
 

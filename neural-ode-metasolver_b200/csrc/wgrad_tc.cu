@@ -61,7 +61,7 @@ template <int C, int WIMG, bool MC, bool P3>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_go, const __grid_constant__ CUtensorMap tmap_in,
                    float* __restrict__ partial, const int num_tiles, const int tiles_per_img, const int nparts,
-                   const int accumulate_partial, const uint32_t backoff_ns) {
+                   const int accumulate_partial, const uint32_t backoff_ns, const int uniform_issue) {
     using G = WG<C, WIMG>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -160,38 +160,54 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_go, const __grid_con
                 if (++st == kStages) { st = 0; ph ^= 1; }
             }
             ptx::umma_commit(&bars->done);
-        } else if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_bf16(128, 192, 1, 1);
-            constexpr uint32_t a_lbo = (C == 64) ? G::PLANE_BYTES : G::GO_CHUNK_BYTES;
-            int st = 0; uint32_t ph = 0;
-            uint32_t accumulate = 0;
-            for (int tile = part; tile < num_tiles; tile += nparts) {
-                ptx::mbar_wait(&bars->full[st], ph);
-                ptx::tc_fence_after();
-                const uint32_t go_base = ptx::smem_u32(smem + st * G::STAGE_BYTES);
-                const uint32_t in_base = go_base + G::GO_BYTES;
-                for (int rho = 0; rho < G::ROWS; ++rho)
-                    for (int wg = 0; wg < WIMG / 16; ++wg) {
-                        const uint32_t px_off = (uint32_t)wg * 16 * 128;
+        } else if (!(C == 64 && P3)) {
+            // warp-uniform issue loop (see conv_tcp2.cu): all lanes run it, one elected lane issues
+            auto issue_loop = [&](const bool el) {
+                constexpr uint32_t idesc = ptx::make_idesc_bf16(128, 192, 1, 1);
+                constexpr uint32_t a_lbo = (C == 64) ? G::PLANE_BYTES : G::GO_CHUNK_BYTES;
+                const uint32_t tb = __shfl_sync(__activemask(), tmem_base, 0);
+                const uint32_t smem_u = ptx::smem_u32(smem);
+                int st = 0; uint32_t ph = 0;
+                uint32_t accumulate = 0;
+                for (int tile = part; tile < num_tiles; tile += nparts) {
+                    ptx::mbar_wait(&bars->full[st], ph);
+                    ptx::tc_fence_after();
+                    const uint32_t go_base = smem_u + (uint32_t)(st * G::STAGE_BYTES);
+                    const uint32_t in_base = go_base + G::GO_BYTES;
+                    if (el) {
 #pragma unroll
-                        for (int pa = 0; pa < (C == 64 ? 1 : 2); ++pa) {      // C = 64 (four-product option): [g_hi ; g_lo] is one M = 128 operand
-                            const uint64_t adesc = ptx::make_smem_desc_sw128(
-                                go_base + rho * G::ROW_PAIR_BYTES + pa * G::PLANE_BYTES + px_off, a_lbo, 1024);
+                        for (int rho = 0; rho < G::ROWS; ++rho)
 #pragma unroll
-                            for (int pb = 0; pb < 2; ++pb) {
-                                if (C != 64 && pa == 1 && pb == 1) continue;   // lo x lo (2^-18 relative) is dropped
-                                const uint64_t bdesc = ptx::make_smem_desc_sw128(
-                                    in_base + rho * G::ROW_PAIR_BYTES + pb * G::PLANE_BYTES + px_off, G::ROW_PAIR_BYTES, 1024);
-                                ptx::umma_bf16(tmem_base, adesc, bdesc, idesc, accumulate);
-                                accumulate = 1;
+                            for (int wg = 0; wg < WIMG / 16; ++wg) {
+                                const uint32_t px_off = (uint32_t)wg * 16 * 128;
+#pragma unroll
+                                for (int pa = 0; pa < (C == 64 ? 1 : 2); ++pa) {      // C = 64: [g_hi ; g_lo] is one M = 128 operand
+                                    const uint64_t adesc = ptx::make_smem_desc_sw128(
+                                        go_base + rho * G::ROW_PAIR_BYTES + pa * G::PLANE_BYTES + px_off, a_lbo, 1024);
+#pragma unroll
+                                    for (int pb = 0; pb < 2; ++pb) {
+                                        if (C != 64 && pa == 1 && pb == 1) continue;   // lo x lo (2^-18 relative) is dropped
+                                        const uint64_t bdesc = ptx::make_smem_desc_sw128(
+                                            in_base + rho * G::ROW_PAIR_BYTES + pb * G::PLANE_BYTES + px_off, G::ROW_PAIR_BYTES, 1024);
+                                        ptx::umma_bf16(tb, adesc, bdesc, idesc, (rho | wg | pa | pb) ? 1u : accumulate);
+                                    }
+                                }
                             }
-                        }
+                        ptx::umma_commit(&bars->empty[st]);
+                        if (MC) ptx::umma_commit_multicast(&bars->gempty[st], (uint16_t)1);      // -> rank 0
                     }
-                ptx::umma_commit(&bars->empty[st]);
-                if (MC) ptx::umma_commit_multicast(&bars->gempty[st], (uint16_t)1);      // -> rank 0
-                if (++st == kStages) { st = 0; ph ^= 1; }
+                    accumulate = 1;
+                    if (++st == kStages) { st = 0; ph ^= 1; }
+                }
+                if (el) ptx::umma_commit(&bars->done);
+            };
+            if (uniform_issue) {
+                uint32_t e;
+                asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(e));
+                issue_loop(e != 0);
+            } else if (lane == 0) {
+                issue_loop(true);
             }
-            ptx::umma_commit(&bars->done);
         }
     } else if (warp >= 4) {
         const int q = warp & 3;
@@ -303,10 +319,10 @@ int launch_impl(const __nv_bfloat16* gout, const __nv_bfloat16* in, float* parti
         cfg.attrs = attr;
         cfg.numAttrs = tune_get(TUNE_PDL) ? 2 : 1;
         le = cudaLaunchKernelEx(&cfg, kern, tm_go, tm_in, partial, num_tiles, tiles_per_img, np, accumulate,
-                                (uint32_t)tune_get(TUNE_WAIT_BACKOFF));
+                                (uint32_t)tune_get(TUNE_WAIT_BACKOFF), tune_get(TUNE_UNIFORM_ISSUE) & 2);
     } else {
         le = launch_maybe_pdl(kern, np * G::GROUPS, kThreads, smem, st, tm_go, tm_in, partial, num_tiles, tiles_per_img, np,
-                              accumulate, (uint32_t)tune_get(TUNE_WAIT_BACKOFF));
+                              accumulate, (uint32_t)tune_get(TUNE_WAIT_BACKOFF), tune_get(TUNE_UNIFORM_ISSUE) & 2);
     }
     count_launch();
     *nparts_out = np * G::HALVES;

@@ -19,9 +19,9 @@ sets = [S(1), S(2), S(2, prod=3), S(2, band=8), S(2, pf=1)]
 C, HW = 64, 32
 if os.environ.get("CONV_AB_C") == "128":          # CTA-pair kernel: role placement A/B
     C, HW = 128, 16
-    sets = [dict(mma_warp_high=0), dict(mma_warp_high=1)]
+    sets = [dict(uniform_issue=0), dict(uniform_issue=1), dict(uniform_issue=0), dict(uniform_issue=1)]
 elif os.environ.get("CONV_AB_C") == "64wg":
-    sets = [dict(wgrad64_products=4), dict(wgrad64_products=3), dict(wgrad64_products=4), dict(wgrad64_products=3)]
+    sets = [dict(uniform_issue=0), dict(uniform_issue=1), dict(uniform_issue=0), dict(uniform_issue=1)]
 elif os.environ.get("CONV_AB_C") == "64pm":
     sets = [dict(tc_form_c64=1, mma_warp_high=0), dict(tc_form_c64=1, mma_warp_high=1), dict(tc_form_c64=2)]
 blk = MetaODEBlock(PreBasicBlock2(C, norm_layer=Identity, act_layer=F.gelu)).cuda()
