@@ -87,7 +87,9 @@ xt, yt = xin[:256], y[:256]
 
 
 def train_step():
-    s = sample_solver_by_noising_params(base, std=0.0125, bernoulli_p=1.0, noise_type="normal")
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):      # the sampler prints its draw (as the reference does)
+        s = sample_solver_by_noising_params(base, std=0.0125, bernoulli_p=1.0, noise_type="normal")
     kws = {"solvers": [s], "solver_options": opts}
     opt.zero_grad()
     xa, _ = atk(xt, yt, kws)

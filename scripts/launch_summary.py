@@ -21,4 +21,4 @@ for name, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
 conv = sum(ms for k, (n, ms) in agg.items() if "conv3x3_tc" in k)
 wg = sum(ms for k, (n, ms) in agg.items() if "wgrad3x3_tc" in k)
 other = sum(ms for k, (n, ms) in agg.items() if "msb" not in k)
-print("# conv3x3_tcp + conv3x3_tcp2 share %.1f%%, wgrad3x3_tc share %.1f%%, non-msb kernels share %.1f%%" % (100 * conv / tot, 100 * wg / tot, 100 * other / tot))
+print("# conv3x3_tct + conv3x3_tcp2 (+ tcp) share %.1f%%, wgrad3x3_tc share %.1f%%, non-msb kernels share %.1f%%" % (100 * conv / tot, 100 * wg / tot, 100 * other / tot))

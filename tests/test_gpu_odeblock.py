@@ -374,7 +374,8 @@ def test_mnist_fused_single_launch_solve_matches_multi_launch_path():
                     # ~1e-3 (see the golden test above: one of 8 samples there).  Samples are independent: most must agree
                     # tightly, the flipped ones loosely.
                     per = np.abs(a - b).reshape(a.shape[0], -1).max(1) / np.abs(b).max()
-                    assert np.median(per) <= 2e-5 and (per <= 5e-5).mean() >= 0.7 and per.max() <= 2e-2, (sv, np.sort(per)[-5:])
+                    # measured (scripts/diag_mnist_fused.py): no flip -> every gradient agrees to ~4e-6; 3-4 % of the images flip
+                    assert np.median(per) <= 2e-5 and (per <= 5e-5).mean() >= 0.9 and per.max() <= 0.1, (sv, np.sort(per)[-5:])
                 else:
                     # parameter gradients: sums over all images incl. the flipped ones (random weights, zero-mean GroupNorm
                     # outputs: flips are far more frequent here than with the trained weights of the golden test, which
