@@ -46,10 +46,12 @@ extern "C" {
 enum { MSB_RHS_PREACT_NF = 0,   /* conv2(act(conv1(act(x))))          cifar10/layers.py:148-161 */
        MSB_RHS_POSTACT_NF = 1,  /* act(conv2(act(conv1(x))))          cifar10/layers.py:108-121 */
        MSB_RHS_MNIST_GN_T = 2,  /* GN-ReLU-cconv(t)-GN-ReLU-cconv(t)-GN  mnist/layers.py:158-171 */
-       MSB_RHS_PREACT_GN = 3    /* conv2(act(GN2(conv1(act(GN1(x))))))  cifar10/layers.py:148-161 with the
+       MSB_RHS_PREACT_GN = 3,   /* conv2(act(GN2(conv1(act(GN1(x))))))  cifar10/layers.py:148-161 with the
                                    'GN' / 'LN' / 'IN' normalisations of cifar10/utils.py:26-36 (all nn.GroupNorm).
                                    Parameters travel in MsbMnistParams: norm_w/b[0..1], conv_w[0..1] = OIHW (C,C,3,3)
-                                   without bias (conv_b, norm_w/b[2] ignored). */ };
+                                   without bias (conv_b, norm_w/b[2] ignored). */
+       MSB_RHS_POSTACT_GN = 4   /* act(GN2(conv2(act(GN1(conv1(x))))))  BasicBlock2 (cifar10/layers.py:108-121) with the same
+                                   per-sample normalisations; parameters as for MSB_RHS_PREACT_GN. */ };
 /* activations */
 enum { MSB_ACT_NONE = 0, MSB_ACT_GELU_ERF = 1, MSB_ACT_RELU = 2 };
 /* GEMM engines */

@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("MSB_LIB_PATH") or os.path.join(HERE, "libmetasolver_b
 MSB_MAX_STAGES = 4
 TABLEAU_GRAD_DOUBLES = MSB_MAX_STAGES + MSB_MAX_STAGES * MSB_MAX_STAGES + MSB_MAX_STAGES   # [b | w | c]
 ABI_VERSION = 4
-RHS_PREACT_NF, RHS_POSTACT_NF, RHS_MNIST_GN_T, RHS_PREACT_GN = 0, 1, 2, 3
+RHS_PREACT_NF, RHS_POSTACT_NF, RHS_MNIST_GN_T, RHS_PREACT_GN, RHS_POSTACT_GN = 0, 1, 2, 3, 4
 ACT_NONE, ACT_GELU_ERF, ACT_RELU = 0, 1, 2
 (ATTACK_UNNORMALIZE, ATTACK_NORMALIZE, ATTACK_FGSM_STEP, ATTACK_PGD_STEP, ATTACK_FGSMR_INIT,
  ATTACK_FGSMR_STEP) = range(6)

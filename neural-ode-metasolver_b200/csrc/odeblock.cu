@@ -182,8 +182,8 @@ namespace {
 int validate(const MsbOdeDesc* d) {
     if (!d) { set_error("null descriptor"); return -1; }
     if (d->rhs_kind != MSB_RHS_PREACT_NF && d->rhs_kind != MSB_RHS_POSTACT_NF && d->rhs_kind != MSB_RHS_MNIST_GN_T &&
-        d->rhs_kind != MSB_RHS_PREACT_GN) {
-        set_error("rhs_kind %d is not implemented (supported: PREACT_NF, POSTACT_NF, MNIST_GN_T, PREACT_GN)", d->rhs_kind);
+        d->rhs_kind != MSB_RHS_PREACT_GN && d->rhs_kind != MSB_RHS_POSTACT_GN) {
+        set_error("rhs_kind %d is not implemented (supported: PREACT_NF, POSTACT_NF, MNIST_GN_T, PREACT_GN, POSTACT_GN)", d->rhs_kind);
         return -1;
     }
     if (d->act != MSB_ACT_GELU_ERF && d->act != MSB_ACT_RELU && d->act != MSB_ACT_NONE) {
@@ -200,7 +200,7 @@ int validate(const MsbOdeDesc* d) {
     if (d->n_solvers > 1) {
         if (!d->solver_tableaus) { set_error("n_solvers = %d but solver_tableaus is NULL", d->n_solvers); return -1; }
         if (d->batch % d->n_solvers) { set_error("batch %d is not divisible into %d solver slices", d->batch, d->n_solvers); return -1; }
-        if (d->rhs_kind == MSB_RHS_MNIST_GN_T || d->rhs_kind == MSB_RHS_PREACT_GN) {
+        if (d->rhs_kind == MSB_RHS_MNIST_GN_T || d->rhs_kind == MSB_RHS_PREACT_GN || d->rhs_kind == MSB_RHS_POSTACT_GN) {
             set_error("the stacked solver axis is not implemented for the GroupNorm right-hand sides");
             return -1;
         }
@@ -357,11 +357,12 @@ size_t msb_odeblock_workspace_bytes(const MsbOdeDesc* d) {
     if (d->rhs_kind == MSB_RHS_MNIST_GN_T)                     // conv output, stage input, 2 tapmaps; fused path: packed weights + maps
         n += 2 * align_up(E * 4) + 2 * align_up((size_t)d->height * d->width * d->channels * 4) + mnist_fused_workspace_bytes() + 1024;
     if (d->rhs_kind == MSB_RHS_PREACT_GN) n += 2 * align_up(E * 4);     // conv1 output, stage input
+    if (d->rhs_kind == MSB_RHS_POSTACT_GN) n += 3 * align_up(E * 4);    // conv1 / conv2 outputs, stage input
     return n + 4096;
 }
 size_t msb_odeblock_tape_bytes(const MsbOdeDesc* d) {
     if (validate(d)) return 0;
-    const int per_slot = d->rhs_kind == MSB_RHS_MNIST_GN_T ? 5 : 4;      // MNIST: X, P1, P2, A, Hs;  PREACT_GN: X, P1, A, Hs
+    const int per_slot = d->rhs_kind == MSB_RHS_MNIST_GN_T ? 5 : 4;      // MNIST: X, P1, P2, A, Hs;  PREACT_GN: X, P1, A, Hs;  POSTACT_GN: P1, P2, A, Hs
     return (size_t)d->n_steps * d->stages * per_slot * align_up(state_elems(d) * 4);
 }
 size_t msb_odeblock_bwd_workspace_bytes(const MsbOdeDesc* d) {
@@ -386,7 +387,7 @@ size_t msb_odeblock_bwd_workspace_bytes(const MsbOdeDesc* d) {
     n += (size_t)(d->stages - 1) * align_up(E * 4);            // xbar_1 .. xbar_{s-1}
     n += 2 * align_up(E * 4);                                  // Kbar / DP split
     n += 2 * align_up((size_t)wgrad_nparts(engine, s) * 9 * d->channels * d->channels * 4);
-    if (d->rhs_kind == MSB_RHS_PREACT_GN)                      // dH (fp32) + per-sample dgamma / dbeta partials of 2 norms
+    if (d->rhs_kind == MSB_RHS_PREACT_GN || d->rhs_kind == MSB_RHS_POSTACT_GN)     // dH (fp32) + per-sample dgamma / dbeta partials of 2 norms
         n += align_up(E * 4) + 4 * align_up((size_t)d->batch * d->channels * 4);
     return n + 4096;
 }
@@ -683,6 +684,180 @@ static int gn_preact_backward(const MsbOdeDesc* d, const float* grad_y, const Ms
     return check_cuda(cudaGetLastError(), "odeblock backward (preact GN)");
 }
 
+// ---------------------------------------------------------------------------------------------
+// CIFAR POST-activation right-hand side with GroupNorm (BasicBlock2, cifar10/layers.py:108-121 with the 'GN' / 'LN' /
+// 'IN' normalisations of utils.py:26-36):      f(x) = act(GN2(conv2(act(GN1(conv1(x))))))
+// conv1 reads split(x_i); each GroupNorm (+ activation) is its own launch; k_i = act(GN2(.)) and the Runge-Kutta stage
+// combination are the epilogue of the GN2 launch.  Tape per (step, stage): P1, P2 (conv outputs), A = split(x_i),
+// Hs = split(act(GN1(P1))).
+// ---------------------------------------------------------------------------------------------
+struct PgSlot { float *P1, *P2; __nv_bfloat16 *A, *Hs; };
+static PgSlot pg_slot(void* tape, size_t E, int slot) {
+    const size_t q = align_up(E * 4);
+    char* p = (char*)tape + (size_t)slot * 4 * q;
+    return PgSlot{(float*)p, (float*)(p + q), (__nv_bfloat16*)(p + 2 * q), (__nv_bfloat16*)(p + 3 * q)};
+}
+
+static int gn_postact_forward(const MsbOdeDesc* d, const float* x, const MsbMnistParams* mp, float* y_out, void* workspace,
+                              size_t workspace_bytes, void* tape, size_t tape_bytes, cudaStream_t st) {
+    const bool save = d->save_tape != 0;
+    if (save && (!tape || tape_bytes < msb_odeblock_tape_bytes(d))) { set_error("tape missing or too small"); return -1; }
+    if (gn_check_params(mp)) return -1;
+    if (!x || !y_out || !workspace) { set_error("null pointer argument"); return -1; }
+    if (workspace_bytes < msb_odeblock_workspace_bytes(d)) { set_error("workspace too small"); return -1; }
+    const int engine = resolve_engine(d);
+    if (engine < 0) return -1;
+    const int S = d->stages, N = d->n_steps, C = d->channels;
+    const size_t E = state_elems(d);
+    ConvShape shp{d->batch, d->height, d->width, C};
+    Carver cv(workspace, workspace_bytes);
+    void* wp[2] = {cv.take<char>(packed_w_bytes(engine, C)), cv.take<char>(packed_w_bytes(engine, C))};
+    float* ybuf[2] = {cv.take<float>(E * 4), cv.take<float>(E * 4)};
+    float* kbuf[MSB_MAX_STAGES] = {nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < S - 1; ++i) kbuf[i] = cv.take<float>(E * 4);
+    __nv_bfloat16* A = cv.take<__nv_bfloat16>(E * 4);
+    __nv_bfloat16* Hs = cv.take<__nv_bfloat16>(E * 4);
+    float* P1 = cv.take<float>(E * 4);
+    float* P2 = cv.take<float>(E * 4);
+    float* xbuf = cv.take<float>(E * 4);
+    if (!cv.ok()) { set_error("internal: workspace carve overflow"); return -1; }
+    for (int k = 0; k < 2; ++k) pack_w(engine, mp->conv_w[k], wp[k], C, 0, st, d->height, d->width);
+    const float* y_cur = x;
+    for (int n = 0; n < N; ++n) {
+        const float dt = d->time_grid[n + 1] - d->time_grid[n];
+        float* y_next = (n == N - 1) ? y_out : ybuf[n & 1];
+        for (int i = 0; i < S; ++i) {
+            PgSlot sl = save ? pg_slot(tape, E, n * S + i) : PgSlot{P1, P2, A, Hs};
+            const float* xi = (i == 0) ? y_cur : xbuf;
+            launch_act_split(xi, nullptr, ACT_NONE, 1.f, sl.A, nullptr, d->batch, d->height, d->width, C, st);
+            EpiParams c1 = epi_default();
+            c1.out_f32 = sl.P1;
+            if (run_conv(engine, sl.A, wp[0], c1, shp, st)) return -1;
+            EpiParams g1 = epi_default();
+            g1.act = d->act; g1.out_split = sl.Hs;
+            if (launch_groupnorm_epi(sl.P1, mp->norm_w[0], mp->norm_b[0], g1, shp, mp->groups, mp->eps, st)) return -1;
+            EpiParams c2 = epi_default();
+            c2.out_f32 = sl.P2;
+            if (run_conv(engine, sl.Hs, wp[1], c2, shp, st)) return -1;
+            EpiParams g2 = epi_default();                       // k_i = act(GN2(.)) and the RK combination
+            g2.act_v = d->act;
+            g2.base = y_cur; g2.k[0].dt = dt;
+            if (i < S - 1) {
+                g2.v_out = kbuf[i];
+                g2.nsrc = i;
+                for (int j = 0; j < i; ++j) { g2.src[j] = kbuf[j]; g2.k[0].coef[j] = d->w[(i + 1) * MSB_MAX_STAGES + j]; }
+                g2.k[0].coef_v = d->w[(i + 1) * MSB_MAX_STAGES + i];
+                g2.out_f32 = xbuf;
+            } else {
+                g2.nsrc = S - 1;
+                for (int j = 0; j < S - 1; ++j) { g2.src[j] = kbuf[j]; g2.k[0].coef[j] = d->b[j]; }
+                g2.k[0].coef_v = d->b[S - 1];
+                g2.out_f32 = y_next;
+            }
+            if (launch_groupnorm_epi(sl.P2, mp->norm_w[1], mp->norm_b[1], g2, shp, mp->groups, mp->eps, st)) return -1;
+        }
+        y_cur = y_next;
+    }
+    return check_cuda(cudaGetLastError(), "odeblock forward (postact GN)");
+}
+
+//   kbar_i --act', GN2'--> dP2 --conv2^T--> dH --act', GN1'--> dP1 --conv1^T--> xbar_i  (+ the RK adjoint combination in the
+//   epilogue of the last convolution, as in the normalisation-free path)
+static int gn_postact_backward(const MsbOdeDesc* d, const float* grad_y, const MsbMnistParams* mp, const void* tape,
+                               size_t tape_bytes, float* grad_x, const MsbMnistGrads* grads, void* workspace,
+                               size_t workspace_bytes, cudaStream_t st) {
+    if (gn_check_params(mp)) return -1;
+    if (!grad_y || !tape || !grad_x || !workspace) { set_error("null pointer argument"); return -1; }
+    if (tape_bytes < msb_odeblock_tape_bytes(d)) { set_error("tape too small"); return -1; }
+    if (workspace_bytes < msb_odeblock_bwd_workspace_bytes(d)) { set_error("workspace too small"); return -1; }
+    const bool need_w = grads != nullptr;
+    if (need_w)
+        for (int i = 0; i < 2; ++i)
+            if (!grads->norm_w[i] || !grads->norm_b[i] || !grads->conv_w[i]) { set_error("POSTACT_GN grads: null pointer"); return -1; }
+    const int engine = resolve_engine(d);
+    if (engine < 0) return -1;
+    const int S = d->stages, N = d->n_steps, C = d->channels;
+    const size_t E = state_elems(d);
+    ConvShape shp{d->batch, d->height, d->width, C};
+    Carver cv(workspace, workspace_bytes);
+    void* wt[2] = {cv.take<char>(packed_w_bytes(engine, C)), cv.take<char>(packed_w_bytes(engine, C))};
+    float* gbuf[2] = {cv.take<float>(E * 4), cv.take<float>(E * 4)};
+    float* xbar[MSB_MAX_STAGES] = {nullptr, nullptr, nullptr, nullptr};
+    for (int i = 1; i < S; ++i) xbar[i] = cv.take<float>(E * 4);
+    __nv_bfloat16* DP2 = cv.take<__nv_bfloat16>(E * 4);
+    __nv_bfloat16* DP1 = cv.take<__nv_bfloat16>(E * 4);
+    const size_t part_bytes = (size_t)wgrad_nparts(engine, shp) * 9 * C * C * 4;
+    WgradAcc acc1{cv.take<float>(part_bytes), need_w ? grads->conv_w[0] : nullptr, 0, 0};
+    WgradAcc acc2{cv.take<float>(part_bytes), need_w ? grads->conv_w[1] : nullptr, 0, 0};
+    // one fp32 scratch tensor, reused along the chain: kbar_i (input of GN2') -> dH (conv2^T output, input of GN1') ->
+    // kbar_{i-1} (written by the epilogue of conv1^T once dH has been consumed)
+    float* kbar = cv.take<float>(E * 4);
+    float* gnpart[4];
+    for (int i = 0; i < 4; ++i) gnpart[i] = cv.take<float>((size_t)d->batch * C * 4);     // (dgamma_k, dbeta_k), k = 1, 2
+    if (!cv.ok()) { set_error("internal: workspace carve overflow"); return -1; }
+    for (int k = 0; k < 2; ++k) pack_w(engine, mp->conv_w[k], wt[k], C, 1, st, d->height, d->width);
+
+    auto dt_of = [&](int n) { return d->time_grid[n + 1] - d->time_grid[n]; };
+    int evals = 0;
+    const float* g_cur = grad_y;
+    for (int n = N - 1; n >= 0; --n) {
+        const float dt = dt_of(n);
+        float* g_next = (n == 0) ? grad_x : gbuf[n & 1];
+        for (int i = S - 1; i >= 0; --i) {
+            const PgSlot sl = pg_slot(const_cast<void*>(tape), E, n * S + i);
+            const int acc = evals > 0;
+            // dP2 = GN2'(act'(.) kbar_i);  kbar_S = dt b_S gbar (folded into the scale), kbar_i (i < S) from the previous epilogue
+            const float* dy = (i == S - 1) ? g_cur : kbar;
+            const float sc = (i == S - 1) ? dt * d->b[S - 1] : 1.f;
+            EpiParams e = epi_default();
+            e.out_split = DP2;
+            if (launch_groupnorm_bwd_epi(sl.P2, mp->norm_w[1], mp->norm_b[1], dy, sc, d->act, e, need_w ? gnpart[2] : nullptr,
+                                         need_w ? gnpart[3] : nullptr, acc, shp, mp->groups, mp->eps, st)) return -1;
+            // dW2 += dP2 (x) Hs_i ;  dH = dgrad_W2(dP2)
+            if (need_w && run_wgrad(engine, DP2, sl.Hs, acc2, shp, st)) return -1;
+            e = epi_default();
+            e.out_f32 = kbar;                                         // dH (kbar_i has been consumed by GN2')
+            if (run_conv(engine, DP2, wt[1], e, shp, st)) return -1;
+            // dP1 = GN1'(act'(.) dH)
+            e = epi_default();
+            e.out_split = DP1;
+            if (launch_groupnorm_bwd_epi(sl.P1, mp->norm_w[0], mp->norm_b[0], kbar, 1.f, d->act, e, need_w ? gnpart[0] : nullptr,
+                                         need_w ? gnpart[1] : nullptr, acc, shp, mp->groups, mp->eps, st)) return -1;
+            // dW1 += dP1 (x) A_i ;  xbar_i = dgrad_W1(dP1) and the adjoint stage combination
+            if (need_w && run_wgrad(engine, DP1, sl.A, acc1, shp, st)) return -1;
+            EpiParams e4 = epi_default();
+            e4.base = g_cur;
+            if (i > 0) {
+                e4.v_out = xbar[i];
+                e4.base_is_one = 0;
+                e4.k[0].base_coef = dt * d->b[i - 1];
+                int ns = 0;
+                for (int j = S - 1; j > i; --j) { e4.src[ns] = xbar[j]; e4.k[0].coef[ns] = d->w[j * MSB_MAX_STAGES + (i - 1)]; ++ns; }
+                e4.nsrc = ns;
+                e4.k[0].coef_v = d->w[i * MSB_MAX_STAGES + (i - 1)];
+                e4.k[0].dt = dt;
+                e4.out_f32 = kbar;                                    // = kbar_{i-1} (fp32: GN2' of the next stage reads it)
+            } else {
+                int ns = 0;
+                for (int j = S - 1; j > 0; --j) { e4.src[ns] = xbar[j]; e4.k[0].coef[ns] = 1.f; ++ns; }
+                e4.nsrc = ns;
+                e4.out_f32 = g_next;
+            }
+            if (run_conv(engine, DP1, wt[0], e4, shp, st)) return -1;
+            ++evals;
+        }
+        g_cur = g_next;
+    }
+    if (need_w) {
+        if (wgrad_finish(engine, acc1, shp, st) || wgrad_finish(engine, acc2, shp, st)) return -1;
+        for (int k = 0; k < 2; ++k) {
+            launch_sum_over_batch(gnpart[2 * k], grads->norm_w[k], d->batch, C, st);
+            launch_sum_over_batch(gnpart[2 * k + 1], grads->norm_b[k], d->batch, C, st);
+        }
+    }
+    return check_cuda(cudaGetLastError(), "odeblock backward (postact GN)");
+}
+
 int msb_odeblock_forward(const MsbOdeDesc* d, const float* x, const float* w1, const float* w2,
                          const MsbMnistParams* mnist, float* y_out, void* workspace, size_t workspace_bytes,
                          void* tape, size_t tape_bytes, void* cuda_stream) {
@@ -691,6 +866,8 @@ int msb_odeblock_forward(const MsbOdeDesc* d, const float* x, const float* w1, c
         return mnist_forward(d, x, mnist, y_out, workspace, workspace_bytes, tape, tape_bytes, (cudaStream_t)cuda_stream);
     if (d->rhs_kind == MSB_RHS_PREACT_GN)
         return gn_preact_forward(d, x, mnist, y_out, workspace, workspace_bytes, tape, tape_bytes, (cudaStream_t)cuda_stream);
+    if (d->rhs_kind == MSB_RHS_POSTACT_GN)
+        return gn_postact_forward(d, x, mnist, y_out, workspace, workspace_bytes, tape, tape_bytes, (cudaStream_t)cuda_stream);
     int engine = resolve_engine(d);
     if (engine < 0) return -1;
     if (!x || !w1 || !w2 || !y_out || !workspace) { set_error("null pointer argument"); return -1; }
@@ -808,7 +985,7 @@ static int odeblock_backward_impl(const MsbOdeDesc* d, const float* grad_y, cons
                                   const void* tape, size_t tape_bytes, float* grad_x, float* grad_w1, float* grad_w2,
                                   double* grad_tab, void* workspace, size_t workspace_bytes, void* cuda_stream) {
     if (validate(d)) return -1;
-    if (d->rhs_kind == MSB_RHS_MNIST_GN_T || d->rhs_kind == MSB_RHS_PREACT_GN) {
+    if (d->rhs_kind == MSB_RHS_MNIST_GN_T || d->rhs_kind == MSB_RHS_PREACT_GN || d->rhs_kind == MSB_RHS_POSTACT_GN) {
         set_error("use msb_odeblock_backward_mnist for the GroupNorm right-hand sides");
         return -1;
     }
@@ -977,10 +1154,10 @@ static int odeblock_backward_mnist_impl(const MsbOdeDesc* d, const float* grad_y
                                         size_t tape_bytes, float* grad_x, const MsbMnistGrads* grads, double* grad_tab,
                                         void* workspace, size_t workspace_bytes, void* cuda_stream) {
     if (validate(d)) return -1;
-    if (d->rhs_kind == MSB_RHS_PREACT_GN) {
-        if (grad_tab) { set_error("tableau gradients are not implemented for MSB_RHS_PREACT_GN"); return -1; }
-        return gn_preact_backward(d, grad_y, mp, tape, tape_bytes, grad_x, grads, workspace, workspace_bytes,
-                                  (cudaStream_t)cuda_stream);
+    if (d->rhs_kind == MSB_RHS_PREACT_GN || d->rhs_kind == MSB_RHS_POSTACT_GN) {
+        if (grad_tab) { set_error("tableau gradients are not implemented for the CIFAR GroupNorm right-hand sides"); return -1; }
+        return (d->rhs_kind == MSB_RHS_PREACT_GN ? gn_preact_backward : gn_postact_backward)(
+            d, grad_y, mp, tape, tape_bytes, grad_x, grads, workspace, workspace_bytes, (cudaStream_t)cuda_stream);
     }
     if (d->rhs_kind != MSB_RHS_MNIST_GN_T) { set_error("msb_odeblock_backward_mnist: rhs_kind must be a GroupNorm right-hand side"); return -1; }
     if (grad_tab && d->n_solvers > 1) { set_error("tableau gradients are not implemented for a stacked solver axis"); return -1; }

@@ -391,9 +391,11 @@ def ode_block_integrate_mnist(x, params, tableau, time_grid, groups, eps=1e-5, t
     return _GnOdeBlockFn.apply(x, prob, groups, eps, _MNIST_KEYS, tableau_coef, _wants_tape(x, tableau_coef, *ps), *ps)
 
 
-def ode_block_integrate_gn(x, params, tableau, time_grid, groups, eps=1e-5, act=_cabi.ACT_GELU_ERF, engine=None):
-    """CIFAR pre-activation right-hand side with GroupNorm, conv2(act(GN2(conv1(act(GN1(x)))))) (cifar10/layers.py:148-161
-    with the 'GN' / 'LN' / 'IN' normalisations of cifar10/utils.py:26-36).  `params`: dict(norm{1,2}_{w,b}, conv{1,2}_w)."""
+def ode_block_integrate_gn(x, params, tableau, time_grid, groups, eps=1e-5, act=_cabi.ACT_GELU_ERF, engine=None,
+                           rhs_kind=_cabi.RHS_PREACT_GN):
+    """CIFAR right-hand sides with GroupNorm: pre-activation conv2(act(GN2(conv1(act(GN1(x)))))) (cifar10/layers.py:148-161)
+    or, with rhs_kind = RHS_POSTACT_GN, post-activation act(GN2(conv2(act(GN1(conv1(x)))))) (:108-121), with the 'GN' /
+    'LN' / 'IN' normalisations of cifar10/utils.py:26-36.  `params`: dict(norm{1,2}_{w,b}, conv{1,2}_w)."""
     if not x.is_cuda:
         raise RuntimeError("metasolver_b200: the ODE-block path runs on CUDA only (got a %s tensor); "
                            "there is no CPU fallback" % x.device)
@@ -403,7 +405,9 @@ def ode_block_integrate_gn(x, params, tableau, time_grid, groups, eps=1e-5, act=
             raise RuntimeError("metasolver_b200: conv weight must be (%d, %d, 3, 3), got %s" % (C, C, tuple(params[k].shape)))
     if C % groups:
         raise RuntimeError("metasolver_b200: %d channels are not divisible into %d groups" % (C, groups))
-    prob = OdeProblem(_cabi.RHS_PREACT_GN, act, tableau, time_grid, engine)
+    if rhs_kind not in (_cabi.RHS_PREACT_GN, _cabi.RHS_POSTACT_GN):
+        raise ValueError("ode_block_integrate_gn: rhs_kind must be RHS_PREACT_GN or RHS_POSTACT_GN")
+    prob = OdeProblem(rhs_kind, act, tableau, time_grid, engine)
     ps = [params[k] for k in _GN_KEYS]
     return _GnOdeBlockFn.apply(x, prob, groups, eps, _GN_KEYS, None, _wants_tape(x, *ps), *ps)
 

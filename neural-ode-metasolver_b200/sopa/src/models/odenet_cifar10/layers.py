@@ -170,10 +170,8 @@ class _FusedRhs(nn.Module):
             raise NotImplementedError("metasolver_b200: ODE-block normalisation %s / %s is not implemented on the fused "
                                       "path (implemented: 'NF', and the per-sample 'GN' / 'LN' / 'IN'; batch statistics "
                                       "would couple the samples of a batch)" % (type(self.bn1).__name__, type(self.bn2).__name__))
-        if self.rhs_kind != _cabi.RHS_PREACT_NF:
-            raise NotImplementedError("metasolver_b200: GroupNorm inside the post-activation right-hand side (BasicBlock2) "
-                                      "is not implemented; the pre-activation one (PreBasicBlock2) is")
-        return dict(rhs_kind=_cabi.RHS_PREACT_GN, act=_act_code(self.act), groups=n1[2], eps=n1[3],
+        kind = _cabi.RHS_PREACT_GN if self.rhs_kind == _cabi.RHS_PREACT_NF else _cabi.RHS_POSTACT_GN
+        return dict(rhs_kind=kind, act=_act_code(self.act), groups=n1[2], eps=n1[3],
                     params=dict(norm1_w=n1[0], norm1_b=n1[1], norm2_w=n2[0], norm2_b=n2[1],
                                 conv1_w=self.conv1.weight, conv2_w=self.conv2.weight))
 

@@ -216,12 +216,12 @@ class RKParametricSolver(object, metaclass=abc.ABCMeta):
         if spec["rhs_kind"] == _cabi.RHS_MNIST_GN_T:
             y = ode_block_integrate_mnist(x, spec["params"], self._host_tableau, grid.tolist(), spec["groups"],
                                           spec["eps"], tableau_coef=coef)
-        elif spec["rhs_kind"] == _cabi.RHS_PREACT_GN:
+        elif spec["rhs_kind"] in (_cabi.RHS_PREACT_GN, _cabi.RHS_POSTACT_GN):
             if coef is not None:
                 raise NotImplementedError("metasolver_b200: gradients w.r.t. the solver parameters are not implemented for "
                                           "the GroupNorm CIFAR right-hand side; call freeze_params()")
             y = ode_block_integrate_gn(x, spec["params"], self._host_tableau, grid.tolist(), spec["groups"], spec["eps"],
-                                       act=spec["act"], engine=spec.get("engine"))
+                                       act=spec["act"], engine=spec.get("engine"), rhs_kind=spec["rhs_kind"])
         else:
             y = ode_block_integrate(x, spec["w1"], spec["w2"], self._host_tableau, grid.tolist(),
                                     rhs_kind=spec["rhs_kind"], act=spec["act"], engine=spec.get("engine"),
@@ -250,7 +250,7 @@ def can_stack(solvers, rhs_func, t):
     if not (2 <= len(solvers) <= _cabi.MSB_MAX_SOLVERS):
         return False
     spec = getattr(rhs_func, "fused_rhs_spec", None)
-    if spec is None or spec()["rhs_kind"] in (_cabi.RHS_MNIST_GN_T, _cabi.RHS_PREACT_GN):
+    if spec is None or spec()["rhs_kind"] in (_cabi.RHS_MNIST_GN_T, _cabi.RHS_PREACT_GN, _cabi.RHS_POSTACT_GN):
         return False
     if any(s.n_stages != solvers[0].n_stages for s in solvers):
         return False

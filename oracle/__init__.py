@@ -18,5 +18,5 @@ called here exactly as the reference calls them.
 """
 from .detrand import det_uniform, det_normal  # noqa: F401
 from .tableau import butcher_tableau  # noqa: F401
-from .rk import (make_time_grid, integrate, ode_block_forward, rhs_preact, rhs_preact_gn, rhs_postact,  # noqa: F401
+from .rk import (make_time_grid, integrate, ode_block_forward, rhs_preact, rhs_preact_gn, rhs_postact, rhs_postact_gn,  # noqa: F401
                  rhs_mnist, RhsCounter)

@@ -143,6 +143,26 @@ def rhs_preact_gn(p, groups, eps=1e-5, act="gelu", counter=None, instance_norm=F
     return f
 
 
+def rhs_postact_gn(p, groups, eps=1e-5, act="gelu", counter=None, instance_norm=False):
+    """BasicBlock2 with a per-sample normalisation ('GN' / 'LN' / 'IN' of cifar10/utils.py:26-36):
+    act(GN2(conv2(act(GN1(conv1(x)))))); cifar10/layers.py:108-121.  p: dict(norm{1,2}_{w,b}, conv{1,2}_w)."""
+    a = _act(act)
+    if instance_norm:
+        norm = lambda z, k: F.instance_norm(z, eps=eps)
+    else:
+        norm = lambda z, k: F.group_norm(z, groups, p["norm%d_w" % k], p["norm%d_b" % k], eps)
+
+    def f(t, x):
+        if counter is not None:
+            counter.nfe += 1
+        out = F.conv2d(x, p["conv1_w"], None, 1, 1)
+        out = a(norm(out, 1))
+        out = F.conv2d(out, p["conv2_w"], None, 1, 1)
+        out = a(norm(out, 2))
+        return out
+    return f
+
+
 def rhs_postact(w1, w2, act="gelu", counter=None):
     """BasicBlock2 with NF norm: act(conv2(act(conv1(x)))); cifar10/layers.py:108-121."""
     a = _act(act)

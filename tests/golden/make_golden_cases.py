@@ -103,6 +103,15 @@ GN_CASES = [
 ]
 
 
+# the same normalisations inside the POST-activation right-hand side (BasicBlock2)
+GN_POST_CASES = [
+    ("pgn_c64_rk2_n3", 64, 8, 32, 2, "GN", 32, ("rk2", "u", 3, -1, 0.5, -1)),
+    ("pln_c128_rk2_n2", 128, 16, 16, 2, "LN", 32, ("rk2", "u", 2, -1, 0.3, -1)),
+    ("pin_c64_rk4_n1", 64, 8, 32, 2, "IN", 32, ("rk4", "u2", 1, -1, 1 / 3., -1)),
+    ("pgn_c16_odd_euler_n2", 16, 5, 7, 3, "GN", 4, ("euler", None, 2, -1, -1, -1)),
+]
+
+
 def gn_affine(C, k):
     """deterministic, non-trivial GroupNorm weight / bias of norm layer k"""
     return det_uniform((C,), 61 + k, 0.5, 1.5), det_uniform((C,), 71 + k, -0.3, 0.3)

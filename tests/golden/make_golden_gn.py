@@ -18,15 +18,16 @@ sys.path.insert(0, "/root/reference")
 
 from oracle.detrand import det_uniform  # noqa: E402
 from sopa.src.solvers.utils import create_solver  # noqa: E402
-from sopa.src.models.odenet_cifar10.layers import MetaODEBlock, PreBasicBlock2  # noqa: E402
+from sopa.src.models.odenet_cifar10.layers import MetaODEBlock, PreBasicBlock2, BasicBlock2  # noqa: E402
 from sopa.src.models.odenet_cifar10.utils import get_normalization  # noqa: E402
-from make_golden_cases import GN_CASES, WG_STRIDE, ode_case_inputs, gn_affine  # noqa: E402
+from make_golden_cases import GN_CASES, GN_POST_CASES, WG_STRIDE, ode_case_inputs, gn_affine  # noqa: E402
 
 torch.set_num_threads(8)
+POST = "--post" in sys.argv          # python make_golden_gn.py --post  ->  gn_post_blocks.npz (BasicBlock2)
 res = {}
-for name, C, H, W, B, norm_key, groups, sv in GN_CASES:
+for name, C, H, W, B, norm_key, groups, sv in (GN_POST_CASES if POST else GN_CASES):
     x, w1, w2, r = [torch.from_numpy(a) for a in ode_case_inputs(C, H, W, B)]
-    blk = MetaODEBlock(PreBasicBlock2(C, norm_layer=get_normalization(norm_key, groups), act_layer=F.gelu))
+    blk = MetaODEBlock((BasicBlock2 if POST else PreBasicBlock2)(C, norm_layer=get_normalization(norm_key, groups), act_layer=F.gelu))
     rf = blk.rhs_func
     with torch.no_grad():
         rf.conv1.weight.copy_(w1)
@@ -51,4 +52,4 @@ for name, C, H, W, B, norm_key, groups, sv in GN_CASES:
             res["%s_gnorm%d_b" % (name, k + 1)] = bn.bias.grad.numpy().copy()
     res[name + "_nfe"] = np.int64(rf.nfe)
     print(name, float(np.abs(res[name + "_y"]).max()), rf.nfe, type(rf.bn1).__name__)
-np.savez_compressed(os.path.join(HERE, "gn_blocks.npz"), **res)
+np.savez_compressed(os.path.join(HERE, "gn_post_blocks.npz" if POST else "gn_blocks.npz"), **res)

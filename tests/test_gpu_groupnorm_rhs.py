@@ -1,4 +1,4 @@
-"""GPU: the CIFAR pre-activation right-hand side with a per-sample normalisation inside the ODE block (SURVEY 8(f-3):
+"""GPU: the CIFAR pre- and post-activation right-hand sides with a per-sample normalisation inside the ODE block (SURVEY 8(f-3):
 'GN', 'LN', 'IN' of sopa/src/models/odenet_cifar10/utils.py:26-36 -- all group norms) through the sopa API, against golden
 vectors from the REAL reference: outputs, input gradient, conv and norm parameter gradients, nfe.  Tolerance 1e-4."""
 import os
@@ -24,17 +24,22 @@ def _engines(C, H, W):
     return ["simt"] + (["tcgen05"] if _cabi.lib().msb_shape_supports_tcgen05(C, H, W) else [])
 
 
-@pytest.mark.parametrize("case", cases.GN_CASES, ids=[c[0] for c in cases.GN_CASES])
-def test_group_norm_ode_block_vs_reference_golden(case):
+ALL_GN = [(c, "pre") for c in cases.GN_CASES] + [(c, "post") for c in cases.GN_POST_CASES]
+
+
+@pytest.mark.parametrize("case,order", ALL_GN, ids=[c[0] for c, _ in ALL_GN])
+def test_group_norm_ode_block_vs_reference_golden(case, order):
+    """order 'pre': PreBasicBlock2 (cifar10/layers.py:148-161); 'post': BasicBlock2 (cifar10/layers.py:108-121)."""
     import metasolver_b200 as msb
     from metasolver_b200.sopa.src.solvers.utils import create_solver
-    from metasolver_b200.sopa.src.models.odenet_cifar10.layers import MetaODEBlock, PreBasicBlock2
+    from metasolver_b200.sopa.src.models.odenet_cifar10.layers import MetaODEBlock, PreBasicBlock2, BasicBlock2
     from metasolver_b200.sopa.src.models.odenet_cifar10.utils import get_normalization
     name, C, H, W, B, norm_key, groups, sv = case
-    g = golden("gn_blocks.npz")
+    g = golden("gn_blocks.npz" if order == "pre" else "gn_post_blocks.npz")
+    block_cls = PreBasicBlock2 if order == "pre" else BasicBlock2
     for engine in _engines(C, H, W):
         x, w1, w2, r = [torch.from_numpy(a).cuda() for a in cases.ode_case_inputs(C, H, W, B)]
-        blk = MetaODEBlock(PreBasicBlock2(C, norm_layer=get_normalization(norm_key, groups), act_layer=F.gelu)).cuda()
+        blk = MetaODEBlock(block_cls(C, norm_layer=get_normalization(norm_key, groups), act_layer=F.gelu)).cuda()
         rf = blk.rhs_func
         with torch.no_grad():
             rf.conv1.weight.copy_(w1)
@@ -79,8 +84,8 @@ def test_group_norm_rhs_limits():
     opts = Namespace(solver_mode="standalone")
     with pytest.raises(NotImplementedError):        # batch statistics couple the samples: not a per-sample right-hand side
         MetaODEBlock(PreBasicBlock2(64, norm_layer=get_normalization("BN"), act_layer=F.gelu)).cuda()(x, [s], opts)
-    with pytest.raises(NotImplementedError):        # post-activation ordering with GroupNorm
-        MetaODEBlock(BasicBlock2(64, norm_layer=get_normalization("GN"), act_layer=F.gelu)).cuda()(x, [s], opts)
+    with pytest.raises(NotImplementedError):        # batch statistics in the post-activation block as well
+        MetaODEBlock(BasicBlock2(64, norm_layer=get_normalization("BN"), act_layer=F.gelu)).cuda()(x, [s], opts)
     blk = MetaODEBlock(PreBasicBlock2(64, norm_layer=get_normalization("GN"), act_layer=F.gelu)).cuda()
     s.unfreeze_params()
     with pytest.raises(NotImplementedError):        # d/du through the GroupNorm right-hand side

@@ -362,7 +362,7 @@ def test_mnist_fused_single_launch_solve_matches_multi_launch_path():
                 (y * r).sum().backward()
                 res[fused] = [y_inf, y.detach(), xg.grad.clone()] + [p.grad.clone() for p in blk.parameters()] + [launches]
             assert torch.equal(res[1][0], res[1][1])                      # inference forward == tape-recording forward
-            assert res[1][-1] <= 6 and res[0][-1] > 10 * res[1][-1], (res[1][-1], res[0][-1])   # ONE solve launch (+ 4 weight-pack / tap-map launches) against ~5 per stage evaluation
+            assert res[1][-1] <= 6 and res[0][-1] > 4 * res[1][-1], (res[1][-1], res[0][-1])   # ONE solve launch (+ 4 weight-pack / tap-map launches) against ~5 per stage evaluation
             for k, (a, b) in enumerate(zip(res[1][:-1], res[0][:-1])):
                 a, b = a.cpu().numpy().astype(np.float64), b.cpu().numpy().astype(np.float64)
                 if k < 2:                                   # outputs: different GEMM engines, same algorithm

@@ -367,3 +367,29 @@ def test_group_norm_ode_block_bit_exact(case):
     assert np.array_equal(p["conv1_w"].grad.numpy().reshape(-1)[::cases.WG_STRIDE], g[name + "_gw1"])
     if norm_key != "IN":
         assert np.array_equal(p["norm2_b"].grad.numpy(), g[name + "_gnorm2_b"])
+
+
+@pytest.mark.parametrize("case", cases.GN_POST_CASES, ids=[c[0] for c in cases.GN_POST_CASES])
+def test_group_norm_postact_ode_block_bit_exact(case):
+    """BasicBlock2 (post-activation right-hand side, cifar10/layers.py:108-121) with the per-sample normalisations."""
+    from oracle import rhs_postact_gn
+    name, C, H, W, B, norm_key, groups, sv = case
+    g = golden("gn_post_blocks.npz")
+    x, w1, w2, r = [torch.from_numpy(a) for a in cases.ode_case_inputs(C, H, W, B)]
+    G = {"GN": groups, "LN": 1, "IN": C}[norm_key]
+    p = dict(conv1_w=w1, conv2_w=w2)
+    for k in (0, 1):
+        gw, gb = cases.gn_affine(C, k) if norm_key != "IN" else (np.ones(C, np.float32), np.zeros(C, np.float32))
+        p["norm%d_w" % (k + 1)], p["norm%d_b" % (k + 1)] = torch.from_numpy(gw), torch.from_numpy(gb)
+    for t in list(p.values()) + [x]:
+        t.requires_grad_(True)
+    cnt = RhsCounter()
+    tab = butcher_tableau(sv[0], sv[1], None if sv[0] == "euler" else np.float32(sv[4]), None if sv[5] == -1 else np.float32(sv[5]))
+    y = integrate(tab, rhs_postact_gn(p, G, 1e-5, "gelu", cnt, instance_norm=(norm_key == "IN")), x, torch.tensor([0., 1.]), n_steps=sv[2])[-1]
+    (y * r).sum().backward()
+    assert cnt.nfe == int(g[name + "_nfe"])
+    assert np.array_equal(y.detach().numpy(), g[name + "_y"])
+    assert np.array_equal(x.grad.numpy(), g[name + "_gx"])
+    assert np.array_equal(p["conv1_w"].grad.numpy().reshape(-1)[::cases.WG_STRIDE], g[name + "_gw1"])
+    if norm_key != "IN":
+        assert np.array_equal(p["norm2_b"].grad.numpy(), g[name + "_gnorm2_b"])
