@@ -142,8 +142,10 @@ int msb_odeblock_backward(const MsbOdeDesc* d, const float* grad_y, const float*
  * grad_tableau (device, MSB_TABLEAU_GRAD_DOUBLES doubles: dL/db_i [M], dL/dw_ij row-major [M*M], dL/dc_i [M],
  * M = MSB_MAX_STAGES) -- what autograd yields for solver.u / solver.v after unfreeze_params()
  * (rk_parametric_order2stage2.py:104-109) once chained through the closed-form tableau on the host.  dL/dc_i is
- * non-zero only for the time-dependent MNIST right-hand side (t_i = t_n + c_i dt, order2stage2.py:81-86).  One solver
- * per call.  Needs msb_odeblock_bwd_workspace_bytes_tableau() bytes of workspace. */
+ * non-zero only for the time-dependent MNIST right-hand side (t_i = t_n + c_i dt, order2stage2.py:81-86).  With a stacked
+ * solver axis (n_solvers = K > 1; msb_odeblock_backward_tableau only) grad_tableau holds K consecutive blocks of
+ * MSB_TABLEAU_GRAD_DOUBLES doubles, block s reduced over the images of slice s.  Needs
+ * msb_odeblock_bwd_workspace_bytes_tableau() bytes of workspace. */
 #define MSB_TABLEAU_GRAD_DOUBLES (MSB_MAX_STAGES + MSB_MAX_STAGES * MSB_MAX_STAGES + MSB_MAX_STAGES)
 size_t msb_odeblock_bwd_workspace_bytes_tableau(const MsbOdeDesc* d);
 int msb_odeblock_backward_tableau(const MsbOdeDesc* d, const float* grad_y, const float* w1, const float* w2,

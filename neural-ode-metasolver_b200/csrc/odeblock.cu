@@ -997,7 +997,6 @@ static int odeblock_backward_impl(const MsbOdeDesc* d, const float* grad_y, cons
         set_error("workspace too small");
         return -1;
     }
-    if (grad_tab && d->n_solvers > 1) { set_error("tableau gradients are not implemented for a stacked solver axis"); return -1; }
     if ((grad_w1 == nullptr) != (grad_w2 == nullptr)) { set_error("grad_w1 and grad_w2 must both be given or both be NULL"); return -1; }
     const bool need_w = grad_w1 != nullptr;
     cudaStream_t st = (cudaStream_t)cuda_stream;
@@ -1042,6 +1041,14 @@ static int odeblock_backward_impl(const MsbOdeDesc* d, const float* grad_y, cons
     __nv_bfloat16* const DP = DP_full + 2 * off;
     auto slot = [&](int n, int i) { return slot_at(tape_slot(const_cast<void*>(tape), E, n * S + i), off); };
     auto g2_of = [&](int n, int i) { return slot(n, i).G0; };
+    // grad_tab[q * MSB_TABLEAU_GRAD_DOUBLES + idx] += scale <a, b> over the images of slice q (stacked solver axis: slice q
+    // is the contiguous image range [q * slice_batch, (q+1) * slice_batch) and owns its own tableau, hence its own sums)
+    auto dot_slices = [&](const float* a, const float* b, size_t n_mb, double scale, int idx) {
+        if (tabs.K <= 1) { launch_dot_accumulate(a + off, b + off, n_mb, scale, grad_tab + idx, dot_scratch, st); return; }
+        const size_t se = (size_t)tabs.slice_batch * img_elems;
+        for (int q = 0; q < tabs.K; ++q)
+            launch_dot_accumulate(a + q * se, b + q * se, se, scale, grad_tab + q * MSB_TABLEAU_GRAD_DOUBLES + idx, dot_scratch, st);
+    };
     {
         float scales[kMaxSlices];
         for (int q = 0; q < tabs.K; ++q) scales[q] = dt_of(N - 1) * tabs.t[q].b[S - 1];
@@ -1060,7 +1067,7 @@ static int odeblock_backward_impl(const MsbOdeDesc* d, const float* grad_y, cons
                 ek.v_out = kre[j] + off;
                 if (post) ek.act_v = d->act;
                 if (run_conv(engine, slot(n, j).Hs, wp2f, ek, shp, st)) return -1;
-                launch_dot_accumulate(g_cur, kre[j] + off, n_mb, (double)dt, grad_tab + j, dot_scratch, st);
+                dot_slices(g_cur - off, kre[j], n_mb, (double)dt, j);
             }
         }
         for (int i = S - 1; i >= 0; --i) {
@@ -1119,8 +1126,7 @@ static int odeblock_backward_impl(const MsbOdeDesc* d, const float* grad_y, cons
             if (run_conv(engine, DP, wt1, e4, shp, st)) return -1;
             if (grad_tab && i > 0)                     // dL/dw_ij += dt <xbar_i, k_j>, j < i
                 for (int j = 0; j < i; ++j)
-                    launch_dot_accumulate(xbar[i] + off, kre[j] + off, n_mb, (double)dt,
-                                          grad_tab + MSB_MAX_STAGES + i * MSB_MAX_STAGES + j, dot_scratch, st);
+                    dot_slices(xbar[i], kre[j], n_mb, (double)dt, MSB_MAX_STAGES + i * MSB_MAX_STAGES + j);
         }
         g_cur = g_next;
     }

@@ -236,7 +236,7 @@ class _OdeBlockFn(torch.autograd.Function):
                 if ws_bytes == 0:
                     _cabi.check(-1, "odeblock tableau-gradient workspace query")
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-                gtab = torch.zeros(_cabi.TABLEAU_GRAD_DOUBLES, dtype=torch.float64, device=dev)
+                gtab = torch.zeros(len(ctx.prob.tableaus) * _cabi.TABLEAU_GRAD_DOUBLES, dtype=torch.float64, device=dev)
                 rc = lib.msb_odeblock_backward_tableau(ctypes.byref(d), _ptr(gyc), _ptr(w1c), _ptr(w2c), _ptr(ctx.tape),
                                                        ctx.tape_bytes, _ptr(gx), _ptr(gw1), _ptr(gw2), _ptr(gtab), _ptr(ws),
                                                        ws_bytes, _stream(dev))
@@ -253,11 +253,13 @@ class _OdeBlockFn(torch.autograd.Function):
         return gx, gw1, gw2, None, gcoef, None
 
 
-def _check_coef(prob, coef):
-    if len(prob.tableaus) != 1:
-        raise NotImplementedError("metasolver_b200: gradients w.r.t. solver parameters on a stacked solver axis")
-    if coef.dtype != torch.float64 or coef.is_cuda or coef.numel() != _cabi.TABLEAU_GRAD_DOUBLES:
-        raise ValueError("tableau_coef must be a host float64 tensor of %d elements" % _cabi.TABLEAU_GRAD_DOUBLES)
+def _check_coef(prob, coef, stacked_ok=False):
+    K = len(prob.tableaus)
+    if K != 1 and not stacked_ok:
+        raise NotImplementedError("metasolver_b200: gradients w.r.t. solver parameters on a stacked solver axis are "
+                                  "implemented for the normalisation-free CIFAR right-hand sides only")
+    if coef.dtype != torch.float64 or coef.is_cuda or coef.numel() != K * _cabi.TABLEAU_GRAD_DOUBLES:
+        raise ValueError("tableau_coef must be a host float64 tensor of %d x %d elements" % (K, _cabi.TABLEAU_GRAD_DOUBLES))
 
 
 def ode_block_integrate(x, w1, w2, tableau, time_grid, rhs_kind=_cabi.RHS_PREACT_NF, act=_cabi.ACT_GELU_ERF,
@@ -266,21 +268,24 @@ def ode_block_integrate(x, w1, w2, tableau, time_grid, rhs_kind=_cabi.RHS_PREACT
     by the explicit RK method `tableau`; differentiable w.r.t. x, w1, w2.
 
     `tableau` may be a list of K tableaus (same stage count): the batch is then K equal slices along
-    dim 0 and slice s is integrated by solver s, all inside the same kernel launches (stacked solver axis)."""
+    dim 0 and slice s is integrated by solver s, all inside the same kernel launches (stacked solver axis).
+    `tableau_coef` (host float64, K x 20, built differentiably from the solvers' u / v): when it requires grad the
+    backward pass also returns dL/d(b, w, c) per solver, reduced over that solver's slice."""
     prob = OdeProblem(rhs_kind, act, tableau, time_grid, engine)
     if tableau_coef is not None:
-        _check_coef(prob, tableau_coef)
+        _check_coef(prob, tableau_coef, stacked_ok=True)
     return _OdeBlockFn.apply(x, w1, w2, prob, tableau_coef, _wants_tape(x, w1, w2, tableau_coef))
 
 
 def ode_block_integrate_stacked(x, w1, w2, tableaus, time_grid, rhs_kind=_cabi.RHS_PREACT_NF,
-                                act=_cabi.ACT_GELU_ERF, engine=None):
+                                act=_cabi.ACT_GELU_ERF, engine=None, tableau_coef=None):
     """Solver ensembling on a stacked solver axis: integrate the SAME state x (B,C,H,W) with each of the K
     solvers in one batched set of launches -> (K, B, C, H, W).  Replaces the reference's sequential loop over
     solvers (cifar10/layers.py:198-203); each slice is bit-identical to the one-solver call."""
     K = len(tableaus)
     xs = x.unsqueeze(0).expand(K, *x.shape).reshape(K * x.shape[0], *x.shape[1:])
-    y = ode_block_integrate(xs, w1, w2, list(tableaus), time_grid, rhs_kind=rhs_kind, act=act, engine=engine)
+    y = ode_block_integrate(xs, w1, w2, list(tableaus), time_grid, rhs_kind=rhs_kind, act=act, engine=engine,
+                            tableau_coef=tableau_coef)
     return y.view(K, *x.shape)
 
 
@@ -363,7 +368,7 @@ class _GnOdeBlockFn(torch.autograd.Function):
                 grads = {k: torch.zeros_like(v) for k, v in keep.items()}
                 gstruct = _gn_params_struct(grads, None, None, cls=_cabi.MsbMnistGrads)
             if need_coef:
-                gtab = torch.zeros(_cabi.TABLEAU_GRAD_DOUBLES, dtype=torch.float64, device=dev)
+                gtab = torch.zeros(len(ctx.prob.tableaus) * _cabi.TABLEAU_GRAD_DOUBLES, dtype=torch.float64, device=dev)
                 rc = lib.msb_odeblock_backward_mnist_tableau(ctypes.byref(d), _ptr(gyc), ctypes.byref(mp), _ptr(ctx.tape),
                                                              ctx.tape_bytes, _ptr(gx), ctypes.byref(gstruct) if need_w else None,
                                                              _ptr(gtab), _ptr(ws), ws_bytes, _stream(dev))

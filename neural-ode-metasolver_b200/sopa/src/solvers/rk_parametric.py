@@ -254,8 +254,6 @@ def can_stack(solvers, rhs_func, t):
         return False
     if any(s.n_stages != solvers[0].n_stages for s in solvers):
         return False
-    if torch.is_grad_enabled() and any(s._params_need_grad() for s in solvers):
-        return False                # gradients w.r.t. u / v are reduced per solver: integrate them one by one
     g0 = solvers[0].host_time_grid(t)
     return all(torch.equal(s.host_time_grid(t), g0) for s in solvers[1:])
 
@@ -276,6 +274,11 @@ def integrate_stacked(solvers, rhs_func, x, t, replicate=True):
         s._fused_args(rhs_func, t)
     tabs = [s.host_tableau() for s in solvers]
     kw = dict(rhs_kind=spec["rhs_kind"], act=spec["act"], engine=spec.get("engine"))
+    if torch.is_grad_enabled() and any(s._params_need_grad() for s in solvers):
+        # unfrozen u / v (unfreeze_params()): one row of Butcher coefficients per solver, built differentiably on the host;
+        # the backward pass reduces dL/d(b, w) per slice and autograd chains each row to its solver's parameters
+        kw["tableau_coef"] = torch.stack([s.tableau_coef() if s._params_need_grad()
+                                          else torch.zeros(_cabi.TABLEAU_GRAD_DOUBLES, dtype=torch.float64) for s in solvers])
     if replicate:
         y = ode_block_integrate_stacked(x, spec["w1"], spec["w2"], tabs, grid.tolist(), **kw)
     else:

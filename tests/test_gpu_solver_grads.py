@@ -8,7 +8,8 @@ closed-form tableau.  Checks:
     sum (changing u keeps the order of the method: the reference's own fp32 run is 0.2-20 % off its fp64 run), so the
     tolerance is 1e-4 of the UN-cancelled magnitude sum_i |dL/dcoef_i * dcoef_i/du| plus the reference's own
     fp32-vs-fp64 deviation;
-  * a clamped parameter (u > 1) gets exactly zero gradient; frozen solvers and weight / input gradients are unchanged.
+  * a clamped parameter (u > 1) gets exactly zero gradient; frozen solvers and weight / input gradients are unchanged;
+  * K unfrozen solvers on a stacked solver axis get the gradients they get when integrated one by one.
 """
 import os
 import sys
@@ -121,13 +122,67 @@ def test_frozen_solver_and_stacked_axis_behaviour():
     s.unfreeze_params()
     with torch.no_grad():                                      # unfrozen but no grad mode: plain forward
         blk(x, [s], Namespace(solver_mode="standalone"))
-    # unfrozen solvers are never folded onto a stacked solver axis (their gradients are reduced per solver)
+    # unfrozen solvers share a stacked solver axis as frozen ones do (per-slice reductions of the coefficient gradients)
     from metasolver_b200.sopa.src.solvers.rk_parametric import can_stack
     s2 = create_solver("rk2", "u", 2, -1, 0.7, -1, torch.float32, "cuda")
     s2.freeze_params()
-    assert not can_stack([s, s2], blk.rhs_func, blk.integration_time)
+    assert can_stack([s, s2], blk.rhs_func, blk.integration_time)
     s.freeze_params()
     assert can_stack([s, s2], blk.rhs_func, blk.integration_time)
+
+
+@pytest.mark.parametrize("method,param,uv", [("rk2", "u", [(0.5, -1), (0.3, -1), (0.8, -1)]),
+                                             ("rk4", "uv", [(0.3, 0.7), (0.25, 0.6)])])
+def test_solver_parameter_gradients_on_a_stacked_solver_axis(method, param, uv):
+    """Solver ensembling (cifar10/layers.py:198-203) with unfrozen solvers: all K solvers in the same launches, each u / v
+    receiving the gradient reduced over its own slice == the gradient of the solver integrated alone (which the test
+    above pins to the reference)."""
+    import metasolver_b200  # noqa: F401
+    from metasolver_b200.sopa.src.solvers.utils import create_solver
+    from metasolver_b200.sopa.src.solvers.rk_parametric import integrate_stacked
+    from metasolver_b200.sopa.src.models.odenet_cifar10.layers import MetaODEBlock, PreBasicBlock2
+    from metasolver_b200.sopa.src.models.odenet_cifar10.utils import Identity
+    C, H, W, B = 64, 8, 32, 2
+    x0, w1, w2, r = [torch.from_numpy(a).cuda() for a in cases.ode_case_inputs(C, H, W, B)]
+    blk = MetaODEBlock(PreBasicBlock2(C, norm_layer=Identity, act_layer=F.gelu)).cuda()
+    with torch.no_grad():
+        blk.rhs_func.conv1.weight.copy_(w1)
+        blk.rhs_func.conv2.weight.copy_(w2)
+    K = len(uv)
+    weights = [1.0, -0.5, 2.0][:K]                       # a different loss weight per solver: slices must not mix
+
+    def make():
+        ss = [create_solver(method, param, 2, -1, u, v, torch.float32, "cuda") for u, v in uv]
+        for s in ss:
+            s.unfreeze_params()
+        return ss
+    # one by one
+    alone = make()
+    xa = x0.clone().requires_grad_(True)
+    blk.zero_grad()
+    loss = sum(wk * (s.integrate(blk.rhs_func, xa, blk.integration_time)[-1] * r).sum() for wk, s in zip(weights, alone))
+    loss.backward()
+    gw_alone = blk.rhs_func.conv1.weight.grad.clone()
+    # stacked
+    stacked = make()
+    stacked[-1].freeze_params()                          # a frozen member among unfrozen ones gets no gradient
+    xs = x0.clone().requires_grad_(True)
+    blk.zero_grad()
+    l0 = metasolver_b200.launch_count()
+    ys = integrate_stacked(stacked, blk.rhs_func, xs, blk.integration_time, replicate=True)
+    assert tuple(ys.shape) == (K, B, C, H, W)
+    sum(wk * (ys[k] * r).sum() for k, wk in enumerate(weights)).backward()
+    torch.cuda.synchronize()
+    assert max_rel(xs.grad.cpu().numpy(), xa.grad.cpu().numpy()) <= 1e-5
+    assert max_rel(blk.rhs_func.conv1.weight.grad.cpu().numpy(), gw_alone.cpu().numpy()) <= 1e-5
+    for k in range(K - 1):
+        for name in ("u", "v"):
+            pa, ps = getattr(alone[k], name), getattr(stacked[k], name)
+            if pa is None:
+                continue
+            ga, gs = float(pa.grad.reshape(-1)[0]), float(ps.grad.reshape(-1)[0])
+            assert abs(ga - gs) <= 1e-5 * max(abs(ga), 1e-3) + 1e-7, (k, name, ga, gs)
+    assert stacked[-1].u.grad is None
 
 
 @pytest.mark.parametrize("case", cases.MNIST_SOLVER_GRAD_CASES, ids=[c[0] for c in cases.MNIST_SOLVER_GRAD_CASES])

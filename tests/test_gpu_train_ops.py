@@ -146,3 +146,20 @@ def test_fused_sgd_sees_gradients_detached_by_zero_grad_set_to_none():
             o.step()
         for a, b in zip(net.parameters(), ref.parameters()):
             assert torch.allclose(a, b, rtol=1e-6, atol=1e-7), it
+
+
+def test_host_fed_loop_returns_every_result_in_order_one_call_late():
+    import metasolver_b200 as msb
+    seen = []
+
+    def step(xd, yd):
+        assert xd.is_cuda and yd.is_cuda
+        seen.append(xd.data_ptr())
+        return (xd * yd).sum()
+    loop = msb.HostFedLoop(step, lag=1)
+    n = 1 << 20                                         # large enough for the copies to take a while
+    hosts = [(torch.full((n,), float(k)).pin_memory(), torch.full((n,), 0.5).pin_memory()) for k in range(6)]
+    got = [loop(*h) for h in hosts]
+    assert got[0] is None and got[1:] == [0.5 * n * k for k in range(5)]
+    assert loop.drain() == [0.5 * n * 5] and loop.drain() == []
+    assert len(set(seen)) == 2                          # two staging sets, alternating
