@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define MSB_ABI_VERSION 4   /* v3: + tuning options, attack / SGD steps, tableau gradients, MSB_RHS_PREACT_GN; v4: + network head (pool + FC, cross-entropy) (structs unchanged) */
+#define MSB_ABI_VERSION 5   /* v3: + tuning options, attack / SGD steps, tableau gradients, MSB_RHS_PREACT_GN; v4: + network head (pool + FC, cross-entropy); v5: + MSB_RHS_POSTACT_GN, stacked tableau gradients, msb_augment_batch (structs unchanged) */
 #define MSB_MAX_STAGES 4
 
 /* right-hand-side families */
@@ -232,6 +232,19 @@ enum { MSB_ATTACK_UNNORMALIZE = 0, MSB_ATTACK_NORMALIZE = 1, MSB_ATTACK_FGSM_STE
 int msb_attack_step(int kind, const float* a, const float* grad, const float* ref, float* out, int64_t n_elements,
                     int channels, int hw, int channels_last, float eps, float step, int normalize_out,
                     const float* chan_consts /* host */, void* cuda_stream);
+
+/* Training-input transform on the device (replaces the per-sample torchvision pipeline RandomCrop(32, padding=4) +
+ * RandomHorizontalFlip + ToTensor + Normalize of sopa/src/models/odenet_cifar10/data.py:40-46, and the test-time
+ * ToTensor + Normalize of :54-57 when dx = dy = flip = NULL):
+ *   out[b][y][x][c] = (pad0(images_u8[index[b]])[y + dy[b]][xf + dx[b]][c] / 255 - mean[c]) / std[c],
+ *   xf = flip[b] ? width-1-x : x,   pad0 = the uint8 image zero-padded by `padding` on every side,  dx, dy in 0..2*padding.
+ * images_u8: uint8 [N][height][width][channels] (the dataset, resident in HBM); index (int64, NULL = 0..batch-1), dx, dy
+ * (int32, NULL = padding: centred window), flip (uint8, NULL = none): device arrays of `batch` entries (the random draws
+ * stay with the caller's generator); mean, std: HOST arrays of `channels` floats.  out: fp32 NHWC = the stem's input
+ * layout.  Same fp32 operations in the same order as torchvision: bit-identical. */
+int msb_augment_batch(const uint8_t* images_u8, const int64_t* index, const int32_t* dx, const int32_t* dy, const uint8_t* flip,
+                      int batch, int height, int width, int channels, int padding, const float* mean /* host */,
+                      const float* std /* host */, float* out_nhwc, void* cuda_stream);
 
 /* SGD with momentum and weight decay (torch.optim.SGD semantics, no dampening / nesterov;
  * examples/cifar10/train_and_attack.py:98-99,322) over ONE flat fp32 buffer:

@@ -11,6 +11,6 @@ from .ops import (ode_block_integrate, input_grad_only, set_default_engine, laun
                   profile_enable, profile_read, profile_read_executed, set_option, get_option, pool_fc, cross_entropy,
                   set_library_fallback, library_fallback_allowed)
 from .graphs import GraphedStep, HostFedLoop  # noqa: F401
-from .train_ops import attack_step, FusedSGD  # noqa: F401
+from .train_ops import attack_step, FusedSGD, CyclicLR, augment_normalize  # noqa: F401
 
 __version__ = "0.1.0"

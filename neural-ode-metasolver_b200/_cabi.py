@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("MSB_LIB_PATH") or os.path.join(HERE, "libmetasolver_b
 
 MSB_MAX_STAGES = 4
 TABLEAU_GRAD_DOUBLES = MSB_MAX_STAGES + MSB_MAX_STAGES * MSB_MAX_STAGES + MSB_MAX_STAGES   # [b | w | c]
-ABI_VERSION = 4
+ABI_VERSION = 5
 RHS_PREACT_NF, RHS_POSTACT_NF, RHS_MNIST_GN_T, RHS_PREACT_GN, RHS_POSTACT_GN = 0, 1, 2, 3, 4
 ACT_NONE, ACT_GELU_ERF, ACT_RELU = 0, 1, 2
 (ATTACK_UNNORMALIZE, ATTACK_NORMALIZE, ATTACK_FGSM_STEP, ATTACK_PGD_STEP, ATTACK_FGSMR_INIT,
@@ -32,6 +32,7 @@ EXPORTS = [
     "msb_set_option", "msb_get_option", "msb_attack_step", "msb_sgd_step",
     "msb_odeblock_bwd_workspace_bytes_tableau", "msb_odeblock_backward_tableau", "msb_odeblock_backward_mnist_tableau",
     "msb_pool_fc_forward", "msb_pool_fc_backward", "msb_cross_entropy_forward", "msb_cross_entropy_backward",
+    "msb_augment_batch",
 ]
 
 
@@ -125,6 +126,7 @@ def _declare(lib):
     f32, i64 = ctypes.c_float, ctypes.c_int64
     lib.msb_attack_step.argtypes = [i32, vp, vp, vp, vp, i64, i32, i32, i32, f32, f32, i32, ctypes.POINTER(f32), vp]
     lib.msb_sgd_step.argtypes = [vp, vp, vp, i64, f32, f32, f32, f32, i32, vp]
+    lib.msb_augment_batch.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, ctypes.POINTER(f32), ctypes.POINTER(f32), vp, vp]
     lib.msb_pool_fc_forward.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.msb_pool_fc_backward.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.msb_cross_entropy_forward.argtypes = [vp, vp, vp, vp, i32, i32, vp]

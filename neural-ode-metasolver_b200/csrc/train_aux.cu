@@ -5,6 +5,8 @@
 //     (no contraction: every op is an explicit round-to-nearest intrinsic), so results are bit-identical;
 //   * the SGD-momentum / weight-decay update of examples/cifar10/train_and_attack.py:98-99, 322 on ONE flat
 //     parameter buffer, with the 1/world gradient average of the data-parallel all-reduce folded in.
+//   * the training-input transform of sopa/src/models/odenet_cifar10/data.py:40-46 (random crop with zero padding, random
+//     horizontal flip, ToTensor, Normalize) from a uint8 dataset resident in HBM into the stem's fp32 NHWC input.
 // HBM-bound, tiny (3 x 32 x 32 images, 675 k parameters): the point is one launch instead of ~10 per step.
 #include "metasolver_b200.h"
 #include "msb_internal.h"
@@ -163,11 +165,55 @@ void launch_dot_bcast_accumulate(const float* a, const float* b, size_t n, size_
     count_launch(2);
 }
 
+// Training-input pipeline of data.py:40-46 for a batch whose uint8 source images are resident in HBM:
+// RandomCrop(size, padding) (zero padding of the uint8 image), RandomHorizontalFlip, ToTensor (/255), Normalize, written
+// straight into the fp32 NHWC layout the stem kernel reads.  One thread per output pixel (3 channels, 12 B out, 3 B in).
+namespace {
+struct AugConst { float mean[MSB_ATTACK_MAX_CHANNELS], std[MSB_ATTACK_MAX_CHANNELS]; };
+__global__ void __launch_bounds__(256) augment_kernel(const uint8_t* __restrict__ img, const int64_t* __restrict__ index,
+                                                      const int32_t* __restrict__ dx, const int32_t* __restrict__ dy,
+                                                      const uint8_t* __restrict__ flip, int B, int H, int W, int C, int pad,
+                                                      AugConst k, float* __restrict__ out) {
+    const size_t npix = (size_t)B * H * W;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W), y = (int)((i / W) % H), b = (int)(i / ((size_t)W * H));
+        const int64_t src = index ? index[b] : b;
+        const int xc = (flip && flip[b]) ? W - 1 - x : x;                  // flip acts on the cropped image
+        const int sx = xc + (dx ? dx[b] : pad) - pad, sy = y + (dy ? dy[b] : pad) - pad;   // crop window offset in the padded image
+        const bool inside = sx >= 0 && sx < W && sy >= 0 && sy < H;
+        const uint8_t* s = img + (((size_t)src * H + (inside ? sy : 0)) * W + (inside ? sx : 0)) * C;
+        float* o = out + i * C;
+        for (int c = 0; c < C; ++c) {
+            const float v = inside ? __fdiv_rn((float)s[c], 255.f) : 0.f;                  // ToTensor: uint8 -> float, div(255)
+            o[c] = __fdiv_rn(__fsub_rn(v, k.mean[c]), k.std[c]);                           // Normalize: sub_(mean).div_(std)
+        }
+    }
+}
+}  // namespace
+
 }  // namespace msb
 
 using namespace msb;
 
 extern "C" {
+
+int msb_augment_batch(const uint8_t* images_u8, const int64_t* index, const int32_t* dx, const int32_t* dy, const uint8_t* flip,
+                      int batch, int height, int width, int channels, int padding, const float* mean, const float* std,
+                      float* out_nhwc, void* cuda_stream) {
+    if (batch < 0 || height < 1 || width < 1 || channels < 1 || channels > MSB_ATTACK_MAX_CHANNELS || padding < 0) {
+        set_error("msb_augment_batch: bad geometry (batch=%d, %dx%dx%d, padding=%d)", batch, height, width, channels, padding);
+        return -1;
+    }
+    if (batch == 0) return 0;
+    if (!images_u8 || !out_nhwc || !mean || !std) { set_error("msb_augment_batch: null buffer"); return -1; }
+    AugConst k;
+    for (int c = 0; c < MSB_ATTACK_MAX_CHANNELS; ++c) { k.mean[c] = c < channels ? mean[c] : 0.f; k.std[c] = c < channels ? std[c] : 1.f; }
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    augment_kernel<<<grid_for((size_t)batch * height * width), 256, 0, st>>>(images_u8, index, dx, dy, flip, batch, height, width,
+                                                                             channels, padding, k, out_nhwc);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "augment_batch launch");
+}
 
 int msb_attack_step(int kind, const float* a, const float* grad, const float* ref, float* out, int64_t n_elements,
                     int channels, int hw, int channels_last, float eps, float step, int normalize_out,

@@ -4,11 +4,16 @@
     93-105, pgd.py:28-53) as ONE CUDA kernel each, bit-identical to the reference's chain of torch calls;
   * `FusedSGD`: torch.optim.SGD (momentum, weight decay; examples/cifar10/train_and_attack.py:98-99) over ONE flat
     parameter / gradient buffer: one all-reduce over the flat gradient (no pack / unpack copies) and one update
-    kernel with the 1/world average folded in.
+    kernel with the 1/world average folded in;
+  * `CyclicLR`: the learning-rate / momentum schedule of examples/cifar10/train_and_attack.py:500-505
+    (torch.optim.lr_scheduler.CyclicLR, which only accepts torch.optim.Optimizer instances) for `FusedSGD`: host
+    arithmetic, value for value what torch computes;
+  * `augment_normalize`: the training-input transform (crop / flip / ToTensor / Normalize) as ONE kernel.
 
-Both call the C ABI (include/metasolver_b200.h: msb_attack_step, msb_sgd_step); CUDA fp32 tensors only.
+They call the C ABI (include/metasolver_b200.h: msb_attack_step, msb_sgd_step, msb_augment_batch); CUDA fp32 tensors only.
 """
 import ctypes
+import math
 
 import torch
 import torch.distributed as dist
@@ -153,6 +158,9 @@ class FusedSGD:
                                "captured step would replay a frozen learning rate.  Call it outside the CUDA graph.")
         has = self._gather_grads()
         self.lr = float(self.param_groups[0]["lr"])
+        self.momentum = float(self.param_groups[0].get("momentum", self.momentum))      # CyclicLR(cycle_momentum=True) pokes it
+        if self.momentum != 0.0 and self.momentum_buf is None:
+            self.momentum_buf = torch.zeros_like(self.flat_param)
         dev = self.flat_param.device
         # contiguous runs of parameters that have a gradient and share the "first update" state: ONE run (one kernel)
         # in the normal case; parameters without a gradient are skipped entirely (no weight decay, no momentum
@@ -176,3 +184,97 @@ class FusedSGD:
                 _cabi.check(_cabi.lib().msb_sgd_step(_ptr(self.flat_param[off:off + k]), _ptr(self.flat_grad[off:off + k]),
                                                      _ptr(mom), k, self.lr, self.momentum, self.weight_decay,
                                                      float(grad_scale), 1 if first else 0, st), "sgd_step")
+
+
+class CyclicLR:
+    """torch.optim.lr_scheduler.CyclicLR (examples/cifar10/train_and_attack.py:500-505) for any optimizer object with
+    `param_groups` (FusedSGD): same constructor arguments, same values -- the arithmetic below is torch's, in Python
+    doubles.  Construction sets lr = base_lr (and momentum = max_momentum when cycle_momentum); call `step()` after every
+    optimizer step."""
+
+    def __init__(self, optimizer, base_lr, max_lr, step_size_up=2000, step_size_down=None, mode="triangular", gamma=1.0,
+                 scale_fn=None, scale_mode="cycle", cycle_momentum=True, base_momentum=0.8, max_momentum=0.9):
+        if mode not in ("triangular", "triangular2", "exp_range") and scale_fn is None:
+            raise ValueError("mode is invalid and scale_fn is None")
+        self.optimizer = optimizer
+        self.base_lr, self.max_lr = float(base_lr), float(max_lr)
+        up = float(step_size_up)
+        down = float(step_size_down) if step_size_down is not None else up
+        self.total_size = up + down
+        self.step_ratio = up / self.total_size
+        self.gamma = gamma
+        if scale_fn is not None:
+            self.scale_fn, self.scale_mode = scale_fn, scale_mode
+        elif mode == "triangular":
+            self.scale_fn, self.scale_mode = (lambda x: 1.0), "cycle"
+        elif mode == "triangular2":
+            self.scale_fn, self.scale_mode = (lambda x: 1 / (2.0 ** (x - 1))), "cycle"
+        else:
+            self.scale_fn, self.scale_mode = (lambda x: self.gamma ** x), "iterations"
+        self.cycle_momentum = bool(cycle_momentum)
+        self.base_momentum, self.max_momentum = float(base_momentum), float(max_momentum)
+        if self.cycle_momentum and "momentum" not in optimizer.param_groups[0]:
+            raise ValueError("optimizer must support momentum with `cycle_momentum` option enabled")
+        self.last_epoch = -1
+        self._last_lr = [self.base_lr]
+        self.step()
+
+    def _values(self):
+        cycle = math.floor(1 + self.last_epoch / self.total_size)
+        x = 1.0 + self.last_epoch / self.total_size - cycle
+        scale_factor = x / self.step_ratio if x <= self.step_ratio else (x - 1) / (self.step_ratio - 1)
+        arg = cycle if self.scale_mode == "cycle" else self.last_epoch
+        lr = self.base_lr + (self.max_lr - self.base_lr) * scale_factor * self.scale_fn(arg)
+        momentum = self.max_momentum - (self.max_momentum - self.base_momentum) * scale_factor * self.scale_fn(arg)
+        return lr, momentum
+
+    def step(self):
+        self.last_epoch += 1
+        lr, momentum = self._values()
+        for g in self.optimizer.param_groups:
+            g["lr"] = lr
+            if self.cycle_momentum:
+                g["momentum"] = momentum
+        self._last_lr = [lr for _ in self.optimizer.param_groups]
+
+    def get_last_lr(self):
+        return self._last_lr
+
+
+def augment_normalize(images_u8, index=None, generator=None, padding=4, train=True, mean=None, std=None, draws=None):
+    """The input transform of sopa/src/models/odenet_cifar10/data.py:40-57 for a batch taken from a uint8 dataset resident
+    on the GPU, as ONE kernel (msb_augment_batch): RandomCrop(H, padding) + RandomHorizontalFlip + ToTensor + Normalize when
+    `train`, ToTensor + Normalize otherwise.  images_u8: uint8 (N, H, W, C) CUDA tensor (CIFAR's native layout); index:
+    int64 CUDA tensor of sample ids (None = all N in order); crop offsets / flip bits are drawn on the device from
+    `generator` (or given as draws = (dx, dy, flip)).  Returns the normalised float32 batch (B, C, H, W) in channels_last
+    memory -- the stem kernel's input layout -- bit-identical to torchvision's result for the same draws."""
+    from .sopa.src.models.odenet_cifar10.data import CIFAR_MEAN, CIFAR_STD
+    if not images_u8.is_cuda or images_u8.dtype != torch.uint8 or images_u8.dim() != 4 or not images_u8.is_contiguous():
+        raise RuntimeError("metasolver_b200.augment_normalize: contiguous uint8 CUDA tensor (N, H, W, C) required")
+    N, H, W, C = images_u8.shape
+    dev = images_u8.device
+    mean = tuple(CIFAR_MEAN if mean is None else mean)
+    std = tuple(CIFAR_STD if std is None else std)
+    if len(mean) != C or len(std) != C or C > _cabi.ATTACK_MAX_CHANNELS:
+        raise ValueError("augment_normalize: %d channels need %d means / stds (at most %d channels)" % (C, C, _cabi.ATTACK_MAX_CHANNELS))
+    if index is not None:
+        index = index.to(device=dev, dtype=torch.int64).contiguous()
+    B = N if index is None else index.numel()
+    dx = dy = flip = None
+    if draws is not None:
+        dx, dy, flip = draws
+    elif train:
+        dx = torch.randint(0, 2 * padding + 1, (B,), device=dev, generator=generator)
+        dy = torch.randint(0, 2 * padding + 1, (B,), device=dev, generator=generator)
+        flip = torch.rand(B, device=dev, generator=generator) < 0.5
+    if dx is not None:
+        dx = dx.to(device=dev, dtype=torch.int32).contiguous()
+        dy = dy.to(device=dev, dtype=torch.int32).contiguous()
+        flip = flip.to(device=dev, dtype=torch.uint8).contiguous()
+    out = torch.empty((B, C, H, W), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
+    f3 = ctypes.c_float * C
+    with torch.cuda.device(dev):
+        st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _cabi.check(_cabi.lib().msb_augment_batch(_ptr(images_u8), _ptr(index), _ptr(dx), _ptr(dy), _ptr(flip), B, H, W, C,
+                                                  int(padding), f3(*mean), f3(*std), _ptr(out), st), "augment_batch")
+    return out

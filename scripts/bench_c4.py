@@ -7,8 +7,9 @@
 One step per rank (examples/cifar10/train_and_attack.py:246-327 with --opt-level O0): draw u ~ N(0.5, 0.0125) on rank 0
 and broadcast it (parallel.sync_solver_params), zero_grad, FGSM-random attack pass (forward + backward; its parameter
 gradients accumulate, fgsm.py:98), training pass (forward + backward) on the adversarial batch, ONE all-reduce of the flat
-fp32 gradient (FusedSGD.all_reduce), fused SGD-momentum update with the CyclicLR learning rate of :104-108 computed on
-the host.  Per-GPU batch fixed (weak scaling).  Timing: CUDA events, max over ranks.  One JSON line on rank 0."""
+fp32 gradient (FusedSGD.all_reduce), fused SGD-momentum update, CyclicLR schedule of :500-505 (metasolver_b200.CyclicLR).
+The batch comes from a uint8 dataset resident in HBM through the one-kernel crop / flip / normalise transform
+(metasolver_b200.augment_normalize, data.py:40-46).  Per-GPU batch fixed (weak scaling).  Timing: CUDA events, max over ranks.  One JSON line on rank 0."""
 import argparse
 import json
 import os
@@ -17,14 +18,6 @@ from argparse import Namespace
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-
-
-def cyclic_lr(it, base_lr=0.0, max_lr=0.2, step_up=2000, step_down=3000):
-    """torch.optim.lr_scheduler.CyclicLR(triangular) as a host function (train_and_attack.py:480-508 uses lr_max 0.2)."""
-    period = step_up + step_down
-    k = it % period
-    frac = k / step_up if k < step_up else 1.0 - (k - step_up) / step_down
-    return base_lr + (max_lr - base_lr) * frac
 
 
 def main():
@@ -41,26 +34,29 @@ def main():
     from metasolver_b200.sopa.src.solvers.utils import create_solver, sample_solver_by_noising_params
     from metasolver_b200.sopa.src.models.odenet_cifar10.layers import premetanode10
     from metasolver_b200.sopa.src.models.odenet_cifar10.utils import Identity
-    from metasolver_b200.sopa.src.models.odenet_cifar10.data import CIFAR_MEAN, CIFAR_STD, normalize, augment_batch
+    from metasolver_b200.sopa.src.models.odenet_cifar10.data import CIFAR_MEAN, CIFAR_STD
     from metasolver_b200.MegaAdversarial.src.attacks import FGSMRandom
     rank, world, dev = parallel.init_distributed()
     torch.manual_seed(602)
     model = premetanode10((Identity,) * 3, (lambda t: t,) * 3, (F.gelu,) * 3, in_planes=64, is_odenet=True)
     model = model.to(dev).to(memory_format=torch.channels_last).train()
     opt = msb.FusedSGD(model.parameters(), lr=0.05, momentum=0.9, weight_decay=5e-4)
+    sched = msb.CyclicLR(opt, base_lr=1e-4, max_lr=0.2, step_size_up=2000, mode="triangular2", cycle_momentum=True)
     atk = FGSMRandom(model, alpha=10 / 255., epsilon=8 / 255., mu=CIFAR_MEAN, std=CIFAR_STD)
     base = create_solver("rk2", "u", 8, -1, 0.5, -1, torch.float32, dev)
     base.freeze_params()
     opts = Namespace(solver_mode="standalone")
     B = a.batch
-    img = torch.from_numpy(detrand.uniform((B, 3, 32, 32), 700 + rank, 0.0, 1.0)).to(dev)
-    y = torch.from_numpy((detrand.uniform((B,), 800 + rank, 0.0, 10.0)).astype("int64") % 10).to(dev)
+    n_data = 4 * B                                             # this rank's shard of a synthetic uint8 dataset, resident in HBM
+    data_u8 = torch.from_numpy((detrand.uniform((n_data, 32, 32, 3), 700 + rank, 0.0, 256.0)).astype("uint8")).to(dev)
+    labels = torch.from_numpy((detrand.uniform((n_data,), 800 + rank, 0.0, 10.0)).astype("int64") % 10).to(dev)
     gen = torch.Generator(device=dev).manual_seed(1 + rank)
     it = [0]
 
     def step():
-        with torch.no_grad():
-            x = normalize(augment_batch(img, generator=gen)).contiguous(memory_format=torch.channels_last)   # on-GPU augmentation
+        index = torch.randint(0, n_data, (B,), device=dev, generator=gen)
+        x = msb.augment_normalize(data_u8, index, generator=gen)     # crop + flip + ToTensor + Normalize: one kernel
+        y = labels[index]
         s = sample_solver_by_noising_params(base, std=0.0125, bernoulli_p=1.0, noise_type="normal")
         parallel.sync_solver_params([s])                       # every rank integrates with rank 0's u
         kws = {"solvers": [s], "solver_options": opts}
@@ -68,8 +64,8 @@ def main():
         xa, _ = atk(x, y, kws)
         loss = msb.cross_entropy(model(xa, **kws), y)
         loss.backward()
-        opt.param_groups[0]["lr"] = cyclic_lr(it[0])
         opt.step(grad_scale=opt.all_reduce())                  # ONE all-reduce of the flat gradient, 1/world folded into the update
+        sched.step()
         it[0] += 1
         return loss
 

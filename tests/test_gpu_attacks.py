@@ -45,6 +45,13 @@ def _frac_diff(a, b, step):
     return float((np.abs(a - b) > 0.25 * step).mean())
 
 
+# Bounds on the fraction of adversarial pixels that differ from the reference's: sign(grad) flips where |grad| is within the
+# engines' rounding distance of zero.  Measured on B200 (this test prints them with -s): 0 of 24 576 pixels for FGSM and 0
+# for PGD-7 with the round-2 build; the bounds leave room for a handful of flips (round 1 allowed 5e-3 / 2e-2).
+FGSM_FLIP_BOUND = 2e-4
+PGD_FLIP_BOUND = 1e-3
+
+
 def test_fgsm_and_pgd_vs_reference_golden():
     from metasolver_b200.MegaAdversarial.src.attacks import FGSM, PGD
     g = golden("attacks.npz")
@@ -56,10 +63,13 @@ def test_fgsm_and_pgd_vs_reference_golden():
     assert (clean.argmax(1) == g["clean_logits"].argmax(1)).all()
     min_std = min(std)
     xf, _ = FGSM(model, eps=8 / 255., mean=mean, std=std)(x, y, kw)
-    assert _frac_diff(xf.cpu().numpy(), g["fgsm_x"], (8 / 255.) / max(std)) < 5e-3
+    ff = _frac_diff(xf.cpu().numpy(), g["fgsm_x"], (8 / 255.) / max(std))
+    assert ff < FGSM_FLIP_BOUND, ff
     xp, _ = PGD(model, eps=8 / 255., lr=2 / 255., n_iter=7, mean=mean, std=std)(
         x, y, kw, noise=torch.from_numpy(g["pgd_start"]))
-    assert _frac_diff(xp.cpu().numpy(), g["pgd_x"], (2 / 255.) / max(std)) < 2e-2
+    fp = _frac_diff(xp.cpu().numpy(), g["pgd_x"], (2 / 255.) / max(std))
+    print("measured fraction of differing adversarial pixels: fgsm %.3e, pgd-7 %.3e" % (ff, fp))
+    assert fp < PGD_FLIP_BOUND, fp
     with torch.no_grad():
         lf = model(xf, **kw).cpu().numpy()
         lp = model(xp, **kw).cpu().numpy()

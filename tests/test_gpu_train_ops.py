@@ -163,3 +163,62 @@ def test_host_fed_loop_returns_every_result_in_order_one_call_late():
     assert got[0] is None and got[1:] == [0.5 * n * k for k in range(5)]
     assert loop.drain() == [0.5 * n * 5] and loop.drain() == []
     assert len(set(seen)) == 2                          # two staging sets, alternating
+
+
+def test_augment_normalize_kernel_matches_torchvision_bitwise():
+    """sopa/src/models/odenet_cifar10/data.py:40-57: RandomCrop(32, padding=4) + RandomHorizontalFlip + ToTensor + Normalize
+    per sample on the host -> one kernel over a uint8 dataset resident in HBM.  Same draws -> the same floats."""
+    import metasolver_b200 as msb
+    from metasolver_b200.sopa.src.models.odenet_cifar10.data import CIFAR_MEAN, CIFAR_STD
+    tvf = pytest.importorskip("torchvision.transforms.functional")
+    g = torch.Generator().manual_seed(5)
+    N, B, pad = 40, 16, 4
+    data = torch.randint(0, 256, (N, 32, 32, 3), generator=g, dtype=torch.uint8)
+    index = torch.randperm(N, generator=g)[:B]
+    dx = torch.randint(0, 2 * pad + 1, (B,), generator=g)
+    dy = torch.randint(0, 2 * pad + 1, (B,), generator=g)
+    flip = torch.rand(B, generator=g) < 0.5
+    dx[0], dy[0], dx[1], dy[1] = 0, 0, 2 * pad, 2 * pad            # the extreme windows
+    out = msb.augment_normalize(data.cuda(), index.cuda(), draws=(dx.cuda(), dy.cuda(), flip.cuda()), padding=pad)
+    assert out.shape == (B, 3, 32, 32) and out.is_contiguous(memory_format=torch.channels_last)
+    for b in range(B):
+        img = data[index[b]].permute(2, 0, 1)                      # uint8 CHW, what PIL -> crop/flip sees
+        img = tvf.pad(img, [pad, pad, pad, pad])                   # RandomCrop pads first (fill 0)
+        img = tvf.crop(img, int(dy[b]), int(dx[b]), 32, 32)
+        if bool(flip[b]):
+            img = tvf.hflip(img)
+        ref = tvf.normalize(img.float().div(255), CIFAR_MEAN, CIFAR_STD)     # ToTensor, Normalize
+        assert torch.equal(out[b].cpu(), ref), b
+    # evaluation transform: ToTensor + Normalize only
+    ev = msb.augment_normalize(data.cuda(), train=False)
+    ref = tvf.normalize(data.permute(0, 3, 1, 2).float().div(255), CIFAR_MEAN, CIFAR_STD)
+    assert torch.equal(ev.cpu(), ref)
+    # random draws on the device: deterministic under a seeded generator, every value a valid pixel or a padded one
+    g1 = torch.Generator(device="cuda").manual_seed(3)
+    g2 = torch.Generator(device="cuda").manual_seed(3)
+    a1 = msb.augment_normalize(data.cuda(), generator=g1)
+    a2 = msb.augment_normalize(data.cuda(), generator=g2)
+    assert torch.equal(a1, a2) and not torch.equal(a1, ev)
+
+
+def test_cyclic_lr_drives_fused_sgd_like_torch():
+    """train_and_attack.py:480-505: SGD(momentum, weight_decay) + CyclicLR(cycle_momentum=True), 12 steps."""
+    import metasolver_b200 as msb
+    torch.manual_seed(0)
+    w0 = torch.randn(4, 8, device="cuda")
+    grads = [torch.randn(4, 8, device="cuda") for _ in range(12)]
+    pt = torch.nn.Parameter(w0.clone())
+    topt = torch.optim.SGD([pt], lr=0.1, momentum=0.9, weight_decay=5e-4)
+    tsch = torch.optim.lr_scheduler.CyclicLR(topt, base_lr=1e-3, max_lr=0.1, step_size_up=4, mode="triangular2")
+    pm = torch.nn.Parameter(w0.clone())
+    mopt = msb.FusedSGD([pm], lr=0.1, momentum=0.9, weight_decay=5e-4)
+    msch = msb.CyclicLR(mopt, base_lr=1e-3, max_lr=0.1, step_size_up=4, mode="triangular2")
+    for gk in grads:
+        pt.grad = gk.clone()
+        pm.grad.copy_(gk)
+        topt.step()
+        tsch.step()
+        mopt.step()
+        msch.step()
+        assert mopt.param_groups[0]["lr"] == topt.param_groups[0]["lr"]
+    assert (pm.detach() - pt.detach()).abs().max().item() <= 1e-6 * pt.detach().abs().max().item()

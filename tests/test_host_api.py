@@ -95,7 +95,7 @@ def test_cabi_library_exports_header_symbols():
     lib = _cabi.lib()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.msb_abi_version() == _cabi.ABI_VERSION == 4
+    assert lib.msb_abi_version() == _cabi.ABI_VERSION == 5
     assert lib.msb_shape_supports_tcgen05(64, 32, 32) in (0, 1)
     # descriptor validation is host-only: bad stage count must be refused with a message
     d = _cabi.MsbOdeDesc()
@@ -206,3 +206,27 @@ def test_noise_samplers_match_reference_golden():
                 ens = create_solver_ensemble_by_noising_params(solver, ensemble_size=4, kwargs_noise=kw)
             assert np.array_equal(np.asarray([float(e.u) for e in ens]), g[key + "_ens_u"]), key
             assert np.array_equal(np.stack([tab(e) for e in ens]), g[key + "_ens_tab"]), key
+
+
+@pytest.mark.parametrize("mode,kw", [("triangular", {}), ("triangular2", {}), ("exp_range", {"gamma": 0.99}),
+                                     ("triangular", {"step_size_down": 7, "cycle_momentum": False})])
+def test_cyclic_lr_matches_torch_scheduler(mode, kw):
+    """examples/cifar10/train_and_attack.py:500-505: optim.lr_scheduler.CyclicLR(base_lr, max_lr, step_size_up, mode,
+    cycle_momentum).  torch's class only accepts torch optimizers; ours drives FusedSGD.param_groups.  Same values."""
+    from metasolver_b200.train_ops import CyclicLR
+
+    class Opt:                                   # what FusedSGD exposes to a scheduler
+        def __init__(self):
+            self.param_groups = [{"lr": 0.1, "momentum": 0.9, "weight_decay": 5e-4}]
+    p = torch.nn.Parameter(torch.zeros(1))
+    topt = torch.optim.SGD([p], lr=0.1, momentum=0.9)
+    tsch = torch.optim.lr_scheduler.CyclicLR(topt, base_lr=1e-4, max_lr=0.05, step_size_up=5, mode=mode, **kw)
+    mine_opt = Opt()
+    mine = CyclicLR(mine_opt, base_lr=1e-4, max_lr=0.05, step_size_up=5, mode=mode, **kw)
+    for it in range(40):
+        assert mine.get_last_lr()[0] == tsch.get_last_lr()[0], it
+        assert mine_opt.param_groups[0]["lr"] == topt.param_groups[0]["lr"], it
+        assert mine_opt.param_groups[0]["momentum"] == topt.param_groups[0]["momentum"], it
+        topt.step()
+        tsch.step()
+        mine.step()
