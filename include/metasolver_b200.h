@@ -295,8 +295,13 @@ int msb_cross_entropy_backward(const float* logits, const int64_t* labels, const
  *                      griddepcontrol.wait orders every access to the predecessor's outputs   (env MSB_PDL)
  *   "wgrad_multicast"  1 = weight-gradient GEMM as clusters of the tap groups with the shared gout box loaded once by
  *                      TMA multicast (measured slower with the current two-stage ring; default 0)  (env MSB_WGRAD_MULTICAST)
- * Results do not depend on any option except the products formed (tc_form_c64, tct_products: last-bit differences) and
- * tct_debug.  Returns 0, or -1 for an unknown name. */
+ *   "wgrad64_products" hi/lo products of the C = 64 weight gradient: 4 (default) or 3 (roles swapped; measured slower)
+ *   "mnist_fused"      1 (default) = the MNIST ODE-block forward runs as ONE persistent tcgen05 launch; 0 = multi-launch path
+ *   "uniform_issue"    warp-uniform MMA issue loops: bit 0 = CTA-pair convolution (default on), bit 1 = weight gradient
+ *   "gn_block"         1 (default) = GroupNorm of large states (CIFAR 'GN' / 'LN' / 'IN' right-hand sides) as one CTA per
+ *                      sample; 0 = the warp-per-(sample, group) kernels of the MNIST state      (env MSB_GN_BLOCK)
+ * Results do not depend on any option except the products formed (tc_form_c64, tct_products, wgrad64_products: last-bit
+ * differences), the summation orders of mnist_fused / gn_block (same), and tct_debug.  Returns 0, or -1 for an unknown name. */
 int msb_set_option(const char* name, int value);
 int msb_get_option(const char* name, int* value);
 

@@ -33,6 +33,8 @@ enum { TUNE_EPI_L2_PREFETCH = 0,   // conv epilogue operands: bulk L2 prefetch d
        TUNE_MNIST_FUSED = 13,      // MNIST right-hand side forward: whole solve in one persistent tcgen05 launch (1, default) or the SIMT multi-launch path
        TUNE_UNIFORM_ISSUE = 14,    // warp-uniform MMA issue loop instead of the one-lane loop of round 1: bit 0 = CTA-pair conv (default on: -2..3 %),
                                    // bit 1 = weight gradient (default off: no gain measured)
+       TUNE_GN_BLOCK = 15,         // GroupNorm of large states (CIFAR GN / LN / IN right-hand sides): one CTA per sample (1, default)
+                                   // or the warp-per-(sample, group) kernels written for the MNIST state (0)
        TUNE_COUNT };
 int tune_get(int which);
 
