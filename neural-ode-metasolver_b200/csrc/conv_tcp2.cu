@@ -4,9 +4,13 @@
 //   D[pixel][c_out] = sum_{tap, c_in} X[pixel + tap][c_in] * W[c_out][tap][c_in]
 //
 //   A (M = 256)  = activations: each CTA supplies ITS 128 pixels (one bf16 plane, K-major) from its own shared memory
-//   B (N rows)   = weights [W_hi ; W_lo]: each CTA holds HALF of the N rows (rank 0: W_hi, rank 1: W_lo for the N = 2C
-//                  product; rank r: rows r*C/2.. of W_hi for the N = C product X_lo * W_hi)
-//   D            = 128 TMEM lanes (own pixels) x 2C fp32 columns in each CTA, same layout as the single-CTA kernel
+//   B (N rows)   = weights: each CTA holds HALF of the N rows -- rank r: [W_hi of channel half r ; W_lo of the other half]
+//                  (C rows).  The N = 2C product X_hi * [..] reads all of them; the N = C product X_lo * W_hi reads the
+//                  first C/2 rows of each CTA (W_hi of both halves) from the SAME region (round 2; round 1 kept a
+//                  separate copy: 3/2 of the bytes, 3 ring stages instead of 5).
+//   D            = 128 TMEM lanes (own pixels) x 2C fp32 columns in each CTA:
+//                  [hi half 0 | lo half 1 + (X_lo W_hi) half 1 | hi half 1 | lo half 0]; the epilogue adds a channel's two
+//                  columns (resident variant: the round-1 layout [hi | lo])
 //
 // Why: with both operands in shared memory a single-CTA MMA is limited by the shared-memory operand feed (~72 B/clk):
 // per k-step the single-CTA form reads 128 + 2C and 128 + C operand rows, the pair form 128 + C and 128 + C/2 -- for
@@ -25,6 +29,23 @@
 
 #include "msb_internal.h"
 #include "msb_ptx.cuh"
+
+#ifdef MSB_CONV_DEBUG
+// instrumented build only: clocks the MMA-issuing warp spends in each of its waits, summed over the leader CTAs
+// [0] weights full  [1] activations full  [2] accumulator empty  [3] whole issue loop  [4] leaders counted
+static __device__ unsigned long long g_tcp2_wait[8];
+extern "C" int msb_debug_tcp2_read(unsigned long long* out8, int reset) {
+    if (out8 && cudaMemcpyFromSymbol(out8, g_tcp2_wait, sizeof(g_tcp2_wait)) != cudaSuccess) return -1;
+    if (reset) {
+        unsigned long long zero[8] = {0};
+        if (cudaMemcpyToSymbol(g_tcp2_wait, zero, sizeof(zero)) != cudaSuccess) return -1;
+    }
+    return 0;
+}
+#define TCP2_WAIT(bar, parity, slot) do { const long long _t = clock64(); ptx::mbar_wait(bar, parity); wait_clk[slot] += clock64() - _t; } while (0)
+#else
+#define TCP2_WAIT(bar, parity, slot) ptx::mbar_wait(bar, parity)
+#endif
 
 namespace msb {
 
@@ -57,12 +78,18 @@ template <int C, int WIMG, int EW> struct Geom2 {
     static constexpr int ROW_BYTES = WIMG * 128;
     static constexpr int WA_BYTES = C * 128;                          // this CTA's half of [W_hi ; W_lo]
     static constexpr int WB_BYTES = (C / 2) * 128;                    // this CTA's half of W_hi
-    static constexpr int W_STAGE_BYTES = WA_BYTES + WB_BYTES;
+    // ring form: ONE region of C rows per CTA serves both MMAs of a k-step (see the weight producer); the resident
+    // variant keeps the round-1 layout (region A + a separate half of W_hi for the lo-plane MMA)
+    static constexpr int W_STAGE_BYTES = RES ? WA_BYTES + WB_BYTES : WA_BYTES;
     static constexpr int X_STAGES = 2;
     static constexpr int STAGE_BYTES = RES ? EW * (kStageBytesPerWarp / 2) : EW * kStageBytesPerWarp;
     static constexpr int THREADS = (kEpiWarp0 + EW) * 32;
     static constexpr int RING = kSmemBudget - STAGE_BYTES - X_STAGES * X_STAGE_BYTES;
+#ifdef MSB_TCP2_WSTAGES_CAP
+    static constexpr int W_STAGES = RES ? 9 * (C / 64) : (RING / W_STAGE_BYTES > MSB_TCP2_WSTAGES_CAP ? MSB_TCP2_WSTAGES_CAP : RING / W_STAGE_BYTES);
+#else
     static constexpr int W_STAGES = RES ? 9 * (C / 64) : (RING / W_STAGE_BYTES > kMaxStages ? kMaxStages : RING / W_STAGE_BYTES);
+#endif
     static_assert(!RES || 9 * W_STAGE_BYTES <= RING, "resident weights do not fit");
     static constexpr int ACC_COLS = 2 * C;
     static constexpr int ACC_BUFS = (C == 64) ? 4 : 2;
@@ -98,6 +125,10 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
     // physical warps and TMA / MMA / alloc the last four: the schedulers favour the highest warp ids of a sub-partition,
     // and a late MMA issue is a tensor-pipe bubble while a late epilogue instruction is not.  (physical + 4) keeps
     // warp & 3, the TMEM lane quadrant a warp may read.
+#ifdef MSB_CONV_DEBUG
+    __shared__ unsigned long long dbg_epi_end, dbg_loop[2], dbg_t_entry;
+    if (threadIdx.x == 0) { dbg_epi_end = 0; dbg_t_entry = (unsigned long long)clock64(); }
+#endif
     const int warp = (int)(((threadIdx.x >> 5) + role_shift) % (kEpiWarp0 + EW));
     const int lane = threadIdx.x & 31;
     const uint32_t rank = ptx::cluster_ctarank();
@@ -169,11 +200,13 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
                             if (leader) ptx::mbar_arrive_expect_tx(&bars->w_full[st], 2 * G::W_STAGE_BYTES);
                             uint8_t* dst = smem_w + st * G::W_STAGE_BYTES;
                             const int row0 = wt * 2 * C;                    // packed tile: rows [W_hi (C) ; W_lo (C)]
-                            // region A: rank 0 -> W_hi, rank 1 -> W_lo  (two boxes of C/2 rows)
-                            ptx::tma_load_2d_2sm(dst, &tmap_w, full, 0, row0 + (int)rank * C);
-                            ptx::tma_load_2d_2sm(dst + G::WB_BYTES, &tmap_w, full, 0, row0 + (int)rank * C + C / 2);
-                            // region B: rank r -> rows r*C/2 .. of W_hi
-                            ptx::tma_load_2d_2sm(dst + G::WA_BYTES, &tmap_w, full, 0, row0 + (int)rank * (C / 2));
+                            // rank r holds [W_hi of its channel half r ; W_lo of the OTHER half] (two boxes of C/2 rows).
+                            // N = 2C MMA: columns [hi half 0 | lo half 1 | hi half 1 | lo half 0].  The N = C MMA of the lo
+                            // activation plane reads the FIRST C/2 rows of each CTA = W_hi of both halves, and its columns
+                            // [half 0 | half 1] land on accumulator columns that belong to the same channels -- no separate
+                            // copy of W_hi: 2/3 of the bytes per stage, 5 stages instead of 3 in the same shared memory.
+                            ptx::tma_load_2d_2sm(dst, &tmap_w, full, 0, row0 + (int)rank * (C / 2));
+                            ptx::tma_load_2d_2sm(dst + G::WB_BYTES, &tmap_w, full, 0, row0 + C + (1 - (int)rank) * (C / 2));
                             if (++st == kWStages) { st = 0; ph ^= 1; }
                         }
             }
@@ -191,26 +224,30 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
             const uint32_t xs_u32 = ptx::smem_u32(smem_x), ws_u32 = ptx::smem_u32(smem_w);
             int wst = 0, xst = 0; uint32_t wph = 0, xph = 0;
             int acc = 0; uint32_t acc_ph = 0;
+#ifdef MSB_CONV_DEBUG
+            long long wait_clk[3] = {0, 0, 0};
+            const long long loop_t0 = clock64();
+#endif
             if (G::RES) { ptx::mbar_wait(&bars->w_full[0], 0); ptx::tc_fence_after(); }
             for (int pr = cluster_id; pr < num_pairs; pr += num_clusters) {
-                ptx::mbar_wait(&bars->tmem_empty[acc], acc_ph ^ 1);
+                TCP2_WAIT(&bars->tmem_empty[acc], acc_ph ^ 1, 2);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tb + (uint32_t)(acc * G::ACC_COLS);
                 uint32_t accumulate = 0;
                 for (int chunk = 0; chunk < CHUNKS; ++chunk)
                     for (int s = 0; s < 3; ++s) {
-                        ptx::mbar_wait(&bars->x_full[xst], xph);
+                        TCP2_WAIT(&bars->x_full[xst], xph, 1);
                         ptx::tc_fence_after();
                         const uint32_t x_base = xs_u32 + (uint32_t)(xst * G::X_STAGE_BYTES);
                         for (int r = 0; r < 3; ++r) {
                             if (G::RES) wst = r * 3 + s;
-                            else { ptx::mbar_wait(&bars->w_full[wst], wph); ptx::tc_fence_after(); }
+                            else { TCP2_WAIT(&bars->w_full[wst], wph, 0); ptx::tc_fence_after(); }
                             const uint32_t w_base = ws_u32 + (uint32_t)(wst * G::W_STAGE_BYTES);
                             if (el) {
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
                                     const uint64_t wa = ptx::make_smem_desc_sw128(w_base + k * 32, 16, 1024);
-                                    const uint64_t wb = ptx::make_smem_desc_sw128(w_base + G::WA_BYTES + k * 32, 16, 1024);
+                                    const uint64_t wb = ptx::make_smem_desc_sw128(w_base + (G::RES ? G::WA_BYTES : 0) + k * 32, 16, 1024);
                                     const uint64_t xhi = ptx::make_smem_desc_sw128(x_base + r * G::ROW_BYTES + k * 32, 16, 1024);
                                     const uint64_t xlo =
                                         ptx::make_smem_desc_sw128(x_base + G::PLANE_BYTES + r * G::ROW_BYTES + k * 32, 16, 1024);
@@ -228,6 +265,15 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
                 if (el) ptx::umma_commit_2sm(&bars->tmem_full[acc]);
                 if (++acc == kAccBufs) { acc = 0; acc_ph ^= 1; }
             }
+#ifdef MSB_CONV_DEBUG
+            if (el) {
+                dbg_loop[0] = (unsigned long long)loop_t0;
+                dbg_loop[1] = (unsigned long long)clock64();
+                for (int i = 0; i < 3; ++i) atomicAdd(&g_tcp2_wait[i], (unsigned long long)wait_clk[i]);
+                atomicAdd(&g_tcp2_wait[3], (unsigned long long)(clock64() - loop_t0));
+                atomicAdd(&g_tcp2_wait[4], 1ull);
+            }
+#endif
         };
         if (leader) {
             if (uniform_issue) {
@@ -350,12 +396,14 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
             ptx::mbar_wait_backoff(&bars->tmem_full[acc], ph, backoff_ns);
             ptx::tc_fence_after();
             const uint32_t t_acc = tmem_base + (uint32_t)(acc * G::ACC_COLS) + lane_addr + (uint32_t)cb;
+            // the second column set of channel block cb (accumulator columns [hi half 0 | lo half 1 | hi half 1 | lo half 0])
+            const uint32_t other = cb < C / 2 ? 3 * C / 2 : C / 2;
             __syncwarp();
 #pragma unroll
             for (int c8 = 0; c8 < 4; ++c8) {
                 float a[8], b[8];
                 ptx::tmem_ld<8>(t_acc + c8 * 8, a);
-                ptx::tmem_ld<8>(t_acc + C + c8 * 8, b);
+                ptx::tmem_ld<8>(t_acc + other + c8 * 8, b);
                 ptx::tmem_ld_wait();
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
@@ -392,9 +440,19 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
         }
         }
     }
+#ifdef MSB_CONV_DEBUG
+    if (warp >= kEpiWarp0 && lane == 0) atomicMax(&dbg_epi_end, (unsigned long long)clock64());
+#endif
     // nobody leaves while the peer may still signal its barriers or the leader's MMAs write its TMEM
     ptx::tc_fence_before();
     __syncthreads();
+#ifdef MSB_CONV_DEBUG
+    if (leader && threadIdx.x == 0) {          // [5] entry -> MMA loop start, [6] MMA loop end -> last epilogue warp done, [7] entry -> here
+        atomicAdd(&g_tcp2_wait[5], dbg_loop[0] - dbg_t_entry);
+        atomicAdd(&g_tcp2_wait[6], dbg_epi_end > dbg_loop[1] ? dbg_epi_end - dbg_loop[1] : 0ull);
+        atomicAdd(&g_tcp2_wait[7], (unsigned long long)clock64() - dbg_t_entry);
+    }
+#endif
     ptx::cluster_sync();
     if (warp == 2) {
         ptx::tc_fence_after();
