@@ -69,8 +69,12 @@ constexpr int kStageBytesPerWarp = 4096;
 // the shared memory of the epilogue stage: 8 warps with 2 KB each, transposing 16 pixels at a time.  Measured: 185 us per
 // launch vs 197 us for the ring pair and 171 us for the single-CTA kernel (profiles/conv_pair64_resident_ab_r1.txt), so
 // it is an option (tcp_epi_warps = 8 with tc_pair = 1), not the default.
-template <int C, int WIMG, int EW> struct Geom2 {
+// HS (ring form, 16 warps): HALF-size epilogue stage -- a warp transposes its 32 pixels in two passes of 16 (re-reading the
+// accumulator from tensor memory for the second pass) -- and the 32 KB it frees buy a THIRD activation stage: the MMA warp's
+// activation waits were what the 5-stage weight ring left over (scripts/diag_tcp2_waits.py).
+template <int C, int WIMG, int EW, bool HS = false> struct Geom2 {
     static constexpr bool RES = (EW == 8);
+    static_assert(!(RES && HS), "half stage: ring form only");
     static_assert(!RES || C == 64, "resident weights: C = 64 only");
     static constexpr int ROWS = 128 / WIMG;
     static constexpr int PLANE_BYTES = (ROWS + 2) * WIMG * 128;
@@ -81,8 +85,8 @@ template <int C, int WIMG, int EW> struct Geom2 {
     // ring form: ONE region of C rows per CTA serves both MMAs of a k-step (see the weight producer); the resident
     // variant keeps the round-1 layout (region A + a separate half of W_hi for the lo-plane MMA)
     static constexpr int W_STAGE_BYTES = RES ? WA_BYTES + WB_BYTES : WA_BYTES;
-    static constexpr int X_STAGES = 2;
-    static constexpr int STAGE_BYTES = RES ? EW * (kStageBytesPerWarp / 2) : EW * kStageBytesPerWarp;
+    static constexpr int X_STAGES = HS ? 3 : 2;
+    static constexpr int STAGE_BYTES = (RES || HS) ? EW * (kStageBytesPerWarp / 2) : EW * kStageBytesPerWarp;
     static constexpr int THREADS = (kEpiWarp0 + EW) * 32;
     static constexpr int RING = kSmemBudget - STAGE_BYTES - X_STAGES * X_STAGE_BYTES;
 #ifdef MSB_TCP2_WSTAGES_CAP
@@ -104,12 +108,12 @@ struct __align__(8) Barriers2 {
     uint32_t tmem_base;
 };
 
-template <int C, int WIMG, int ACT, int EW>
+template <int C, int WIMG, int ACT, int EW, bool HS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((kEpiWarp0 + EW) * 32, 1)
 conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_w,
                     const EpiParams epi, const int H, const int num_pairs, const int tiles_per_img,
                     const uint32_t backoff_ns, const int role_shift, const int uniform_issue) {
-    using G = Geom2<C, WIMG, EW>;
+    using G = Geom2<C, WIMG, EW, HS>;
     constexpr int CHUNKS = C / 64;
     constexpr int kWStages = G::W_STAGES, kXStages = G::X_STAGES, kAccBufs = G::ACC_BUFS;
     constexpr int NG = C / 32, WPT = 4 * NG, TG = EW / WPT;            // epilogue: channel groups, warps per tile, tile groups
@@ -375,6 +379,79 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
                     }
                 }
             }
+        } else if constexpr (HS) {
+        // ---- half-size stage: 16 pixels x 32 channels (2 KB) per pass, two passes per tile.  Pass p stages the pixels of
+        //      lanes 16p..16p+15 (every lane re-reads its accumulator row, the other half discards it); the quads of lanes
+        //      then read whole 128-byte lines as in the full-size form.  The accumulator is handed back after the second
+        //      pass's read.  Step s = 2 * pass + jj owns pixel q*32 + 16*pass + 2*quad + jj. ----
+        const uint32_t stage = ptx::smem_u32(smem_stage + we * (kStageBytesPerWarp / 2));
+        const int k4 = lane & 3, quad = lane >> 2;
+        auto owned = [&](size_t row0, int sidx_step, size_t& idx, size_t& sidx) {
+            const int pp = q * 32 + 16 * (sidx_step >> 1) + quad * 2 + (sidx_step & 1);
+            const int r2 = pp / WIMG, w2 = pp - r2 * WIMG;
+            idx = ((row0 + r2) * WIMG + w2) * C + cb + 8 * k4;
+            sidx = ((row0 + r2) * 2) * plane_stride + (size_t)w2 * C + cb + 8 * k4;
+        };
+        int it = tg;
+        int pr = cluster_id + tg * num_clusters;
+        EpiVec8 ops;
+        if (pr < num_pairs) { size_t i0, s0; owned(row0_of(pr), 0, i0, s0); epi_prefetch_vec8(epi, i0, ops); }
+        for (; pr < num_pairs; pr += TG * num_clusters, it += TG) {
+            const int acc = it % kAccBufs;
+            const uint32_t ph = (uint32_t)(it / kAccBufs) & 1u;
+            const EpiCoef coef = epi_coef(epi, (2 * pr + (int)rank) / tiles_per_img);
+            const size_t row0 = row0_of(pr);
+            ptx::mbar_wait_backoff(&bars->tmem_full[acc], ph, backoff_ns);
+            ptx::tc_fence_after();
+            const uint32_t t_acc = tmem_base + (uint32_t)(acc * G::ACC_COLS) + lane_addr + (uint32_t)cb;
+            const uint32_t other = cb < C / 2 ? 3 * C / 2 : C / 2;
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                __syncwarp();                                  // the previous half has been read by every lane
+                const int rl = lane & 15;
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    float a[8], b[8];
+                    ptx::tmem_ld<8>(t_acc + c8 * 8, a);
+                    ptx::tmem_ld<8>(t_acc + other + c8 * 8, b);
+                    ptx::tmem_ld_wait();
+                    if ((lane >> 4) == pass) {
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const uint32_t addr = stage + rl * 128 + (((c8 * 2 + u) ^ (rl & 7)) << 4);
+                            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a[4 * u] + b[4 * u]),
+                                         "f"(a[4 * u + 1] + b[4 * u + 1]), "f"(a[4 * u + 2] + b[4 * u + 2]),
+                                         "f"(a[4 * u + 3] + b[4 * u + 3]) : "memory");
+                        }
+                    }
+                }
+                if (pass == 1) ptx::tc_fence_before();
+                __syncwarp();
+                if (pass == 1 && lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->tmem_empty[acc]), 0));
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    const int step = 2 * pass + jj;
+                    const int row = quad * 2 + jj;
+                    float v[8];
+                    {
+                        const uint32_t base = stage + row * 128;
+                        const uint32_t a0 = base + (((2 * k4) ^ (row & 7)) << 4), a1 = base + (((2 * k4 + 1) ^ (row & 7)) << 4);
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a0));
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(a1));
+                    }
+                    size_t idx, sidx;
+                    owned(row0, step, idx, sidx);
+                    epi_finish_v8<ACT>(epi, coef, v, ops, idx, sidx, plane_stride);
+                    if (step < 3) {
+                        owned(row0, step + 1, idx, sidx);
+                        epi_prefetch_vec8(epi, idx, ops);
+                    } else {
+                        const int p2 = pr + TG * num_clusters;
+                        if (p2 < num_pairs) { owned(row0_of(p2), 0, idx, sidx); epi_prefetch_vec8(epi, idx, ops); }
+                    }
+                }
+            }
+        }
         } else {
         const uint32_t stage = ptx::smem_u32(smem_stage + we * kStageBytesPerWarp);
         const int k4 = lane & 3, quad = lane >> 2;
@@ -460,10 +537,10 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
     }
 }
 
-template <int C, int WIMG, int ACT, int EW>
+template <int C, int WIMG, int ACT, int EW, bool HS = false>
 int launch_act_ew(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, const EpiParams& epi, ConvShape s,
                   cudaStream_t st) {
-    using G = Geom2<C, WIMG, EW>;
+    using G = Geom2<C, WIMG, EW, HS>;
     constexpr int kThreads = G::THREADS;
     CUtensorMap tm_act, tm_w;
     if (make_tmap_split_plane(&tm_act, split_in, s.B, s.H, s.W, s.C, WIMG, G::ROWS + 2)) return -1;
@@ -471,7 +548,7 @@ int launch_act_ew(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, c
     constexpr size_t smem = (size_t)G::X_STAGES * G::X_STAGE_BYTES + (size_t)G::W_STAGES * G::W_STAGE_BYTES + G::STAGE_BYTES +
                             sizeof(Barriers2) + 1024;
     static_assert(smem <= 232448, "shared memory per CTA");
-    auto kern = conv3x3_tcp2_kernel<C, WIMG, ACT, EW>;
+    auto kern = conv3x3_tcp2_kernel<C, WIMG, ACT, EW, HS>;
     if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                    "cudaFuncSetAttribute(conv3x3_tcp2)"))
         return -1;
@@ -490,6 +567,9 @@ int launch_act(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, cons
                cudaStream_t st) {
     if constexpr (C == 64) {
         if (tune_get(TUNE_TCP_EPI_WARPS) == 8) return launch_act_ew<C, WIMG, ACT, 8>(split_in, w_tiles, epi, s, st);
+    }
+    if constexpr (C == 128) {
+        if (tune_get(TUNE_TCP2_HALF_STAGE)) return launch_act_ew<C, WIMG, ACT, 16, true>(split_in, w_tiles, epi, s, st);
     }
     return launch_act_ew<C, WIMG, ACT, 16>(split_in, w_tiles, epi, s, st);
 }

@@ -53,6 +53,20 @@ int tct_debug_set(int flags) {
 extern "C" int msb_debug_tct_read(unsigned* out16) {
     return cudaMemcpyFromSymbol(out16, g_tct_dbg, sizeof(g_tct_dbg)) == cudaSuccess ? 0 : -1;
 }
+// kernel timeline, summed over CTAs (clocks): [0] entry -> past griddepcontrol.wait, [1] -> weights in TMEM, [2] -> MMA issue
+// loops done, [3] -> last epilogue warp done, [4] -> exit, [5] CTAs counted
+static __device__ unsigned long long g_tct_time[12];
+// [6..9] clocks the two MMA-issuing warps spend waiting for: a free accumulator, input rows, their turn; and issuing
+extern "C" int msb_debug_tct_time(unsigned long long* out12, int reset) {
+    if (out12 && cudaMemcpyFromSymbol(out12, g_tct_time, sizeof(g_tct_time)) != cudaSuccess) return -1;
+    if (reset) {
+        unsigned long long zero[12] = {0};
+        if (cudaMemcpyToSymbol(g_tct_time, zero, sizeof(zero)) != cudaSuccess) return -1;
+    }
+    return 0;
+}
+#define TCT_STAMP(i) do { if (lane == 0) atomicMax(&dbg_t[i], (unsigned long long)clock64()); } while (0)
+#define TCT_TIMED(slot, stmt) do { const long long _t = clock64(); stmt; dbg_w[slot] += clock64() - _t; } while (0)
 // bounded wait that records its id and gives up (the kernel then finishes with garbage instead of trapping)
 __device__ __forceinline__ void tct_wait(uint64_t* bar, uint32_t parity, int id, int row) {
     uint32_t spins = 0;
@@ -70,6 +84,8 @@ __device__ __forceinline__ void tct_wait(uint64_t* bar, uint32_t parity, int id,
 #else
 #define TCT_WAIT(bar, parity, id) ptx::mbar_wait(bar, parity)
 #define TCT_MARK(slot) ((void)0)
+#define TCT_STAMP(i) ((void)0)
+#define TCT_TIMED(slot, stmt) do { stmt; } while (0)
 #endif
 
 namespace {
@@ -169,6 +185,10 @@ conv3x3_tct_kernel(const __grid_constant__ CUtensorMap tmap_act, const uint4* __
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+#ifdef MSB_CONV_DEBUG
+    __shared__ unsigned long long dbg_t[5];
+    if (threadIdx.x == 0) { dbg_t[0] = (unsigned long long)clock64(); dbg_t[1] = dbg_t[2] = dbg_t[3] = dbg_t[4] = 0; }
+#endif
 
     if (warp == kProducerWarp && lane == 0) {
         ptx::prefetch_tmap(&tmap_act);
@@ -186,7 +206,43 @@ conv3x3_tct_kernel(const __grid_constant__ CUtensorMap tmap_act, const uint4* __
     ptx::tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
     ptx::pdl_launch_dependents();       // the next kernel may set itself up while this one runs ...
-    ptx::pdl_wait();                    // ... and this one touches its inputs only after its predecessor has finished
+
+    // ---- weights -> TMEM, once (epilogue warps): thread (quadrant wq, lane) owns TMEM lane 32 wq + lane; the 18 column
+    // chunks of its row are spread over the four groups.  Packed layout: [chunk][lane 0..127][16 x u32] (coalesced).
+    auto load_weights = [&]() {
+        const int g = warp >> 2, wq = warp & 3;
+        const int L = wq * 32 + lane;
+        auto load_chunk = [&](int ch, uint32_t* r) {
+            const uint4* src = wpacked + ((size_t)ch * 128 + L) * 4;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const uint4 t = __ldg(src + v);
+                r[4 * v] = t.x; r[4 * v + 1] = t.y; r[4 * v + 2] = t.z; r[4 * v + 3] = t.w;
+            }
+        };
+        const uint32_t w_lane = tmem_base + ((uint32_t)(wq * 32) << 16) + kWCol0;
+        {
+            // all (up to five) chunks of this thread are requested before the first is stored: one L2 round trip
+            // instead of two (nothing else is live in registers yet)
+            uint32_t r0[16], r1[16], r2[16], r3[16], r4[16];
+            load_chunk(g, r0); load_chunk(g + 4, r1); load_chunk(g + 8, r2); load_chunk(g + 12, r3);
+            if (g + 16 < kWChunks) load_chunk(g + 16, r4);
+            tmem_st16(w_lane + (uint32_t)g * 16u, r0);
+            tmem_st16(w_lane + (uint32_t)(g + 4) * 16u, r1);
+            tmem_st16(w_lane + (uint32_t)(g + 8) * 16u, r2);
+            tmem_st16(w_lane + (uint32_t)(g + 12) * 16u, r3);
+            if (g + 16 < kWChunks) tmem_st16(w_lane + (uint32_t)(g + 16) * 16u, r4);
+        }
+        tmem_st_wait();
+        ptx::tc_fence_before();
+    };
+    // The packed weights are the one input that the predecessor kernel did not write when the caller says so
+    // (EpiParams::weights_settled: they were packed by a plain, fully ordered launch at least two launches back -- the
+    // ODE-block loops).  They are then fetched BEFORE griddepcontrol.wait, while the predecessor's last CTAs still run.
+    const bool w_early = epi.weights_settled != 0;
+    if (w_early && warp < kEpiWarps) load_weights();
+    ptx::pdl_wait();                    // ... and this one touches its other inputs only after its predecessor has finished
+    if (warp == 0) TCT_STAMP(1);
 
     const int my_items = blockIdx.x < num_items ? (num_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const int my_rows = my_items * BH;
@@ -236,6 +292,7 @@ conv3x3_tct_kernel(const __grid_constant__ CUtensorMap tmap_act, const uint4* __
         const int w = warp - kMmaWarp0;
         named_bar_sync(5, (kEpiWarps + 2) * 32);       // the weights are in TMEM (written by the epilogue warps below)
         ptx::tc_fence_after();
+        TCT_STAMP(2);
         {
             constexpr uint32_t idesc = ptx::make_idesc_bf16(128, P3 ? 32 : 64, 0, 0);
             constexpr uint32_t idesc_hi = ptx::make_idesc_bf16(64, 32, 0, 0);       // P3: the W_hi rows only
@@ -245,11 +302,14 @@ conv3x3_tct_kernel(const __grid_constant__ CUtensorMap tmap_act, const uint4* __
             const bool leader = elect_one();
             uint32_t q0 = 0, confirmed = 0;          // ring index of the first row of the current item / rows seen full
             int j = w;                               // row of the item (BH >= 4 > w)
+#ifdef MSB_CONV_DEBUG
+            long long dbg_w[4] = {0, 0, 0, 0};
+#endif
             for (int i = w; i < my_rows; i += 2) {
                 const int acc = i % kAccBufs;
                 const uint32_t acc_ph = (uint32_t)(i / kAccBufs) & 1u;
 #define TCT_ROW i
-                TCT_WAIT(&bars->tmem_empty[acc], acc_ph ^ 1, 1);
+                TCT_TIMED(0, TCT_WAIT(&bars->tmem_empty[acc], acc_ph ^ 1, 1));
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tb + (uint32_t)acc * kAccCols;
                 uint32_t b_base[3];
@@ -258,14 +318,17 @@ conv3x3_tct_kernel(const __grid_constant__ CUtensorMap tmap_act, const uint4* __
                     const uint32_t qq = q0 + (uint32_t)(j + r);
                     const uint32_t sl = qq % kSlots;
                     if (qq >= confirmed) {
-                        TCT_WAIT(&bars->full[sl], (qq / kSlots) & 1u, 2);
+                        TCT_TIMED(1, TCT_WAIT(&bars->full[sl], (qq / kSlots) & 1u, 2));
                         ptx::tc_fence_after();
                         confirmed = qq + 1;
                     }
                     b_base[r] = rows_u32 + sl * kSlotBytes;
                 }
 #undef TCT_ROW
-                if (i > 0) named_bar_sync(w == 0 ? 7 : 6, 64);      // the other warp has issued row i - 1
+                if (i > 0) TCT_TIMED(2, named_bar_sync(w == 0 ? 7 : 6, 64));      // the other warp has issued row i - 1
+#ifdef MSB_CONV_DEBUG
+                const long long dbg_issue0 = clock64();
+#endif
                 if (leader) {
 #pragma unroll
                     for (int r = 0; r < 3; ++r) {
@@ -288,6 +351,9 @@ conv3x3_tct_kernel(const __grid_constant__ CUtensorMap tmap_act, const uint4* __
                     }
                 }
                 __syncwarp();
+#ifdef MSB_CONV_DEBUG
+                dbg_w[3] += clock64() - dbg_issue0;
+#endif
                 if (i + 1 < my_rows) named_bar_arrive(w == 0 ? 6 : 7, 64);
                 if (leader) {
                     ptx::umma_commit(&bars->tmem_full[i % kFullBars]);
@@ -301,6 +367,9 @@ conv3x3_tct_kernel(const __grid_constant__ CUtensorMap tmap_act, const uint4* __
                 j += 2;
                 if (j >= BH) { j -= BH; q0 += (uint32_t)(BH + 2); }
             }
+#ifdef MSB_CONV_DEBUG
+            if (leader) for (int q = 0; q < 4; ++q) atomicAdd(&g_tct_time[6 + q], (unsigned long long)dbg_w[q]);
+#endif
         }
     } else if (warp < kEpiWarps) {
         // ===================== epilogue =====================
@@ -308,36 +377,8 @@ conv3x3_tct_kernel(const __grid_constant__ CUtensorMap tmap_act, const uint4* __
         const int wq = warp & 3;                              // TMEM lane quadrant of this warp
         const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
 
-        // ---- weights -> TMEM, once: thread (quadrant wq, lane) owns TMEM lane 32 wq + lane; the 18 column chunks of
-        // its row are spread over the four groups.  Packed layout: [chunk][lane 0..127][16 x u32] (coalesced).
+        if (!w_early) load_weights();
         {
-            const int L = wq * 32 + lane;
-            // chunks g, g + 4, g + 8 (always valid), then g + 12 (always) and g + 16 (g < 2): loads of a pass in flight together
-            auto load_chunk = [&](int ch, uint32_t* r) {
-                const uint4* src = wpacked + ((size_t)ch * 128 + L) * 4;
-#pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    const uint4 t = __ldg(src + v);
-                    r[4 * v] = t.x; r[4 * v + 1] = t.y; r[4 * v + 2] = t.z; r[4 * v + 3] = t.w;
-                }
-            };
-            const uint32_t w_lane = tmem_base + lane_addr + kWCol0;
-            {
-                uint32_t r0[16], r1[16], r2[16];
-                load_chunk(g, r0); load_chunk(g + 4, r1); load_chunk(g + 8, r2);
-                tmem_st16(w_lane + (uint32_t)g * 16u, r0);
-                tmem_st16(w_lane + (uint32_t)(g + 4) * 16u, r1);
-                tmem_st16(w_lane + (uint32_t)(g + 8) * 16u, r2);
-            }
-            {
-                uint32_t r0[16], r1[16];
-                load_chunk(g + 12, r0);
-                if (g + 16 < kWChunks) load_chunk(g + 16, r1);
-                tmem_st16(w_lane + (uint32_t)(g + 12) * 16u, r0);
-                if (g + 16 < kWChunks) tmem_st16(w_lane + (uint32_t)(g + 16) * 16u, r1);
-            }
-            tmem_st_wait();
-            ptx::tc_fence_before();
             named_bar_sync(5, (kEpiWarps + 2) * 32);          // with the two MMA warps
         }
 
@@ -447,8 +488,18 @@ conv3x3_tct_kernel(const __grid_constant__ CUtensorMap tmap_act, const uint4* __
             j = j2; n = n2; h = h2;
         }
     }
+    if (warp >= kMmaWarp0) TCT_STAMP(3);
+    if (warp < kEpiWarps) TCT_STAMP(4);
     ptx::tc_fence_before();
     __syncthreads();
+#ifdef MSB_CONV_DEBUG
+    if (threadIdx.x == 0 && my_rows > 0) {
+        const unsigned long long t0 = dbg_t[0];
+        for (int i = 1; i <= 4; ++i) atomicAdd(&g_tct_time[i - 1], dbg_t[i] > t0 ? dbg_t[i] - t0 : 0ull);
+        atomicAdd(&g_tct_time[4], (unsigned long long)clock64() - t0);
+        atomicAdd(&g_tct_time[5], 1ull);
+    }
+#endif
     if (warp == kAllocWarp) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, kTmemCols);

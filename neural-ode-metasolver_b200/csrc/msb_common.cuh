@@ -72,6 +72,9 @@ struct EpiParams {
     int act;
     int act_v;
     int base_is_one;   // base_coef == 1 -> skip the multiply (keeps forward bit-order exact)
+    int weights_settled;   // the packed weights were written by a fully ordered (non-programmatic) launch that is NOT this
+                           // kernel's immediate predecessor: a programmatically launched kernel may read them before its
+                           // griddepcontrol.wait (set by the ODE-block loops; 0 = read them after the wait)
 };
 
 __host__ inline EpiParams epi_default() {
@@ -85,7 +88,7 @@ __host__ inline EpiParams epi_default() {
         e.k[i].base_coef = 1.f; e.k[i].coef_v = 1.f; e.k[i].dt = 1.f; e.k[i].split_scale = 1.f;
     }
     e.pix_bias_scale = 0.f; e.slice_batch = 0;
-    e.nsrc = 0; e.act = ACT_NONE; e.act_v = ACT_NONE; e.base_is_one = 1;
+    e.nsrc = 0; e.act = ACT_NONE; e.act_v = ACT_NONE; e.base_is_one = 1; e.weights_settled = 0;
     return e;
 }
 

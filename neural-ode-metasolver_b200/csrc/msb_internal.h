@@ -35,6 +35,7 @@ enum { TUNE_EPI_L2_PREFETCH = 0,   // conv epilogue operands: bulk L2 prefetch d
                                    // bit 1 = weight gradient (default off: no gain measured)
        TUNE_GN_BLOCK = 15,         // GroupNorm of large states (CIFAR GN / LN / IN right-hand sides): one CTA per sample (1, default)
                                    // or the warp-per-(sample, group) kernels written for the MNIST state (0)
+       TUNE_TCP2_HALF_STAGE = 16,  // C = 128 CTA-pair conv: half-size epilogue stage (two passes) + a third activation stage
        TUNE_COUNT };
 int tune_get(int which);
 

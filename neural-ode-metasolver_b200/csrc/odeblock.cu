@@ -39,10 +39,10 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 static std::atomic<int> g_tune[TUNE_COUNT];
 static std::atomic<bool> g_tune_init{false};
 static const char* const kTuneNames[TUNE_COUNT] = {"epi_l2_prefetch", "tc_resident", "tcp_epi_warps", "tc_form_c64", "tc_pair",
-                                                   "wait_backoff_ns", "pdl", "wgrad_multicast", "tct_band", "tct_debug", "tct_products", "mma_warp_high", "wgrad64_products", "mnist_fused", "uniform_issue", "gn_block"};
+                                                   "wait_backoff_ns", "pdl", "wgrad_multicast", "tct_band", "tct_debug", "tct_products", "mma_warp_high", "wgrad64_products", "mnist_fused", "uniform_issue", "gn_block", "tcp2_half_stage"};
 static const char* const kTuneEnv[TUNE_COUNT] = {"MSB_EPI_L2_PREFETCH", "MSB_TC_RESIDENT", "MSB_TCP_EPI_WARPS", "MSB_TC_FORM_C64",
-                                                 "MSB_TC_PAIR", "MSB_WAIT_BACKOFF_NS", "MSB_PDL", "MSB_WGRAD_MULTICAST", "MSB_TCT_BAND", "MSB_TCT_DEBUG", "MSB_TCT_PRODUCTS", "MSB_MMA_WARP_HIGH", "MSB_WGRAD64_PRODUCTS", "MSB_MNIST_FUSED", "MSB_UNIFORM_ISSUE", "MSB_GN_BLOCK"};
-static const int kTuneDefault[TUNE_COUNT] = {0, 0, 16, 2, 2, 0, 1, 0, 0, 0, 4, 0, 4, 1, 1, 1};
+                                                 "MSB_TC_PAIR", "MSB_WAIT_BACKOFF_NS", "MSB_PDL", "MSB_WGRAD_MULTICAST", "MSB_TCT_BAND", "MSB_TCT_DEBUG", "MSB_TCT_PRODUCTS", "MSB_MMA_WARP_HIGH", "MSB_WGRAD64_PRODUCTS", "MSB_MNIST_FUSED", "MSB_UNIFORM_ISSUE", "MSB_GN_BLOCK", "MSB_TCP2_HALF_STAGE"};
+static const int kTuneDefault[TUNE_COUNT] = {0, 0, 16, 2, 2, 0, 1, 0, 0, 0, 4, 0, 4, 1, 1, 1, 1};
 static void tune_init() {
     if (g_tune_init.load(std::memory_order_acquire)) return;
     for (int i = 0; i < TUNE_COUNT; ++i) {
@@ -919,10 +919,12 @@ int msb_odeblock_forward(const MsbOdeDesc* d, const float* x, const float* w1, c
             TapeSlot cur = slot(n, i);
             // conv1: P = conv(A_i, W1);  Hs_i = split(act(P)),  G1_i = act'(P)
             EpiParams e1 = epi_default();
+            e1.weights_settled = 1;      // packed before the (plain) act_split launch that opens the chain: see conv_tct.cu
             e1.out_split = cur.Hs; e1.act = d->act; e1.dact_out = cur.G1;
             if (run_conv(engine, cur.A, wp1, e1, shp, st)) return -1;
             // conv2: k_i = conv(Hs_i, W2) and the Runge-Kutta combination that follows it
             EpiParams e2 = epi_default();
+            e2.weights_settled = 1;
             e2.base = y_cur; e2.act = act_in; e2.slice_batch = tabs.slice_batch;
             for (int q = 0; q < tabs.K; ++q) e2.k[q].dt = dt;
             if (post) { e2.act_v = d->act; e2.dact_v_out = cur.G0; }
@@ -1064,6 +1066,7 @@ static int odeblock_backward_impl(const MsbOdeDesc* d, const float* grad_y, cons
             // k_j = f(x_j) again (conv2 of the taped act(conv1(..))) and dL/db_j += dt <gbar, k_j>
             for (int j = 0; j < S; ++j) {
                 EpiParams ek = epi_default();
+                ek.weights_settled = 1;
                 ek.v_out = kre[j] + off;
                 if (post) ek.act_v = d->act;
                 if (run_conv(engine, slot(n, j).Hs, wp2f, ek, shp, st)) return -1;
@@ -1076,12 +1079,14 @@ static int odeblock_backward_impl(const MsbOdeDesc* d, const float* grad_y, cons
             if (need_w && run_wgrad(engine, Kbar, cur.Hs, acc2, shp, st)) return -1;
             // dP = dgrad_W2(kbar_i) * act'(P_i)
             EpiParams e3 = epi_default();
+            e3.weights_settled = 1;
             e3.mul = cur.G1; e3.out_split = DP;
             if (run_conv(engine, Kbar, wt2, e3, shp, st)) return -1;
             // dW1 += dP (x) A_i
             if (need_w && run_wgrad(engine, DP, cur.A, acc1, shp, st)) return -1;
             // xbar_i = dgrad_W1(dP) * act'(x_i), then the adjoint stage combination
             EpiParams e4 = epi_default();
+            e4.weights_settled = 1;
             e4.mul = post ? nullptr : cur.G0; e4.base = g_cur; e4.slice_batch = tabs.slice_batch;
             if (i > 0) {
                 // kbar_{i-1} = dt b_{i-1} gbar + dt sum_{j >= i} w[j][i-1] xbar_j
