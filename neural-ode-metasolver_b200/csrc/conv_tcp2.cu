@@ -157,7 +157,11 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
     ptx::tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
     ptx::pdl_launch_dependents();
-    ptx::pdl_wait();                          // inputs are read (TMA, epilogue loads) only after the predecessor has finished
+    // inputs are read (TMA, epilogue loads) and outputs written only after the predecessor has finished.  The weight
+    // producer touches nothing but the packed weights: when the caller vouches that those were written by a fully ordered
+    // launch further back (EpiParams::weights_settled, the ODE-block loops) it fills its ring while the predecessor's
+    // last CTAs still run.
+    if (!(warp == 3 && epi.weights_settled != 0)) ptx::pdl_wait();
 
     if (warp == 0) {
         // ===================== activation producer (both CTAs; own pixels) =====================
