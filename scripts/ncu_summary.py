@@ -3,6 +3,8 @@ import csv, io, subprocess, sys
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "dram__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg",           # non-sampled: MMA count x clocks per MMA x 4 sub-pipes
+        "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_tensor.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__t_sector_hit_rate.pct", "lts__t_bytes.sum", "l1tex__t_bytes.sum",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
@@ -25,3 +27,11 @@ for k in KEYS:
     for c in cols[:1]:
         i = idx[c]
         print("%-80s %-10s %s" % (k, units[i], "  ".join(r[i] for r in data)))
+# tensor-pipe utilisation from the non-sampled counter: (hmma cycles active / 4 sub-pipes) / elapsed cycles
+try:
+    hk = [c for c in h if c.endswith("sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg")][0]
+    ek = [c for c in h if c == "sm__cycles_elapsed.avg"][0]
+    print("%-80s %-10s %s" % ("tensor pipe active = hmma_cycles_active_realtime / 4 / sm__cycles_elapsed", "%",
+                               "  ".join("%.1f" % (100.0 * float(r[idx[hk]].replace(",", "")) / 4 / float(r[idx[ek]].replace(",", ""))) for r in data)))
+except Exception:
+    pass
