@@ -72,20 +72,33 @@ constexpr int kStageBytesPerWarp = 4096;
 // HS (ring form, 16 warps): HALF-size epilogue stage -- a warp transposes its 32 pixels in two passes of 16 (re-reading the
 // accumulator from tensor memory for the second pass) -- and the 32 KB it frees buy a THIRD activation stage: the MMA warp's
 // activation waits were what the 5-stage weight ring left over (scripts/diag_tcp2_waits.py).
-template <int C, int WIMG, int EW, bool HS = false> struct Geom2 {
+// HALO (16-pixel-wide images whose height is a multiple of 16): ONE staged tile per c_in chunk serves all nine taps.
+// tcgen05.mma takes a shared-memory operand whose start lies anywhere inside a 128-byte-swizzle atom and whose 8-row groups
+// follow each other at any stride (the swizzle is a function of the absolute address bits; measured,
+// scripts/probes/mma_rowshift_probe.cu), so a horizontal tap is the same tile read one pixel (128 B) further and needs no
+// copy of its own.  For the 8-row groups of the M operand to sit at ONE stride, a CTA's 128 pixels are 16 image rows x
+// 8 pixels (the left / right half of a 16 x 16 band; a pair = the band): group g = the 8 pixels of image row g, stride =
+// one staged image row of 10 pixels (8 + a halo pixel each side).  Activation L2 -> SM traffic per tile: 2 planes x
+// 18 x 10 pixels per chunk instead of 3 x (2 x 10 x 16): -62 %; a stage lasts 72 MMAs instead of 24.
+constexpr int align1k(int x) { return (x + 1023) / 1024 * 1024; }
+template <int C, int WIMG, int EW, bool HS = false, bool HALO = false> struct Geom2 {
     static constexpr bool RES = (EW == 8);
-    static_assert(!(RES && HS), "half stage: ring form only");
+    static_assert(!(RES && (HS || HALO)), "half stage / halo tile: ring form only");
     static_assert(!RES || C == 64, "resident weights: C = 64 only");
-    static constexpr int ROWS = 128 / WIMG;
-    static constexpr int PLANE_BYTES = (ROWS + 2) * WIMG * 128;
+    static_assert(!HALO || WIMG == 16, "halo tile: 16-pixel-wide images");
+    static constexpr int ROWS = HALO ? 16 : 128 / WIMG;               // image rows of a CTA's tile
+    static constexpr int TILE_W = HALO ? 8 : WIMG;                    // pixels per image row of a CTA's tile
+    static constexpr int BOX_W = HALO ? TILE_W + 2 : WIMG;            // staged pixels per image row
+    static constexpr int ROW_BYTES = BOX_W * 128;                     // one staged image row of one plane
+    static constexpr int PLANE_BYTES = HALO ? align1k((ROWS + 2) * ROW_BYTES) : (ROWS + 2) * ROW_BYTES;
     static constexpr int X_STAGE_BYTES = 2 * PLANE_BYTES;
-    static constexpr int ROW_BYTES = WIMG * 128;
+    static constexpr int A_SBO = HALO ? ROW_BYTES : 1024;             // stride between the 8-pixel groups of the M operand
     static constexpr int WA_BYTES = C * 128;                          // this CTA's half of [W_hi ; W_lo]
     static constexpr int WB_BYTES = (C / 2) * 128;                    // this CTA's half of W_hi
     // ring form: ONE region of C rows per CTA serves both MMAs of a k-step (see the weight producer); the resident
     // variant keeps the round-1 layout (region A + a separate half of W_hi for the lo-plane MMA)
     static constexpr int W_STAGE_BYTES = RES ? WA_BYTES + WB_BYTES : WA_BYTES;
-    static constexpr int X_STAGES = HS ? 3 : 2;
+    static constexpr int X_STAGES = HALO ? 2 : (HS ? 3 : 2);
     static constexpr int STAGE_BYTES = (RES || HS) ? EW * (kStageBytesPerWarp / 2) : EW * kStageBytesPerWarp;
     static constexpr int THREADS = (kEpiWarp0 + EW) * 32;
     static constexpr int RING = kSmemBudget - STAGE_BYTES - X_STAGES * X_STAGE_BYTES;
@@ -108,12 +121,13 @@ struct __align__(8) Barriers2 {
     uint32_t tmem_base;
 };
 
-template <int C, int WIMG, int ACT, int EW, bool HS>
+// tiles_per_img: 128-pixel tiles per image (HALO: 16-row bands = pairs per image)
+template <int C, int WIMG, int ACT, int EW, bool HS, bool HALO>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((kEpiWarp0 + EW) * 32, 1)
 conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_w,
                     const EpiParams epi, const int H, const int num_pairs, const int tiles_per_img,
                     const uint32_t backoff_ns, const int role_shift, const int uniform_issue) {
-    using G = Geom2<C, WIMG, EW, HS>;
+    using G = Geom2<C, WIMG, EW, HS, HALO>;
     constexpr int CHUNKS = C / 64;
     constexpr int kWStages = G::W_STAGES, kXStages = G::X_STAGES, kAccBufs = G::ACC_BUFS;
     constexpr int NG = C / 32, WPT = 4 * NG, TG = EW / WPT;            // epilogue: channel groups, warps per tile, tile groups
@@ -168,6 +182,21 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
         if (lane == 0) {
             int st = 0; uint32_t ph = 0;
             for (int pr = cluster_id; pr < num_pairs; pr += num_clusters) {
+                if constexpr (HALO) {
+                    // one box per plane and chunk: image rows h0 - 1 .. h0 + 16, pixels 8 rank - 1 .. 8 rank + 8 (zero fill outside)
+                    const int n = pr / tiles_per_img;
+                    const int h0 = (pr - n * tiles_per_img) * G::ROWS;
+                    for (int chunk = 0; chunk < CHUNKS; ++chunk) {
+                        ptx::mbar_wait(&bars->x_empty[st], ph ^ 1);
+                        const uint32_t full = ptx::mapa(ptx::smem_u32(&bars->x_full[st]), 0);
+                        if (leader) ptx::mbar_arrive_expect_tx(&bars->x_full[st], 2 * 2 * (G::ROWS + 2) * G::ROW_BYTES);
+                        uint8_t* dst = smem_x + st * G::X_STAGE_BYTES;
+                        ptx::tma_load_5d_2sm(dst, &tmap_act, full, chunk * 64, (int)rank * G::TILE_W - 1, 0, h0 - 1, n);
+                        ptx::tma_load_5d_2sm(dst + G::PLANE_BYTES, &tmap_act, full, chunk * 64, (int)rank * G::TILE_W - 1, 1, h0 - 1, n);
+                        if (++st == kXStages) { st = 0; ph ^= 1; }
+                    }
+                    continue;
+                }
                 const int tile = 2 * pr + (int)rank;
                 const int n = tile / tiles_per_img;
                 const int h0 = (tile - n * tiles_per_img) * G::ROWS;
@@ -244,9 +273,11 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
                 uint32_t accumulate = 0;
                 for (int chunk = 0; chunk < CHUNKS; ++chunk)
                     for (int s = 0; s < 3; ++s) {
-                        TCP2_WAIT(&bars->x_full[xst], xph, 1);
-                        ptx::tc_fence_after();
-                        const uint32_t x_base = xs_u32 + (uint32_t)(xst * G::X_STAGE_BYTES);
+                        if (!HALO || s == 0) {                 // HALO: one staged tile per chunk serves the three horizontal taps
+                            TCP2_WAIT(&bars->x_full[xst], xph, 1);
+                            ptx::tc_fence_after();
+                        }
+                        const uint32_t x_base = xs_u32 + (uint32_t)(xst * G::X_STAGE_BYTES) + (HALO ? (uint32_t)s * 128u : 0u);
                         for (int r = 0; r < 3; ++r) {
                             if (G::RES) wst = r * 3 + s;
                             else { TCP2_WAIT(&bars->w_full[wst], wph, 0); ptx::tc_fence_after(); }
@@ -256,9 +287,9 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
                                 for (int k = 0; k < 4; ++k) {
                                     const uint64_t wa = ptx::make_smem_desc_sw128(w_base + k * 32, 16, 1024);
                                     const uint64_t wb = ptx::make_smem_desc_sw128(w_base + (G::RES ? G::WA_BYTES : 0) + k * 32, 16, 1024);
-                                    const uint64_t xhi = ptx::make_smem_desc_sw128(x_base + r * G::ROW_BYTES + k * 32, 16, 1024);
+                                    const uint64_t xhi = ptx::make_smem_desc_sw128(x_base + r * G::ROW_BYTES + k * 32, 16, G::A_SBO);
                                     const uint64_t xlo =
-                                        ptx::make_smem_desc_sw128(x_base + G::PLANE_BYTES + r * G::ROW_BYTES + k * 32, 16, 1024);
+                                        ptx::make_smem_desc_sw128(x_base + G::PLANE_BYTES + r * G::ROW_BYTES + k * 32, 16, G::A_SBO);
                                     ptx::umma_bf16_2sm(d_tmem, xhi, wa, idesc_full, (k == 0) ? accumulate : 1u);
                                     ptx::umma_bf16_2sm(d_tmem, xlo, wb, idesc_hi, 1u);
                                 }
@@ -267,8 +298,10 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
                             accumulate = 1;
                             if (!G::RES) { if (++wst == kWStages) { wst = 0; wph ^= 1; } }
                         }
-                        if (el) ptx::umma_commit_2sm(&bars->x_empty[xst]);
-                        if (++xst == kXStages) { xst = 0; xph ^= 1; }
+                        if (!HALO || s == 2) {
+                            if (el) ptx::umma_commit_2sm(&bars->x_empty[xst]);
+                            if (++xst == kXStages) { xst = 0; xph ^= 1; }
+                        }
                     }
                 if (el) ptx::umma_commit_2sm(&bars->tmem_full[acc]);
                 if (++acc == kAccBufs) { acc = 0; acc_ph ^= 1; }
@@ -301,10 +334,21 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
         const size_t plane_stride = (size_t)WIMG * C;
         const int tg = we / WPT, wi = we % WPT;
         const int cb = (wi >> 2) * 32;
+        // first global image row (n * H + h) of this CTA's tile of pair `pr`, its image, and pixel pp (0..127 = TMEM lane) of a tile
         auto row0_of = [&](int pr) {
-            const int t = 2 * pr + (int)rank;
-            const int n = t / tiles_per_img;
-            return (size_t)n * H + (size_t)(t - n * tiles_per_img) * G::ROWS;
+            if constexpr (HALO) {
+                const int n = pr / tiles_per_img;
+                return (size_t)n * H + (size_t)(pr - n * tiles_per_img) * G::ROWS;
+            } else {
+                const int t = 2 * pr + (int)rank;
+                const int n = t / tiles_per_img;
+                return (size_t)n * H + (size_t)(t - n * tiles_per_img) * G::ROWS;
+            }
+        };
+        auto img_of = [&](int pr) { return HALO ? pr / tiles_per_img : (2 * pr + (int)rank) / tiles_per_img; };
+        auto pix_rc = [&](int pp, int& r2, int& w2) {
+            r2 = pp / G::TILE_W;
+            w2 = pp - r2 * G::TILE_W + (HALO ? (int)rank * G::TILE_W : 0);
         };
         if constexpr (G::RES) {
             // ---- resident-weight variant: 8 warps, 2 KB stage per warp, 16 pixels transposed at a time ----
@@ -327,7 +371,7 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
             for (; pr < num_pairs; pr += num_clusters, ++it) {
                 const int acc = it % kAccBufs;
                 const uint32_t ph = (uint32_t)(it / kAccBufs) & 1u;
-                const EpiCoef coef = epi_coef(epi, (2 * pr + (int)rank) / tiles_per_img);
+                const EpiCoef coef = epi_coef(epi, img_of(pr));
                 const size_t row0 = row0_of(pr);
                 ptx::mbar_wait_backoff(&bars->tmem_full[acc], ph, backoff_ns);
                 ptx::tc_fence_after();
@@ -392,7 +436,8 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
         const int k4 = lane & 3, quad = lane >> 2;
         auto owned = [&](size_t row0, int sidx_step, size_t& idx, size_t& sidx) {
             const int pp = q * 32 + 16 * (sidx_step >> 1) + quad * 2 + (sidx_step & 1);
-            const int r2 = pp / WIMG, w2 = pp - r2 * WIMG;
+            int r2, w2;
+            pix_rc(pp, r2, w2);
             idx = ((row0 + r2) * WIMG + w2) * C + cb + 8 * k4;
             sidx = ((row0 + r2) * 2) * plane_stride + (size_t)w2 * C + cb + 8 * k4;
         };
@@ -403,7 +448,7 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
         for (; pr < num_pairs; pr += TG * num_clusters, it += TG) {
             const int acc = it % kAccBufs;
             const uint32_t ph = (uint32_t)(it / kAccBufs) & 1u;
-            const EpiCoef coef = epi_coef(epi, (2 * pr + (int)rank) / tiles_per_img);
+            const EpiCoef coef = epi_coef(epi, img_of(pr));
             const size_t row0 = row0_of(pr);
             ptx::mbar_wait_backoff(&bars->tmem_full[acc], ph, backoff_ns);
             ptx::tc_fence_after();
@@ -461,7 +506,8 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
         const int k4 = lane & 3, quad = lane >> 2;
         auto owned = [&](size_t row0, int j, size_t& idx, size_t& sidx) {
             const int pp = q * 32 + quad * 4 + j;
-            const int r2 = pp / WIMG, w2 = pp - r2 * WIMG;
+            int r2, w2;
+            pix_rc(pp, r2, w2);
             idx = ((row0 + r2) * WIMG + w2) * C + cb + 8 * k4;
             sidx = ((row0 + r2) * 2) * plane_stride + (size_t)w2 * C + cb + 8 * k4;
         };
@@ -472,7 +518,7 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
         for (; pr < num_pairs; pr += TG * num_clusters, it += TG) {
             const int acc = it % kAccBufs;
             const uint32_t ph = (uint32_t)(it / kAccBufs) & 1u;
-            const EpiCoef coef = epi_coef(epi, (2 * pr + (int)rank) / tiles_per_img);
+            const EpiCoef coef = epi_coef(epi, img_of(pr));
             const size_t row0 = row0_of(pr);
             ptx::mbar_wait_backoff(&bars->tmem_full[acc], ph, backoff_ns);
             ptx::tc_fence_after();
@@ -541,23 +587,23 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
     }
 }
 
-template <int C, int WIMG, int ACT, int EW, bool HS = false>
+template <int C, int WIMG, int ACT, int EW, bool HS = false, bool HALO = false>
 int launch_act_ew(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, const EpiParams& epi, ConvShape s,
                   cudaStream_t st) {
-    using G = Geom2<C, WIMG, EW, HS>;
+    using G = Geom2<C, WIMG, EW, HS, HALO>;
     constexpr int kThreads = G::THREADS;
     CUtensorMap tm_act, tm_w;
-    if (make_tmap_split_plane(&tm_act, split_in, s.B, s.H, s.W, s.C, WIMG, G::ROWS + 2)) return -1;
+    if (make_tmap_split_plane(&tm_act, split_in, s.B, s.H, s.W, s.C, G::BOX_W, G::ROWS + 2)) return -1;
     if (make_tmap_rows64(&tm_w, w_tiles, tcp_packed_weight_bytes(C) / 128, C / 2)) return -1;
     constexpr size_t smem = (size_t)G::X_STAGES * G::X_STAGE_BYTES + (size_t)G::W_STAGES * G::W_STAGE_BYTES + G::STAGE_BYTES +
                             sizeof(Barriers2) + 1024;
     static_assert(smem <= 232448, "shared memory per CTA");
-    auto kern = conv3x3_tcp2_kernel<C, WIMG, ACT, EW, HS>;
+    auto kern = conv3x3_tcp2_kernel<C, WIMG, ACT, EW, HS, HALO>;
     if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                    "cudaFuncSetAttribute(conv3x3_tcp2)"))
         return -1;
-    const int tiles_per_img = s.H / G::ROWS;
-    const int num_pairs = s.B * tiles_per_img / 2;
+    const int tiles_per_img = s.H / G::ROWS;                                        // HALO: bands = pairs per image
+    const int num_pairs = HALO ? s.B * tiles_per_img : s.B * tiles_per_img / 2;
     const int clusters = std::min(num_pairs, num_sms() / 2);
     const cudaError_t le = launch_maybe_pdl(kern, 2 * clusters, kThreads, smem, st, tm_act, tm_w, epi, s.H, num_pairs,
                                             tiles_per_img, (uint32_t)tune_get(TUNE_WAIT_BACKOFF), tune_get(TUNE_MMA_WARP_HIGH) ? kEpiWarp0 : 0,
@@ -571,6 +617,12 @@ int launch_act(const __nv_bfloat16* split_in, const __nv_bfloat16* w_tiles, cons
                cudaStream_t st) {
     if constexpr (C == 64) {
         if (tune_get(TUNE_TCP_EPI_WARPS) == 8) return launch_act_ew<C, WIMG, ACT, 8>(split_in, w_tiles, epi, s, st);
+    }
+    if constexpr (C == 128 && WIMG == 16) {
+        if (tune_get(TUNE_TCP2_HALO) && s.H % 16 == 0) {
+            if (tune_get(TUNE_TCP2_HALF_STAGE)) return launch_act_ew<C, WIMG, ACT, 16, true, true>(split_in, w_tiles, epi, s, st);
+            return launch_act_ew<C, WIMG, ACT, 16, false, true>(split_in, w_tiles, epi, s, st);
+        }
     }
     if constexpr (C == 128) {
         if (tune_get(TUNE_TCP2_HALF_STAGE)) return launch_act_ew<C, WIMG, ACT, 16, true>(split_in, w_tiles, epi, s, st);

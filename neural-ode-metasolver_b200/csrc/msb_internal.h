@@ -35,7 +35,13 @@ enum { TUNE_EPI_L2_PREFETCH = 0,   // conv epilogue operands: bulk L2 prefetch d
                                    // bit 1 = weight gradient (default off: no gain measured)
        TUNE_GN_BLOCK = 15,         // GroupNorm of large states (CIFAR GN / LN / IN right-hand sides): one CTA per sample (1, default)
                                    // or the warp-per-(sample, group) kernels written for the MNIST state (0)
-       TUNE_TCP2_HALF_STAGE = 16,  // C = 128 CTA-pair conv: half-size epilogue stage (two passes) + a third activation stage
+       TUNE_TCP2_HALF_STAGE = 16,  // C = 128 CTA-pair conv: half-size epilogue stage (two passes) + a third activation stage (halo form:
+                                   // + two more weight stages); default 0 since the halo form removed the activation waits it was for
+       TUNE_TCP2_HALO = 17,        // C = 128, 16-pixel-wide images: one staged halo tile per c_in chunk serves all nine taps (1, default)
+       TUNE_WGRAD_HTAPS = 18,      // weight gradient: a CTA owns a vertical tap, the three horizontal taps are N atoms 128 B apart
+                                   // in one staged copy (1) or a CTA owns a horizontal tap with its own shifted box (0, default:
+                                   // the 34-pixel box of the C = 64 form loads slowly -- 180 vs 113 us -- although it moves 17 % fewer
+                                   // bytes; C = 128 is neutral; profiles/ncu_wgrad_htaps_r2.txt)
        TUNE_COUNT };
 int tune_get(int which);
 

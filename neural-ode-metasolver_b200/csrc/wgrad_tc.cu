@@ -29,26 +29,50 @@ int make_tmap_split5d(CUtensorMap* m, const void* base, int B, int H, int W, int
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kStages = 2;
+constexpr int kMaxStages = 4;
 constexpr uint32_t kTmemCols = 256;
 
-template <int C, int WIMG> struct WG {
+// HT ("horizontal taps on N"; everything but the role-swapped C = 64 three-product option): a CTA owns one VERTICAL tap r and
+// the N = 192 operand is the three HORIZONTAL taps -- three 64-channel atoms ONE PIXEL (LBO = 128 B) apart in a single staged
+// copy of the image rows with a halo pixel each side.  tcgen05.mma reads a swizzled operand from any 128-byte row offset
+// (scripts/probes/mma_rowshift_probe.cu, tests 2 and 4), so the staged `in` box is ROWS x (W + 2) pixels instead of
+// (ROWS + 2) x W: 34 816 instead of 49 152 bytes per tile at C = 64 -- the kernel is bound by L2 -> SM operand traffic -- and
+// three ring stages fit where two did.  Round 1 / HT = false: a CTA owns one horizontal tap s (its own shifted box), the three
+// atoms are the vertical taps, one image row (LBO = a row pair) apart.
+// MEASURED (option wgrad_htaps, default 0): results identical, L2 -> SM bytes 1021 -> 845 MB per C = 64 launch as designed, but
+// the launch takes 180 us instead of 113 (tensor pipe 43 % active instead of 74 %; same shared-memory wavefronts): the
+// 34-pixel-wide box, which overhangs the 32-pixel tensor on both sides, is delivered far more slowly by TMA than the 32-pixel
+// boxes whose (row, plane) lines are contiguous 4 KB runs.  C = 128 (18-pixel boxes of strided 128-byte pieces either way) is
+// neutral.  Kept as an option; the default stays the round-1 geometry.
+template <int C, int WIMG, bool HT> struct WG {
     static constexpr int ROWS = 128 / WIMG;
     static constexpr int CO_CHUNKS = C / 64;
     static constexpr int CI_CHUNKS = C / 64;
     static constexpr int GROUPS = 3 * CI_CHUNKS;
     static constexpr int GO_CHUNK_BYTES = ROWS * 2 * WIMG * 128;          // one 64-channel box of gout
     static constexpr int GO_BYTES = CO_CHUNKS * GO_CHUNK_BYTES;
-    static constexpr int IN_BYTES = (ROWS + 2) * 2 * WIMG * 128;          // halo box of in
-    static constexpr int STAGE_BYTES = GO_BYTES + IN_BYTES;
-    static constexpr int ROW_PAIR_BYTES = 2 * WIMG * 128;
+    static constexpr int ROW_PAIR_BYTES = 2 * WIMG * 128;                 // gout: [row][plane][pixel]
     static constexpr int PLANE_BYTES = WIMG * 128;
+    static constexpr int IN_W = HT ? WIMG + 2 : WIMG;                     // staged pixels per image row of `in`
+    static constexpr int IN_ROWS = HT ? ROWS : ROWS + 2;
+    static constexpr int IN_PLANE_BYTES = IN_W * 128;
+    static constexpr int IN_ROW_PAIR_BYTES = 2 * IN_PLANE_BYTES;
+    static constexpr int IN_BYTES = IN_ROWS * IN_ROW_PAIR_BYTES;
+    static_assert(IN_BYTES % 1024 == 0, "stage bases must stay 1024-byte aligned");
+    static constexpr int STAGE_BYTES = GO_BYTES + IN_BYTES;
+#ifdef MSB_WGRAD_STAGES_CAP
+    static constexpr int STAGES = (225 * 1024 / STAGE_BYTES) > MSB_WGRAD_STAGES_CAP ? MSB_WGRAD_STAGES_CAP : (225 * 1024 / STAGE_BYTES);
+#else
+    static constexpr int STAGES = (225 * 1024 / STAGE_BYTES) > kMaxStages ? kMaxStages : (225 * 1024 / STAGE_BYTES);
+#endif
+    static_assert(STAGES >= 2, "operand ring");
+    static constexpr int B_LBO = HT ? 128 : IN_ROW_PAIR_BYTES;            // stride between the three N atoms
     static constexpr int HALVES = (C == 64) ? 2 : 1;                      // partial slices written per CTA
 };
 
 struct __align__(8) WBarriers {
-    uint64_t full[kStages], empty[kStages];
-    uint64_t gempty[kStages];          // cluster form, rank 0: every CTA of the cluster has released the stage
+    uint64_t full[kMaxStages], empty[kMaxStages];
+    uint64_t gempty[kMaxStages];       // cluster form, rank 0: every CTA of the cluster has released the stage
     uint64_t done;
     uint32_t tmem_base;
 };
@@ -57,12 +81,14 @@ struct __align__(8) WBarriers {
 // the gout box, identical for all of them, is loaded ONCE by rank 0 and multicast into every CTA's stage.  ncu had the
 // kernel at 91 % of the L2 slice throughput cap (983 MB of L2 -> SM traffic per C = 64 launch, 9.4 TB/s): it was
 // L2-bound, and a third (C = 64) / half (C = 128) of that traffic was the same gout tile fetched by each group's CTA.
-template <int C, int WIMG, bool MC, bool P3>
+template <int C, int WIMG, bool MC, bool P3, bool HT>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_go, const __grid_constant__ CUtensorMap tmap_in,
                    float* __restrict__ partial, const int num_tiles, const int tiles_per_img, const int nparts,
                    const int accumulate_partial, const uint32_t backoff_ns, const int uniform_issue) {
-    using G = WG<C, WIMG>;
+    static_assert(!(HT && C == 64 && P3), "the role-swapped three-product form keeps the vertical taps on its operand");
+    using G = WG<C, WIMG, HT>;
+    constexpr int kStages = G::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     WBarriers* bars = reinterpret_cast<WBarriers*>(smem + kStages * G::STAGE_BYTES);
@@ -73,7 +99,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_go, const __grid_con
     const int group = MC ? (int)(blockIdx.x % G::GROUPS) : (int)(blockIdx.x / nparts);
     const int part = MC ? (int)(blockIdx.x / G::GROUPS) : (int)(blockIdx.x - group * nparts);
     constexpr uint16_t kAllCtas = (uint16_t)((1u << G::GROUPS) - 1);
-    const int s = group % 3;
+    const int s = group % 3;            // the tap index this CTA owns: horizontal (HT = false) or VERTICAL (HT = true)
     const int ci_chunk = group / 3;
 
     if (warp == 0 && lane == 0) {
@@ -116,7 +142,8 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_go, const __grid_con
                 } else
                 for (int cc = 0; cc < G::CO_CHUNKS; ++cc)
                     ptx::tma_load_5d(stage + cc * G::GO_CHUNK_BYTES, &tmap_go, &bars->full[st], cc * 64, 0, 0, h0, n);
-                ptx::tma_load_5d(stage + G::GO_BYTES, &tmap_in, &bars->full[st], ci_chunk * 64, s - 1, 0, h0 - 1, n);
+                if (HT) ptx::tma_load_5d(stage + G::GO_BYTES, &tmap_in, &bars->full[st], ci_chunk * 64, -1, 0, h0 - 1 + s, n);
+                else ptx::tma_load_5d(stage + G::GO_BYTES, &tmap_in, &bars->full[st], ci_chunk * 64, s - 1, 0, h0 - 1, n);
                 if (++st == kStages) { st = 0; ph ^= 1; }
             }
         }
@@ -188,7 +215,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_go, const __grid_con
                                     for (int pb = 0; pb < 2; ++pb) {
                                         if (C != 64 && pa == 1 && pb == 1) continue;   // lo x lo (2^-18 relative) is dropped
                                         const uint64_t bdesc = ptx::make_smem_desc_sw128(
-                                            in_base + rho * G::ROW_PAIR_BYTES + pb * G::PLANE_BYTES + px_off, G::ROW_PAIR_BYTES, 1024);
+                                            in_base + rho * G::IN_ROW_PAIR_BYTES + pb * G::IN_PLANE_BYTES + px_off, G::B_LBO, 1024);
                                         ptx::umma_bf16(tb, adesc, bdesc, idesc, (rho | wg | pa | pb) ? 1u : accumulate);
                                     }
                                 }
@@ -259,8 +286,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_go, const __grid_con
             float v[16];
             ptx::tmem_ld16(t_addr + cb, v);
             ptx::tmem_ld_wait();
-            const int r = cb >> 6;
-            const int tap = r * 3 + s;
+            const int tap = HT ? s * 3 + (cb >> 6) : (cb >> 6) * 3 + s;      // column block = the tap the N atom carries
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const int ci = ci_chunk * 64 + (cb & 63) + j;
@@ -281,7 +307,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_go, const __grid_con
 
 template <int C, int WIMG>
 int nparts_impl(ConvShape s) {
-    using G = WG<C, WIMG>;
+    using G = WG<C, WIMG, true>;
     const int num_tiles = s.B * (s.H / G::ROWS);
     int np = num_sms() / G::GROUPS;
     if (np > num_tiles) np = num_tiles;
@@ -289,18 +315,31 @@ int nparts_impl(ConvShape s) {
     return np;
 }
 
+template <int C, int WIMG, bool HT>
+int launch_geom(const __nv_bfloat16* gout, const __nv_bfloat16* in, float* partial, int* nparts_out, int accumulate,
+                ConvShape s, cudaStream_t st, bool mc, bool p3);
+
 template <int C, int WIMG>
 int launch_impl(const __nv_bfloat16* gout, const __nv_bfloat16* in, float* partial, int* nparts_out, int accumulate,
                 ConvShape s, cudaStream_t st) {
-    using G = WG<C, WIMG>;
-    CUtensorMap tm_go, tm_in;
-    if (make_tmap_split5d(&tm_go, gout, s.B, s.H, s.W, s.C, WIMG, G::ROWS)) return -1;
-    if (make_tmap_split5d(&tm_in, in, s.B, s.H, s.W, s.C, WIMG, G::ROWS + 2)) return -1;
-    const size_t smem = (size_t)kStages * G::STAGE_BYTES + sizeof(WBarriers) + 1024;
     const bool mc = tune_get(TUNE_WGRAD_MULTICAST) != 0;
     const bool p3 = C != 64 || tune_get(TUNE_WGRAD64_PRODUCTS) == 3;
-    auto kern = mc ? (p3 ? wgrad3x3_tc_kernel<C, WIMG, true, true> : wgrad3x3_tc_kernel<C, WIMG, true, false>)
-                   : (p3 ? wgrad3x3_tc_kernel<C, WIMG, false, true> : wgrad3x3_tc_kernel<C, WIMG, false, false>);
+    if ((C == 64 && p3) || !tune_get(TUNE_WGRAD_HTAPS)) return launch_geom<C, WIMG, false>(gout, in, partial, nparts_out, accumulate, s, st, mc, p3);
+    return launch_geom<C, WIMG, true>(gout, in, partial, nparts_out, accumulate, s, st, mc, p3);
+}
+
+template <int C, int WIMG, bool HT>
+int launch_geom(const __nv_bfloat16* gout, const __nv_bfloat16* in, float* partial, int* nparts_out, int accumulate,
+                ConvShape s, cudaStream_t st, bool mc, bool p3) {
+    using G = WG<C, WIMG, HT>;
+    CUtensorMap tm_go, tm_in;
+    if (make_tmap_split5d(&tm_go, gout, s.B, s.H, s.W, s.C, WIMG, G::ROWS)) return -1;
+    if (make_tmap_split5d(&tm_in, in, s.B, s.H, s.W, s.C, G::IN_W, G::IN_ROWS)) return -1;
+    const size_t smem = (size_t)G::STAGES * G::STAGE_BYTES + sizeof(WBarriers) + 1024;
+    // (HT never meets the role-swapped C = 64 three-product kernel: launch_impl sends that option to HT = false)
+    constexpr bool kSwapOk = !(HT && C == 64);
+    auto kern = mc ? ((p3 && kSwapOk) ? wgrad3x3_tc_kernel<C, WIMG, true, kSwapOk, HT> : wgrad3x3_tc_kernel<C, WIMG, true, false, HT>)
+                   : ((p3 && kSwapOk) ? wgrad3x3_tc_kernel<C, WIMG, false, kSwapOk, HT> : wgrad3x3_tc_kernel<C, WIMG, false, false, HT>);
     if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                    "cudaFuncSetAttribute(wgrad3x3_tc)"))
         return -1;

@@ -26,8 +26,10 @@ def step():
     blk(x, [s], Namespace(solver_mode="standalone")).sum().backward()
 
 
+import itertools
 for rep in range(3):
-    for hs in (0, 1):
+    for halo, hs in itertools.product((0, 1), (0, 1)):
+        msb.set_option("tcp2_halo", halo)
         msb.set_option("tcp2_half_stage", hs)
         for _ in range(2):
             step()
@@ -38,4 +40,4 @@ for rep in range(3):
         ms, fl, n = msb.profile_read(0)
         wms, wfl, wn = msb.profile_read(1)
         msb.profile_enable(False)
-        print("half_stage=%d  conv: %d launches avg %.1f us   wgrad: %d avg %.1f us" % (hs, n, ms / max(n, 1) * 1e3, wn, wms / max(wn, 1) * 1e3), flush=True)
+        print("halo=%d half_stage=%d  conv: %d launches avg %.1f us   wgrad: %d avg %.1f us" % (halo, hs, n, ms / max(n, 1) * 1e3, wn, wms / max(wn, 1) * 1e3), flush=True)
