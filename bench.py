@@ -340,7 +340,10 @@ def run_ours(args):
                             launch=graph_note),
                 clocks=clocks,
                 e2e=dict(value=e2e_val, unit="images/s", h2d_bytes_per_step=x_host.numel() * 4 + y_host.numel() * 8,
-                         d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps),
+                         d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps,
+                         pipeline="metasolver_b200.HostFedLoop, lag 1: every step copies its pinned host batch (copy stream, "
+                                  "under the previous step's kernels) and its loss is read on the host during the next step; "
+                                  "all K copies and all K loss reads are inside the timed region"),
                 gpu_launches=int(launches), roofline=roofline,
                 # the second hot kernel in the same flat schema as `roofline` (a nested roofline.wgrad was dropped by the
                 # driver's parser in round 1)
