@@ -40,8 +40,8 @@ enum { TUNE_EPI_L2_PREFETCH = 0,   // conv epilogue operands: bulk L2 prefetch d
        TUNE_TCP2_HALO = 17,        // C = 128, 16-pixel-wide images: one staged halo tile per c_in chunk serves all nine taps (1, default)
        TUNE_WGRAD_HTAPS = 18,      // weight gradient: a CTA owns a vertical tap, the three horizontal taps are N atoms 128 B apart
                                    // in one staged copy (1) or a CTA owns a horizontal tap with its own shifted box (0, default:
-                                   // the 34-pixel box of the C = 64 form loads slowly -- 180 vs 113 us -- although it moves 17 % fewer
-                                   // bytes; C = 128 is neutral; profiles/ncu_wgrad_htaps_r2.txt)
+                                   // C = 64 runs 180 vs 113 us although it moves 17 % fewer bytes, cause not identified; C = 128 is
+                                   // neutral; profiles/ncu_wgrad_htaps_r2.txt)
        TUNE_COUNT };
 int tune_get(int which);
 

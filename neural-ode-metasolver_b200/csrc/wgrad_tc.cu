@@ -40,10 +40,10 @@ constexpr uint32_t kTmemCols = 256;
 // three ring stages fit where two did.  Round 1 / HT = false: a CTA owns one horizontal tap s (its own shifted box), the three
 // atoms are the vertical taps, one image row (LBO = a row pair) apart.
 // MEASURED (option wgrad_htaps, default 0): results identical, L2 -> SM bytes 1021 -> 845 MB per C = 64 launch as designed, but
-// the launch takes 180 us instead of 113 (tensor pipe 43 % active instead of 74 %; same shared-memory wavefronts): the
-// 34-pixel-wide box, which overhangs the 32-pixel tensor on both sides, is delivered far more slowly by TMA than the 32-pixel
-// boxes whose (row, plane) lines are contiguous 4 KB runs.  C = 128 (18-pixel boxes of strided 128-byte pieces either way) is
-// neutral.  Kept as an option; the default stays the round-1 geometry.
+// the launch takes 180 us instead of 113 (tensor pipe 43 % active instead of 74 %; same shared-memory wavefronts, no bank
+// conflicts in ncu).  Not the shape of the TMA box: filling the staged lines with one in-bounds 32-pixel box per (row, plane)
+// at a 128-byte offset (which works -- TMA swizzles by absolute address too) and zeroing the halo slots once gave the same
+// 200 us.  C = 128 is neutral.  Cause not identified; kept as an option, the default stays the round-1 geometry.
 template <int C, int WIMG, bool HT> struct WG {
     static constexpr int ROWS = 128 / WIMG;
     static constexpr int CO_CHUNKS = C / 64;
