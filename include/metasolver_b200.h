@@ -300,6 +300,9 @@ int msb_cross_entropy_backward(const float* logits, const int64_t* labels, const
  *   "uniform_issue"    warp-uniform MMA issue loops: bit 0 = CTA-pair convolution (default on), bit 1 = weight gradient
  *   "gn_block"         1 (default) = GroupNorm of large states (CIFAR 'GN' / 'LN' / 'IN' right-hand sides) as one CTA per
  *                      sample; 0 = the warp-per-(sample, group) kernels of the MNIST state      (env MSB_GN_BLOCK)
+ *   "wgrad_htaps"      1 (default) = weight gradient with one vertical tap per CTA and the three horizontal taps as N atoms
+ *                      128 B apart in ONE staged copy of the input rows; 0 = one horizontal tap per CTA with its own shifted
+ *                      copy (round 1)                                     (env MSB_WGRAD_HTAPS)
  *   "tcp2_halo"        1 (default) = C = 128 convolution on 16-pixel-wide images stages ONE halo tile per c_in chunk for all
  *                      nine taps (horizontal taps = the same tile read 128 B further); 0 = three shifted copies (env MSB_TCP2_HALO)
  *   "tcp2_half_stage"  1 = half-size epilogue stage of the C = 128 pair convolution, the memory going to deeper operand rings

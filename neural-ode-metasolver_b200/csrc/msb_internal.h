@@ -39,9 +39,8 @@ enum { TUNE_EPI_L2_PREFETCH = 0,   // conv epilogue operands: bulk L2 prefetch d
                                    // + two more weight stages); default 0 since the halo form removed the activation waits it was for
        TUNE_TCP2_HALO = 17,        // C = 128, 16-pixel-wide images: one staged halo tile per c_in chunk serves all nine taps (1, default)
        TUNE_WGRAD_HTAPS = 18,      // weight gradient: a CTA owns a vertical tap, the three horizontal taps are N atoms 128 B apart
-                                   // in one staged copy (1) or a CTA owns a horizontal tap with its own shifted box (0, default:
-                                   // C = 64 runs 180 vs 113 us although it moves 17 % fewer bytes, cause not identified; C = 128 is
-                                   // neutral; profiles/ncu_wgrad_htaps_r2.txt)
+                                   // in one staged copy (1, default: -17 % L2 -> SM bytes, C = 64 launch -10 % under the power cap) or
+                                   // a CTA owns a horizontal tap with its own shifted box (0, round 1)
        TUNE_COUNT };
 int tune_get(int which);
 

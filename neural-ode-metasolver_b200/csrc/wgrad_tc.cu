@@ -22,6 +22,20 @@
 #include "msb_internal.h"
 #include "msb_ptx.cuh"
 
+#ifdef MSB_CONV_DEBUG
+// instrumented build: clocks summed over CTAs -- [0] MMA warp waiting for a full stage, [1] its whole loop, [2] producer waiting
+// for an empty stage, [3] kernel entry -> MMA loop start, [4] MMA loop end -> exit, [5] CTAs
+static __device__ unsigned long long g_wgrad_dbg[8];
+extern "C" int msb_debug_wgrad_read(unsigned long long* out8, int reset) {
+    if (out8 && cudaMemcpyFromSymbol(out8, g_wgrad_dbg, sizeof(g_wgrad_dbg)) != cudaSuccess) return -1;
+    if (reset) {
+        unsigned long long zero[8] = {0};
+        if (cudaMemcpyToSymbol(g_wgrad_dbg, zero, sizeof(zero)) != cudaSuccess) return -1;
+    }
+    return 0;
+}
+#endif
+
 namespace msb {
 
 int make_tmap_split5d(CUtensorMap* m, const void* base, int B, int H, int W, int C, int box_w, int box_h);
@@ -39,11 +53,11 @@ constexpr uint32_t kTmemCols = 256;
 // (ROWS + 2) x W: 34 816 instead of 49 152 bytes per tile at C = 64 -- the kernel is bound by L2 -> SM operand traffic -- and
 // three ring stages fit where two did.  Round 1 / HT = false: a CTA owns one horizontal tap s (its own shifted box), the three
 // atoms are the vertical taps, one image row (LBO = a row pair) apart.
-// MEASURED (option wgrad_htaps, default 0): results identical, L2 -> SM bytes 1021 -> 845 MB per C = 64 launch as designed, but
-// the launch takes 180 us instead of 113 (tensor pipe 43 % active instead of 74 %; same shared-memory wavefronts, no bank
-// conflicts in ncu).  Not the shape of the TMA box: filling the staged lines with one in-bounds 32-pixel box per (row, plane)
-// at a 128-byte offset (which works -- TMA swizzles by absolute address too) and zeroing the halo slots once gave the same
-// 200 us.  C = 128 is neutral.  Cause not identified; kept as an option, the default stays the round-1 geometry.
+// MEASURED (option wgrad_htaps, default 1): identical results, L2 -> SM bytes 1021 -> 845 MB per C = 64 launch, the issuing
+// warp's wait for full stages 29 % -> 12 % of its loop, MMA loop 163k -> 132k clocks per launch (scripts/diag_wgrad_waits.py);
+// 142 -> 128 us per launch in the power-capped steady state (scripts/wgrad_htaps_ab.py).  C = 128 is neutral.  (The first
+// measurement had it at 180 us: in that instantiation the compiler serialised the final accumulate-into-the-partial pass,
+// see the comment there.)
 template <int C, int WIMG, bool HT> struct WG {
     static constexpr int ROWS = 128 / WIMG;
     static constexpr int CO_CHUNKS = C / 64;
@@ -95,6 +109,10 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_go, const __grid_con
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+#ifdef MSB_CONV_DEBUG
+    __shared__ long long dbg_entry, dbg_loop_end, dbg_epi_start;
+    if (threadIdx.x == 0) dbg_entry = clock64();
+#endif
     // plain launch: blocks [group][part]; cluster launch: blocks [part][group] so that a cluster = the groups of one part
     const int group = MC ? (int)(blockIdx.x % G::GROUPS) : (int)(blockIdx.x / nparts);
     const int part = MC ? (int)(blockIdx.x / G::GROUPS) : (int)(blockIdx.x - group * nparts);
@@ -130,7 +148,11 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_go, const __grid_con
                 const int n = tile / tiles_per_img;
                 const int h0 = (tile - n * tiles_per_img) * G::ROWS;
                 uint8_t* stage = smem + st * G::STAGE_BYTES;
+#ifdef MSB_CONV_DEBUG
+                { const long long t = clock64(); ptx::mbar_wait(&bars->empty[st], ph ^ 1); atomicAdd(&g_wgrad_dbg[2], (unsigned long long)(clock64() - t)); }
+#else
                 ptx::mbar_wait(&bars->empty[st], ph ^ 1);
+#endif
                 ptx::mbar_arrive_expect_tx(&bars->full[st], G::STAGE_BYTES);
                 if (MC) {
                     if (group == 0) {            // (group == cluster rank) one gout load for the whole cluster
@@ -196,8 +218,16 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_go, const __grid_con
                 const uint32_t smem_u = ptx::smem_u32(smem);
                 int st = 0; uint32_t ph = 0;
                 uint32_t accumulate = 0;
+#ifdef MSB_CONV_DEBUG
+                long long dbg_wait = 0;
+                const long long dbg_t0 = clock64();
+#endif
                 for (int tile = part; tile < num_tiles; tile += nparts) {
+#ifdef MSB_CONV_DEBUG
+                    { const long long t = clock64(); ptx::mbar_wait(&bars->full[st], ph); dbg_wait += clock64() - t; }
+#else
                     ptx::mbar_wait(&bars->full[st], ph);
+#endif
                     ptx::tc_fence_after();
                     const uint32_t go_base = smem_u + (uint32_t)(st * G::STAGE_BYTES);
                     const uint32_t in_base = go_base + G::GO_BYTES;
@@ -227,6 +257,14 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_go, const __grid_con
                     if (++st == kStages) { st = 0; ph ^= 1; }
                 }
                 if (el) ptx::umma_commit(&bars->done);
+#ifdef MSB_CONV_DEBUG
+                if (el) {
+                    dbg_loop_end = clock64();
+                    atomicAdd(&g_wgrad_dbg[0], (unsigned long long)dbg_wait);
+                    atomicAdd(&g_wgrad_dbg[1], (unsigned long long)(dbg_loop_end - dbg_t0));
+                    atomicAdd(&g_wgrad_dbg[3], (unsigned long long)(dbg_t0 - dbg_entry));
+                }
+#endif
             };
             if (uniform_issue) {
                 uint32_t e;
@@ -240,6 +278,9 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_go, const __grid_con
         const int q = warp & 3;
         ptx::mbar_wait_backoff(&bars->done, 0, backoff_ns ? 8 * backoff_ns : 0);     // waits for the whole kernel
         ptx::tc_fence_after();
+#ifdef MSB_CONV_DEBUG
+        if (warp == 4 && lane == 0) dbg_epi_start = clock64();
+#endif
         const int row = q * 32 + lane;                       // accumulator row
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         if (C == 64 && P3) {
@@ -287,17 +328,35 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_go, const __grid_con
             ptx::tmem_ld16(t_addr + cb, v);
             ptx::tmem_ld_wait();
             const int tap = HT ? s * 3 + (cb >> 6) : (cb >> 6) * 3 + s;      // column block = the tap the N atom carries
+            float* const q0 = dst + ((size_t)tap * C + ci_chunk * 64 + (cb & 63)) * C + co;      // element j: q0 + j * C
+            // CTA-private slot: deterministic.  All 16 old values are requested before the first store: left to itself the
+            // compiler serialised load -> add -> store per element in one instantiation (it cannot rule out that the stores
+            // alias the later loads), 192 dependent L2 round trips = 131k clocks instead of 11k.
+            if (accumulate_partial) {
+                float old[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int ci = ci_chunk * 64 + (cb & 63) + j;
-                float* q = dst + ((size_t)tap * C + ci) * C + co;
-                *q = accumulate_partial ? *q + v[j] : v[j];        // CTA-private slot: deterministic
+                for (int j = 0; j < 16; ++j) old[j] = __ldcg(q0 + (size_t)j * C);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] += old[j];
             }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) q0[(size_t)j * C] = v[j];
         }
         }
     }
+#ifdef MSB_CONV_DEBUG
+    if (warp == 4 && lane == 0) {      // [6] last MMA issued -> all MMAs complete, [7] the final TMEM -> global pass
+        const long long now = clock64();
+        // dbg_done is only defined inside the branch above: recompute the pieces from shared state
+        atomicAdd(&g_wgrad_dbg[7], (unsigned long long)(now - dbg_epi_start));
+        atomicAdd(&g_wgrad_dbg[6], (unsigned long long)(dbg_epi_start > dbg_loop_end ? dbg_epi_start - dbg_loop_end : 0));
+    }
+#endif
     ptx::tc_fence_before();
     __syncthreads();
+#ifdef MSB_CONV_DEBUG
+    if (threadIdx.x == 0) { atomicAdd(&g_wgrad_dbg[4], (unsigned long long)(clock64() - dbg_loop_end)); atomicAdd(&g_wgrad_dbg[5], 1ull); }
+#endif
     if (MC) ptx::cluster_sync();         // nobody leaves while a peer may still multicast into / signal this CTA
     if (warp == 2) {
         ptx::tc_fence_after();

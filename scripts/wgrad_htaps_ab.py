@@ -14,19 +14,21 @@ from metasolver_b200.sopa.src.models.odenet_cifar10.layers import MetaODEBlock, 
 from metasolver_b200.sopa.src.models.odenet_cifar10.utils import Identity
 
 B = 512
-for C, HW in ((64, 32), (128, 16)):
+import os
+SHAPES = (((64, 32, 32),) if os.environ.get("HT_AB_C64") else ((64, 32, 32), (128, 16, 16))) if not os.environ.get("HT_AB_ALL") else ((64, 32, 32), (64, 64, 16), (128, 16, 16), (128, 8, 32))
+for C, H, W in SHAPES:
     torch.manual_seed(0)
     blk = MetaODEBlock(PreBasicBlock2(C, norm_layer=Identity, act_layer=F.gelu)).cuda()
     s = create_solver("rk2", "u", 4, -1, 0.5, -1, torch.float32, "cuda")
     s.freeze_params()
-    x = torch.randn(B, C, HW, HW, device="cuda").contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    x = torch.randn(B, C, H, W, device="cuda").contiguous(memory_format=torch.channels_last).requires_grad_(True)
 
     def step():
         blk.zero_grad()
         x.grad = None
         blk(x, [s], Namespace(solver_mode="standalone")).sum().backward()
 
-    for rep in range(3):
+    for rep in range(2 if os.environ.get("HT_AB_ALL") else int(os.environ.get("HT_AB_REPS", "3"))):
         for ht in (0, 1):
             msb.set_option("wgrad_htaps", ht)
             for _ in range(2):
@@ -38,4 +40,4 @@ for C, HW in ((64, 32), (128, 16)):
             ms, fl, n = msb.profile_read(0)
             wms, wfl, wn = msb.profile_read(1)
             msb.profile_enable(False)
-            print("C=%d wgrad_htaps=%d  conv: %d launches avg %.1f us   wgrad: %d avg %.1f us" % (C, ht, n, ms / max(n, 1) * 1e3, wn, wms / max(wn, 1) * 1e3), flush=True)
+            print("C=%d %dx%d wgrad_htaps=%d  conv: %d launches avg %.1f us   wgrad: %d avg %.1f us" % (C, H, W, ht, n, ms / max(n, 1) * 1e3, wn, wms / max(wn, 1) * 1e3), flush=True)
