@@ -274,7 +274,13 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_go, const __grid_con
                 issue_loop(true);
             }
         }
-    } else if (warp >= 4) {
+    }
+    // ===================== final pass: accumulator -> this CTA's partial =====================
+    // Role-swapped C = 64 option: warps 4..7.  Everything else: ALL eight warps (the producer / issuer / allocator warps are
+    // idle by now) -- warp w and warp w + 4 share TMEM quadrant w & 3 and take 96 of the 192 columns each, 32 columns (32
+    // outstanding reads of the old partial) at a time: 3 dependent L2 round trips per thread instead of 12.
+    __syncwarp();
+    if (!(C == 64 && P3) || warp >= 4) {
         const int q = warp & 3;
         ptx::mbar_wait_backoff(&bars->done, 0, backoff_ns ? 8 * backoff_ns : 0);     // waits for the whole kernel
         ptx::tc_fence_after();
@@ -322,25 +328,28 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_go, const __grid_con
         if (C == 64) { slice = part * 2 + (row >> 6); co = row & 63; }
         else { slice = part; co = row; }
         float* dst = partial + (size_t)slice * 9 * C * C;
+        const int cb_begin = (warp >> 2) * 96;
 #pragma unroll 1
-        for (int cb = 0; cb < 192; cb += 16) {
-            float v[16];
+        for (int cb = cb_begin; cb < cb_begin + 96; cb += 32) {
+            float v[32];
             ptx::tmem_ld16(t_addr + cb, v);
+            ptx::tmem_ld16(t_addr + cb + 16, v + 16);
             ptx::tmem_ld_wait();
-            const int tap = HT ? s * 3 + (cb >> 6) : (cb >> 6) * 3 + s;      // column block = the tap the N atom carries
+            // the 32 columns lie inside one 64-column block = one tap (column block = the tap the N atom carries)
+            const int tap = HT ? s * 3 + (cb >> 6) : (cb >> 6) * 3 + s;
             float* const q0 = dst + ((size_t)tap * C + ci_chunk * 64 + (cb & 63)) * C + co;      // element j: q0 + j * C
-            // CTA-private slot: deterministic.  All 16 old values are requested before the first store: left to itself the
+            // CTA-private slot: deterministic.  All old values are requested before the first store: left to itself the
             // compiler serialised load -> add -> store per element in one instantiation (it cannot rule out that the stores
             // alias the later loads), 192 dependent L2 round trips = 131k clocks instead of 11k.
             if (accumulate_partial) {
-                float old[16];
+                float old[32];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) old[j] = __ldcg(q0 + (size_t)j * C);
+                for (int j = 0; j < 32; ++j) old[j] = __ldcg(q0 + (size_t)j * C);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] += old[j];
+                for (int j = 0; j < 32; ++j) v[j] += old[j];
             }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) q0[(size_t)j * C] = v[j];
+            for (int j = 0; j < 32; ++j) q0[(size_t)j * C] = v[j];
         }
         }
     }
