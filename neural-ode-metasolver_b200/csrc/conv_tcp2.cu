@@ -553,16 +553,18 @@ conv3x3_tcp2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_c
                     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a0));
                     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(a1));
                 }
-                size_t idx, sidx;
+                size_t idx, sidx, nidx = 0, nsidx;
                 owned(row0, j, idx, sidx);
-                epi_finish_v8<ACT>(epi, coef, v, ops, idx, sidx, plane_stride);
-                if (j < 3) {
-                    owned(row0, j + 1, idx, sidx);
-                    epi_prefetch_vec8(epi, idx, ops);
-                } else {
+                // the next group's operand loads are issued from inside the finish, right after this group's operands are consumed
+                bool has_next = true;
+                if (j < 3) owned(row0, j + 1, nidx, nsidx);
+                else {
                     const int p2 = pr + TG * num_clusters;
-                    if (p2 < num_pairs) { owned(row0_of(p2), 0, idx, sidx); epi_prefetch_vec8(epi, idx, ops); }
+                    has_next = p2 < num_pairs;
+                    if (has_next) owned(row0_of(p2), 0, nidx, nsidx);
                 }
+                epi_finish_v8<ACT>(epi, coef, v, ops, idx, sidx, plane_stride,
+                                   [&]() { if (has_next) epi_prefetch_vec8(epi, nidx, ops); });
             }
         }
         }

@@ -478,12 +478,12 @@ conv3x3_tct_kernel(const __grid_constant__ CUtensorMap tmap_act, const uint4* __
                 }
                 const size_t idx = (row0 * W + px) * C + 8 * k8;
                 const size_t sidx = (row0 * 2) * plane_stride + (size_t)px * C + 8 * k8;
-                epi_finish_v8<ACT>(epi, coef, v, ops, idx, sidx, plane_stride);
-                if (it == 0) {
-                    epi_prefetch_vec8(epi, (row0 * W + 16 + rp) * C + 8 * k8, ops);
-                } else if (i + 4 < my_rows) {
-                    epi_prefetch_vec8(epi, (((size_t)n2 * H + h2) * W + rp) * C + 8 * k8, ops);
-                }
+                // the operand loads of the next 8-channel group are issued from inside the finish, as soon as this group's
+                // operands are consumed: their latency hides behind this group's activation / split arithmetic
+                const bool has_next = it == 0 || i + 4 < my_rows;
+                const size_t nidx = it == 0 ? (row0 * W + 16 + rp) * C + 8 * k8 : (((size_t)n2 * H + h2) * W + rp) * C + 8 * k8;
+                epi_finish_v8<ACT>(epi, coef, v, ops, idx, sidx, plane_stride,
+                                   [&]() { if (has_next) epi_prefetch_vec8(epi, nidx, ops); });
             }
             j = j2; n = n2; h = h2;
         }

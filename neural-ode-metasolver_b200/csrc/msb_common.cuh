@@ -488,9 +488,13 @@ __device__ __forceinline__ void stg256_2(float* p, const f32x2_t* v) {
 }
 
 // The packed form of epi_finish_vec8 (below): same contract, same bits.
-template <int ACT, class OPS>
+// `next` is called as soon as the prefetched operands `r` have been consumed -- before the activation / split arithmetic and
+// the stores -- so that the caller can issue the operand loads of its NEXT element group into the same registers and have
+// their latency covered by this group's arithmetic (they are asm volatile, like the stores: the compiler never hoists them).
+struct EpiNoNext { __device__ __forceinline__ void operator()() const {} };
+template <int ACT, class OPS, class NEXT = EpiNoNext>
 __device__ __forceinline__ void epi_finish_vec8_x2(const EpiParams& e, const EpiCoef& k, const float* acc, const OPS& r,
-                                                   size_t idx0_in, size_t split_idx0_in, size_t plane_stride) {
+                                                   size_t idx0_in, size_t split_idx0_in, size_t plane_stride, NEXT next = NEXT()) {
     constexpr int P = 4;
     const size_t idx0 = MSB_DBG_ST(idx0_in), split_idx0 = MSB_DBG_ST(split_idx0_in);
     f32x2_t v[P], o[P];
@@ -543,6 +547,8 @@ __device__ __forceinline__ void epi_finish_vec8_x2(const EpiParams& e, const Epi
             for (int j = 0; j < P; ++j) o[j] = add2(mul2(pk2(r.base[2 * j], r.base[2 * j + 1]), bcf), o[j]);
         }
     }
+    const bool r_used_late = OPS::SMUL && e.split_mul != nullptr;     // post-activation backward only
+    if (!r_used_late) next();
     if (e.out_f32) stg256_2(e.out_f32 + idx0, o);
     if (e.out_split || e.dact_out) {
         f32x2_t a[P], d[P];
@@ -577,6 +583,7 @@ __device__ __forceinline__ void epi_finish_vec8_x2(const EpiParams& e, const Epi
             *reinterpret_cast<uint4*>(e.out_split + split_idx0 + plane_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
     }
+    if (r_used_late) next();
 }
 
 // split_idx0 = index of element 0 in the hi plane of out_split; the lo plane is plane_stride further.
@@ -667,14 +674,15 @@ __device__ __forceinline__ void epi_finish_vec8(const EpiParams& e, const EpiCoe
 #ifndef MSB_EPI_X2
 #define MSB_EPI_X2 1
 #endif
-template <int ACT, class OPS>
+template <int ACT, class OPS, class NEXT = EpiNoNext>
 __device__ __forceinline__ void epi_finish_v8(const EpiParams& e, const EpiCoef& k, const float* acc, const OPS& r,
-                                              size_t idx0, size_t split_idx0, size_t plane_stride) {
+                                              size_t idx0, size_t split_idx0, size_t plane_stride, NEXT next = NEXT()) {
 #if MSB_EPI_X2
-    epi_finish_vec8_x2<ACT, OPS>(e, k, acc, r, idx0, split_idx0, plane_stride);
+    epi_finish_vec8_x2<ACT, OPS, NEXT>(e, k, acc, r, idx0, split_idx0, plane_stride, next);
 #else
     static_assert(OPS::MAXSRC == 3 && OPS::SMUL, "the scalar A/B build has no lean instantiation");
     epi_finish_vec8<ACT>(e, k, acc, r, idx0, split_idx0, plane_stride);
+    next();
 #endif
 }
 
