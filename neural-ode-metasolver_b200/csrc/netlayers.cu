@@ -81,13 +81,13 @@ __global__ void __launch_bounds__(128) stem_fwd_kernel(const float* __restrict__
         float a[16], d[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) act_both(act, acc[px][j], a[j], d[j]);
-        float4* yo = reinterpret_cast<float4*>(y + pix * C + cg * 16);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) yo[q] = make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+        // 256-bit stores: a lane writes whole 32-byte sectors (four 16-byte stores per lane at a 64-byte lane stride left every
+        // sector of a warp-wide store half written)
+        stg256(y + pix * C + cg * 16, a);
+        stg256(y + pix * C + cg * 16 + 8, a + 8);
         if (dact) {
-            float4* dq = reinterpret_cast<float4*>(dact + pix * C + cg * 16);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) dq[q] = make_float4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]);
+            stg256(dact + pix * C + cg * 16, d);
+            stg256(dact + pix * C + cg * 16 + 8, d + 8);
         }
     }
 }
@@ -110,7 +110,7 @@ int launch_stem_fwd(const float* x, const float* w, int act, float* y, float* da
 constexpr int kStemPix = 64;   // pixels staged per iteration (45 KB of static shared memory)
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ gy, const float* __restrict__ dact,
                                                          const float* __restrict__ x, float* __restrict__ partial, int B,
-                                                         int H, int W, int C, long long pix_per_block) {
+                                                         int H, int W, int C, long long pix_per_block, int wsh, int hsh) {
     __shared__ __align__(16) float sg[kStemPix][64];
     __shared__ __align__(16) float sx[kStemPix][32];       // [pixel][k-group 0..3][8]: 7 taps + 1 pad per group
     __shared__ float sred[3][64][28];
@@ -154,10 +154,19 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
                 if (pix < p_end && (slot & 7) < 7 && k < 27) {
                     const int ci = k / 9, r = (k % 9) / 3, s = k % 3;
                     const unsigned upix = (unsigned)pix;                 // B*H*W < 2^31 (checked by the launcher): 32-bit divides
-                    const int wq = (int)(upix % (unsigned)W);
-                    const unsigned rest = upix / (unsigned)W;
-                    const int h = (int)(rest % (unsigned)H);
-                    const long long n = rest / (unsigned)H;
+                    int wq, h;
+                    long long n;
+                    if (wsh >= 0 && hsh >= 0) {                           // power-of-two image: shifts instead of three divisions
+                        wq = (int)(upix & (unsigned)(W - 1));             // per element (the staging loop was issue-bound on them)
+                        const unsigned rest = upix >> wsh;
+                        h = (int)(rest & (unsigned)(H - 1));
+                        n = rest >> hsh;
+                    } else {
+                        wq = (int)(upix % (unsigned)W);
+                        const unsigned rest = upix / (unsigned)W;
+                        h = (int)(rest % (unsigned)H);
+                        n = rest / (unsigned)H;
+                    }
                     const int ih = h + r - 1, iw = wq + s - 1;
                     if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = x[(((size_t)n * H + ih) * W + iw) * 3 + ci];
                 }
@@ -235,7 +244,8 @@ int launch_stem_wgrad(const float* gy, const float* dact, const float* x, float*
     const long long P = (long long)B * H * W;
     long long per = (P + nb - 1) / nb;
     per = (per + kStemPix - 1) / kStemPix * kStemPix;
-    stem_wgrad_kernel<<<nb, 256, 0, st>>>(gy, dact, x, partial, B, H, W, C, per);
+    auto log2_exact = [](int v) { int l = 0; while ((1 << l) < v) ++l; return (1 << l) == v ? l : -1; };
+    stem_wgrad_kernel<<<nb, 256, 0, st>>>(gy, dact, x, partial, B, H, W, C, per, log2_exact(W), log2_exact(H));
     stem_wgrad_reduce_kernel<<<(27 * C + 127) / 128, 128, 0, st>>>(partial, nb, gw, C);
     count_launch(2);
     return check_cuda(cudaGetLastError(), "stem wgrad launch");

@@ -357,3 +357,35 @@ def test_full_batch_subset_matches_the_oracle(C, HW):
     (yo * r[idx.cuda()].cpu()).sum().backward()
     assert max_rel(y[idx.cuda()].detach().cpu().numpy(), yo.detach().numpy()) <= 1e-4
     assert max_rel(xg.grad[idx.cuda()].cpu().numpy(), xo.grad.numpy()) <= 1e-4
+
+
+@pytest.mark.parametrize("option,C,H,W", [("wgrad_htaps", 64, 32, 32), ("wgrad_htaps", 128, 16, 16), ("wgrad_htaps", 64, 16, 16),
+                                           ("tcp2_halo", 128, 16, 16), ("tcp2_halo", 128, 32, 16), ("tcp2_half_stage", 128, 16, 16),
+                                           ("tcp2_half_stage", 128, 8, 16)])
+def test_operand_staging_options_do_not_change_results(option, C, H, W):
+    """The round-2 operand-staging variants read the same data another way (one staged copy with row-offset operand starts
+    instead of shifted copies; another ring / epilogue-stage split): every accumulation runs over the same terms in the
+    same order, so outputs and gradients must agree with the round-1 geometry to the last bits."""
+    import metasolver_b200
+    blk, solver, opts = _block(C)
+    torch.manual_seed(11)
+    x0 = torch.randn(6, C, H, W, device="cuda").contiguous(memory_format=torch.channels_last)
+    r = torch.randn_like(x0)
+
+    def run():
+        x = x0.clone().requires_grad_(True)
+        for p in blk.parameters():
+            p.grad = None
+        (blk(x, [solver], opts) * r).sum().backward()
+        return [x.grad.clone()] + [p.grad.clone() for p in blk.parameters()]
+
+    d = metasolver_b200.get_option(option)
+    try:
+        metasolver_b200.set_option(option, 0)
+        a = run()
+        metasolver_b200.set_option(option, 1)
+        b = run()
+    finally:
+        metasolver_b200.set_option(option, d)
+    for u, v in zip(a, b):
+        assert max_rel(v.cpu().numpy(), u.cpu().numpy()) <= 2e-6
