@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--engine", default="auto")
     ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly (no CUDA-graph replay)")
+    ap.add_argument("--nccl-allreduce", action="store_true", help="world > 1: NCCL all-reduce instead of the peer-memory kernel")
     return ap.parse_args()
 
 
@@ -196,7 +197,9 @@ def run_ours(args):
     solver = create_solver("rk2", "u", 8, -1, 0.5, -1, torch.float32, dev)
     solver.freeze_params()
     opts = Namespace(solver_mode="standalone")
-    reducer = parallel.GradAllReducer(model.parameters())
+    # world > 1: the ONE gradient all-reduce of the step is our own kernel over peer memory (csrc/peer.cu); NCCL only if the
+    # node refuses the IPC mapping or the cross-check below fails (the line's config.allreduce says which)
+    reducer = parallel.GradAllReducer(model.parameters(), peer=(world > 1 and not args.nccl_allreduce))
 
     g = torch.Generator().manual_seed(1234 + rank)
     img = torch.rand(B, 3, 32, 32, generator=g)
@@ -236,6 +239,26 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step(x_dev, y_dev)
     barrier()
+    allreduce_note = "none (1 rank)"
+    if world > 1:
+        allreduce_note = "nccl all-reduce (ReduceOp.AVG) of the flat fp32 gradient, %d bytes" % reducer.nbytes
+        if reducer.note:
+            allreduce_note += "; " + reducer.note[0]
+        if reducer.peer is not None:
+            # untimed cross-check of the peer-memory reduction against NCCL on this step's gradients (all ranks must agree)
+            want = reducer.flat.clone()
+            dist.all_reduce(want, op=dist.ReduceOp.AVG)
+            err = float((reducer.result - want).abs().max() / want.abs().max().clamp_min(1e-30))
+            bad = torch.tensor([1.0 if (not err < 1e-5 or reducer.peer.status()[0] != 0) else 0.0], device=dev)
+            dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+            if float(bad.item()) != 0.0:
+                reducer = parallel.GradAllReducer(model.parameters(), peer=False)
+                allreduce_note += "; peer-memory kernel failed its cross-check (max rel err %.3g): not used" % err
+            else:
+                allreduce_note = ("one kernel per rank over peer memory (msb_peer_allreduce_sgd: rank-order sum of the %d-byte flat "
+                                  "gradient read from all ranks over NVLink, 1/world folded in; max rel diff to NCCL AVG %.1e)"
+                                  % (reducer.nbytes, err))
+        barrier()
 
     # ---- timed region A: K steps issued eagerly with CUDA events around every convolution-engine launch
     #      (recorded by the library on the launch stream): per-kernel durations for the roofline ----
@@ -337,7 +360,7 @@ def run_ours(args):
                 config=dict(workload=WORKLOAD, batch_per_gpu=B, global_batch=B * world, parallelism="dp%d" % world,
                             l2="per-step working set (activation tape ~13 GB) >> 126 MB L2; no explicit flush needed",
                             precision="bf16 hi/lo split operands, 3 tcgen05 products at C=128 / 4 at C=64 (conv and weight gradient), fp32 accumulate (fp32-grade)",
-                            launch=graph_note),
+                            launch=graph_note, allreduce=allreduce_note),
                 clocks=clocks,
                 e2e=dict(value=e2e_val, unit="images/s", h2d_bytes_per_step=x_host.numel() * 4 + y_host.numel() * 8,
                          d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps,

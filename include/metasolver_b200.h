@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define MSB_ABI_VERSION 5   /* v3: + tuning options, attack / SGD steps, tableau gradients, MSB_RHS_PREACT_GN; v4: + network head (pool + FC, cross-entropy); v5: + MSB_RHS_POSTACT_GN, stacked tableau gradients, msb_augment_batch (structs unchanged) */
+#define MSB_ABI_VERSION 6   /* v3: + tuning options, attack / SGD steps, tableau gradients, MSB_RHS_PREACT_GN; v4: + network head (pool + FC, cross-entropy); v5: + MSB_RHS_POSTACT_GN, stacked tableau gradients, msb_augment_batch (structs unchanged); v6: + msb_peer_* (gradient all-reduce + SGD update as one kernel over peer memory) */
 #define MSB_MAX_STAGES 4
 
 /* right-hand-side families */
@@ -252,6 +252,39 @@ int msb_augment_batch(const uint8_t* images_u8, const int64_t* index, const int3
  * grad_scale carries the 1/world average of the data-parallel all-reduce.  momentum_buf may be NULL if momentum == 0. */
 int msb_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t n, float lr, float momentum,
                  float weight_decay, float grad_scale, int first_step, void* cuda_stream);
+
+/* Data-parallel exchange step over PEER MEMORY (NVLink 5 / NVSwitch), SURVEY 8(e) + 8(f-4): the ONE gradient all-reduce of
+ * a training step (reference: single-process; north_star: "a single NCCL-over-NVLink gradient allreduce per step") fused
+ * with the optimizer update that consumes it (examples/cifar10/train_and_attack.py:98-99,322) -- one launch per rank, no NCCL
+ * call, no intermediate buffer.
+ *   msb_peer_alloc   cudaMalloc of [MSB_PEER_HEADER_BYTES header | payload], zero-filled, + its CUDA IPC handle
+ *                    (MSB_PEER_HANDLE_BYTES bytes the caller ships to the other ranks of the node, e.g. all_gather_object)
+ *   msb_peer_open    map another rank's buffer (enables peer access between the two devices); msb_peer_close unmaps it
+ *   msb_peer_free    release the own buffer (after every peer has closed it)
+ *   msb_peer_status  synchronous read of the own header: error word (0 = ok, MSB_PEER_ERR_*) and the last finished epoch
+ *   msb_peer_allreduce_sgd
+ *       bases[world]: exchange buffers in rank order, bases[rank] = the own one.  The flat fp32 gradient of every rank is
+ *       the payload of its buffer; this launch covers floats [offset, offset + n).  Per element, on every rank:
+ *           s = (((g_0 + g_1) + g_2) + ... + g_{world-1}) * grad_scale            fixed order: bitwise identical on all ranks
+ *           avg_out[i] = s                                                        (if avg_out != NULL; own memory)
+ *           g = s + weight_decay*p;  buf = first_step ? g : momentum*buf + g;  p -= lr*buf     (if params != NULL; = msb_sgd_step)
+ *       avg_out / params / momentum_buf point at element `offset` of their flat arrays.  All ranks must issue the same
+ *       sequence of launches.  The launch starts with a system-scope handshake (all gradients complete) and ends with one
+ *       (all reads finished: the successor on the stream may overwrite the gradient); the epoch ordering the messages is
+ *       kept in the header, so the call can be captured in a CUDA graph.  Waits are bounded by timeout_ms (0 = 10 s): on
+ *       expiry the header's error word is set and the launch completes with undefined results instead of hanging. */
+#define MSB_PEER_MAX_RANKS 16
+#define MSB_PEER_HANDLE_BYTES 64
+#define MSB_PEER_HEADER_BYTES 1024
+enum { MSB_PEER_OK = 0, MSB_PEER_ERR_READY_TIMEOUT = 1, MSB_PEER_ERR_DONE_TIMEOUT = 2 };
+int msb_peer_alloc(size_t payload_bytes, void** base, unsigned char* handle);
+int msb_peer_open(const unsigned char* handle, void** base);
+int msb_peer_close(void* base);
+int msb_peer_free(void* base);
+int msb_peer_status(const void* own_base, unsigned* error_word, unsigned* epoch);
+int msb_peer_allreduce_sgd(void* const* bases, int world, int rank, int64_t offset, int64_t n, float* avg_out, float* params,
+                           float* momentum_buf, float lr, float momentum, float weight_decay, float grad_scale,
+                           int first_step, unsigned timeout_ms, void* cuda_stream);
 
 /* Network head of MetaNODE: AdaptiveAvgPool2d((1,1)) + Flatten + Linear (sopa/src/models/odenet_cifar10/layers.py:390-392,425)
  * on an NHWC fp32 map, and its gradient.  pooled[batch][channels] is an output of the forward (saved for the backward).

@@ -12,12 +12,13 @@ LIB_PATH = os.environ.get("MSB_LIB_PATH") or os.path.join(HERE, "libmetasolver_b
 
 MSB_MAX_STAGES = 4
 TABLEAU_GRAD_DOUBLES = MSB_MAX_STAGES + MSB_MAX_STAGES * MSB_MAX_STAGES + MSB_MAX_STAGES   # [b | w | c]
-ABI_VERSION = 5
+ABI_VERSION = 6
 RHS_PREACT_NF, RHS_POSTACT_NF, RHS_MNIST_GN_T, RHS_PREACT_GN, RHS_POSTACT_GN = 0, 1, 2, 3, 4
 ACT_NONE, ACT_GELU_ERF, ACT_RELU = 0, 1, 2
 (ATTACK_UNNORMALIZE, ATTACK_NORMALIZE, ATTACK_FGSM_STEP, ATTACK_PGD_STEP, ATTACK_FGSMR_INIT,
  ATTACK_FGSMR_STEP) = range(6)
 ATTACK_MAX_CHANNELS = 4
+PEER_MAX_RANKS, PEER_HANDLE_BYTES, PEER_HEADER_BYTES = 16, 64, 1024
 ENGINE_AUTO, ENGINE_TCGEN05, ENGINE_SIMT = 0, 1, 2
 ENGINES = {"auto": ENGINE_AUTO, "tcgen05": ENGINE_TCGEN05, "simt": ENGINE_SIMT}
 
@@ -33,6 +34,7 @@ EXPORTS = [
     "msb_odeblock_bwd_workspace_bytes_tableau", "msb_odeblock_backward_tableau", "msb_odeblock_backward_mnist_tableau",
     "msb_pool_fc_forward", "msb_pool_fc_backward", "msb_cross_entropy_forward", "msb_cross_entropy_backward",
     "msb_augment_batch",
+    "msb_peer_alloc", "msb_peer_open", "msb_peer_close", "msb_peer_free", "msb_peer_status", "msb_peer_allreduce_sgd",
 ]
 
 
@@ -131,6 +133,13 @@ def _declare(lib):
     lib.msb_pool_fc_backward.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.msb_cross_entropy_forward.argtypes = [vp, vp, vp, vp, i32, i32, vp]
     lib.msb_cross_entropy_backward.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp]
+    u32 = ctypes.c_uint
+    lib.msb_peer_alloc.argtypes = [sz, ctypes.POINTER(vp), ctypes.c_char_p]
+    lib.msb_peer_open.argtypes = [ctypes.c_char_p, ctypes.POINTER(vp)]
+    lib.msb_peer_close.argtypes = [vp]
+    lib.msb_peer_free.argtypes = [vp]
+    lib.msb_peer_status.argtypes = [vp, ctypes.POINTER(u32), ctypes.POINTER(u32)]
+    lib.msb_peer_allreduce_sgd.argtypes = [ctypes.POINTER(vp), i32, i32, i64, i64, vp, vp, vp, f32, f32, f32, f32, i32, u32, vp]
     lib.msb_profile_enable.argtypes = [i32]
     lib.msb_profile_read_executed.argtypes = [i32, ctypes.POINTER(ctypes.c_double)]
     lib.msb_profile_read.argtypes = [i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),

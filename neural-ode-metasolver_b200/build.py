@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libmetasolver_b200.so")
 SOURCES = ["odeblock.cu", "blocks.cu", "netlayers.cu", "elementwise.cu", "conv_simt.cu", "conv_tc.cu", "conv_tcp.cu", "conv_tcp2.cu", "conv_tct.cu", "wgrad_tc.cu",
-           "groupnorm.cu", "train_aux.cu", "head.cu", "mnist_fused.cu"]
+           "groupnorm.cu", "train_aux.cu", "head.cu", "mnist_fused.cu", "peer.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",
               "-I", os.path.join(ROOT, "include"), "-I", CSRC] + os.environ.get("MSB_NVCC_EXTRA", "").split()

@@ -1,0 +1,248 @@
+// The one exchange step of the data-parallel path: the gradient all-reduce of a training step
+// and the optimizer update that follows it, as ONE kernel over peer memory (NVLink 5 / NVSwitch loads) instead of an
+// NCCL all-reduce followed by an update kernel.
+//
+//   * every rank owns one exchange buffer [header 1 KB | flat fp32 gradient] allocated with cudaMalloc and exported with a
+//     CUDA IPC handle; the ranks of a node open each other's buffers once (msb_peer_open enables peer access);
+//   * a step is one launch per rank: announce "my gradient is complete" to every peer (release store at system scope into
+//     the peer's header), wait for all announcements, then every rank reads ALL ranks' gradients element by element in
+//     rank order 0..W-1 (the same summation order everywhere: the reduced gradient and hence the updated parameters are
+//     bitwise identical on all ranks), scales by 1/W and applies the SGD-momentum / weight-decay update of
+//     examples/cifar10/train_and_attack.py:98-99,322 to its own replica (and / or writes the averaged gradient);
+//   * the launch ends with the second half of the handshake: the last CTA tells every peer "I have finished reading your
+//     gradient" and waits for the same message from all of them, so that the stream-ordered successor of the kernel (the
+//     next backward pass) may overwrite the gradient buffer.
+// The epoch that orders the messages lives in the header (device memory), not in a kernel argument: the launch is
+// identical every step and can be captured in a CUDA graph.  2.70 MB of gradient x 8 ranks = 21.6 MB of NVLink reads per
+// rank and step: bound by the two handshakes (a few microseconds each) plus ~25 us of peer reads, no intermediate buffer.
+// Every wait is bounded (timeout -> header.error, the launch finishes with garbage instead of hanging the GPU).
+#include <cuda_runtime.h>
+
+#include "metasolver_b200.h"
+#include "msb_internal.h"
+
+namespace msb {
+namespace {
+
+struct PeerHeader {                           // first MSB_PEER_HEADER_BYTES of an exchange buffer
+    uint32_t ready[MSB_PEER_MAX_RANKS];       // ready[r] = e: rank r's gradient of epoch e is complete       (written by rank r)
+    uint32_t done[MSB_PEER_MAX_RANKS];        // done[r]  = e: rank r has finished reading THIS buffer in e   (written by rank r)
+    uint32_t epoch;                           // last finished epoch of the owner                              (owner only)
+    uint32_t ticket;                          // CTAs of the running launch that have finished their reads     (owner only)
+    uint32_t error;                           // != 0: the FIRST wait of the owner that timed out (MSB_PEER_ERR_*), sticky
+    uint32_t pad;
+};
+static_assert(sizeof(PeerHeader) <= MSB_PEER_HEADER_BYTES, "header");
+
+struct PeerArgs {
+    void* base[MSB_PEER_MAX_RANKS];           // exchange buffers, [rank] = own (peer ones through IPC mappings)
+    int world, rank;
+    long long offset, n;                      // floats of the gradient region this launch reduces: [offset, offset + n)
+    float* avg_out;                           // optional: averaged gradient (own memory, not the exchange buffer)
+    float* params; float* mom;                // optional: SGD update of the own replica
+    float lr, momentum, wd, scale;
+    int first;
+    unsigned long long timeout_ns;
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// gradient loads: system-scope relaxed (never served from a stale non-coherent line of a peer's memory)
+__device__ __forceinline__ float4 ld_sys_f4(const float4* p) {
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_sys_f1(const float* p) {
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// wait until *flag has reached epoch e (wrap-safe); false = timed out
+__device__ __forceinline__ bool wait_epoch(const uint32_t* flag, uint32_t e, unsigned long long timeout_ns) {
+    if ((int32_t)(ld_acquire_sys(flag) - e) >= 0) return true;
+    const unsigned long long t0 = globaltimer_ns();
+    while ((int32_t)(ld_acquire_sys(flag) - e) < 0) {
+        if (globaltimer_ns() - t0 > timeout_ns) return false;
+        __nanosleep(32);
+    }
+    return true;
+}
+
+__device__ __forceinline__ float sgd_update(float g, float* p, float* mom, float lr, float momentum, float wd, int first) {
+    // same operations, same order as sgd_step_kernel (train_aux.cu)
+    const float w = *p;
+    if (wd != 0.f) g = __fadd_rn(g, __fmul_rn(wd, w));
+    float b = g;
+    if (momentum != 0.f) {
+        b = first ? g : __fadd_rn(__fmul_rn(momentum, *mom), g);
+        *mom = b;
+    }
+    *p = __fsub_rn(w, __fmul_rn(lr, b));
+    return g;
+}
+
+template <int W>
+__global__ void __launch_bounds__(256) peer_allreduce_sgd_kernel(PeerArgs a) {
+    PeerHeader* own = reinterpret_cast<PeerHeader*>(a.base[a.rank]);
+    const uint32_t e = own->epoch + 1;        // written by the last CTA of the previous launch (stream order)
+    const int tid = threadIdx.x;
+    __shared__ int s_last;
+
+    // ---- handshake 1: gradients complete everywhere ----
+    if (blockIdx.x == 0 && tid < a.world) {
+        __threadfence_system();               // the gradient was written by earlier kernels of this stream
+        st_release_sys(&reinterpret_cast<PeerHeader*>(a.base[tid])->ready[a.rank], e);
+    }
+    if (tid < a.world && !wait_epoch(&own->ready[tid], e, a.timeout_ns)) atomicCAS(&own->error, 0u, (uint32_t)MSB_PEER_ERR_READY_TIMEOUT);
+    __syncthreads();
+
+    // ---- reduce in rank order + update ----
+    const bool do_sgd = a.params != nullptr;
+    const bool vec = (a.offset & 3) == 0 && (reinterpret_cast<uintptr_t>(a.avg_out) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(a.params) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.mom) & 15) == 0;
+    const long long n4 = vec ? a.n / 4 : 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < n4; i += stride) {
+        float4 g[W];
+#pragma unroll
+        for (int r = 0; r < W; ++r)
+            if (r < a.world)
+                g[r] = ld_sys_f4(reinterpret_cast<const float4*>(reinterpret_cast<const char*>(a.base[r]) + MSB_PEER_HEADER_BYTES) + a.offset / 4 + i);
+        float4 s = g[0];
+#pragma unroll
+        for (int r = 1; r < W; ++r)
+            if (r < a.world) {
+                s.x = __fadd_rn(s.x, g[r].x); s.y = __fadd_rn(s.y, g[r].y);
+                s.z = __fadd_rn(s.z, g[r].z); s.w = __fadd_rn(s.w, g[r].w);
+            }
+        if (a.scale != 1.f) { s.x = __fmul_rn(s.x, a.scale); s.y = __fmul_rn(s.y, a.scale); s.z = __fmul_rn(s.z, a.scale); s.w = __fmul_rn(s.w, a.scale); }
+        if (a.avg_out) reinterpret_cast<float4*>(a.avg_out)[i] = s;
+        if (do_sgd) {
+            float4 p = reinterpret_cast<float4*>(a.params)[i];
+            float4 m = (a.momentum != 0.f && !a.first) ? reinterpret_cast<float4*>(a.mom)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            sgd_update(s.x, &p.x, &m.x, a.lr, a.momentum, a.wd, a.first);
+            sgd_update(s.y, &p.y, &m.y, a.lr, a.momentum, a.wd, a.first);
+            sgd_update(s.z, &p.z, &m.z, a.lr, a.momentum, a.wd, a.first);
+            sgd_update(s.w, &p.w, &m.w, a.lr, a.momentum, a.wd, a.first);
+            reinterpret_cast<float4*>(a.params)[i] = p;
+            if (a.momentum != 0.f) reinterpret_cast<float4*>(a.mom)[i] = m;
+        }
+    }
+    for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + tid; i < a.n; i += stride) {      // tail / unaligned runs
+        float s = 0.f;
+        for (int r = 0; r < a.world; ++r) {
+            const float g = ld_sys_f1(reinterpret_cast<const float*>(reinterpret_cast<const char*>(a.base[r]) + MSB_PEER_HEADER_BYTES) + a.offset + i);
+            s = r == 0 ? g : __fadd_rn(s, g);
+        }
+        if (a.scale != 1.f) s = __fmul_rn(s, a.scale);
+        if (a.avg_out) a.avg_out[i] = s;
+        if (do_sgd) sgd_update(s, a.params + i, a.mom ? a.mom + i : nullptr, a.lr, a.momentum, a.wd, a.first);
+    }
+
+    // ---- handshake 2: nobody reads a gradient buffer any more when the launches end ----
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        s_last = atomicAdd(&own->ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    if (tid < a.world) {
+        st_release_sys(&reinterpret_cast<PeerHeader*>(a.base[tid])->done[a.rank], e);
+        if (!wait_epoch(&own->done[tid], e, a.timeout_ns)) atomicCAS(&own->error, 0u, (uint32_t)MSB_PEER_ERR_DONE_TIMEOUT);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        own->ticket = 0;
+        own->epoch = e;
+    }
+}
+
+}  // namespace
+}  // namespace msb
+
+using namespace msb;
+
+extern "C" {
+
+int msb_peer_alloc(size_t payload_bytes, void** base, unsigned char* handle) {
+    if (!base || !handle) { set_error("msb_peer_alloc: null argument"); return -1; }
+    void* p = nullptr;
+    const size_t bytes = MSB_PEER_HEADER_BYTES + (payload_bytes + 15) / 16 * 16;
+    if (check_cuda(cudaMalloc(&p, bytes), "msb_peer_alloc: cudaMalloc")) return -1;
+    if (check_cuda(cudaMemset(p, 0, bytes), "msb_peer_alloc: cudaMemset")) { cudaFree(p); return -1; }
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(h) == MSB_PEER_HANDLE_BYTES, "IPC handle size");
+    if (check_cuda(cudaIpcGetMemHandle(&h, p), "msb_peer_alloc: cudaIpcGetMemHandle")) { cudaFree(p); return -1; }
+    if (check_cuda(cudaDeviceSynchronize(), "msb_peer_alloc: sync")) { cudaFree(p); return -1; }
+    memcpy(handle, &h, sizeof(h));
+    *base = p;
+    return 0;
+}
+
+int msb_peer_open(const unsigned char* handle, void** base) {
+    if (!base || !handle) { set_error("msb_peer_open: null argument"); return -1; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void* p = nullptr;
+    if (check_cuda(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "msb_peer_open: cudaIpcOpenMemHandle")) return -1;
+    *base = p;
+    return 0;
+}
+
+int msb_peer_close(void* base) { return base ? check_cuda(cudaIpcCloseMemHandle(base), "msb_peer_close") : 0; }
+int msb_peer_free(void* base) { return base ? check_cuda(cudaFree(base), "msb_peer_free") : 0; }
+
+int msb_peer_status(const void* own_base, unsigned* error_word, unsigned* epoch) {
+    if (!own_base) { set_error("msb_peer_status: null buffer"); return -1; }
+    PeerHeader h;
+    if (check_cuda(cudaMemcpy(&h, own_base, sizeof(h), cudaMemcpyDeviceToHost), "msb_peer_status: copy")) return -1;
+    if (error_word) *error_word = h.error;
+    if (epoch) *epoch = h.epoch;
+    return 0;
+}
+
+int msb_peer_allreduce_sgd(void* const* bases, int world, int rank, int64_t offset, int64_t n, float* avg_out, float* params,
+                           float* momentum_buf, float lr, float momentum, float weight_decay, float grad_scale,
+                           int first_step, unsigned timeout_ms, void* cuda_stream) {
+    if (!bases || world < 1 || world > MSB_PEER_MAX_RANKS || rank < 0 || rank >= world || offset < 0 || n < 0) {
+        set_error("msb_peer_allreduce_sgd: bad arguments (world=%d rank=%d offset=%lld n=%lld; at most %d ranks)", world, rank,
+                  (long long)offset, (long long)n, MSB_PEER_MAX_RANKS);
+        return -1;
+    }
+    if (params && momentum != 0.f && !momentum_buf) { set_error("msb_peer_allreduce_sgd: momentum without a momentum buffer"); return -1; }
+    if (!params && !avg_out) { set_error("msb_peer_allreduce_sgd: neither parameters to update nor an output for the average"); return -1; }
+    PeerArgs a;
+    for (int r = 0; r < MSB_PEER_MAX_RANKS; ++r) {
+        a.base[r] = r < world ? bases[r] : nullptr;
+        if (r < world && !bases[r]) { set_error("msb_peer_allreduce_sgd: exchange buffer of rank %d is null", r); return -1; }
+    }
+    a.world = world; a.rank = rank; a.offset = offset; a.n = n;
+    a.avg_out = avg_out; a.params = params; a.mom = params ? momentum_buf : nullptr;
+    a.lr = lr; a.momentum = momentum; a.wd = weight_decay; a.scale = grad_scale; a.first = first_step;
+    a.timeout_ns = (unsigned long long)(timeout_ms ? timeout_ms : 10000u) * 1000000ull;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const long long work = std::max<long long>((n + 3) / 4, 1);
+    const int grid = (int)std::min<long long>((work + 255) / 256, 2LL * num_sms());
+    if (world <= 2) peer_allreduce_sgd_kernel<2><<<grid, 256, 0, st>>>(a);
+    else if (world <= 4) peer_allreduce_sgd_kernel<4><<<grid, 256, 0, st>>>(a);
+    else if (world <= 8) peer_allreduce_sgd_kernel<8><<<grid, 256, 0, st>>>(a);
+    else peer_allreduce_sgd_kernel<16><<<grid, 256, 0, st>>>(a);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "peer_allreduce_sgd launch");
+}
+
+}  // extern "C"

@@ -83,7 +83,10 @@ class FusedSGD:
     gradient buffer, so that `step()` is a single kernel and a data-parallel run all-reduces the flat gradient in
     place (one all-reduce of 2.70 MB per step for premetanode10)."""
 
-    def __init__(self, params, lr, momentum=0.0, weight_decay=0.0):
+    def __init__(self, params, lr, momentum=0.0, weight_decay=0.0, peer=None):
+        """peer: None = gradients in ordinary device memory, `all_reduce()` is an NCCL / gloo call; True = allocate a
+        `parallel.PeerExchange` for the flat gradient (collective; multi-rank CUDA job on one node; falls back to None
+        when the mapping is refused) or pass one: `reduce_and_step()` is then ONE kernel per rank (msb_peer_allreduce_sgd)."""
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("FusedSGD: no parameters")
@@ -94,7 +97,15 @@ class FusedSGD:
         self.param_groups = [{"lr": self.lr, "momentum": self.momentum, "weight_decay": self.weight_decay}]   # schedulers poke "lr"
         n = sum(p.numel() for p in self.params)
         self.flat_param = torch.empty(n, dtype=torch.float32, device=dev)
-        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.peer_note = []
+        if peer is True:
+            from . import parallel
+            peer = parallel.peer_exchange_or_none(n, self.peer_note)
+        if peer is not None and (peer.n != n or peer.device != dev):
+            raise ValueError("metasolver_b200.FusedSGD: the PeerExchange holds %d floats on %s, the parameters %d on %s"
+                             % (peer.n, peer.device, n, dev))
+        self.peer = peer
+        self.flat_grad = peer.grad if peer is not None else torch.zeros(n, dtype=torch.float32, device=dev)
         self.momentum_buf = torch.zeros(n, dtype=torch.float32, device=dev) if self.momentum != 0.0 else None
         self._seen = [False] * len(self.params)      # torch.optim.SGD creates a momentum buffer at a parameter's first update
         off = 0
@@ -152,7 +163,7 @@ class FusedSGD:
             return 1.0 / dist.get_world_size()
         return 1.0
 
-    def step(self, grad_scale=1.0):
+    def _begin_step(self):
         if torch.cuda.is_current_stream_capturing():
             raise RuntimeError("metasolver_b200.FusedSGD.step() passes lr / grad_scale / the first-step flag by value: a "
                                "captured step would replay a frozen learning rate.  Call it outside the CUDA graph.")
@@ -161,7 +172,9 @@ class FusedSGD:
         self.momentum = float(self.param_groups[0].get("momentum", self.momentum))      # CyclicLR(cycle_momentum=True) pokes it
         if self.momentum != 0.0 and self.momentum_buf is None:
             self.momentum_buf = torch.zeros_like(self.flat_param)
-        dev = self.flat_param.device
+        return self._runs(has)
+
+    def _runs(self, has):
         # contiguous runs of parameters that have a gradient and share the "first update" state: ONE run (one kernel)
         # in the normal case; parameters without a gradient are skipped entirely (no weight decay, no momentum
         # update), exactly like torch.optim.SGD
@@ -177,6 +190,22 @@ class FusedSGD:
                     runs.append([off, k, first])
                 self._seen[i] = True
             off += k
+        return runs
+
+    def reduce_and_step(self):
+        """The exchange step of data-parallel training: average the flat gradient over the ranks and apply the update.
+        With a PeerExchange this is ONE kernel per rank (peer-memory reads in rank order + update, csrc/peer.cu) -- every
+        rank must hold gradients for the same parameters; without one it is `step(all_reduce())`."""
+        if self.peer is None:
+            return self.step(self.all_reduce())
+        for off, k, first in self._begin_step():
+            mom = self.momentum_buf[off:off + k] if self.momentum_buf is not None else None
+            self.peer.allreduce_sgd(params=self.flat_param[off:off + k], momentum_buf=mom, lr=self.lr, momentum=self.momentum,
+                                    weight_decay=self.weight_decay, first_step=first, offset=off, n=k)
+
+    def step(self, grad_scale=1.0):
+        runs = self._begin_step()
+        dev = self.flat_param.device
         with torch.cuda.device(dev):
             st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             for off, k, first in runs:

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--nccl-allreduce", action="store_true", help="NCCL all-reduce + update kernel instead of the one peer-memory kernel")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -40,7 +41,8 @@ def main():
     torch.manual_seed(602)
     model = premetanode10((Identity,) * 3, (lambda t: t,) * 3, (F.gelu,) * 3, in_planes=64, is_odenet=True)
     model = model.to(dev).to(memory_format=torch.channels_last).train()
-    opt = msb.FusedSGD(model.parameters(), lr=0.05, momentum=0.9, weight_decay=5e-4)
+    # world > 1: the gradient lives in a PeerExchange buffer, all-reduce + SGD update = ONE kernel per rank (csrc/peer.cu)
+    opt = msb.FusedSGD(model.parameters(), lr=0.05, momentum=0.9, weight_decay=5e-4, peer=(world > 1 and not a.nccl_allreduce))
     sched = msb.CyclicLR(opt, base_lr=1e-4, max_lr=0.2, step_size_up=2000, mode="triangular2", cycle_momentum=True)
     atk = FGSMRandom(model, alpha=10 / 255., epsilon=8 / 255., mu=CIFAR_MEAN, std=CIFAR_STD)
     base = create_solver("rk2", "u", 8, -1, 0.5, -1, torch.float32, dev)
@@ -64,7 +66,7 @@ def main():
         xa, _ = atk(x, y, kws)
         loss = msb.cross_entropy(model(xa, **kws), y)
         loss.backward()
-        opt.step(grad_scale=opt.all_reduce())                  # ONE all-reduce of the flat gradient, 1/world folded into the update
+        opt.reduce_and_step()                                  # ONE exchange of the flat gradient, 1/world and the update folded in
         sched.step()
         it[0] += 1
         return loss
@@ -88,11 +90,24 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item()) / a.steps
+    exchange = "single rank: update kernel only"
+    identical = None
+    if world > 1:
+        if opt.peer is not None:
+            opt.peer.check()                                   # raises if a handshake timed out
+            exchange = "one kernel per rank over peer memory (msb_peer_allreduce_sgd): rank-order sum + SGD update"
+        else:
+            exchange = "NCCL all-reduce + update kernel" + ("".join("; " + n for n in opt.peer_note))
+        chk = torch.stack([opt.flat_param.double().sum(), opt.flat_param.double().abs().sum()])
+        allchk = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(allchk, chk)
+        identical = all(bool(torch.equal(c, allchk[0])) for c in allchk)      # replicas after warmup + steps updates
     if rank == 0:
         print(json.dumps(dict(config="C4 FGSM-random adversarial training step, solver smoothing u~N(0.5,0.0125) per batch, FusedSGD + CyclicLR, "
                                      "on-GPU crop/flip augmentation", n_gpus=world, batch_per_gpu=B, ms_per_step=ms,
                               images_per_s=world * B / ms * 1e3, scaling="weak", final_loss=float(loss.item()),
-                              collectives_per_step="1 all-reduce of %d B + 1 broadcast of 16 B" % (opt.flat_grad.numel() * 4))))
+                              collectives_per_step="1 all-reduce of %d B + 1 broadcast of 16 B" % (opt.flat_grad.numel() * 4),
+                              exchange=exchange, replicas_identical=identical)))
     if world > 1:
         dist.destroy_process_group()
 

@@ -1,0 +1,167 @@
+"""The data-parallel exchange step as ONE kernel over peer memory (csrc/peer.cu, parallel.PeerExchange).
+
+Two ranks as two PROCESSES on cuda:0 (gloo carries the IPC handles): each maps the other's gradient buffer and runs
+msb_peer_allreduce_sgd.  Checked: the averaged gradient equals (g0 + g1) * 0.5 BITWISE on both ranks (fixed rank-order sum),
+the fused update equals msb_sgd_step on that average bitwise and torch.optim.SGD to rounding, unaligned runs, the
+GradAllReducer / FusedSGD wiring, and that a missing peer ends in a reported timeout, not a hang."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+N_PARAMS = 674762          # premetanode10's flat gradient (2.70 MB)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _grad_of(rank, step, n):
+    g = torch.Generator().manual_seed(1000 * step + rank)
+    return torch.randn(n, generator=g) * (1.0 + rank)
+
+
+def _worker(rank, world, port, q):
+    try:
+        sys.path.insert(0, ROOT)
+        os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK="0", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        import torch.distributed as dist
+        import metasolver_b200 as msb
+        from metasolver_b200 import parallel
+        torch.cuda.set_device(0)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        dev = torch.device("cuda", 0)
+        out = {}
+        n = N_PARAMS
+        ex = parallel.PeerExchange(n, timeout_ms=30000)
+        l0 = msb.launch_count()
+
+        # 1. averaged gradient, three epochs: bitwise (g0 + g1) * 0.5 on every rank
+        avg = torch.empty(n, device=dev)
+        ok = True
+        for step in range(3):
+            ex.grad.copy_(_grad_of(rank, step, n).to(dev))
+            ex.allreduce_sgd(avg_out=avg)
+            want = ((_grad_of(0, step, n).to(dev) + _grad_of(1, step, n).to(dev)) * 0.5)
+            ok = ok and torch.equal(avg, want)
+        out["avg_bitwise"] = ok
+        out["launches"] = msb.launch_count() - l0
+
+        # 2. fused update == msb_sgd_step on the average (bitwise) == torch.optim.SGD (rounding); momentum + weight decay
+        torch.manual_seed(7)
+        w0 = torch.randn(n, device=dev)
+        p_fused, m_fused = w0.clone(), torch.zeros(n, device=dev)
+        p_ref = torch.nn.Parameter(w0.clone())
+        opt = torch.optim.SGD([p_ref], lr=0.05, momentum=0.9, weight_decay=5e-4)
+        p_two, m_two = w0.clone(), torch.zeros(n, device=dev)
+        from metasolver_b200 import _cabi
+        import ctypes
+        for step in range(3):
+            ex.grad.copy_(_grad_of(rank, 10 + step, n).to(dev))
+            ex.allreduce_sgd(params=p_fused, momentum_buf=m_fused, lr=0.05, momentum=0.9, weight_decay=5e-4, first_step=(step == 0))
+            want = ((_grad_of(0, 10 + step, n).to(dev) + _grad_of(1, 10 + step, n).to(dev)) * 0.5)
+            p_ref.grad = want.clone()
+            opt.step()
+            _cabi.check(_cabi.lib().msb_sgd_step(ctypes.c_void_p(p_two.data_ptr()), ctypes.c_void_p(want.data_ptr()),
+                                                 ctypes.c_void_p(m_two.data_ptr()), n, 0.05, 0.9, 5e-4, 1.0, 1 if step == 0 else 0,
+                                                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "sgd_step")
+        out["sgd_bitwise_vs_two_kernels"] = torch.equal(p_fused, p_two) and torch.equal(m_fused, m_two)
+        out["sgd_vs_torch"] = float((p_fused - p_ref.detach()).abs().max() / p_ref.detach().abs().max())
+        out["params_sum"] = float(p_fused.double().sum())          # compared across ranks by the parent
+
+        # 3. an unaligned run (offset and length not multiples of 4): scalar path
+        ex.grad.copy_(_grad_of(rank, 20, n).to(dev))
+        off, k = 1001, 30003
+        part = torch.full((k,), -7.0, device=dev)
+        ex.allreduce_sgd(avg_out=part, offset=off, n=k)
+        want = ((_grad_of(0, 20, n).to(dev) + _grad_of(1, 20, n).to(dev)) * 0.5)[off:off + k]
+        out["unaligned_bitwise"] = torch.equal(part, want)
+
+        # 4. GradAllReducer(peer=True) and FusedSGD(peer=True).reduce_and_step() on a small model
+        torch.manual_seed(0)
+        model = torch.nn.Sequential(torch.nn.Linear(5, 4), torch.nn.Linear(4, 3)).to(dev)
+        x = torch.full((2, 5), float(rank + 1), device=dev)
+        model(x).sum().backward()
+        local = [p.grad.clone() for p in model.parameters()]
+        red = parallel.GradAllReducer(model.parameters(), peer=True)
+        out["reducer_peer"] = red.peer is not None
+        red()
+        gathered = [[torch.empty_like(g).cpu() for _ in range(world)] for g in local]
+        for g, slot in zip(local, gathered):
+            dist.all_gather(slot, g.cpu())
+        out["reducer_ok"] = all(torch.equal(p.grad.cpu(), (s[0] + s[1]) * 0.5) for p, s in zip(model.parameters(), gathered))
+        model.zero_grad(set_to_none=True)
+        before = [p.detach().clone() for p in model.parameters()]
+        opt2 = msb.FusedSGD(model.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-3, peer=True)
+        out["fused_peer"] = opt2.peer is not None
+        model(x).sum().backward()
+        opt2.reduce_and_step()
+        want = [(b - 0.1 * ((s[0] + s[1]) * 0.5).to(dev) - 0.1 * 1e-3 * b) for b, s in zip(before, gathered)]
+        out["fused_step_err"] = max(float((p.detach() - w).abs().max()) for p, w in zip(model.parameters(), want))
+
+        err, epoch = ex.status()
+        out["status"] = (err, epoch)
+        dist.barrier()
+
+        # 5. a peer that never shows up: bounded wait, error reported (rank 1 stays away)
+        ex2 = parallel.PeerExchange(1024, timeout_ms=300)
+        if rank == 0:
+            ex2.allreduce_sgd(avg_out=torch.empty(1024, device=dev))
+            out["timeout_status"] = ex2.status()[0]
+            try:
+                ex2.check()
+                out["timeout_raises"] = False
+            except RuntimeError:
+                out["timeout_raises"] = True
+        dist.barrier()
+        ex2.close()
+        red.peer.close()
+        opt2.peer.close()
+        ex.close()
+        q.put((rank, out))
+        dist.destroy_process_group()
+    except Exception as exc:          # surface the failure instead of a silent dead worker
+        import traceback
+        q.put((rank, {"exception": "%s\n%s" % (exc, traceback.format_exc())}))
+
+
+def test_peer_memory_allreduce_and_fused_sgd_two_ranks_one_device():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = {}
+    try:
+        for _ in range(world):
+            r, out = q.get(timeout=240)
+            res[r] = out
+    finally:
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.kill()
+    for r in range(world):
+        assert "exception" not in res[r], res[r]["exception"]
+        o = res[r]
+        assert o["avg_bitwise"] and o["launches"] == 3, o          # one launch per exchange
+        assert o["sgd_bitwise_vs_two_kernels"], o
+        assert o["sgd_vs_torch"] < 1e-6, o
+        assert o["unaligned_bitwise"], o
+        assert o["reducer_peer"] and o["reducer_ok"], o
+        assert o["fused_peer"] and o["fused_step_err"] < 1e-6, o
+        assert o["status"][0] == 0 and o["status"][1] == 7, o      # 3 + 3 + 1 launches on `ex`, no timeout
+    assert res[0]["params_sum"] == res[1]["params_sum"]            # replicas stay bitwise identical
+    assert res[0]["timeout_status"] == 1 and res[0]["timeout_raises"], res[0]

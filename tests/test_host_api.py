@@ -95,7 +95,7 @@ def test_cabi_library_exports_header_symbols():
     lib = _cabi.lib()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.msb_abi_version() == _cabi.ABI_VERSION == 5
+    assert lib.msb_abi_version() == _cabi.ABI_VERSION == 6
     assert lib.msb_shape_supports_tcgen05(64, 32, 32) in (0, 1)
     # descriptor validation is host-only: bad stage count must be refused with a message
     d = _cabi.MsbOdeDesc()

@@ -56,6 +56,16 @@ def _worker(rank, world, port, q):
     lo, hi = parallel.shard_range(11, rank, world)
     out["shard"] = (lo, hi)
     out["count"] = parallel.allreduce_sum_int(hi - lo, dev)
+    out["counts"] = parallel.allreduce_sum_counts(torch.tensor([hi - lo, rank + 1, 0]))     # whole sweep vector, one all-reduce
+    # the peer-memory exchange needs CUDA devices: refused loudly here, and the reducers keep the collective path
+    try:
+        parallel.PeerExchange(8)
+        out["peer_refused"] = False
+    except RuntimeError as exc:
+        out["peer_refused"] = "CUDA" in str(exc)
+    out["peer_or_none"] = parallel.peer_exchange_or_none(8) is None
+    red_p = parallel.GradAllReducer(model.parameters(), peer=True)
+    out["reducer_peer_is_none"] = red_p.peer is None
     # 4. a sharded synthetic evaluation set (scripts/eval_pgd_sweep.py): every rank generates only its slice
     from metasolver_b200 import detrand
     out["shard_data"] = detrand.uniform((hi - lo, 3, 4, 4), 9100, 0.0, 1.0, offset=lo * 48).tolist()
@@ -90,3 +100,6 @@ def test_data_parallel_host_logic_world2():
     assert a["tab"] == b["tab"]
     assert a["shard"] == (0, 6) and b["shard"] == (6, 11)
     assert a["count"] == b["count"] == 11
+    assert a["counts"] == b["counts"] == [11, 3, 0]
+    for o in (a, b):
+        assert o["peer_refused"] is True and o["peer_or_none"] and o["reducer_peer_is_none"]
