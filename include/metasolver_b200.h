@@ -263,16 +263,21 @@ int msb_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t
  *   msb_peer_free    release the own buffer (after every peer has closed it)
  *   msb_peer_status  synchronous read of the own header: error word (0 = ok, MSB_PEER_ERR_*) and the last finished epoch
  *   msb_peer_allreduce_sgd
- *       bases[world]: exchange buffers in rank order, bases[rank] = the own one.  The flat fp32 gradient of every rank is
- *       the payload of its buffer; this launch covers floats [offset, offset + n).  Per element, on every rank:
+ *       bases[world]: exchange buffers in rank order, bases[rank] = the own one.  The payload of every buffer holds the rank's
+ *       flat fp32 gradient at float 0 and, if result_offset >= 0, a result array of the same indexing at float result_offset.
+ *       This launch covers floats [offset, offset + n).  Per element, on every rank:
  *           s = (((g_0 + g_1) + g_2) + ... + g_{world-1}) * grad_scale            fixed order: bitwise identical on all ranks
- *           avg_out[i] = s                                                        (if avg_out != NULL; own memory)
+ *           result[i] = s                                       (when write_result, and always in the two-shot form)
  *           g = s + weight_decay*p;  buf = first_step ? g : momentum*buf + g;  p -= lr*buf     (if params != NULL; = msb_sgd_step)
- *       avg_out / params / momentum_buf point at element `offset` of their flat arrays.  All ranks must issue the same
- *       sequence of launches.  The launch starts with a system-scope handshake (all gradients complete) and ends with one
- *       (all reads finished: the successor on the stream may overwrite the gradient); the epoch ordering the messages is
- *       kept in the header, so the call can be captured in a CUDA graph.  Waits are bounded by timeout_ms (0 = 10 s): on
- *       expiry the header's error word is set and the launch completes with undefined results instead of hanging. */
+ *       params / momentum_buf point at element `offset` of their flat arrays (own memory).  Two forms of the same launch:
+ *       one-shot (every rank reads all gradients) and, with a result array and from three ranks on, two-shot (rank r reduces
+ *       slice r and stores the average into every rank's result array, then updates from its own result array); option
+ *       "peer_form" forces one.  All ranks must issue the same sequence of launches.  The launch starts with a system-scope
+ *       handshake (all gradients complete) and contains a second one (nobody reads a gradient any more / all slices have
+ *       landed): when it has finished, the stream's successor may overwrite the gradient, and the result array is valid until
+ *       the next exchange launch of this rank.  The epoch ordering the messages is kept in the header, so the call can be
+ *       captured in a CUDA graph.  Waits are bounded by timeout_ms (0 = 10 s): on expiry the header's error word is set and
+ *       the launch completes with undefined results instead of hanging. */
 #define MSB_PEER_MAX_RANKS 16
 #define MSB_PEER_HANDLE_BYTES 64
 #define MSB_PEER_HEADER_BYTES 1024
@@ -282,9 +287,9 @@ int msb_peer_open(const unsigned char* handle, void** base);
 int msb_peer_close(void* base);
 int msb_peer_free(void* base);
 int msb_peer_status(const void* own_base, unsigned* error_word, unsigned* epoch);
-int msb_peer_allreduce_sgd(void* const* bases, int world, int rank, int64_t offset, int64_t n, float* avg_out, float* params,
-                           float* momentum_buf, float lr, float momentum, float weight_decay, float grad_scale,
-                           int first_step, unsigned timeout_ms, void* cuda_stream);
+int msb_peer_allreduce_sgd(void* const* bases, int world, int rank, int64_t offset, int64_t n, int64_t result_offset,
+                           int write_result, float* params, float* momentum_buf, float lr, float momentum, float weight_decay,
+                           float grad_scale, int first_step, unsigned timeout_ms, void* cuda_stream);
 
 /* Network head of MetaNODE: AdaptiveAvgPool2d((1,1)) + Flatten + Linear (sopa/src/models/odenet_cifar10/layers.py:390-392,425)
  * on an NHWC fp32 map, and its gradient.  pooled[batch][channels] is an output of the forward (saved for the backward).
@@ -338,6 +343,8 @@ int msb_cross_entropy_backward(const float* logits, const int64_t* labels, const
  *                      copy (round 1)                                     (env MSB_WGRAD_HTAPS)
  *   "tcp2_halo"        1 (default) = C = 128 convolution on 16-pixel-wide images stages ONE halo tile per c_in chunk for all
  *                      nine taps (horizontal taps = the same tile read 128 B further); 0 = three shifted copies (env MSB_TCP2_HALO)
+ *   "peer_form"        gradient exchange over peer memory (msb_peer_allreduce_sgd): 0 (default) = two-shot from three ranks on,
+ *                      1 = always one-shot, 2 = always two-shot           (env MSB_PEER_FORM)
  *   "tcp2_half_stage"  1 = half-size epilogue stage of the C = 128 pair convolution, the memory going to deeper operand rings
  *                      (default 0)                                        (env MSB_TCP2_HALF_STAGE)
  * Results do not depend on any option except the products formed (tc_form_c64, tct_products, wgrad64_products: last-bit

@@ -139,7 +139,7 @@ def _declare(lib):
     lib.msb_peer_close.argtypes = [vp]
     lib.msb_peer_free.argtypes = [vp]
     lib.msb_peer_status.argtypes = [vp, ctypes.POINTER(u32), ctypes.POINTER(u32)]
-    lib.msb_peer_allreduce_sgd.argtypes = [ctypes.POINTER(vp), i32, i32, i64, i64, vp, vp, vp, f32, f32, f32, f32, i32, u32, vp]
+    lib.msb_peer_allreduce_sgd.argtypes = [ctypes.POINTER(vp), i32, i32, i64, i64, i64, i32, vp, vp, f32, f32, f32, f32, i32, u32, vp]
     lib.msb_profile_enable.argtypes = [i32]
     lib.msb_profile_read_executed.argtypes = [i32, ctypes.POINTER(ctypes.c_double)]
     lib.msb_profile_read.argtypes = [i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),

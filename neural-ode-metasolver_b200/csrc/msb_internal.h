@@ -41,6 +41,8 @@ enum { TUNE_EPI_L2_PREFETCH = 0,   // conv epilogue operands: bulk L2 prefetch d
        TUNE_WGRAD_HTAPS = 18,      // weight gradient: a CTA owns a vertical tap, the three horizontal taps are N atoms 128 B apart
                                    // in one staged copy (1, default: -17 % L2 -> SM bytes, C = 64 launch -10 % under the power cap) or
                                    // a CTA owns a horizontal tap with its own shifted box (0, round 1)
+       TUNE_PEER_FORM = 19,        // gradient exchange over peer memory (peer.cu): 0 = two-shot from three ranks on (default), 1 = always
+                                   // one-shot (every rank reads every gradient), 2 = always two-shot (reduce-scatter + peer stores)
        TUNE_COUNT };
 int tune_get(int which);
 

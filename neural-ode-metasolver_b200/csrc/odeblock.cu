@@ -39,10 +39,10 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 static std::atomic<int> g_tune[TUNE_COUNT];
 static std::atomic<bool> g_tune_init{false};
 static const char* const kTuneNames[TUNE_COUNT] = {"epi_l2_prefetch", "tc_resident", "tcp_epi_warps", "tc_form_c64", "tc_pair",
-                                                   "wait_backoff_ns", "pdl", "wgrad_multicast", "tct_band", "tct_debug", "tct_products", "mma_warp_high", "wgrad64_products", "mnist_fused", "uniform_issue", "gn_block", "tcp2_half_stage", "tcp2_halo", "wgrad_htaps"};
+                                                   "wait_backoff_ns", "pdl", "wgrad_multicast", "tct_band", "tct_debug", "tct_products", "mma_warp_high", "wgrad64_products", "mnist_fused", "uniform_issue", "gn_block", "tcp2_half_stage", "tcp2_halo", "wgrad_htaps", "peer_form"};
 static const char* const kTuneEnv[TUNE_COUNT] = {"MSB_EPI_L2_PREFETCH", "MSB_TC_RESIDENT", "MSB_TCP_EPI_WARPS", "MSB_TC_FORM_C64",
-                                                 "MSB_TC_PAIR", "MSB_WAIT_BACKOFF_NS", "MSB_PDL", "MSB_WGRAD_MULTICAST", "MSB_TCT_BAND", "MSB_TCT_DEBUG", "MSB_TCT_PRODUCTS", "MSB_MMA_WARP_HIGH", "MSB_WGRAD64_PRODUCTS", "MSB_MNIST_FUSED", "MSB_UNIFORM_ISSUE", "MSB_GN_BLOCK", "MSB_TCP2_HALF_STAGE", "MSB_TCP2_HALO", "MSB_WGRAD_HTAPS"};
-static const int kTuneDefault[TUNE_COUNT] = {0, 0, 16, 2, 2, 0, 1, 0, 0, 0, 4, 0, 4, 1, 1, 1, 0, 1, 1};
+                                                 "MSB_TC_PAIR", "MSB_WAIT_BACKOFF_NS", "MSB_PDL", "MSB_WGRAD_MULTICAST", "MSB_TCT_BAND", "MSB_TCT_DEBUG", "MSB_TCT_PRODUCTS", "MSB_MMA_WARP_HIGH", "MSB_WGRAD64_PRODUCTS", "MSB_MNIST_FUSED", "MSB_UNIFORM_ISSUE", "MSB_GN_BLOCK", "MSB_TCP2_HALF_STAGE", "MSB_TCP2_HALO", "MSB_WGRAD_HTAPS", "MSB_PEER_FORM"};
+static const int kTuneDefault[TUNE_COUNT] = {0, 0, 16, 2, 2, 0, 1, 0, 0, 0, 4, 0, 4, 1, 1, 1, 0, 1, 1, 0};
 static void tune_init() {
     if (g_tune_init.load(std::memory_order_acquire)) return;
     for (int i = 0; i < TUNE_COUNT; ++i) {

@@ -52,7 +52,9 @@ class PeerExchange:
 
         ex = PeerExchange(n_floats)          # collective: every rank of the group calls it (handles travel by all_gather_object)
         ex.grad                              # this rank's flat gradient: a torch view of the exchange buffer's payload
-        ex.allreduce_sgd(avg_out=..., params=..., momentum_buf=..., lr=..., ...)      # one kernel, see msb_peer_allreduce_sgd
+        ex.result                            # the averaged gradient after an exchange (second array of the payload)
+        ex.allreduce_sgd(params=..., momentum_buf=..., lr=..., ...)      # one kernel: average + SGD update (msb_peer_allreduce_sgd)
+        ex.allreduce_sgd()                                               # one kernel: average into ex.result
         ex.check()                           # synchronises and raises if a handshake of this rank timed out
 
     Works between devices with peer access and between processes sharing one device (the GPU tests run two ranks on
@@ -67,6 +69,7 @@ class PeerExchange:
         if self.world > _cabi.PEER_MAX_RANKS:
             raise RuntimeError("metasolver_b200.PeerExchange: at most %d ranks (one node)" % _cabi.PEER_MAX_RANKS)
         self.n = int(n_floats)
+        self._result_off = (self.n + 3) // 4 * 4           # payload = [gradient | result], both 16-byte aligned
         self.timeout_ms = int(timeout_ms)
         self.device = torch.device("cuda", torch.cuda.current_device())
         lib = _cabi.lib()
@@ -77,7 +80,7 @@ class PeerExchange:
         try:
             base = ctypes.c_void_p()
             with torch.cuda.device(self.device):
-                _cabi.check(lib.msb_peer_alloc(self.n * 4, ctypes.byref(base), handle), "peer_alloc")
+                _cabi.check(lib.msb_peer_alloc((self._result_off + self.n) * 4, ctypes.byref(base), handle), "peer_alloc")
             self._own = base.value
         except Exception as exc:
             err = "rank %d: %s" % (self.rank, str(exc).splitlines()[0][:160])
@@ -114,24 +117,28 @@ class PeerExchange:
         elif err:
             raise RuntimeError("metasolver_b200.PeerExchange: " + err)
         self._bases = (ctypes.c_void_p * self.world)(*bases)
-        self._carrier = _DeviceArray(self._own + _cabi.PEER_HEADER_BYTES, self.n)
-        self.grad = torch.as_tensor(self._carrier, device=self.device)
+        self._carrier = _DeviceArray(self._own + _cabi.PEER_HEADER_BYTES, self._result_off + self.n)
+        payload = torch.as_tensor(self._carrier, device=self.device)
+        self.grad = payload[:self.n]
+        self.result = payload[self._result_off:]
 
-    def allreduce_sgd(self, avg_out=None, params=None, momentum_buf=None, lr=0.0, momentum=0.0, weight_decay=0.0,
-                      grad_scale=None, first_step=False, offset=0, n=None):
-        """Reduce floats [offset, offset+n) of every rank's gradient (rank order), scale (default 1/world) and write the
-        average to `avg_out` and / or apply the SGD update to `params` (`momentum_buf`): flat fp32 CUDA tensors of n
-        elements.  Enqueued on the current stream; all ranks must make the same calls."""
+    def allreduce_sgd(self, params=None, momentum_buf=None, lr=0.0, momentum=0.0, weight_decay=0.0, grad_scale=None,
+                      first_step=False, offset=0, n=None):
+        """Reduce floats [offset, offset+n) of every rank's gradient (rank order), scale (default 1/world) and apply the SGD
+        update to `params` (`momentum_buf`): flat fp32 CUDA tensors of n elements; without `params` the average is left in
+        `self.result[offset:offset+n]` (valid until this rank's next exchange).  Enqueued on the current stream; all ranks
+        must make the same calls."""
         n = self.n - offset if n is None else int(n)
-        for t in (avg_out, params, momentum_buf):
+        for t in (params, momentum_buf):
             if t is not None and (t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous() or t.numel() != n):
                 raise ValueError("metasolver_b200.PeerExchange.allreduce_sgd: operands must be contiguous CUDA float32 of %d elements" % n)
         scale = 1.0 / self.world if grad_scale is None else float(grad_scale)
         vp = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
         with torch.cuda.device(self.device):
-            _cabi.check(_cabi.lib().msb_peer_allreduce_sgd(self._bases, self.world, self.rank, int(offset), n, vp(avg_out), vp(params),
-                                                           vp(momentum_buf), float(lr), float(momentum), float(weight_decay),
-                                                           scale, 1 if first_step else 0, self.timeout_ms,
+            _cabi.check(_cabi.lib().msb_peer_allreduce_sgd(self._bases, self.world, self.rank, int(offset), n, self._result_off,
+                                                           1 if params is None else 0, vp(params), vp(momentum_buf), float(lr),
+                                                           float(momentum), float(weight_decay), scale, 1 if first_step else 0,
+                                                           self.timeout_ms,
                                                            ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)),
                         "peer_allreduce_sgd")
 
@@ -152,7 +159,7 @@ class PeerExchange:
     def close(self, collective=True):
         """Unmap the peers' buffers, then (after a barrier when `collective`) free the own one."""
         lib = _cabi.lib()
-        self.grad = None
+        self.grad = self.result = None
         with torch.cuda.device(self.device):
             torch.cuda.synchronize(self.device)
             for p in self._opened:
@@ -186,8 +193,8 @@ class GradAllReducer:
     copies, the all-reduce, a scale and ~36 unpack copies.
 
     peer=True (multi-rank CUDA job on one node): the flat buffer is the payload of a `PeerExchange` and the reduction is
-    ONE kernel per rank over peer memory (rank-order sum, bitwise identical on all ranks, 1/world folded in) writing the
-    average into a second flat buffer; when the mapping is refused (`note` says why) or peer is False: NCCL
+    ONE kernel per rank over peer memory (rank-order sum, bitwise identical on all ranks, 1/world folded in) leaving the
+    average in the exchange buffer's result array; when the mapping is refused (`note` says why) or peer is False: NCCL
     (`ReduceOp.AVG` in place) / gloo."""
 
     def __init__(self, params, peer=False):
@@ -197,7 +204,7 @@ class GradAllReducer:
         self.note = []
         self.peer = peer_exchange_or_none(n, self.note) if peer and dev.type == "cuda" else None
         self.flat = self.peer.grad if self.peer is not None else torch.zeros(n, dtype=torch.float32, device=dev)
-        self.result = torch.zeros(n, dtype=torch.float32, device=dev) if self.peer is not None else self.flat
+        self.result = self.peer.result if self.peer is not None else self.flat
         self.views = []
         self._in_views = []
         off = 0
@@ -224,7 +231,7 @@ class GradAllReducer:
             with torch.no_grad():
                 torch.cat(pieces, out=self.flat)                  # one gather kernel (no-op when grads already live in `flat`)
         if self.peer is not None:
-            self.peer.allreduce_sgd(avg_out=self.result, grad_scale=None if average else 1.0)
+            self.peer.allreduce_sgd(grad_scale=None if average else 1.0)          # average -> peer.result = self.result
         elif average and dist.get_backend() == "nccl":
             dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
         else:

@@ -84,7 +84,7 @@ class FusedSGD:
     place (one all-reduce of 2.70 MB per step for premetanode10)."""
 
     def __init__(self, params, lr, momentum=0.0, weight_decay=0.0, peer=None):
-        """peer: None = gradients in ordinary device memory, `all_reduce()` is an NCCL / gloo call; True = allocate a
+        """peer: None / False = gradients in ordinary device memory, `all_reduce()` is an NCCL / gloo call; True = allocate a
         `parallel.PeerExchange` for the flat gradient (collective; multi-rank CUDA job on one node; falls back to None
         when the mapping is refused) or pass one: `reduce_and_step()` is then ONE kernel per rank (msb_peer_allreduce_sgd)."""
         self.params = [p for p in params if p.requires_grad]
@@ -101,6 +101,8 @@ class FusedSGD:
         if peer is True:
             from . import parallel
             peer = parallel.peer_exchange_or_none(n, self.peer_note)
+        elif peer is False:
+            peer = None
         if peer is not None and (peer.n != n or peer.device != dev):
             raise ValueError("metasolver_b200.FusedSGD: the PeerExchange holds %d floats on %s, the parameters %d on %s"
                              % (peer.n, peer.device, n, dev))

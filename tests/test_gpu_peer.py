@@ -1,9 +1,10 @@
 """The data-parallel exchange step as ONE kernel over peer memory (csrc/peer.cu, parallel.PeerExchange).
 
-Two ranks as two PROCESSES on cuda:0 (gloo carries the IPC handles): each maps the other's gradient buffer and runs
-msb_peer_allreduce_sgd.  Checked: the averaged gradient equals (g0 + g1) * 0.5 BITWISE on both ranks (fixed rank-order sum),
-the fused update equals msb_sgd_step on that average bitwise and torch.optim.SGD to rounding, unaligned runs, the
-GradAllReducer / FusedSGD wiring, and that a missing peer ends in a reported timeout, not a hang."""
+The ranks are PROCESSES sharing cuda:0 (gloo carries the IPC handles): each maps the others' exchange buffers and runs
+msb_peer_allreduce_sgd, in the one-shot form (2 ranks), the two-shot form forced on 2 ranks and the two-shot form as chosen
+for 4 ranks.  Checked: the averaged gradient equals ((g0 + g1) + ...) / W BITWISE on every rank (fixed rank-order sum), the
+fused update equals msb_sgd_step on that average bitwise and torch.optim.SGD to rounding, unaligned runs, the
+GradAllReducer / FusedSGD wiring, and that missing peers end in a reported timeout, not a hang."""
 import os
 import socket
 import sys
@@ -31,7 +32,14 @@ def _grad_of(rank, step, n):
     return torch.randn(n, generator=g) * (1.0 + rank)
 
 
-def _worker(rank, world, port, q):
+def _avg_of(step, n, world, dev):
+    want = _grad_of(0, step, n).to(dev)
+    for r in range(1, world):
+        want = want + _grad_of(r, step, n).to(dev)          # rank order, like the kernel
+    return want * (1.0 / world)
+
+
+def _worker(rank, world, port, q, form):
     try:
         sys.path.insert(0, ROOT)
         os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK="0", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -41,19 +49,18 @@ def _worker(rank, world, port, q):
         torch.cuda.set_device(0)
         dist.init_process_group("gloo", rank=rank, world_size=world)
         dev = torch.device("cuda", 0)
+        msb.set_option("peer_form", form)
         out = {}
         n = N_PARAMS
         ex = parallel.PeerExchange(n, timeout_ms=30000)
         l0 = msb.launch_count()
 
         # 1. averaged gradient, three epochs: bitwise (g0 + g1) * 0.5 on every rank
-        avg = torch.empty(n, device=dev)
         ok = True
         for step in range(3):
             ex.grad.copy_(_grad_of(rank, step, n).to(dev))
-            ex.allreduce_sgd(avg_out=avg)
-            want = ((_grad_of(0, step, n).to(dev) + _grad_of(1, step, n).to(dev)) * 0.5)
-            ok = ok and torch.equal(avg, want)
+            ex.allreduce_sgd()
+            ok = ok and torch.equal(ex.result, _avg_of(step, n, world, dev))
         out["avg_bitwise"] = ok
         out["launches"] = msb.launch_count() - l0
 
@@ -69,7 +76,7 @@ def _worker(rank, world, port, q):
         for step in range(3):
             ex.grad.copy_(_grad_of(rank, 10 + step, n).to(dev))
             ex.allreduce_sgd(params=p_fused, momentum_buf=m_fused, lr=0.05, momentum=0.9, weight_decay=5e-4, first_step=(step == 0))
-            want = ((_grad_of(0, 10 + step, n).to(dev) + _grad_of(1, 10 + step, n).to(dev)) * 0.5)
+            want = _avg_of(10 + step, n, world, dev)
             p_ref.grad = want.clone()
             opt.step()
             _cabi.check(_cabi.lib().msb_sgd_step(ctypes.c_void_p(p_two.data_ptr()), ctypes.c_void_p(want.data_ptr()),
@@ -82,10 +89,14 @@ def _worker(rank, world, port, q):
         # 3. an unaligned run (offset and length not multiples of 4): scalar path
         ex.grad.copy_(_grad_of(rank, 20, n).to(dev))
         off, k = 1001, 30003
-        part = torch.full((k,), -7.0, device=dev)
-        ex.allreduce_sgd(avg_out=part, offset=off, n=k)
-        want = ((_grad_of(0, 20, n).to(dev) + _grad_of(1, 20, n).to(dev)) * 0.5)[off:off + k]
-        out["unaligned_bitwise"] = torch.equal(part, want)
+        ex.result.fill_(-7.0)
+        dist.barrier()                                    # (the fill is ordered before the peers' stores only by the next handshake)
+        torch.cuda.synchronize()
+        dist.barrier()
+        ex.allreduce_sgd(offset=off, n=k)
+        want = _avg_of(20, n, world, dev)[off:off + k]
+        out["unaligned_bitwise"] = (torch.equal(ex.result[off:off + k], want) and float(ex.result[off - 1]) == -7.0
+                                    and float(ex.result[off + k]) == -7.0)
 
         # 4. GradAllReducer(peer=True) and FusedSGD(peer=True).reduce_and_step() on a small model
         torch.manual_seed(0)
@@ -99,14 +110,15 @@ def _worker(rank, world, port, q):
         gathered = [[torch.empty_like(g).cpu() for _ in range(world)] for g in local]
         for g, slot in zip(local, gathered):
             dist.all_gather(slot, g.cpu())
-        out["reducer_ok"] = all(torch.equal(p.grad.cpu(), (s[0] + s[1]) * 0.5) for p, s in zip(model.parameters(), gathered))
+        mean = lambda s: sum(s[1:], s[0]) * (1.0 / world)
+        out["reducer_ok"] = all(torch.equal(p.grad.cpu(), mean(s)) for p, s in zip(model.parameters(), gathered))
         model.zero_grad(set_to_none=True)
         before = [p.detach().clone() for p in model.parameters()]
         opt2 = msb.FusedSGD(model.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-3, peer=True)
         out["fused_peer"] = opt2.peer is not None
         model(x).sum().backward()
         opt2.reduce_and_step()
-        want = [(b - 0.1 * ((s[0] + s[1]) * 0.5).to(dev) - 0.1 * 1e-3 * b) for b, s in zip(before, gathered)]
+        want = [(b - 0.1 * mean(s).to(dev) - 0.1 * 1e-3 * b) for b, s in zip(before, gathered)]
         out["fused_step_err"] = max(float((p.detach() - w).abs().max()) for p, w in zip(model.parameters(), want))
 
         err, epoch = ex.status()
@@ -116,7 +128,7 @@ def _worker(rank, world, port, q):
         # 5. a peer that never shows up: bounded wait, error reported (rank 1 stays away)
         ex2 = parallel.PeerExchange(1024, timeout_ms=300)
         if rank == 0:
-            ex2.allreduce_sgd(avg_out=torch.empty(1024, device=dev))
+            ex2.allreduce_sgd()
             out["timeout_status"] = ex2.status()[0]
             try:
                 ex2.check()
@@ -135,12 +147,12 @@ def _worker(rank, world, port, q):
         q.put((rank, {"exception": "%s\n%s" % (exc, traceback.format_exc())}))
 
 
-def test_peer_memory_allreduce_and_fused_sgd_two_ranks_one_device():
-    world = 2
+@pytest.mark.parametrize("world,form", [(2, 0), (2, 2), (4, 0)], ids=["2ranks_one_shot", "2ranks_two_shot", "4ranks_two_shot"])
+def test_peer_memory_allreduce_and_fused_sgd_ranks_sharing_one_device(world, form):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, form)) for r in range(world)]
     for p in procs:
         p.start()
     res = {}
@@ -163,5 +175,5 @@ def test_peer_memory_allreduce_and_fused_sgd_two_ranks_one_device():
         assert o["reducer_peer"] and o["reducer_ok"], o
         assert o["fused_peer"] and o["fused_step_err"] < 1e-6, o
         assert o["status"][0] == 0 and o["status"][1] == 7, o      # 3 + 3 + 1 launches on `ex`, no timeout
-    assert res[0]["params_sum"] == res[1]["params_sum"]            # replicas stay bitwise identical
+    assert all(res[r]["params_sum"] == res[0]["params_sum"] for r in range(world))      # replicas stay bitwise identical
     assert res[0]["timeout_status"] == 1 and res[0]["timeout_raises"], res[0]
