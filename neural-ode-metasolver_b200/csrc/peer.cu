@@ -19,7 +19,7 @@
 // averaged slice into the result array of EVERY rank's exchange buffer (peer stores), a second handshake says "my slice has
 // landed everywhere" (which also tells the peers that this rank no longer reads their gradients), and after it every rank
 // updates its replica from its own, now complete, result array.  Same rank-order sum, same bitwise-identical replicas,
-// 2 x (W-1)/W x 2.70 MB of NVLink traffic per rank instead of (W-1) x 2.70 MB.
+// 2 x (W-1)/W x 2.70 MB of NVLink traffic per rank instead of (W-1) x 2.70 MB: 8 ranks 30.0 us (1.56 x NCCL + update).
 // The epoch that orders the messages lives in the header (device memory), not in a kernel argument: the launch is
 // identical every step and can be captured in a CUDA graph.
 // Every wait is bounded (timeout -> header.error, the launch finishes with garbage instead of hanging the GPU).
