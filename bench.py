@@ -255,9 +255,9 @@ def run_ours(args):
                 reducer = parallel.GradAllReducer(model.parameters(), peer=False)
                 allreduce_note += "; peer-memory kernel failed its cross-check (max rel err %.3g): not used" % err
             else:
-                allreduce_note = ("one kernel per rank over peer memory (msb_peer_allreduce_sgd: rank-order sum of the %d-byte flat "
-                                  "gradient read from all ranks over NVLink, 1/world folded in; max rel diff to NCCL AVG %.1e)"
-                                  % (reducer.nbytes, err))
+                allreduce_note = ("one kernel per rank over peer memory (msb_peer_allreduce_sgd, %s form: rank-order sum of the "
+                                  "%d-byte flat gradient over NVLink, 1/world folded in; max rel diff to NCCL AVG %.1e)"
+                                  % ("two-shot" if world >= 3 else "one-shot", reducer.nbytes, err))
         barrier()
 
     # ---- timed region A: K steps issued eagerly with CUDA events around every convolution-engine launch
@@ -321,6 +321,11 @@ def run_ours(args):
     ms_e2e = timed(e2e_step, args.steps, finish=lambda: losses.extend(loop.drain()))
     assert len(losses) == args.steps and all(l == l for l in losses), losses
 
+    if world > 1 and reducer.peer is not None:
+        err_word, epochs = reducer.peer.status()            # every rank looks at its own header after the timed regions
+        bad = torch.tensor([float(err_word != 0)], device=dev)
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        allreduce_note += "; %d exchanges, handshake time-outs: %s" % (epochs, "none" if float(bad.item()) == 0.0 else "YES (results invalid)")
     if rank != 0:
         return
     peaks = {}

@@ -60,7 +60,7 @@ class PeerExchange:
     Works between devices with peer access and between processes sharing one device (the GPU tests run two ranks on
     cuda:0).  Raises if the ranks are not on one host.  `timeout_ms` bounds every in-kernel wait."""
 
-    def __init__(self, n_floats, group=None, timeout_ms=10000):
+    def __init__(self, n_floats, group=None, timeout_ms=30000):
         if not torch.cuda.is_available():
             raise RuntimeError("metasolver_b200.PeerExchange: needs CUDA devices (the CPU tests use the gloo all-reduce)")
         self.group = group
