@@ -154,7 +154,7 @@ class PeerExchange:
         err, _ = self.status()
         if err:
             raise RuntimeError("metasolver_b200.PeerExchange: a peer handshake timed out on rank %d (error %d: %s)"
-                               % (self.rank, err, {1: "a rank never announced its gradient", 2: "a rank never finished reading"}.get(err, "?")))
+                               % (self.rank, err, {1: "a rank never announced its gradient", 2: "a rank never finished reading / its slice of the average never arrived"}.get(err, "?")))
 
     def close(self, collective=True):
         """Unmap the peers' buffers, then (after a barrier when `collective`) free the own one."""

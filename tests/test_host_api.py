@@ -104,6 +104,24 @@ def test_cabi_library_exports_header_symbols():
     assert b"stages" in lib.msb_last_error() or b"rhs" in lib.msb_last_error()
 
 
+def test_binding_constants_match_the_header():
+    header = open(os.path.join(ROOT, "include", "metasolver_b200.h")).read()
+    defs = {k: int(v) for k, v in re.findall(r"#define\s+(MSB_[A-Z_]+)\s+(\d+)", header)}
+    assert defs["MSB_ABI_VERSION"] == _cabi.ABI_VERSION
+    assert (defs["MSB_PEER_MAX_RANKS"], defs["MSB_PEER_HANDLE_BYTES"], defs["MSB_PEER_HEADER_BYTES"]) == (
+        _cabi.PEER_MAX_RANKS, _cabi.PEER_HANDLE_BYTES, _cabi.PEER_HEADER_BYTES)
+    assert defs["MSB_ATTACK_MAX_CHANNELS"] == _cabi.ATTACK_MAX_CHANNELS
+    # the peer exchange validates its arguments on the host before any CUDA call
+    lib = _cabi.lib()
+    bases = (ctypes.c_void_p * 2)(None, None)
+    assert lib.msb_peer_allreduce_sgd(bases, 2, 5, 0, 16, 16, 1, None, None, 0.0, 0.0, 0.0, 1.0, 0, 0, None) == -1
+    assert b"bad arguments" in lib.msb_last_error()
+    assert lib.msb_peer_allreduce_sgd(bases, 2, 0, 0, 16, -1, 1, None, None, 0.0, 0.0, 0.0, 1.0, 0, 0, None) == -1
+    assert b"result" in lib.msb_last_error()
+    assert lib.msb_peer_allreduce_sgd(bases, 2, 0, 0, 16, 16, 1, None, None, 0.0, 0.0, 0.0, 1.0, 0, 0, None) == -1
+    assert b"null" in lib.msb_last_error()
+
+
 def test_binding_struct_layouts_match_the_library():
     lib = _cabi.lib()
     for which, cls in enumerate((_cabi.MsbOdeDesc, _cabi.MsbTableau, _cabi.MsbMnistParams, _cabi.MsbMnistGrads,
