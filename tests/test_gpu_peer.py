@@ -158,15 +158,28 @@ def test_peer_memory_allreduce_and_fused_sgd_ranks_sharing_one_device(world, for
     res = {}
     try:
         for _ in range(world):
-            r, out = q.get(timeout=240)
+            try:
+                r, out = q.get(timeout=240)
+            except Exception:              # queue.Empty: a worker died or is stuck behind one that failed
+                break
             res[r] = out
+            if "exception" in out:         # its peers are waiting for it in a collective: do not wait for them
+                break
     finally:
         for p in procs:
             p.join(timeout=30)
             if p.is_alive():
                 p.kill()
-    for r in range(world):
+    # an environment that cannot host the test at all (exclusive-process compute mode, CUDA IPC not permitted) is a skip with
+    # its reason; anything else -- wrong sums, time-outs, crashes inside the exchange -- is a failure
+    refused = [res[r]["exception"] for r in res if "exception" in res[r] and any(
+        k in res[r]["exception"] for k in ("cudaIpcGetMemHandle", "cudaIpcOpenMemHandle", "busy or unavailable", "peer_alloc"))]
+    if refused:
+        pytest.skip("this box cannot share one device between processes over CUDA IPC: " + refused[0].splitlines()[0][:200])
+    for r in res:
         assert "exception" not in res[r], res[r]["exception"]
+    assert sorted(res) == list(range(world)), "workers %s did not report" % sorted(set(range(world)) - set(res))
+    for r in range(world):
         o = res[r]
         assert o["avg_bitwise"] and o["launches"] == 3, o          # one launch per exchange
         assert o["sgd_bitwise_vs_two_kernels"], o
