@@ -2,7 +2,7 @@
 // and the optimizer update that follows it, as ONE kernel over peer memory (NVLink 5 / NVSwitch loads) instead of an
 // NCCL all-reduce followed by an update kernel.
 //
-//   * every rank owns one exchange buffer [header 1 KB | flat fp32 gradient] allocated with cudaMalloc and exported with a
+//   * every rank owns one exchange buffer [header 1 KB | flat fp32 gradient | result] allocated with cudaMalloc, exported with a
 //     CUDA IPC handle; the ranks of a node open each other's buffers once (msb_peer_open enables peer access);
 //   * a step is one launch per rank: announce "my gradient is complete" to every peer (release store at system scope into
 //     the peer's header), wait for all announcements, then every rank reads ALL ranks' gradients element by element in
